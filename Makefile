@@ -1,0 +1,24 @@
+# Builds the B200-native daligner library (sm_100a only) and the oracle.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC      := damar_b200/csrc
+OBJS      := $(CSRC)/api.o $(CSRC)/scan.o $(CSRC)/radix_sort.o $(CSRC)/kmer_index.o $(CSRC)/seed_merge.o $(CSRC)/pair_align.o $(CSRC)/las_sink.o
+LIB       := damar_b200/libdamar_b200.so
+
+.PHONY: all lib oracle clean
+all: lib oracle
+
+lib: $(LIB)
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/damar_b200.h
+	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart_static -lpthread -ldl -lrt
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -f $(OBJS) $(CSRC)/*.ptxas.log $(LIB)

@@ -1,0 +1,351 @@
+"""Python host mirror of the reference's filter interface, bound to libdamar_b200.so via ctypes.
+
+The three operators keep the reference's names and argument meaning
+(dalign/filter.h:64-70):
+
+    set_filter_params(kmer, binshift, suppress, hitmin, nthreads)   -> Set_Filter_Params
+    sort_kmers(block, comp=0)                                       -> Sort_Kmers
+    match_filter(ablock, bblock, atable, btable, self_, comp)       -> Match_Filter
+
+and ``daligner(...)`` replays daligner.c:958-1073 on top of them (index A once, compare against
+every B block in both orientations, Write_Overlap_Buffer per block pair).  All arithmetic happens
+in the CUDA library; this file only moves host buffers.  There is no CPU fallback: importing works
+anywhere, calling any operator without the built library or without a GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .dbio import Block
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdamar_b200.so")
+
+
+class BlockDesc(C.Structure):
+    _fields_ = [("nreads", C.c_int32), ("maxlen", C.c_int32), ("totlen", C.c_int64), ("ufirst", C.c_int32),
+                ("part", C.c_int32), ("bases", C.c_void_p), ("boff", C.c_void_p), ("rlen", C.c_void_p),
+                ("mask_anno", C.c_void_p), ("mask_data", C.c_void_p), ("freq", C.c_float * 4),
+                ("sizeof_db", C.c_int64)]
+
+
+class Options(C.Structure):
+    _fields_ = [("verbose", C.c_int32), ("minover", C.c_int32), ("hgap_min", C.c_int32), ("symmetric", C.c_int32),
+                ("identity", C.c_int32), ("trace_spacing", C.c_int32), ("no_trace", C.c_int32),
+                ("reserved", C.c_int32), ("ave_corr", C.c_double), ("freq", C.c_float * 4),
+                ("mem_limit", C.c_uint64)]
+
+
+class Overlaps(C.Structure):
+    _fields_ = [("novl", C.c_int64), ("ovl", C.c_void_p), ("trace_off", C.c_void_p), ("trace", C.c_void_p),
+                ("ntrace", C.c_int64), ("nhits", C.c_int64), ("nfilt", C.c_int64), ("ncheck", C.c_int64),
+                ("limit", C.c_int32), ("multi_la_pairs", C.c_int32)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("upload_ms", C.c_float), ("extract_ms", C.c_float), ("ksort_ms", C.c_float),
+                ("count_ms", C.c_float), ("merge_ms", C.c_float), ("hsort_ms", C.c_float),
+                ("pairs_ms", C.c_float), ("align_ms", C.c_float), ("download_ms", C.c_float),
+                ("kmers", C.c_int64), ("hits", C.c_int64), ("pairs", C.c_int64), ("la_calls", C.c_int64),
+                ("wave_cells", C.c_int64), ("kernel_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+KMER_DT = np.dtype([("code", "<u8"), ("rpos", "<i4"), ("read", "<i4")])
+HIT_DT = np.dtype([("diag", "<i4"), ("apos", "<i4"), ("aread", "<i4"), ("bread", "<i4")])
+
+EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_error", "damar_set_filter_params",
+           "damar_set_options", "damar_block_upload", "damar_block_free", "damar_sort_kmers", "damar_index_free",
+           "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
+           "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
+           "damar_sink_serialise", "damar_free"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree CUDA library (no compute happens here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `make lib` (or __graft_entry__.build()); "
+                           "damar_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.damar_abi_version.restype = C.c_int
+    L.damar_init.argtypes = [C.c_int]
+    L.damar_last_error.restype = C.c_char_p
+    L.damar_set_filter_params.argtypes = [C.c_int] * 5
+    L.damar_set_options.argtypes = [C.POINTER(Options)]
+    L.damar_block_upload.restype = C.c_void_p
+    L.damar_block_upload.argtypes = [C.POINTER(BlockDesc)]
+    L.damar_block_free.argtypes = [C.c_void_p]
+    L.damar_sort_kmers.restype = C.c_void_p
+    L.damar_sort_kmers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    L.damar_index_free.argtypes = [C.c_void_p]
+    L.damar_match_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.POINTER(Overlaps)]
+    L.damar_index_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.damar_last_hits_download.restype = C.c_int64
+    L.damar_last_hits_download.argtypes = [C.c_void_p, C.c_int64]
+    L.damar_get_timings.argtypes = [C.POINTER(Timings)]
+    L.damar_sink_new.restype = C.c_void_p
+    L.damar_sink_free.argtypes = [C.c_void_p]
+    L.damar_sink_reset.argtypes = [C.c_void_p]
+    L.damar_sink_add.argtypes = [C.c_void_p, C.POINTER(Overlaps)]
+    L.damar_sink_count.restype = C.c_int64
+    L.damar_sink_count.argtypes = [C.c_void_p]
+    L.damar_sink_serialise.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.damar_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def init(device: int = -1) -> None:
+    L = load_library()
+    if L.damar_init(device) != 0:
+        raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Settings:
+    """daligner's command-line state (daligner.c:676-703) -- defaults are the reference's."""
+    kmer: int = 14            # -k
+    binshift: int = 6         # -w
+    hitmin: int = 35          # -h
+    suppress: int = 0         # -t
+    ave_corr: float = 0.70    # -e
+    minlen: int = 1000        # -l  (MINOVER = 2*minlen)
+    trace_spacing: int = 100  # -s
+    nthreads: int = 4         # -j
+    mem_limit_gb: int = 0     # -M  (0 == no cap; the reference defaults to physical RAM)
+    symmetric: bool = True    # not -A
+    identity: bool = False    # -I
+    only_identity: bool = False  # -O
+    no_trace: bool = False    # -T
+    verbose: bool = False     # -v
+    run_id: int = 1           # -r
+
+
+class DeviceBlockHandle:
+    """A DB block resident in HBM (2-bit packed) plus its lazily built k-mer indexes."""
+
+    def __init__(self, blk: Block):
+        L = load_library()
+        self.blk = blk
+        self._keep = (np.ascontiguousarray(blk.bases, np.uint8), np.ascontiguousarray(blk.boff, np.int64),
+                      np.ascontiguousarray(blk.rlen, np.int32),
+                      None if blk.mask_anno is None else np.ascontiguousarray(blk.mask_anno, np.int64),
+                      None if blk.mask_data is None else np.ascontiguousarray(
+                          blk.mask_data if blk.mask_data.size else np.zeros(1, np.int32), np.int32))
+        d = BlockDesc()
+        d.nreads, d.maxlen, d.totlen, d.ufirst, d.part = blk.nreads, blk.maxlen, blk.totlen, blk.ufirst, blk.part
+        d.bases = self._keep[0].ctypes.data + 1            # HITS_DB.bases points past the leading 4
+        d.boff = self._keep[1].ctypes.data
+        d.rlen = self._keep[2].ctypes.data
+        d.mask_anno = None if self._keep[3] is None else self._keep[3].ctypes.data
+        d.mask_data = None if self._keep[4] is None else self._keep[4].ctypes.data
+        for i in range(4):
+            d.freq[i] = float(blk.freq[i])
+        d.sizeof_db = blk.sizeof_db()
+        self.handle = L.damar_block_upload(C.byref(d))
+        if not self.handle:
+            raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
+
+    def free(self):
+        if self.handle:
+            load_library().damar_block_free(self.handle)
+            self.handle = None
+
+
+class KmerIndex:
+    def __init__(self, handle, length, dblock, comp):
+        self.handle, self.len, self.dblock, self.comp = handle, length, dblock, comp
+
+    def download(self) -> np.ndarray:
+        """Sorted list in the reference's KmerPos layout (for parity tests)."""
+        out = np.zeros(self.len, KMER_DT)
+        if self.len and load_library().damar_index_download(self.handle, out.ctypes.data, self.len) != 0:
+            raise RuntimeError("damar_index_download failed")
+        return out
+
+    def free(self):
+        if self.handle:
+            load_library().damar_index_free(self.handle)
+            self.handle = None
+
+
+def set_filter_params(kmer: int, binshift: int, suppress: int, hitmin: int, nthreads: int) -> int:
+    """Set_Filter_Params (filter.c:171): returns 1 for an illegal combination."""
+    return load_library().damar_set_filter_params(kmer, binshift, suppress, hitmin, nthreads)
+
+
+def set_options(s: Settings, freq: Sequence[float]) -> None:
+    o = Options()
+    o.verbose = int(s.verbose)
+    o.minover = 2 * s.minlen
+    o.hgap_min = 0
+    o.symmetric = int(s.symmetric)
+    o.identity = int(s.identity or s.only_identity)
+    o.trace_spacing = s.trace_spacing
+    o.no_trace = int(s.no_trace)
+    o.ave_corr = s.ave_corr
+    for i in range(4):
+        o.freq[i] = float(freq[i])
+    o.mem_limit = int(s.mem_limit_gb) * (1 << 30)
+    load_library().damar_set_options(C.byref(o))
+
+
+def sort_kmers(dblock: DeviceBlockHandle, comp: int = 0) -> Optional[KmerIndex]:
+    """Sort_Kmers (filter.c:753).  comp=1 indexes the reverse-complemented block on the device."""
+    n = C.c_int64(0)
+    h = load_library().damar_sort_kmers(dblock.handle, comp, C.byref(n))
+    if not h:
+        return None
+    return KmerIndex(h, n.value, dblock, comp)
+
+
+def match_filter(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, atable: Optional[KmerIndex],
+                 btable: Optional[KmerIndex], self_: bool, comp: int) -> Overlaps:
+    """Match_Filter (filter.c:2519) for one orientation; the result lives in the library until the next call."""
+    out = Overlaps()
+    rc = load_library().damar_match_filter(ablock.handle, bblock.handle, atable.handle if atable else None,
+                                           btable.handle if btable else None, int(self_), comp, C.byref(out))
+    if rc != 0:
+        raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
+    return out
+
+
+def last_hits() -> np.ndarray:
+    L = load_library()
+    n = L.damar_last_hits_download(None, 0)
+    out = np.zeros(n, HIT_DT)
+    if n:
+        L.damar_last_hits_download(out.ctypes.data, n)
+    return out
+
+
+def timings() -> dict:
+    t = Timings()
+    load_library().damar_get_timings(C.byref(t))
+    return t.as_dict()
+
+
+class LasSink:
+    """Overlap_IO_Buffer + Write_Overlap_Buffer (align.c:5969-6380)."""
+
+    def __init__(self):
+        self.h = load_library().damar_sink_new()
+
+    def add(self, ov: Overlaps):
+        load_library().damar_sink_add(self.h, C.byref(ov))
+
+    def reset(self):
+        load_library().damar_sink_reset(self.h)
+
+    def count(self) -> int:
+        return load_library().damar_sink_count(self.h)
+
+    def serialise(self, s: Settings, split_read: int = -1) -> Tuple[bytes, Optional[bytes]]:
+        L = load_library()
+        b1, b2 = C.c_void_p(), C.c_void_p()
+        l1, l2 = C.c_int64(0), C.c_int64(0)
+        if L.damar_sink_serialise(self.h, s.trace_spacing, int(s.no_trace), int(s.only_identity), split_read,
+                                  C.byref(b1), C.byref(l1), C.byref(b2), C.byref(l2)) != 0:
+            raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
+        o1 = C.string_at(b1, l1.value)
+        L.damar_free(b1)
+        o2 = None
+        if b2.value:
+            o2 = C.string_at(b2, l2.value)
+            L.damar_free(b2)
+        return o1, o2
+
+    def free(self):
+        if self.h:
+            load_library().damar_sink_free(self.h)
+            self.h = None
+
+
+def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list] = None,
+             dcache: Optional[Dict[str, DeviceBlockHandle]] = None) -> Dict[str, bytes]:
+    """`daligner [flags] A B1 B2 ...` (daligner.c:958-1073): returns {las file name: bytes}."""
+    init()
+    if set_filter_params(s.kmer, s.binshift, s.suppress, s.hitmin, s.nthreads):
+        raise ValueError("Illegal combination of filter parameters")       # daligner.c:862-866
+    symmetric = s.symmetric and all(b.root == ablk.root for b in bblks)     # daligner.c:911-946
+    s = Settings(**{**s.__dict__, "symmetric": symmetric})
+    set_options(s, ablk.freq)
+    own = dcache is None
+    dcache = {} if dcache is None else dcache
+    out: Dict[str, bytes] = {}
+
+    def resident(b: Block) -> DeviceBlockHandle:
+        if b.name not in dcache:
+            dcache[b.name] = DeviceBlockHandle(b)
+        return dcache[b.name]
+
+    da = resident(ablk)
+    aidx = sort_kmers(da, 0)
+    sink = LasSink()
+    for bblk in bblks:
+        selfcmp = bblk.name == ablk.name
+        db = da if selfcmp else resident(bblk)
+        st = {}
+        for comp in (0, 1):
+            bidx = aidx if (selfcmp and comp == 0) else sort_kmers(db, comp)
+            ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
+            sink.add(ov)
+            st[f"nhits{comp}"], st[f"nfilt{comp}"], st[f"novl{comp}"] = ov.nhits, ov.nfilt, ov.novl
+            st[f"multi{comp}"] = ov.multi_la_pairs
+            st[f"t{comp}"] = timings()
+            if bidx is not None and bidx is not aidx:
+                bidx.free()
+        if stats is not None:
+            stats.append(st)
+        an, bn = ablk.name, bblk.name
+        if selfcmp or not symmetric:                                        # align.c:6235
+            b1, _ = sink.serialise(s, -1)
+            out[f"{an}.{bn}.las"] = b1
+        else:
+            last = (bblk.ufirst + bblk.nreads - 1) if bblk.part < ablk.part else (ablk.ufirst + ablk.nreads - 1)
+            b1, b2 = sink.serialise(s, last)
+            n1, n2 = f"{an}.{bn}.las", f"{bn}.{an}.las"
+            if bblk.part < ablk.part:                                       # align.c:6308-6313
+                n1, n2 = n2, n1
+            out[n1], out[n2] = b1, b2
+        sink.reset()
+    sink.free()
+    if aidx is not None:
+        aidx.free()
+    if own:
+        for h in dcache.values():
+            h.free()
+    return out
+
+
+def las_dir(run_id: int, part: int) -> str:
+    """getDir (db/DB.c:1851): d<run:03d>_<block:05d>."""
+    return f"d{run_id:03d}_{part:05d}"
+
+
+def write_outputs(outdir: str, files: Dict[str, bytes], run_id: int = 1) -> List[str]:
+    paths = []
+    for name, data in files.items():
+        part = int(name.split(".")[1])
+        d = os.path.join(outdir, las_dir(run_id, part))
+        os.makedirs(d, exist_ok=True)
+        p = os.path.join(d, name)
+        with open(p, "wb") as f:
+            f.write(data)
+        paths.append(p)
+    return paths

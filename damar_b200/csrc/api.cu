@@ -1,0 +1,210 @@
+// api.cu -- the C-ABI of include/damar_b200.h on top of the stage implementations.
+#include <cstdarg>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace damar {
+
+static std::string g_last_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_last_error = buf;
+    fprintf(stderr, "damar_b200: %s\n", buf);
+}
+void fatal(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    fprintf(stderr, "damar_b200: fatal: %s\n", buf);
+    fflush(stderr);
+    exit(1);                                   // reference behaviour: message + exit(1), db/DB.h:84-86
+}
+
+Context &ctx() { static Context c; return c; }
+
+static int pick_device() {
+    const char *e = getenv("DAMAR_DEVICE");
+    if (e && *e) return atoi(e);
+    e = getenv("LOCAL_RANK");
+    if (e && *e) return atoi(e);
+    return 0;
+}
+
+static int do_init(int device) {
+    Context &c = ctx();
+    if (c.ready) return 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error("no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return 1;
+    }
+    if (device < 0) device = pick_device();
+    if (device >= n) device = device % n;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name, prop.major, prop.minor);
+        return 1;
+    }
+    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.device = device;
+    // defaults of daligner.c:688-703
+    c.opt.minover = 2000; c.opt.symmetric = 1; c.opt.trace_spacing = 100; c.opt.ave_corr = .70;
+    c.opt.freq[0] = c.opt.freq[1] = c.opt.freq[2] = c.opt.freq[3] = .25f;
+    c.ready = true;
+    return 0;
+}
+
+void ensure_init() {
+    if (!ctx().ready && do_init(-1) != 0) fatal("%s", g_last_error.c_str());
+}
+
+// ---- results of the last match_filter call ----
+static HostOverlaps g_out;
+static SeedHits g_hits;
+static const DeviceBlock *g_hits_a = nullptr, *g_hits_b = nullptr;
+
+void SeedHits::release() {
+    if (keys) cudaFree(keys);
+    if (bpos) cudaFree(bpos);
+    keys = nullptr; bpos = nullptr; n = 0;
+}
+
+}  // namespace damar
+
+using namespace damar;
+
+extern "C" {
+
+int damar_abi_version(void) { return DAMAR_B200_ABI_VERSION; }
+int damar_init(int device) { return do_init(device); }
+const char *damar_last_error(void) { return g_last_error.c_str(); }
+
+void damar_shutdown(void) {
+    Context &c = ctx();
+    if (!c.ready) return;
+    g_hits.release();
+    cudaStreamSynchronize(c.stream);
+    cudaStreamDestroy(c.stream);
+    c.ready = false;
+}
+
+int damar_set_filter_params(int kmer, int binshift, int suppress, int hitmin, int nthreads) {
+    if (kmer <= 1 || kmer > 32) return 1;                     // filter.c:173-174 (+ u64 code limit)
+    FilterParams &fp = ctx().fp;
+    fp.kmer = kmer; fp.binshift = binshift; fp.suppress = suppress; fp.hitmin = hitmin; fp.nthreads = nthreads;
+    fp.kmask = (kmer == 32) ? ~0ull : ((1ull << (2 * kmer)) - 1);
+    fp.nthreads_pow2 = 1; fp.nshift = 0;
+    while (2 * fp.nthreads_pow2 <= nthreads) { fp.nthreads_pow2 *= 2; fp.nshift++; }   // filter.c:192-198
+    fp.set = true;
+    return 0;
+}
+
+void damar_set_options(const damar_options *opt) { ctx().opt = *opt; }
+
+damar_block *damar_block_upload(const damar_block_desc *desc) {
+    ensure_init();
+    return reinterpret_cast<damar_block *>(upload_block(desc));
+}
+void damar_block_free(damar_block *blk) { delete reinterpret_cast<DeviceBlock *>(blk); }
+
+damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len) {
+    ensure_init();
+    DeviceIndex *idx = build_index(reinterpret_cast<DeviceBlock *>(blk), comp);
+    if (len) *len = idx->len;
+    ctx().tm.kernel_launches = ctx().launches;
+    if (idx->len == 0) { delete idx; return nullptr; }        // filter.c:990-993
+    return reinterpret_cast<damar_index *>(idx);
+}
+void damar_index_free(damar_index *idx) { delete reinterpret_cast<DeviceIndex *>(idx); }
+
+int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
+                       int self, int comp, damar_overlaps *out) {
+    ensure_init();
+    Context &c = ctx();
+    DeviceBlock *ab = reinterpret_cast<DeviceBlock *>(ablk), *bb = reinterpret_cast<DeviceBlock *>(bblk);
+    DeviceIndex *ai = reinterpret_cast<DeviceIndex *>(aidx), *bi = reinterpret_cast<DeviceIndex *>(bidx);
+    g_out.ovl.clear(); g_out.toff.clear(); g_out.trace.clear();
+    g_out.nfilt = g_out.multi = g_out.cells = g_out.pairs = 0;
+    g_hits.release();
+    g_hits_a = ab; g_hits_b = bb;
+    memset(out, 0, sizeof(*out));
+    c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
+    c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0;
+    if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
+        if (comp) ensure_revcomp(bb);
+        seed_hits(ai, bi, self, comp, g_hits);
+        if (g_hits.n > 0) report_and_align(ab, bb, comp, self, g_hits, g_out);
+    }
+    out->novl = (int64_t)g_out.ovl.size();
+    out->ovl = g_out.ovl.data();
+    out->trace_off = g_out.toff.data();
+    out->trace = g_out.trace.data();
+    out->ntrace = (int64_t)g_out.trace.size();
+    out->nhits = g_hits.n;
+    out->nfilt = g_out.nfilt;
+    out->ncheck = out->novl;
+    out->limit = g_hits.limit;
+    out->multi_la_pairs = (int32_t)g_out.multi;
+    c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs;
+    c.tm.kernel_launches = c.launches;
+    return 0;
+}
+
+// ---- stage read-backs for the parity tests ----
+namespace {
+__global__ void to_kmerpos(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ gpos, int64_t n,
+                           const uint32_t *__restrict__ boff, int nreads, uint4 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t p = gpos[i];
+    int lo = 0, hi = nreads;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (boff[mid] <= p) lo = mid; else hi = mid; }
+    uint64_t c = codes[i];
+    out[i] = make_uint4((uint32_t)c, (uint32_t)(c >> 32), p - boff[lo], (uint32_t)lo);
+}
+__global__ void to_seedpair(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ bpos, int64_t n, int pbits, int abits,
+                            int4 *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i];
+    int apos = (int)(k & ((1ull << pbits) - 1));
+    int aread = (int)((k >> pbits) & ((1ull << abits) - 1));
+    int bread = (int)(k >> (pbits + abits));
+    out[i] = make_int4(apos - (int)bpos[i], apos, aread, bread);
+}
+}  // namespace
+
+int damar_index_download(const damar_index *idx_, void *kmerpos_out, int64_t capacity) {
+    const DeviceIndex *idx = reinterpret_cast<const DeviceIndex *>(idx_);
+    if (idx == nullptr || idx->len > capacity) return 1;
+    Context &c = ctx();
+    DevBuf<uint4> tmp; tmp.reserve((size_t)idx->len);
+    to_kmerpos<<<(unsigned)((idx->len + 255) / 256), 256, 0, c.stream>>>(idx->codes, idx->gpos, idx->len, idx->blk->boff,
+                                                                         idx->blk->nreads, tmp.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(kmerpos_out, tmp.p, sizeof(uint4) * idx->len, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
+    if (g_hits.n == 0) return 0;
+    if (seedpair_out == nullptr || g_hits.n > capacity) return g_hits.n;
+    Context &c = ctx();
+    DevBuf<int4> tmp; tmp.reserve((size_t)g_hits.n);
+    to_seedpair<<<(unsigned)((g_hits.n + 255) / 256), 256, 0, c.stream>>>(g_hits.keys, g_hits.bpos, g_hits.n, g_hits.pbits,
+                                                                         g_hits.abits, tmp.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(seedpair_out, tmp.p, sizeof(int4) * g_hits.n, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return g_hits.n;
+}
+
+void damar_get_timings(damar_timings *t) { *t = ctx().tm; }
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// common.cuh -- shared declarations of the damar_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/damar_b200.h"
+
+namespace damar {
+
+// ---- error handling: the reference prints to stderr and exit(1)s (db/DB.h:84-86); so do we ----
+void set_error(const char *fmt, ...);
+[[noreturn]] void fatal(const char *fmt, ...);
+
+#define CUDA_CHECK(expr)                                                                       \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            ::damar::fatal("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,      \
+                           __LINE__, cudaGetErrorString(_e));                                  \
+    } while (0)
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+constexpr int NUM_SMS_B200 = 148;
+constexpr int PACK_FRONT_PAD = 4;     // words of zero padding in front of every packed base array
+
+// ---- simple owning device buffer ----
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;      // capacity in elements
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    // grow-only (contents are NOT preserved)
+    void reserve(size_t want) {
+        if (want <= n) return;
+        release();
+        size_t cap = want + want / 8 + 256;
+        CUDA_CHECK(cudaMalloc((void **)&p, cap * sizeof(T)));
+        n = cap;
+    }
+    T *steal() { T *q = p; p = nullptr; n = 0; return q; }
+};
+
+// ---- filter parameters (Set_Filter_Params, filter.c:171-201) ----
+struct FilterParams {
+    int kmer = 14, binshift = 6, suppress = 0, hitmin = 35, nthreads = 4;
+    int nthreads_pow2 = 4, nshift = 2;
+    uint64_t kmask = (1ull << 28) - 1;
+    bool set = false;
+};
+
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st) {
+        CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+        CUDA_CHECK(cudaEventRecord(a, s));
+    }
+    float stop() {
+        float ms = 0;
+        CUDA_CHECK(cudaEventRecord(b, s)); CUDA_CHECK(cudaEventSynchronize(b));
+        CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+        return ms;
+    }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+// ---- process-wide context ----
+struct Context {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    FilterParams fp;
+    damar_options opt{};
+    damar_timings tm{};
+    int64_t launches = 0;
+    bool ready = false;
+};
+Context &ctx();
+void ensure_init();
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// ---- device-side block (stage 0) ----
+// gpos = index into the reference's unpacked `bases` array: read i occupies
+// [boff[i], boff[i]+rlen[i]) and position boff[i]+rlen[i] is its terminator slot.
+struct DeviceBlock {
+    int32_t nreads = 0, maxlen = 0, ufirst = 0, part = 0;
+    int64_t totlen = 0, nbases = 0;             // nbases = boff[nreads]
+    int64_t sizeof_db = 0;
+    float freq[4] = {0, 0, 0, 0};
+    uint32_t *packed[2] = {nullptr, nullptr};   // 2 bit/base, 16 bases per word, [0]=forward [1]=revcomp
+    int64_t npacked_words = 0;
+    uint32_t *boff = nullptr;                   // [nreads+1] (blocks are < 2^31 bases, filter.c:794)
+    int32_t *rlen = nullptr;                    // [nreads]
+    bool has_mask = false;
+    int64_t *mask_anno[2] = {nullptr, nullptr}; // [nreads+1], forward / mirrored
+    int32_t *mask_data[2] = {nullptr, nullptr};
+    int64_t mask_len = 0;
+    std::vector<int64_t> h_boff;                // host copies (small)
+    std::vector<int32_t> h_rlen;
+    ~DeviceBlock();
+};
+
+// ---- device-side sorted k-mer list (stage 1 result) ----
+struct DeviceIndex {
+    DeviceBlock *blk = nullptr;
+    int comp = 0;
+    int64_t len = 0;
+    uint64_t *codes = nullptr;   // ascending, stable: ties in gpos order
+    uint32_t *gpos = nullptr;    // position of the k-mer's LAST base (rpos = gpos - boff[read])
+    ~DeviceIndex();
+};
+
+// ---- stage entry points (implemented in the .cu files) ----
+// radix_sort.cu : stable LSD radix sort of (u64 key, u32 value) on bits [0, nbits)
+struct SortScratch;
+void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uint32_t *&vals_alt,
+                      int64_t n, int nbits, cudaStream_t st);
+// scan.cu
+void exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int64_t n, uint64_t *total_dev, cudaStream_t st);
+void exclusive_scan_u32_inplace(uint32_t *data, int64_t n, uint32_t *total_dev, cudaStream_t st);
+
+// kmer_index.cu
+DeviceBlock *upload_block(const damar_block_desc *d);
+void ensure_revcomp(DeviceBlock *b);
+DeviceIndex *build_index(DeviceBlock *b, int comp);
+
+// seed_merge.cu
+struct SeedHits {
+    uint64_t *keys = nullptr;   // (bread << (abits+pbits)) | (aread << pbits) | apos
+    uint32_t *bpos = nullptr;
+    int64_t n = 0;
+    int pbits = 0, abits = 0, bbits = 0;
+    int32_t limit = 0;
+    void release();
+};
+void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out);
+
+// pair_align.cu
+struct HostOverlaps {
+    std::vector<damar_overlap> ovl;
+    std::vector<uint64_t> toff;
+    std::vector<uint16_t> trace;
+    int64_t nfilt = 0, multi = 0, cells = 0, pairs = 0;
+};
+void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
+                      HostOverlaps &out);
+
+}  // namespace damar

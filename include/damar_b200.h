@@ -1,0 +1,146 @@
+/*
+ * damar_b200.h -- C-ABI of the B200-native daligner overlap kernel.
+ *
+ * This is the drop-in boundary for the one hot path of MartinPippel/DAmar that this
+ * repository accelerates: the three entry points of dalign/filter.h:64-70
+ *
+ *     int   Set_Filter_Params(int kmer, int binshift, int suppress, int hitmin, int nthreads);
+ *     void *Sort_Kmers(HITS_DB *block, int *len);
+ *     void  Match_Filter(char *aname, HITS_DB *ablock, char *bname, HITS_DB *bblock,
+ *                        void *atable, int alen, void *btable, int blen,
+ *                        int comp, Align_Spec *asettings);
+ *
+ * restated with plain pointers and sizes (no HITS_DB / Align_Spec / torch types), so that
+ * any host (the reference's daligner.c through the shim in include/damar_filter_compat.h,
+ * our own C++ driver, or Python via ctypes) can bind it.  Everything below runs on the GPU;
+ * there is no CPU fallback: every call fails loudly (message on stderr + non-zero return /
+ * NULL) when no CUDA device is usable.
+ *
+ * Reference citations are relative to the reference root (dalign/..., db/...).
+ */
+#ifndef DAMAR_B200_H
+#define DAMAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAMAR_B200_ABI_VERSION 1
+
+/* ---- host view of one DB block (what read_DB leaves in a HITS_DB, daligner.c:442-509) ---- */
+typedef struct damar_block_desc {
+    int32_t        nreads;      /* HITS_DB.nreads                                            */
+    int32_t        maxlen;      /* HITS_DB.maxlen                                            */
+    int64_t        totlen;      /* HITS_DB.totlen                                            */
+    int32_t        ufirst;      /* HITS_DB.ufirst : DB-global id of read 0                   */
+    int32_t        part;        /* HITS_DB.part   : block number (0 = whole DB)              */
+    const uint8_t *bases;       /* HITS_DB.bases  : 1 byte/base (0..3), 4 after every read   */
+    const int64_t *boff;        /* [nreads+1] in-memory offsets  (HITS_READ.boff)            */
+    const int32_t *rlen;        /* [nreads]                       (HITS_READ.rlen)            */
+    const int64_t *mask_anno;   /* merged mask track: [nreads+1] offsets in ints, or NULL    */
+    const int32_t *mask_data;   /* sorted [beg,end) pairs (daligner.c:474-497)               */
+    float          freq[4];     /* HITS_DB.freq                                              */
+    int64_t        sizeof_db;   /* sizeof_DB(block), db/DB.c:726 (enters the -M rule)        */
+} damar_block_desc;
+
+/* ---- the globals of daligner.c:131-140 that filter.c reads, plus the Align_Spec fields ---- */
+typedef struct damar_options {
+    int32_t  verbose;           /* VERBOSE                                                   */
+    int32_t  minover;           /* MINOVER, already doubled (daligner.c:861)                 */
+    int32_t  hgap_min;          /* HGAP_MIN (always 0 in DAmar, daligner.c:688)              */
+    int32_t  symmetric;         /* SYMMETRIC (0 with -A or across DBs)                       */
+    int32_t  identity;          /* IDENTITY (-I / -O)                                        */
+    int32_t  trace_spacing;     /* Trace_Spacing(spec)          (-s)                         */
+    int32_t  no_trace;          /* -T                                                        */
+    int32_t  reserved;
+    double   ave_corr;          /* Average_Correlation(spec)    (-e)                         */
+    float    freq[4];           /* Base_Frequencies(spec) = A block freq (daligner.c:951)    */
+    uint64_t mem_limit;         /* MEM_LIMIT in bytes, 0 == -M0                              */
+} damar_options;
+
+/* ---- one overlap as Write_Overlap serialises it (align.c:3345-3373): 40 bytes ---- */
+typedef struct damar_overlap {
+    int32_t  tlen, diffs, abpos, bbpos, aepos, bepos;
+    uint32_t flags;
+    int32_t  aread, bread;
+    int32_t  pad;               /* always 0 (the reference leaves struct padding here)       */
+} damar_overlap;
+
+typedef struct damar_overlaps {
+    int64_t              novl;
+    const damar_overlap *ovl;        /* novl records, in emission order                       */
+    const uint64_t      *trace_off;  /* novl offsets (in values) into trace                   */
+    const uint16_t      *trace;      /* uncompressed trace values (d_i, b_i pairs)            */
+    int64_t              ntrace;
+    /* counters printed by -v (filter.c:2910-2928) */
+    int64_t              nhits;      /* seed hits (k-mer matches)                             */
+    int64_t              nfilt;      /* Local_Alignment calls                                 */
+    int64_t              ncheck;     /* records                                               */
+    int32_t              limit;      /* k-mer match cap chosen by the -M rule                 */
+    int32_t              multi_la_pairs;
+} damar_overlaps;
+
+typedef struct damar_block damar_block;      /* device-resident block                         */
+typedef struct damar_index damar_index;      /* device-resident sorted k-mer list             */
+
+/* library / device life cycle.  damar_init returns 0 on success; every other entry point
+ * calls it implicitly with device = $DAMAR_DEVICE or LOCAL_RANK or 0.                          */
+int         damar_abi_version(void);
+int         damar_init(int device);
+void        damar_shutdown(void);
+const char *damar_last_error(void);
+
+/* Set_Filter_Params (filter.c:171-201).  Returns 1 for an illegal combination. */
+int  damar_set_filter_params(int kmer, int binshift, int suppress, int hitmin, int nthreads);
+void damar_set_options(const damar_options *opt);
+
+/* block residency: ships the block to HBM and packs it to 2 bit/base.                          */
+damar_block *damar_block_upload(const damar_block_desc *desc);
+void         damar_block_free(damar_block *blk);
+
+/* Sort_Kmers (filter.c:753-994).  comp != 0 builds the index of the reverse-complemented block
+ * (what daligner.c:998-1003 obtains with complement_DB + Sort_Kmers) without touching host memory.
+ * *len receives the k-mer count; NULL/0 when the block has no k-mers.                          */
+damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len);
+void         damar_index_free(damar_index *idx);
+
+/* Match_Filter (filter.c:2519-2929) for one orientation.  `self` is the reference's
+ * MG_self (aname == bname).  Results are owned by the library and stay valid until the next
+ * damar_match_filter / damar_shutdown call.  Returns 0 on success.                             */
+int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
+                       int self, int comp, damar_overlaps *out);
+
+/* ---- stage-level read-backs (used by the parity tests; not needed by a host) ---- */
+/* sorted k-mer list in the reference's KmerPos layout {u64 code; i32 rpos; i32 read}           */
+int damar_index_download(const damar_index *idx, void *kmerpos_out, int64_t capacity);
+/* sorted seed hits of the last damar_match_filter call in SeedPair layout {diag,apos,aread,bread} */
+int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity);
+/* per-stage device timings (ms) of the last damar_sort_kmers / damar_match_filter call          */
+typedef struct damar_timings {
+    float upload_ms, extract_ms, ksort_ms;
+    float count_ms, merge_ms, hsort_ms, pairs_ms, align_ms, download_ms;
+    int64_t kmers, hits, pairs, la_calls, wave_cells, kernel_launches;
+} damar_timings;
+void damar_get_timings(damar_timings *t);
+
+/* ---- output path: Overlap_IO_Buffer + Write_Overlap_Buffer (align.c:5969-6380), host only ---- */
+typedef struct damar_las_sink damar_las_sink;
+damar_las_sink *damar_sink_new(void);
+void            damar_sink_free(damar_las_sink *s);
+void            damar_sink_reset(damar_las_sink *s);                         /* Reset_Overlap_Buffer */
+void            damar_sink_add(damar_las_sink *s, const damar_overlaps *o);  /* AddOverlapToBuffer x novl */
+int64_t         damar_sink_count(const damar_las_sink *s);
+/* Sort by SORT_OVL (align.c:6104) and serialise to malloc'd .las images (header int64 novl,
+ * int32 tspace; 40-byte records; u8 traces when trace_spacing <= 125).  split_read >= 0 writes
+ * records with aread <= split_read to buf1 and the rest to buf2 (align.c:6330-6354).
+ * Free the buffers with damar_free.  Returns 1 if a trace value does not fit 8 bits.           */
+int  damar_sink_serialise(damar_las_sink *s, int trace_spacing, int no_trace, int only_identity, int split_read,
+                          uint8_t **buf1, int64_t *len1, uint8_t **buf2, int64_t *len2);
+void damar_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAMAR_B200_H */

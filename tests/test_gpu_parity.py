@@ -1,0 +1,106 @@
+"""GPU parity: the CUDA path (through the C-ABI of include/damar_b200.h) against
+  (1) the committed reference .las files of every golden case, bit for bit (padding bytes masked),
+  (2) the oracle, stage by stage: sorted k-mer list (Sort_Kmers contract) and sorted seed hits.
+"""
+import numpy as np
+import pytest
+
+import oracle_ffi as O
+from cases import CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from damar_b200 import api, dbio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    api.init()
+    yield
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_las_matches_reference(case):
+    o = parse_flags(CASES[case]["flags"])
+    blks = [load_block(TINY, n, tuple(o["masks"])) for n in CASES[case]["blocks"]]
+    stats = []
+    out = api.daligner(blks[0], blks[1:], settings(o), stats=stats)
+    gold = golden_files(case)
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+@pytest.mark.parametrize("case,comp", [("default", 0), ("default", 1), ("rndmask", 0), ("rndmask", 1),
+                                       ("k16s200", 0), ("twomasks", 1)])
+def test_sorted_kmers_match_oracle(case, comp):
+    o = parse_flags(CASES[case]["flags"])
+    blk = load_block(TINY, CASES[case]["blocks"][0], tuple(o["masks"]))
+    p = O.make_params(**oracle_kwargs(o))
+    hb = O.HostBlock(blk)
+    L = O.lib()
+    if comp:
+        import ctypes as C
+        cb = L.ora_complement_block(C.byref(hb.c))
+        n = C.c_int64(0)
+        ptr = L.ora_sort_kmers(cb, C.byref(p), C.byref(n))
+        ref = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n.value * 16,)).view(O.KMER_DT).copy()
+        L.ora_free(ptr); L.ora_free_block(cb)
+    else:
+        ptr, n, arr = O.sort_kmers(hb, p)
+        ref = arr[:n].copy()
+        L.ora_free(ptr)
+    assert api.set_filter_params(o["k"], o["w"], o["t"], o["h"], o["j"]) == 0
+    api.set_options(settings(o), blk.freq)
+    d = api.DeviceBlockHandle(blk)
+    idx = api.sort_kmers(d, comp)
+    got = idx.download()
+    idx.free(); d.free()
+    assert len(got) == len(ref)
+    assert np.array_equal(got["code"], ref["code"])
+    assert np.array_equal(got["read"], ref["read"])
+    assert np.array_equal(got["rpos"], ref["rpos"])
+
+
+@pytest.mark.parametrize("case,comp", [("default", 0), ("default", 1), ("identity", 0), ("identity", 1), ("memlimit", 0)])
+def test_sorted_hits_match_oracle(case, comp):
+    import ctypes as C
+    o = parse_flags(CASES[case]["flags"])
+    names = CASES[case]["blocks"]
+    ablk = load_block(TINY, names[0], tuple(o["masks"]))
+    bblk = load_block(TINY, names[1], tuple(o["masks"]))
+    selfcmp = names[0] == names[1]
+    kw = oracle_kwargs(o)
+    kw["freq"] = tuple(float(x) for x in ablk.freq)
+    p = O.make_params(**kw)
+    p.sizeof_a, p.sizeof_b = ablk.sizeof_db(), bblk.sizeof_db()
+    L = O.lib()
+    ha = O.HostBlock(ablk)
+    hb = ha if selfcmp else O.HostBlock(bblk)
+    aptr, alen, _ = O.sort_kmers(ha, p)
+    if comp:
+        cb = L.ora_complement_block(C.byref(hb.c))
+        n = C.c_int64(0)
+        bptr = L.ora_sort_kmers(cb, C.byref(p), C.byref(n)); blen = n.value
+        nh = C.c_int64(0); lim = C.c_int32(0)
+        hp = L.ora_seed_hits(C.byref(ha.c), cb, aptr, alen, bptr, blen, int(selfcmp), 1, C.byref(p), C.byref(nh), C.byref(lim))
+    else:
+        if selfcmp:
+            bptr, blen = aptr, alen
+        else:
+            bptr, blen, _ = O.sort_kmers(hb, p)
+        nh = C.c_int64(0); lim = C.c_int32(0)
+        hp = L.ora_seed_hits(C.byref(ha.c), C.byref(hb.c), aptr, alen, bptr, blen, int(selfcmp), 0, C.byref(p), C.byref(nh), C.byref(lim))
+    ref = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(nh.value * 16,)).view(O.HIT_DT).copy()
+
+    assert api.set_filter_params(o["k"], o["w"], o["t"], o["h"], o["j"]) == 0
+    api.set_options(settings(o), ablk.freq)
+    da = api.DeviceBlockHandle(ablk)
+    db = da if selfcmp else api.DeviceBlockHandle(bblk)
+    ai = api.sort_kmers(da, 0)
+    bi = ai if (selfcmp and not comp) else api.sort_kmers(db, comp)
+    ov = api.match_filter(da, db, ai, bi, selfcmp, comp)
+    got = api.last_hits()
+    assert ov.nhits == nh.value and ov.limit == lim.value
+    for f in ("bread", "aread", "apos", "diag"):
+        assert np.array_equal(got[f], ref[f]), f
