@@ -6,8 +6,13 @@ CSRC      := damar_b200/csrc
 OBJS      := $(CSRC)/api.o $(CSRC)/scan.o $(CSRC)/radix_sort.o $(CSRC)/kmer_index.o $(CSRC)/seed_merge.o $(CSRC)/pair_align.o $(CSRC)/las_sink.o
 LIB       := damar_b200/libdamar_b200.so
 
-.PHONY: all lib oracle clean
-all: lib oracle
+.PHONY: all lib host oracle clean
+all: lib host oracle
+
+host: damar_b200/host/simdb
+
+damar_b200/host/simdb: damar_b200/host/simdb.cpp
+	g++ -O2 -o $@ $<
 
 lib: $(LIB)
 

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- daligner overlaps/s on B200 (and the reference CPU daligner beside it).
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line.  A *step* is one pass of the whole hot path over the workload: every job of the
+HPCdaligner plan of the synthetic DB (all block pairs, both orientations), from k-mer tuples to
+sorted `.las` images in host memory.
+
+Workload (default, `config.workload`): BASELINE.json configs[1] -- simulator.c model, 4.6 Mbp genome
+at 60x, 12% error, ~10 kbp reads, DBsplit -s70 -> 4 blocks, 10 block pairs, `daligner -k14 -w6 -h35
+-e.70 -l1000 -s100 -M32`.  Data are synthetic (damar_b200/host/simdb restates db/simulator.c +
+FA2db + DBsplit and writes a real Dazzler DB under a scratch directory; nothing is downloaded).
+
+  value : overlaps/s with the blocks already resident in HBM when the timed region starts
+  e2e   : overlaps/s through the public API with HOST buffers: every step uploads the unpacked
+          blocks from host memory (H2D inside the timed region) and ends with the sorted .las
+          images in host memory (D2H inside the timed region)
+  roofline : the radix-sort scatter kernel (the dominant HBM-bound kernel), algorithmic bytes =
+          32 B per element per pass on the reference's 16-byte records (SURVEY.md section 8d / DESIGN.md),
+          duration measured with CUDA events around every launch, peak from MEASURED_PEAKS.json
+  cpu_baseline : the unmodified reference daligner (oracle/_ref/daligner, `-j<P>`) on a bounded
+          sample (one block pair) on this host's cores
+
+Multi-GPU (N > 1, torchrun): block pairs are independent; every rank runs the same number of
+units (its own copy of the plan on its own synthetic DB, seed = base + rank), no data-path
+collective; value = total overlaps of all ranks / max-over-ranks device-timed duration ("weak").
+
+`--impl reference` times the reference CPU daligner on the same config (bounded sample per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (simdb args, block size Mbp, root, daligner flags)
+    "c2": dict(sim=["4.6", "-c60", "-r2", "-e.12", "-m10000", "-s2000", "-x4000"], split=70, root="E",
+               desc="E. coli-scale 4.6 Mbp x60 (simulator.c model, 12% error), DBsplit -s70 -> 4 blocks, all 10 block pairs"),
+    "c1": dict(sim=["5.0", "-c30", "-r1", "-e.12", "-m10000", "-s2000", "-x4000"], split=200, root="G",
+               desc="5 Mbp x30 CLR-like, one block self-compare"),
+    "small": dict(sim=["1.0", "-c20", "-r1", "-e.12"], split=10, root="S",
+                  desc="1 Mbp x20, 2 blocks (smoke-sized)"),
+}
+DAL_FLAGS = dict(k=14, w=6, h=35, e=0.70, l=1000, s=100, M=32)
+
+
+def scratch_dir():
+    for d in ("/dev/shm", "/tmp"):
+        if os.path.isdir(d) and os.access(d, os.W_OK):
+            return d
+    return ROOT
+
+
+def make_db(workload: str, seed_shift: int = 0):
+    """Generate (once) the synthetic Dazzler DB for the workload; returns (dir, root, nblocks)."""
+    w = WORKLOADS[workload]
+    d = os.path.join(scratch_dir(), f"damar_bench_{workload}_{seed_shift}_{os.getuid()}")
+    stub = os.path.join(d, w["root"] + ".db")
+    if not os.path.exists(stub):
+        os.makedirs(d, exist_ok=True)
+        simdb = os.path.join(ROOT, "damar_b200", "host", "simdb")
+        if not os.path.exists(simdb):
+            subprocess.run(["make", "-s", "-C", ROOT, "host"], check=True)
+        args = list(w["sim"])
+        if seed_shift:
+            args = [a if not a.startswith("-r") else f"-r{int(a[2:]) + 1000 * seed_shift}" for a in args]
+        subprocess.run([simdb, d, w["root"]] + args + ["-X1000", f"-S{w['split']}"], check=True, stdout=subprocess.DEVNULL)
+    from damar_b200 import dbio
+    _, nblocks, _, _ = dbio.read_stub(stub)
+    return d, w["root"], nblocks
+
+
+def plan(nblocks: int):
+    """HPCdaligner's job list (dalign/HPCdaligner.c:709-788, one job per A block):
+    `daligner R.i R.1 ... R.i`."""
+    return [(i, list(range(1, i + 1))) for i in range(1, nblocks + 1)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu: int):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ref_flags(threads: int):
+    f = DAL_FLAGS
+    return [f"-j{threads}", f"-k{f['k']}", f"-w{f['w']}", f"-h{f['h']}", f"-e{f['e']}", f"-l{f['l']}", f"-s{f['s']}", f"-M{f['M']}"]
+
+
+def pow2_floor(n: int) -> int:
+    p = 1
+    while 2 * p <= n:
+        p *= 2
+    return p
+
+
+def run_reference_job(dbdir: str, root: str, a: int, bs, threads: int):
+    """One reference daligner job (oracle/_ref/daligner, built from the unmodified reference)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "daligner")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/daligner missing (built by oracle/Makefile where /root/reference exists)")
+    import shutil
+    import struct
+    for d in os.listdir(dbdir):
+        if d.startswith("d001_"):
+            shutil.rmtree(os.path.join(dbdir, d))
+    t0 = time.perf_counter()
+    subprocess.run([exe] + ref_flags(threads) + [f"{root}.{a}"] + [f"{root}.{b}" for b in bs], cwd=dbdir, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    dt = time.perf_counter() - t0
+    novl = 0
+    for d in os.listdir(dbdir):
+        if d.startswith("d001_"):
+            for fn in os.listdir(os.path.join(dbdir, d)):
+                with open(os.path.join(dbdir, d, fn), "rb") as f:
+                    novl += struct.unpack("<q", f.read(8))[0]
+            shutil.rmtree(os.path.join(dbdir, d))
+    return novl, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    config = {"workload": args.workload, "desc": WORKLOADS[args.workload]["desc"],
+              "daligner": "-k14 -w6 -h35 -e.70 -l1000 -s100 -M32", "l2": "inputs larger than L2 (every block's tuple list > 126 MB)"}
+
+    # ---------------- reference arm: the reference's own CPU implementation ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        dbdir, root, nblocks = make_db(args.workload)
+        P = pow2_floor(cores)
+        a, bs = 1, [1]                                   # bounded sample: one job of the plan
+        for _ in range(max(0, min(args.warmup, 1))):
+            run_reference_job(dbdir, root, a, bs, P)
+        tot, dt = 0, 0.0
+        for _ in range(args.steps):
+            n, t = run_reference_job(dbdir, root, a, bs, P)
+            tot += n; dt += t
+        v = tot / dt
+        sample = f"job `daligner -j{P} {root}.{a} {root}.{bs[0]}` (1 of {nblocks * (nblocks + 1) // 2} block pairs) per step"
+        print(json.dumps({"impl": "reference", "metric": "daligner overlaps/s", "value": v, "unit": "overlaps/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                          "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "overlaps/s", "cores": P, "kind": "reference", "sample": sample},
+                          "e2e": {"value": v, "unit": "overlaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    from damar_b200 import api, dbio
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    api.init(local_rank)
+
+    dbdir, root, nblocks = make_db(args.workload, seed_shift=rank)
+    blocks = {i: dbio.read_block(os.path.join(dbdir, f"{root}.{i}")) for i in range(1, nblocks + 1)}
+    s = api.Settings(kmer=DAL_FLAGS["k"], binshift=DAL_FLAGS["w"], hitmin=DAL_FLAGS["h"], ave_corr=DAL_FLAGS["e"],
+                     minlen=DAL_FLAGS["l"], trace_spacing=DAL_FLAGS["s"], mem_limit_gb=DAL_FLAGS["M"], nthreads=4)
+    jobs = plan(nblocks)
+    h2d = sum(int(b.bases.nbytes + b.boff.nbytes + b.rlen.nbytes) for b in blocks.values())
+
+    def one_pass(resident):
+        """All jobs of the plan.  resident=None -> blocks are uploaded inside (e2e)."""
+        novl, d2h = 0, 0
+        cache = dict(resident) if resident is not None else {}
+        for a, bs in jobs:
+            files = api.daligner(blocks[a], [blocks[b] for b in bs], s, dcache=cache)
+            for v in files.values():
+                novl += int.from_bytes(v[:8], "little")
+                d2h += len(v)
+        if resident is None:
+            for h in cache.values():
+                h.free()
+        return novl, d2h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (untimed): builds caches, loads kernels
+    resident = {blocks[i].name: api.DeviceBlockHandle(blocks[i]) for i in blocks}
+    for _ in range(args.warmup):
+        one_pass(resident)
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident timing ("value") ----
+    api.reset_kernel_timers()
+    l0 = api.timings()["kernel_launches"]
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    novl = 0
+    for _ in range(args.steps):
+        n, d2h = one_pass(resident)
+        novl += n
+    ev1.record()
+    barrier()
+    dt = time.perf_counter() - t0
+    dt_dev = ev0.elapsed_time(ev1) / 1000.0
+    tm = api.timings()
+    launches = tm["kernel_launches"] - l0
+    for h in resident.values():
+        h.free()
+
+    # ---- end-to-end timing through the public API with host buffers ("e2e") ----
+    barrier()
+    t1 = time.perf_counter()
+    novl_e = 0
+    for _ in range(args.steps):
+        n, d2h = one_pass(None)
+        novl_e += n
+    barrier()
+    dt_e = time.perf_counter() - t1
+    clocks = sampler.stop()
+
+    if world > 1:
+        t = torch.tensor([dt, dt_e, float(novl), float(novl_e), float(launches)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, dt_e = float(tmax[0]), float(tmax[1])
+        novl, novl_e, launches = int(tsum[2]), int(tsum[3]), int(tsum[4])
+    value = novl / dt
+    e2e = novl_e / dt_e
+
+    peak, peak_src = peaks()
+    sc_ms, sc_el, sc_n = tm["scatter_ms"], tm["scatter_elems"], tm["scatter_launches"]
+    alg_bytes = 32.0 * sc_el / max(sc_n, 1)                       # per launch: 16 B read + 16 B write per record
+    achieved = (32.0 * sc_el) / (sc_ms / 1000.0) / 1e9 if sc_ms > 0 else 0.0
+    roofline = {"kernel": "rs_scatter (radix sort pass: stable rank + scatter)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launches": sc_n, "avg_launch_ms": sc_ms / max(sc_n, 1),
+                "share_of_step": (sc_ms / 1000.0) / dt if world == 1 else None}
+    line = {"metric": "daligner overlaps/s", "value": value, "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000 * dt_e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "overlaps_per_step": novl // max(args.steps, 1) // max(world, 1),
+            "device_event_ms_per_step_rank0": 1000 * dt_dev / args.steps,
+            "align_kernel_ms_per_step": tm["align_kernel_ms"] / max(args.steps, 1)}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            P = pow2_floor(cores)
+            n, t = run_reference_job(dbdir, root, 1, [1], P)
+            line["cpu_baseline"] = {"value": n / t, "unit": "overlaps/s", "cores": P, "kind": "reference",
+                                    "sample": f"reference `daligner -j{P} {root}.1 {root}.1` (1 of {len(jobs) * (len(jobs) + 1) // 2} block pairs, "
+                                              f"{n} overlaps in {t:.1f} s) on {cores} host cores"}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "overlaps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

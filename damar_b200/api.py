@@ -52,7 +52,9 @@ class Timings(C.Structure):
                 ("count_ms", C.c_float), ("merge_ms", C.c_float), ("hsort_ms", C.c_float),
                 ("pairs_ms", C.c_float), ("align_ms", C.c_float), ("download_ms", C.c_float),
                 ("kmers", C.c_int64), ("hits", C.c_int64), ("pairs", C.c_int64), ("la_calls", C.c_int64),
-                ("wave_cells", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("wave_cells", C.c_int64), ("kernel_launches", C.c_int64),
+                ("scatter_ms", C.c_double), ("scatter_elems", C.c_int64), ("scatter_launches", C.c_int64),
+                ("align_kernel_ms", C.c_double), ("align_launches", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -65,7 +67,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_set_options", "damar_block_upload", "damar_block_free", "damar_sort_kmers", "damar_index_free",
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
-           "damar_sink_serialise", "damar_free"]
+           "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers"]
 
 _lib = None
 
@@ -232,6 +234,10 @@ def last_hits() -> np.ndarray:
     if n:
         L.damar_last_hits_download(out.ctypes.data, n)
     return out
+
+
+def reset_kernel_timers() -> None:
+    load_library().damar_reset_kernel_timers()
 
 
 def timings() -> dict:

@@ -205,6 +205,10 @@ int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
     return g_hits.n;
 }
 
-void damar_get_timings(damar_timings *t) { *t = ctx().tm; }
+void damar_get_timings(damar_timings *t) { *t = ctx().tm; t->kernel_launches = ctx().launches; }
+void damar_reset_kernel_timers(void) {
+    damar_timings &t = ctx().tm;
+    t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.align_kernel_ms = 0; t.align_launches = 0;
+}
 
 }  // extern "C"

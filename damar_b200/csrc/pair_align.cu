@@ -838,8 +838,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         P.recs = recs.p; P.rec_cap = rec_cap; P.rec_count = counters.p + 5;
         P.trace = trace.p; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
         P.stats = counters.p;
+        Timer t_k(st);
         align_pairs<<<blocks, AL_WARPS * 32, 0, st>>>(P);
         KERNEL_CHECK(); count_launch();
+        c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
         CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if ((hc[3] & 1ull) && attempt < 4) {            // output buffers too small: grow and rerun

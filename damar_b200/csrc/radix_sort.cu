@@ -132,15 +132,27 @@ void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uin
         CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         attr_set = true;
     }
-    for (int shift = 0; shift < nbits; shift += 8) {
+    static cudaEvent_t ev[16][2];
+    static bool ev_init = false;
+    if (!ev_init) { for (auto &e : ev) { CUDA_CHECK(cudaEventCreate(&e[0])); CUDA_CHECK(cudaEventCreate(&e[1])); } ev_init = true; }
+    int npass = 0;
+    for (int shift = 0; shift < nbits; shift += 8, npass++) {
         rs_hist<<<ntiles, RS_THREADS, 0, st>>>(keys, n, shift, g_tile_hist.p, ntiles);
         KERNEL_CHECK();
         exclusive_scan_u32_inplace(g_tile_hist.p, (int64_t)ntiles * 256, nullptr, st);
+        CUDA_CHECK(cudaEventRecord(ev[npass][0], st));
         rs_scatter<<<ntiles, RS_THREADS, dyn, st>>>(keys, vals, keys_alt, vals_alt, n, shift, g_tile_hist.p, ntiles);
         KERNEL_CHECK();
+        CUDA_CHECK(cudaEventRecord(ev[npass][1], st));
         count_launch(2);
         uint64_t *tk = keys; keys = keys_alt; keys_alt = tk;
         uint32_t *tv = vals; vals = vals_alt; vals_alt = tv;
+    }
+    // per-launch device time of the scatter kernel (feeds bench.py's roofline line)
+    CUDA_CHECK(cudaEventSynchronize(ev[npass - 1][1]));
+    for (int i = 0; i < npass; i++) {
+        float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i][0], ev[i][1]));
+        ctx().tm.scatter_ms += ms; ctx().tm.scatter_elems += n; ctx().tm.scatter_launches += 1;
     }
 }
 

@@ -122,7 +122,11 @@ typedef struct damar_timings {
     float upload_ms, extract_ms, ksort_ms;
     float count_ms, merge_ms, hsort_ms, pairs_ms, align_ms, download_ms;
     int64_t kmers, hits, pairs, la_calls, wave_cells, kernel_launches;
+    /* accumulated since damar_reset_kernel_timers(): the radix-sort scatter kernel (dominant HBM kernel) */
+    double  scatter_ms; int64_t scatter_elems; int64_t scatter_launches;
+    double  align_kernel_ms; int64_t align_launches;
 } damar_timings;
+void damar_reset_kernel_timers(void);
 void damar_get_timings(damar_timings *t);
 
 /* ---- output path: Overlap_IO_Buffer + Write_Overlap_Buffer (align.c:5969-6380), host only ---- */
