@@ -237,9 +237,9 @@ def main():
         novl, d2h = 0, 0
         cache = dict(resident) if resident is not None else {}
         for a, bs in jobs:
-            files = api.daligner(blocks[a], [blocks[b] for b in bs], s, dcache=cache)
+            files = api.daligner(blocks[a], [blocks[b] for b in bs], s, dcache=cache, as_bytes=False)
             for v in files.values():
-                novl += int.from_bytes(v[:8], "little")
+                novl += v.novl
                 d2h += len(v)
         if resident is None:
             for h in cache.values():

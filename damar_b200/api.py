@@ -42,8 +42,9 @@ class Options(C.Structure):
 
 
 class Overlaps(C.Structure):
-    _fields_ = [("novl", C.c_int64), ("ovl", C.c_void_p), ("trace_off", C.c_void_p), ("trace", C.c_void_p),
-                ("ntrace", C.c_int64), ("nhits", C.c_int64), ("nfilt", C.c_int64), ("ncheck", C.c_int64),
+    _fields_ = [("novl", C.c_int64), ("ovl", C.c_void_p), ("trace_off", C.c_void_p), ("seq", C.c_void_p),
+                ("trace", C.c_void_p), ("ntrace", C.c_int64), ("trace_bytes", C.c_int32), ("reserved", C.c_int32),
+                ("nhits", C.c_int64), ("nfilt", C.c_int64), ("ncheck", C.c_int64),
                 ("limit", C.c_int32), ("multi_la_pairs", C.c_int32)]
 
 
@@ -246,6 +247,35 @@ def timings() -> dict:
     return t.as_dict()
 
 
+class LasImage:
+    """A serialised .las file held in library memory (no Python-side copy until asked)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    @property
+    def novl(self) -> int:
+        return C.c_int64.from_address(self.ptr).value
+
+    def view(self) -> np.ndarray:
+        return np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(self.nbytes,))
+
+    def tobytes(self) -> bytes:
+        return C.string_at(self.ptr, self.nbytes)
+
+    def write(self, path: str) -> None:
+        with open(path, "wb") as f:
+            f.write(self.view())
+
+    def __len__(self) -> int:
+        return self.nbytes
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            load_library().damar_free(self.ptr)
+            self.ptr = None
+
+
 class LasSink:
     """Overlap_IO_Buffer + Write_Overlap_Buffer (align.c:5969-6380)."""
 
@@ -261,19 +291,16 @@ class LasSink:
     def count(self) -> int:
         return load_library().damar_sink_count(self.h)
 
-    def serialise(self, s: Settings, split_read: int = -1) -> Tuple[bytes, Optional[bytes]]:
+    def serialise(self, s: Settings, split_read: int = -1):
+        """Write_Overlap_Buffer into memory: returns (LasImage, LasImage | None)."""
         L = load_library()
         b1, b2 = C.c_void_p(), C.c_void_p()
         l1, l2 = C.c_int64(0), C.c_int64(0)
         if L.damar_sink_serialise(self.h, s.trace_spacing, int(s.no_trace), int(s.only_identity), split_read,
                                   C.byref(b1), C.byref(l1), C.byref(b2), C.byref(l2)) != 0:
             raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
-        o1 = C.string_at(b1, l1.value)
-        L.damar_free(b1)
-        o2 = None
-        if b2.value:
-            o2 = C.string_at(b2, l2.value)
-            L.damar_free(b2)
+        o1 = LasImage(b1.value, l1.value)
+        o2 = LasImage(b2.value, l2.value) if b2.value else None
         return o1, o2
 
     def free(self):
@@ -283,8 +310,9 @@ class LasSink:
 
 
 def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list] = None,
-             dcache: Optional[Dict[str, DeviceBlockHandle]] = None) -> Dict[str, bytes]:
-    """`daligner [flags] A B1 B2 ...` (daligner.c:958-1073): returns {las file name: bytes}."""
+             dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
+    """`daligner [flags] A B1 B2 ...` (daligner.c:958-1073): returns {las file name: bytes}
+    (or LasImage objects with as_bytes=False, which avoids one host copy per file)."""
     init()
     if set_filter_params(s.kmer, s.binshift, s.suppress, s.hitmin, s.nthreads):
         raise ValueError("Illegal combination of filter parameters")       # daligner.c:862-866
@@ -294,6 +322,7 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
     own = dcache is None
     dcache = {} if dcache is None else dcache
     out: Dict[str, bytes] = {}
+    conv = (lambda im: im.tobytes()) if as_bytes else (lambda im: im)
 
     def resident(b: Block) -> DeviceBlockHandle:
         if b.name not in dcache:
@@ -321,14 +350,14 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
         an, bn = ablk.name, bblk.name
         if selfcmp or not symmetric:                                        # align.c:6235
             b1, _ = sink.serialise(s, -1)
-            out[f"{an}.{bn}.las"] = b1
+            out[f"{an}.{bn}.las"] = conv(b1)
         else:
             last = (bblk.ufirst + bblk.nreads - 1) if bblk.part < ablk.part else (ablk.ufirst + ablk.nreads - 1)
             b1, b2 = sink.serialise(s, last)
             n1, n2 = f"{an}.{bn}.las", f"{bn}.{an}.las"
             if bblk.part < ablk.part:                                       # align.c:6308-6313
                 n1, n2 = n2, n1
-            out[n1], out[n2] = b1, b2
+            out[n1], out[n2] = conv(b1), conv(b2)
         sink.reset()
     sink.free()
     if aidx is not None:
@@ -351,7 +380,10 @@ def write_outputs(outdir: str, files: Dict[str, bytes], run_id: int = 1) -> List
         d = os.path.join(outdir, las_dir(run_id, part))
         os.makedirs(d, exist_ok=True)
         p = os.path.join(d, name)
-        with open(p, "wb") as f:
-            f.write(data)
+        if isinstance(data, LasImage):
+            data.write(p)
+        else:
+            with open(p, "wb") as f:
+                f.write(data)
         paths.append(p)
     return paths

@@ -1,5 +1,7 @@
 // api.cu -- the C-ABI of include/damar_b200.h on top of the stage implementations.
+#include <chrono>
 #include <cstdarg>
+#include <map>
 #include <mutex>
 
 #include "common.cuh"
@@ -23,6 +25,15 @@ void fatal(const char *fmt, ...) {
 }
 
 Context &ctx() { static Context c; return c; }
+
+static std::map<std::string, std::pair<double, long>> g_prof;
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+HostProf::HostProf(const char *n) : name(n), t0(now_s()) {}
+HostProf::~HostProf() { auto &e = g_prof[name]; e.first += now_s() - t0; e.second++; }
+void dump_profile() {
+    for (auto &kv : g_prof) fprintf(stderr, "[damar profile] %-28s %9.1f ms  (%ld calls)\n", kv.first.c_str(), kv.second.first * 1e3, kv.second.second);
+    g_prof.clear();
+}
 
 static int pick_device() {
     const char *e = getenv("DAMAR_DEVICE");
@@ -51,12 +62,27 @@ static int do_init(int device) {
     }
     CUDA_CHECK(cudaSetDevice(device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;                 // never hand freed blocks back to the driver
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     c.device = device;
     // defaults of daligner.c:688-703
     c.opt.minover = 2000; c.opt.symmetric = 1; c.opt.trace_spacing = 100; c.opt.ave_corr = .70;
     c.opt.freq[0] = c.opt.freq[1] = c.opt.freq[2] = c.opt.freq[3] = .25f;
     c.ready = true;
     return 0;
+}
+
+void *dev_alloc_bytes(size_t bytes) {
+    void *p = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, ctx().stream));
+    return p;
+}
+void dev_free(void *p) {
+    if (p && ctx().ready) cudaFreeAsync(p, ctx().stream);
 }
 
 void ensure_init() {
@@ -69,8 +95,8 @@ static SeedHits g_hits;
 static const DeviceBlock *g_hits_a = nullptr, *g_hits_b = nullptr;
 
 void SeedHits::release() {
-    if (keys) cudaFree(keys);
-    if (bpos) cudaFree(bpos);
+    if (keys) dev_free(keys);
+    if (bpos) dev_free(bpos);
     keys = nullptr; bpos = nullptr; n = 0;
 }
 
@@ -108,12 +134,14 @@ void damar_set_options(const damar_options *opt) { ctx().opt = *opt; }
 
 damar_block *damar_block_upload(const damar_block_desc *desc) {
     ensure_init();
+    HostProf hp("block_upload");
     return reinterpret_cast<damar_block *>(upload_block(desc));
 }
 void damar_block_free(damar_block *blk) { delete reinterpret_cast<DeviceBlock *>(blk); }
 
 damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len) {
     ensure_init();
+    HostProf hp("sort_kmers");
     DeviceIndex *idx = build_index(reinterpret_cast<DeviceBlock *>(blk), comp);
     if (len) *len = idx->len;
     ctx().tm.kernel_launches = ctx().launches;
@@ -128,8 +156,7 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     Context &c = ctx();
     DeviceBlock *ab = reinterpret_cast<DeviceBlock *>(ablk), *bb = reinterpret_cast<DeviceBlock *>(bblk);
     DeviceIndex *ai = reinterpret_cast<DeviceIndex *>(aidx), *bi = reinterpret_cast<DeviceIndex *>(bidx);
-    g_out.ovl.clear(); g_out.toff.clear(); g_out.trace.clear();
-    g_out.nfilt = g_out.multi = g_out.cells = g_out.pairs = 0;
+    g_out = HostOverlaps();
     g_hits.release();
     g_hits_a = ab; g_hits_b = bb;
     memset(out, 0, sizeof(*out));
@@ -137,14 +164,16 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0;
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
         if (comp) ensure_revcomp(bb);
-        seed_hits(ai, bi, self, comp, g_hits);
-        if (g_hits.n > 0) report_and_align(ab, bb, comp, self, g_hits, g_out);
+        { HostProf hp("mf.seed_hits"); seed_hits(ai, bi, self, comp, g_hits); }
+        if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); report_and_align(ab, bb, comp, self, g_hits, g_out); }
     }
-    out->novl = (int64_t)g_out.ovl.size();
-    out->ovl = g_out.ovl.data();
-    out->trace_off = g_out.toff.data();
-    out->trace = g_out.trace.data();
-    out->ntrace = (int64_t)g_out.trace.size();
+    out->novl = g_out.novl;
+    out->ovl = g_out.ovl;
+    out->trace_off = g_out.toff;
+    out->seq = g_out.seq;
+    out->trace = g_out.trace;
+    out->ntrace = g_out.ntrace;
+    out->trace_bytes = g_out.tbytes;
     out->nhits = g_hits.n;
     out->nfilt = g_out.nfilt;
     out->ncheck = out->novl;
@@ -205,6 +234,7 @@ int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
     return g_hits.n;
 }
 
+void damar_dump_profile(void) { dump_profile(); }
 void damar_get_timings(damar_timings *t) { *t = ctx().tm; t->kernel_launches = ctx().launches; }
 void damar_reset_kernel_timers(void) {
     damar_timings &t = ctx().tm;

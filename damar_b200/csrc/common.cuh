@@ -29,6 +29,13 @@ void set_error(const char *fmt, ...);
 constexpr int NUM_SMS_B200 = 148;
 constexpr int PACK_FRONT_PAD = 4;     // words of zero padding in front of every packed base array
 
+// ---- device memory: stream-ordered allocations from the device's default pool, whose release
+//      threshold is raised at init so freed blocks are recycled instead of returned to the driver
+//      (a block pair allocates and frees tens of GB of tuple / hit lists) ----
+void *dev_alloc_bytes(size_t bytes);
+void dev_free(void *p);
+template <typename T> inline T *dev_alloc(size_t n) { return reinterpret_cast<T *>(dev_alloc_bytes(n * sizeof(T))); }
+
 // ---- simple owning device buffer ----
 template <typename T>
 struct DevBuf {
@@ -39,7 +46,7 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr; n = 0;
     }
     // grow-only (contents are NOT preserved)
@@ -47,10 +54,25 @@ struct DevBuf {
         if (want <= n) return;
         release();
         size_t cap = want + want / 8 + 256;
-        CUDA_CHECK(cudaMalloc((void **)&p, cap * sizeof(T)));
+        p = dev_alloc<T>(cap);
         n = cap;
     }
     T *steal() { T *q = p; p = nullptr; n = 0; return q; }
+};
+
+// ---- grow-only pinned host buffer (D2H / H2D staging at full PCIe rate) ----
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void reserve(size_t want) {
+        if (want <= n) return;
+        if (p) cudaFreeHost(p);
+        size_t cap = want + want / 4 + 4096;
+        CUDA_CHECK(cudaHostAlloc((void **)&p, cap * sizeof(T), cudaHostAllocDefault));
+        n = cap;
+    }
 };
 
 // ---- filter parameters (Set_Filter_Params, filter.c:171-201) ----
@@ -76,6 +98,14 @@ struct Timer {
     }
     ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
 };
+
+// ---- host wall-clock profile (DAMAR_PROFILE=1 prints it at damar_shutdown / damar_dump_profile) ----
+struct HostProf {
+    const char *name; double t0;
+    explicit HostProf(const char *n);
+    ~HostProf();
+};
+void dump_profile();
 
 // ---- process-wide context ----
 struct Context {
@@ -148,10 +178,12 @@ struct SeedHits {
 void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out);
 
 // pair_align.cu
-struct HostOverlaps {
-    std::vector<damar_overlap> ovl;
-    std::vector<uint64_t> toff;
-    std::vector<uint16_t> trace;
+struct HostOverlaps {                 // views of pinned staging buffers, valid until the next call
+    const damar_overlap *ovl = nullptr;
+    const uint64_t *toff = nullptr, *seq = nullptr;
+    const void *trace = nullptr;
+    int64_t novl = 0, ntrace = 0;
+    int tbytes = 2;
     int64_t nfilt = 0, multi = 0, cells = 0, pairs = 0;
 };
 void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,

@@ -9,22 +9,24 @@
 // A k-mer entry is (code, gpos): gpos indexes the reference's unpacked `bases` array and names
 // the k-mer's LAST base, so (read, rpos) = (r, gpos - boff[r]).  Sorting stably on code with
 // entries generated in gpos order reproduces the reference's (code, read, rpos) order.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace damar {
 
 DeviceBlock::~DeviceBlock() {
     for (int i = 0; i < 2; i++) {
-        if (packed[i]) cudaFree(packed[i] - PACK_FRONT_PAD);
-        if (mask_anno[i]) cudaFree(mask_anno[i]);
-        if (mask_data[i]) cudaFree(mask_data[i]);
+        if (packed[i]) dev_free(packed[i] - PACK_FRONT_PAD);
+        if (mask_anno[i]) dev_free(mask_anno[i]);
+        if (mask_data[i]) dev_free(mask_data[i]);
     }
-    if (boff) cudaFree(boff);
-    if (rlen) cudaFree(rlen);
+    if (boff) dev_free(boff);
+    if (rlen) dev_free(rlen);
 }
 DeviceIndex::~DeviceIndex() {
-    if (codes) cudaFree(codes);
-    if (gpos) cudaFree(gpos);
+    if (codes) dev_free(codes);
+    if (gpos) dev_free(gpos);
 }
 
 namespace {
@@ -199,7 +201,7 @@ __global__ void compact_kept(const uint64_t *__restrict__ codes, const uint32_t 
 // (reverse wave) may start before base 0
 static uint32_t *alloc_packed(int64_t nwords, cudaStream_t st) {
     uint32_t *p = nullptr;
-    CUDA_CHECK(cudaMalloc((void **)&p, sizeof(uint32_t) * (nwords + PACK_FRONT_PAD)));
+    p = (std::remove_reference<decltype(p)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nwords + PACK_FRONT_PAD));
     CUDA_CHECK(cudaMemsetAsync(p, 0, sizeof(uint32_t) * PACK_FRONT_PAD, st));
     return p + PACK_FRONT_PAD;
 }
@@ -219,8 +221,8 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
 
     std::vector<uint32_t> boff32(d->nreads + 1);
     for (int i = 0; i <= d->nreads; i++) boff32[i] = (uint32_t)d->boff[i];
-    CUDA_CHECK(cudaMalloc((void **)&b->boff, sizeof(uint32_t) * (d->nreads + 1)));
-    CUDA_CHECK(cudaMalloc((void **)&b->rlen, sizeof(int32_t) * (d->nreads + 1)));
+    b->boff = (std::remove_reference<decltype(b->boff)>::type)dev_alloc_bytes(sizeof(uint32_t) * (d->nreads + 1));
+    b->rlen = (std::remove_reference<decltype(b->rlen)>::type)dev_alloc_bytes(sizeof(int32_t) * (d->nreads + 1));
     CUDA_CHECK(cudaMemcpyAsync(b->boff, boff32.data(), sizeof(uint32_t) * (d->nreads + 1), cudaMemcpyHostToDevice, c.stream));
     CUDA_CHECK(cudaMemcpyAsync(b->rlen, d->rlen, sizeof(int32_t) * d->nreads, cudaMemcpyHostToDevice, c.stream));
 
@@ -228,7 +230,7 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
     const int64_t nbytes = b->nbases;
     b->npacked_words = (nbytes + 15) / 16 + 8;            // slack words so window reads never fault
     uint8_t *dbytes = nullptr;
-    CUDA_CHECK(cudaMalloc((void **)&dbytes, (size_t)nbytes + 64));
+    dbytes = (std::remove_reference<decltype(dbytes)>::type)dev_alloc_bytes((size_t)nbytes + 64);
     CUDA_CHECK(cudaMemcpyAsync(dbytes, d->bases, (size_t)nbytes, cudaMemcpyHostToDevice, c.stream));
     b->packed[0] = alloc_packed(b->npacked_words, c.stream);
     {
@@ -239,14 +241,14 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
     if (d->mask_anno != nullptr) {
         b->has_mask = true;
         b->mask_len = d->mask_anno[d->nreads];
-        CUDA_CHECK(cudaMalloc((void **)&b->mask_anno[0], sizeof(int64_t) * (d->nreads + 1)));
-        CUDA_CHECK(cudaMalloc((void **)&b->mask_data[0], sizeof(int32_t) * (b->mask_len + 1)));
+        b->mask_anno[0] = (std::remove_reference<decltype(b->mask_anno[0])>::type)dev_alloc_bytes(sizeof(int64_t) * (d->nreads + 1));
+        b->mask_data[0] = (std::remove_reference<decltype(b->mask_data[0])>::type)dev_alloc_bytes(sizeof(int32_t) * (b->mask_len + 1));
         CUDA_CHECK(cudaMemcpyAsync(b->mask_anno[0], d->mask_anno, sizeof(int64_t) * (d->nreads + 1), cudaMemcpyHostToDevice, c.stream));
         if (b->mask_len > 0)
             CUDA_CHECK(cudaMemcpyAsync(b->mask_data[0], d->mask_data, sizeof(int32_t) * b->mask_len, cudaMemcpyHostToDevice, c.stream));
     }
     CUDA_CHECK(cudaStreamSynchronize(c.stream));
-    CUDA_CHECK(cudaFree(dbytes));
+    dev_free(dbytes);
     c.tm.upload_ms = tm.stop();
     return b;
 }
@@ -260,7 +262,7 @@ void ensure_revcomp(DeviceBlock *b) {
                                                                       b->nreads, b->nbases);
     KERNEL_CHECK(); count_launch();
     if (b->has_mask) {
-        CUDA_CHECK(cudaMalloc((void **)&b->mask_data[1], sizeof(int32_t) * (b->mask_len + 1)));
+        b->mask_data[1] = (std::remove_reference<decltype(b->mask_data[1])>::type)dev_alloc_bytes(sizeof(int32_t) * (b->mask_len + 1));
         b->mask_anno[1] = nullptr;   // offsets are identical; reuse [0]
         mirror_mask<<<(b->nreads + 255) / 256, 256, 0, c.stream>>>(b->mask_anno[0], b->mask_data[0], b->mask_data[1], b->rlen, b->nreads);
         KERNEL_CHECK(); count_launch();
@@ -301,10 +303,10 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     if (kmers <= 0) { c.tm.extract_ms = t_ex.stop(); c.tm.ksort_ms = 0; c.tm.kmers = 0; return idx; }
 
     uint64_t *k0, *k1; uint32_t *g0, *g1;
-    CUDA_CHECK(cudaMalloc((void **)&k0, sizeof(uint64_t) * (kmers + 2)));
-    CUDA_CHECK(cudaMalloc((void **)&k1, sizeof(uint64_t) * (kmers + 2)));
-    CUDA_CHECK(cudaMalloc((void **)&g0, sizeof(uint32_t) * (kmers + 2)));
-    CUDA_CHECK(cudaMalloc((void **)&g1, sizeof(uint32_t) * (kmers + 2)));
+    k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
+    k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
+    g0 = (std::remove_reference<decltype(g0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 2));
+    g1 = (std::remove_reference<decltype(g1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 2));
     extract_tuples<<<(unsigned)((b->nbases + 255) / 256), 256, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, b->nbases, K,
                                                                         anno, data, per_read.p, gap_pref.p, k0, g0);
     KERNEL_CHECK(); count_launch();
@@ -328,7 +330,7 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
         std::swap(k0, k1); std::swap(g0, g1);
     }
     c.tm.ksort_ms = t_sort.stop();
-    CUDA_CHECK(cudaFree(k1)); CUDA_CHECK(cudaFree(g1));
+    dev_free(k1); dev_free(g1);
     idx->codes = k0; idx->gpos = g0; idx->len = kmers;
     c.tm.kmers = kmers;
     return idx;

@@ -1,9 +1,10 @@
 // las_sink.cu -- host side of the output path: the per-job overlap buffer and the .las writer.
 // Mirrors Overlap_IO_Buffer / AddOverlapToBuffer / Write_Overlap_Buffer / Reset_Overlap_Buffer
 // (reference dalign/align.c:5969-6380), Write_Overlap (align.c:3365-3373) and Compress_TraceTo8
-// (align.c:3375-3396).  Host-only code; nothing here touches the device.
+// (align.c:3375-3396).  Host-only code; nothing here touches the device.  The final sort and the
+// image build are spread over host threads (the reference does both single-threaded).
 #include <algorithm>
-#include <sys/stat.h>
+#include <thread>
 
 #include "common.cuh"
 
@@ -11,49 +12,98 @@ namespace damar {
 
 struct LasSink {
     std::vector<damar_overlap> ovl;
-    std::vector<uint64_t> toff;
-    std::vector<uint16_t> trace;
+    std::vector<uint64_t> toff;      // byte offsets into `trace`
+    std::vector<uint64_t> seq;       // (call ordinal << 48) | emission rank inside the call
+    std::vector<uint8_t> trace;      // raw trace bytes (uint8 or uint16 values)
+    int tbytes = 0;
+    uint64_t calls = 0;
 };
 
-// SORT_OVL (align.c:6104-6164).  The reference's last resort on a full key tie is the record
-// address inside its gathered array, i.e. emission order; a stable sort reproduces that.
-static bool ovl_less(const damar_overlap &l, const damar_overlap &r) {
-    if (l.aread != r.aread) return l.aread < r.aread;
-    if (l.bread != r.bread) return l.bread < r.bread;
-    const int cl = l.flags & 1, cr = r.flags & 1;
-    if (cl != cr) return cl < cr;
-    if (l.abpos != r.abpos) return l.abpos < r.abpos;
-    if (l.aepos != r.aepos) return l.aepos < r.aepos;
-    if (l.bbpos != r.bbpos) return l.bbpos < r.bbpos;
-    return l.bepos < r.bepos;
+struct SortKey {                     // SORT_OVL (align.c:6104-6164) flattened into integers
+    uint64_t k0;                     // aread, bread
+    uint64_t k1;                     // comp, abpos, aepos
+    uint64_t k2;                     // bbpos, bepos
+    uint64_t seq;                    // the reference falls back to the record address = emission order
+    uint32_t idx;
+    bool operator<(const SortKey &o) const {
+        if (k0 != o.k0) return k0 < o.k0;
+        if (k1 != o.k1) return k1 < o.k1;
+        if (k2 != o.k2) return k2 < o.k2;
+        return seq < o.seq;
+    }
+};
+
+static int host_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 4;
+    if (n > 32) n = 32;
+    return (int)n;
 }
 
-static int put_range(const LasSink &s, const std::vector<uint32_t> &idx, size_t from, size_t to, int tspace, int no_trace,
+// sorted order of the selected records
+static void sorted_order(const LasSink &s, int only_identity, std::vector<SortKey> &keys) {
+    keys.clear();
+    keys.reserve(s.ovl.size());
+    for (uint32_t i = 0; i < s.ovl.size(); i++) {
+        const damar_overlap &r = s.ovl[i];
+        if (only_identity && r.aread != r.bread) continue;                       // align.c:6185-6194
+        SortKey k;
+        k.k0 = ((uint64_t)(uint32_t)r.aread << 32) | (uint32_t)r.bread;          // ids and coordinates are >= 0
+        k.k1 = ((uint64_t)(r.flags & 1u) << 62) | ((uint64_t)(uint32_t)r.abpos << 31) | (uint32_t)r.aepos;
+        k.k2 = ((uint64_t)(uint32_t)r.bbpos << 32) | (uint32_t)r.bepos;
+        k.seq = s.seq[i]; k.idx = i;
+        keys.push_back(k);
+    }
+    const size_t n = keys.size();
+    const int T = host_threads();
+    if (n < 50000 || T < 2) { std::sort(keys.begin(), keys.end()); return; }
+    // bucket by aread range, sort buckets in parallel, concatenate
+    uint32_t amin = ~0u, amax = 0;
+    for (const SortKey &k : keys) { uint32_t a = (uint32_t)(k.k0 >> 32); if (a < amin) amin = a; if (a > amax) amax = a; }
+    const uint64_t span = (uint64_t)amax - amin + 1;
+    std::vector<size_t> cnt(T + 1, 0);
+    auto bucket = [&](const SortKey &k) { return (size_t)((((k.k0 >> 32) - amin) * (uint64_t)T) / span); };
+    for (const SortKey &k : keys) cnt[bucket(k) + 1]++;
+    for (int t = 0; t < T; t++) cnt[t + 1] += cnt[t];
+    std::vector<SortKey> tmp(n);
+    { std::vector<size_t> pos(cnt.begin(), cnt.end() - 1); for (const SortKey &k : keys) tmp[pos[bucket(k)]++] = k; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([&, t] { std::sort(tmp.begin() + cnt[t], tmp.begin() + cnt[t + 1]); });
+    for (auto &x : th) x.join();
+    keys.swap(tmp);
+}
+
+static int put_range(const LasSink &s, const std::vector<SortKey> &keys, size_t from, size_t to, int tspace, int no_trace,
                      uint8_t **out, int64_t *len) {
     const int tbytes = (tspace <= 125) ? 1 : 2;               // TRACE_XOVR, align.h:58
-    size_t sz = 12;
-    for (size_t i = from; i < to; i++) sz += 40 + (no_trace ? 0 : (size_t)tbytes * s.ovl[idx[i]].tlen);
-    uint8_t *buf = (uint8_t *)malloc(sz ? sz : 1);
-    if (!buf) fatal("out of host memory serialising %zu bytes of .las", sz);
-    int64_t n = (int64_t)(to - from); int32_t ts = tspace;
-    memcpy(buf, &n, 8); memcpy(buf + 8, &ts, 4);
-    size_t o = 12;
-    for (size_t i = from; i < to; i++) {
-        damar_overlap r = s.ovl[idx[i]];
-        const uint16_t *t = s.trace.data() + s.toff[idx[i]];
-        const int tl = r.tlen;
-        if (no_trace) r.tlen = 0;                             // align.c:6086-6090
-        r.pad = 0;
-        memcpy(buf + o, &r, 40); o += 40;
-        if (no_trace) continue;
-        if (tbytes == 1) {
-            for (int j = 0; j < tl; j++) {
-                if (t[j] > 255) { free(buf); set_error("Compression of trace to bytes fails, value too big"); return 1; }
-                buf[o++] = (uint8_t)t[j];
-            }
-        } else { memcpy(buf + o, t, 2 * (size_t)tl); o += 2 * (size_t)tl; }
+    if (!no_trace && to > from && s.tbytes != tbytes) { set_error("trace width of the buffered overlaps (%d) does not match -s%d", s.tbytes, tspace); return 1; }
+    const size_t n = to - from;
+    std::vector<size_t> offs(n + 1);
+    offs[0] = 12;
+    for (size_t i = 0; i < n; i++) offs[i + 1] = offs[i] + 40 + (no_trace ? 0 : (size_t)tbytes * s.ovl[keys[from + i].idx].tlen);
+    uint8_t *buf = (uint8_t *)malloc(offs[n] ? offs[n] : 1);
+    if (!buf) fatal("out of host memory serialising %zu bytes of .las", offs[n]);
+    int64_t n64 = (int64_t)n; int32_t ts = tspace;
+    memcpy(buf, &n64, 8); memcpy(buf + 8, &ts, 4);
+    auto work = [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const uint32_t id = keys[from + i].idx;
+            damar_overlap r = s.ovl[id];
+            const int tl = r.tlen;
+            if (no_trace) r.tlen = 0;                         // align.c:6086-6090
+            r.pad = 0;
+            memcpy(buf + offs[i], &r, 40);
+            if (!no_trace && tl > 0) memcpy(buf + offs[i] + 40, s.trace.data() + s.toff[id], (size_t)tbytes * tl);
+        }
+    };
+    const int T = host_threads();
+    if (n < 20000 || T < 2) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, n * t / T, n * (t + 1) / T);
+        for (auto &x : th) x.join();
     }
-    *out = buf; *len = (int64_t)o;
+    *out = buf; *len = (int64_t)offs[n];
     return 0;
 }
 
@@ -67,34 +117,44 @@ damar_las_sink *damar_sink_new(void) { return reinterpret_cast<damar_las_sink *>
 void damar_sink_free(damar_las_sink *s) { delete reinterpret_cast<LasSink *>(s); }
 void damar_sink_reset(damar_las_sink *s_) {
     LasSink *s = reinterpret_cast<LasSink *>(s_);
-    s->ovl.clear(); s->toff.clear(); s->trace.clear();
+    s->ovl.clear(); s->toff.clear(); s->seq.clear(); s->trace.clear(); s->calls = 0; s->tbytes = 0;
 }
 int64_t damar_sink_count(const damar_las_sink *s) { return (int64_t) reinterpret_cast<const LasSink *>(s)->ovl.size(); }
 
 void damar_sink_add(damar_las_sink *s_, const damar_overlaps *o) {
+    HostProf hp("sink_add");
     LasSink *s = reinterpret_cast<LasSink *>(s_);
+    if (o->novl == 0) { s->calls++; return; }
+    if (s->tbytes == 0) s->tbytes = o->trace_bytes;
+    if (s->tbytes != o->trace_bytes) fatal("damar_sink_add: mixed trace widths in one sink");
     const uint64_t base = s->trace.size();
+    const size_t n0 = s->ovl.size();
     s->ovl.insert(s->ovl.end(), o->ovl, o->ovl + o->novl);
-    for (int64_t i = 0; i < o->novl; i++) s->toff.push_back(base + o->trace_off[i]);
-    s->trace.insert(s->trace.end(), o->trace, o->trace + o->ntrace);
+    s->toff.resize(n0 + o->novl); s->seq.resize(n0 + o->novl);
+    for (int64_t i = 0; i < o->novl; i++) {
+        s->toff[n0 + i] = base + o->trace_off[i] * (uint64_t)o->trace_bytes;
+        s->seq[n0 + i] = (s->calls << 48) | (o->seq ? o->seq[i] : (uint64_t)i);
+    }
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(o->trace);
+    s->trace.insert(s->trace.end(), tb, tb + (size_t)o->ntrace * o->trace_bytes);
+    s->calls++;
 }
 
 int damar_sink_serialise(damar_las_sink *s_, int trace_spacing, int no_trace, int only_identity, int split_read,
                          uint8_t **buf1, int64_t *len1, uint8_t **buf2, int64_t *len2) {
+    HostProf hp("sink_serialise");
     LasSink *s = reinterpret_cast<LasSink *>(s_);
-    std::vector<uint32_t> idx;
-    idx.reserve(s->ovl.size());
-    for (uint32_t i = 0; i < s->ovl.size(); i++)
-        if (!only_identity || s->ovl[i].aread == s->ovl[i].bread) idx.push_back(i);   // align.c:6185-6194
-    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return ovl_less(s->ovl[x], s->ovl[y]); });
+    std::vector<SortKey> keys;
+    sorted_order(*s, only_identity, keys);
     if (split_read < 0) {
         if (buf2) { *buf2 = nullptr; *len2 = 0; }
-        return put_range(*s, idx, 0, idx.size(), trace_spacing, no_trace, buf1, len1);
+        return put_range(*s, keys, 0, keys.size(), trace_spacing, no_trace, buf1, len1);
     }
-    size_t cut = 0;
-    while (cut < idx.size() && s->ovl[idx[cut]].aread <= split_read) cut++;          // align.c:6330-6336
-    if (put_range(*s, idx, 0, cut, trace_spacing, no_trace, buf1, len1)) return 1;
-    return put_range(*s, idx, cut, idx.size(), trace_spacing, no_trace, buf2, len2);
+    // first index with aread > split_read (align.c:6330-6336); keys are sorted by aread first
+    size_t lo = 0, hi = keys.size();
+    while (lo < hi) { size_t m = (lo + hi) >> 1; if ((int32_t)(keys[m].k0 >> 32) <= split_read) lo = m + 1; else hi = m; }
+    if (put_range(*s, keys, 0, lo, trace_spacing, no_trace, buf1, len1)) return 1;
+    return put_range(*s, keys, lo, keys.size(), trace_spacing, no_trace, buf2, len2);
 }
 
 void damar_free(void *p) { free(p); }

@@ -83,15 +83,6 @@ __global__ void collect_work_pairs(const uint32_t *__restrict__ flag, const uint
 // ---------------------------------------------------------------------------------------------
 // alignment kernel
 // ---------------------------------------------------------------------------------------------
-struct OutRec {                        // 64 bytes
-    int32_t tlen, diffs, abpos, bbpos, aepos, bepos;
-    uint32_t flags;
-    int32_t aread, bread;
-    uint32_t pad;
-    uint64_t toff;
-    uint64_t seq;
-    uint64_t unused;
-};
 
 struct AlignArgs {
     // hits
@@ -110,8 +101,8 @@ struct AlignArgs {
     uint16_t *tbuf; int maxtp;         // [nwarps][8*maxtp]
     int32_t *bscore; int nbuck, dmin;  // [nwarps][2][nbuck]  (score, lastp) indexed by d - dmin
     // output
-    OutRec *recs; unsigned long long rec_cap; unsigned long long *rec_count;
-    uint16_t *trace; unsigned long long trace_cap; unsigned long long *trace_count;
+    damar_overlap *recs; uint64_t *rec_toff, *rec_seq; unsigned long long rec_cap; unsigned long long *rec_count;
+    void *trace; int tbytes; unsigned long long trace_cap; unsigned long long *trace_count;
     unsigned long long *stats;         // [0]=LA calls [1]=multi-LA pairs [2]=wave cells [3]=overflow flags [4]=pairs
 };
 
@@ -551,12 +542,20 @@ __device__ void emit_record(const AlignArgs &P, const Path &p, int aread, int br
     ri = __shfl_sync(FULL, ri, 0); to = __shfl_sync(FULL, to, 0);
     if (ri >= P.rec_cap || to + p.tlen > P.trace_cap) { if (lane == 0) atomicOr(&P.stats[3], 1ull); return; }
     if (lane == 0) {
-        OutRec r;
+        damar_overlap r;
         r.tlen = p.tlen; r.diffs = p.diffs; r.abpos = p.abpos; r.bbpos = p.bbpos; r.aepos = p.aepos; r.bepos = p.bepos;
-        r.flags = (uint32_t)P.comp; r.aread = aread; r.bread = bread; r.pad = 0; r.toff = to; r.seq = seq; r.unused = 0;
-        P.recs[ri] = r;
+        r.flags = (uint32_t)P.comp; r.aread = aread; r.bread = bread; r.pad = 0;
+        P.recs[ri] = r; P.rec_toff[ri] = to; P.rec_seq[ri] = seq;
     }
-    for (int i = lane; i < p.tlen; i += 32) P.trace[to + i] = p.trace[i];
+    if (P.tbytes == 1) {                                     // Compress_TraceTo8 (align.c:3375-3396)
+        uint8_t *t8 = reinterpret_cast<uint8_t *>(P.trace);
+        bool big = false;
+        for (int i = lane; i < p.tlen; i += 32) { const uint16_t v = p.trace[i]; big |= v > 255; t8[to + i] = (uint8_t)v; }
+        if (__any_sync(FULL, big) && lane == 0) atomicOr(&P.stats[3], 8ull);
+    } else {
+        uint16_t *t16 = reinterpret_cast<uint16_t *>(P.trace);
+        for (int i = lane; i < p.tlen; i += 32) t16[to + i] = p.trace[i];
+    }
 }
 
 __global__ void __launch_bounds__(AL_WARPS * 32) align_pairs(AlignArgs P) {
@@ -765,6 +764,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     const int minhit = (fp.hitmin - 1) / fp.kmer + 1;
 
     // ---- work list ----
+    HostProf *hp1 = new HostProf("ra.worklist");
     Timer t_pairs(st);
     DevBuf<int64_t> ends; ends.reserve(fp.nthreads_pow2);
     DevBuf<uint32_t> flag; flag.reserve((size_t)n);
@@ -784,9 +784,11 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     KERNEL_CHECK();
     count_launch(3);
     c.tm.pairs_ms = t_pairs.stop();
-    if (nwork == 0) return;
+    if (nwork == 0) { delete hp1; return; }
 
+    delete hp1;
     // ---- alignment ----
+    HostProf *hp2 = new HostProf("ra.align_setup");
     Timer t_align(st);
     int ave_path; std::vector<int16_t> hs, ht;
     build_trim_tables(c.opt, ave_path, hs, ht);
@@ -814,13 +816,16 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
 
     DevBuf<unsigned long long> counters; counters.reserve(8);
     DevBuf<unsigned int> next; next.reserve(1);
+    const int tbytes = (TS <= 125) ? 1 : 2;                  // TRACE_XOVR, align.h:58
     unsigned long long rec_cap = 4 * nwork + 1024;
     unsigned long long trace_cap = (unsigned long long)rec_cap * (unsigned long long)(2 * (maxlen / TS + 2)) / 8 + (1ull << 20);
-    DevBuf<OutRec> recs; DevBuf<uint16_t> trace;
-    std::vector<OutRec> hrecs;
+    DevBuf<damar_overlap> recs; DevBuf<uint64_t> rtoff, rseq; DevBuf<uint8_t> trace;
     unsigned long long hc[8];
+    delete hp2;
+    HostProf *hp3 = new HostProf("ra.align_run");
     for (int attempt = 0;; attempt++) {
-        recs.reserve((size_t)rec_cap); trace.reserve((size_t)trace_cap);
+        recs.reserve((size_t)rec_cap); rtoff.reserve((size_t)rec_cap); rseq.reserve((size_t)rec_cap);
+        trace.reserve((size_t)trace_cap * tbytes);
         CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 8, st));
         CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int), st));
         AlignArgs P{};
@@ -835,8 +840,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         P.ring = ring; P.V = V.p; P.HA = HA.p; P.HB = HB.p; P.HM = HM.p; P.HN = HN.p; P.NA = NA.p; P.NB = NB.p; P.T = T.p;
         P.cells = cells.p; P.cells_cap = cells_cap; P.tbuf = tbuf.p; P.maxtp = maxtp;
         P.bscore = bscore.p; P.nbuck = nbuck; P.dmin = dmin;
-        P.recs = recs.p; P.rec_cap = rec_cap; P.rec_count = counters.p + 5;
-        P.trace = trace.p; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
+        P.recs = recs.p; P.rec_toff = rtoff.p; P.rec_seq = rseq.p; P.rec_cap = rec_cap; P.rec_count = counters.p + 5;
+        P.trace = trace.p; P.tbytes = tbytes; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
         P.stats = counters.p;
         Timer t_k(st);
         align_pairs<<<blocks, AL_WARPS * 32, 0, st>>>(P);
@@ -853,33 +858,29 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         break;
     }
     c.tm.align_ms = t_align.stop();
+    delete hp3;
     if (hc[3] & 6ull)
         fatal("alignment scratch overflow (flags %llu): wave wider than %d diagonals, pebble arena or per-pair alignment list exhausted",
               hc[3], ring);
     if (hc[3] & 1ull) fatal("alignment output buffers overflowed repeatedly");
+    if (hc[3] & 8ull) fatal("Compression of trace to bytes fails, value too big");   // align.c:3385-3388
 
-    // ---- download + order as the reference's thread buffers would hold them ----
+    // ---- download into pinned staging; records stay in device emission order, `seq` carries the
+    //      order the reference's thread buffers would have had ----
+    HostProf hp4("ra.download");
     Timer t_dl(st);
+    static PinnedBuf<damar_overlap> h_recs; static PinnedBuf<uint64_t> h_toff, h_seq; static PinnedBuf<uint8_t> h_trace;
     const uint64_t nrec = hc[5], ntr = hc[6];
-    hrecs.resize(nrec);
-    std::vector<uint16_t> htrace(ntr);
-    if (nrec) CUDA_CHECK(cudaMemcpyAsync(hrecs.data(), recs.p, sizeof(OutRec) * nrec, cudaMemcpyDeviceToHost, st));
-    if (ntr) CUDA_CHECK(cudaMemcpyAsync(htrace.data(), trace.p, sizeof(uint16_t) * ntr, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    std::vector<uint32_t> order(nrec);
-    for (uint32_t i = 0; i < nrec; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return hrecs[x].seq < hrecs[y].seq; });
-    out.ovl.resize(nrec); out.toff.resize(nrec); out.trace.resize(ntr);
-    uint64_t tt = 0;
-    for (uint64_t i = 0; i < nrec; i++) {
-        const OutRec &r = hrecs[order[i]];
-        damar_overlap &o = out.ovl[i];
-        o.tlen = r.tlen; o.diffs = r.diffs; o.abpos = r.abpos; o.bbpos = r.bbpos; o.aepos = r.aepos; o.bepos = r.bepos;
-        o.flags = r.flags; o.aread = r.aread; o.bread = r.bread; o.pad = 0;
-        out.toff[i] = tt;
-        memcpy(out.trace.data() + tt, htrace.data() + r.toff, sizeof(uint16_t) * r.tlen);
-        tt += r.tlen;
+    h_recs.reserve(nrec + 1); h_toff.reserve(nrec + 1); h_seq.reserve(nrec + 1); h_trace.reserve(ntr * tbytes + 16);
+    if (nrec) {
+        CUDA_CHECK(cudaMemcpyAsync(h_recs.p, recs.p, sizeof(damar_overlap) * nrec, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(h_toff.p, rtoff.p, sizeof(uint64_t) * nrec, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(h_seq.p, rseq.p, sizeof(uint64_t) * nrec, cudaMemcpyDeviceToHost, st));
     }
+    if (ntr) CUDA_CHECK(cudaMemcpyAsync(h_trace.p, trace.p, (size_t)ntr * tbytes, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = h_trace.p;
+    out.novl = (int64_t)nrec; out.ntrace = (int64_t)ntr; out.tbytes = tbytes;
     out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)hc[4];
     c.tm.download_ms = t_dl.stop();
 }

@@ -16,6 +16,8 @@
 //         key = bread << (abits+pbits) | aread << pbits | apos
 //   6. stable radix sort on the key: ties keep merge order (= bpos ascending), which is the
 //      order report_thread depends on.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace damar {
@@ -174,6 +176,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     out.release();
     out.limit = INT32_MAX;
 
+    HostProf *hp1 = new HostProf("sh.count");
     Timer t_count(st);
     // 1. groups of A
     DevBuf<uint32_t> gid, gstart, gjb, gnb, gct, cnt;
@@ -232,7 +235,9 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     out.limit = (int32_t)limit;
     c.tm.count_ms = t_count.stop();
 
+    delete hp1;
     // 4. per-entry partner counts + scan
+    HostProf *hp2 = new HostProf("sh.merge");
     Timer t_merge(st);
     cnt.reserve((size_t)alen); off.reserve((size_t)alen);
     EntryArgs ea{};
@@ -248,7 +253,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     CUDA_CHECK(cudaMemcpyAsync(&nhits, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (c.opt.verbose) { printf("   Hit count = %lld\n", (long long)nhits); fflush(stdout); }
-    if (nhits == 0) { c.tm.merge_ms = t_merge.stop(); return; }
+    if (nhits == 0) { c.tm.merge_ms = t_merge.stop(); delete hp2; return; }
 
     out.pbits = bits_for(ab->maxlen);
     out.abits = bits_for(ab->nreads);
@@ -257,19 +262,21 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
         fatal("seed-hit key needs %d bits (> 64): block too large for this build", out.pbits + out.abits + out.bbits);
 
     uint64_t *k0, *k1; uint32_t *v0, *v1;
-    CUDA_CHECK(cudaMalloc((void **)&k0, sizeof(uint64_t) * (nhits + 1)));
-    CUDA_CHECK(cudaMalloc((void **)&k1, sizeof(uint64_t) * (nhits + 1)));
-    CUDA_CHECK(cudaMalloc((void **)&v0, sizeof(uint32_t) * (nhits + 1)));
-    CUDA_CHECK(cudaMalloc((void **)&v1, sizeof(uint32_t) * (nhits + 1)));
+    k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 1));
+    k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 1));
+    v0 = (std::remove_reference<decltype(v0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 1));
+    v1 = (std::remove_reference<decltype(v1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 1));
     ea.keys = k0; ea.bpos = v0; ea.pbits = out.pbits; ea.abits = out.abits;
     emit_hits<<<eb, 256, 0, st>>>(ea);
     KERNEL_CHECK(); count_launch();
     c.tm.merge_ms = t_merge.stop();
 
+    delete hp2;
+    HostProf hp3("sh.sort+free");
     Timer t_sort(st);
     radix_sort_pairs(k0, v0, k1, v1, (int64_t)nhits, out.pbits + out.abits + out.bbits, st);
     c.tm.hsort_ms = t_sort.stop();
-    CUDA_CHECK(cudaFree(k1)); CUDA_CHECK(cudaFree(v1));
+    dev_free(k1); dev_free(v1);
     out.keys = k0; out.bpos = v0; out.n = (int64_t)nhits;
 }
 

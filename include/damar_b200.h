@@ -70,10 +70,16 @@ typedef struct damar_overlap {
 
 typedef struct damar_overlaps {
     int64_t              novl;
-    const damar_overlap *ovl;        /* novl records, in emission order                       */
+    const damar_overlap *ovl;        /* novl records, in no particular order                  */
     const uint64_t      *trace_off;  /* novl offsets (in values) into trace                   */
-    const uint16_t      *trace;      /* uncompressed trace values (d_i, b_i pairs)            */
+    const uint64_t      *seq;        /* novl emission ranks: the order in which the reference's
+                                        report threads would have buffered the records (pair order,
+                                        A records before B records); breaks full SORT_OVL ties      */
+    const void          *trace;      /* trace values (d_i, b_i pairs): uint8 if trace_bytes == 1
+                                        (trace_spacing <= 125, Compress_TraceTo8), else uint16      */
     int64_t              ntrace;
+    int32_t              trace_bytes;
+    int32_t              reserved;
     /* counters printed by -v (filter.c:2910-2928) */
     int64_t              nhits;      /* seed hits (k-mer matches)                             */
     int64_t              nfilt;      /* Local_Alignment calls                                 */
@@ -127,6 +133,7 @@ typedef struct damar_timings {
     double  align_kernel_ms; int64_t align_launches;
 } damar_timings;
 void damar_reset_kernel_timers(void);
+void damar_dump_profile(void);   /* host wall-clock breakdown to stderr */
 void damar_get_timings(damar_timings *t);
 
 /* ---- output path: Overlap_IO_Buffer + Write_Overlap_Buffer (align.c:5969-6380), host only ---- */

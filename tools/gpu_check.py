@@ -38,6 +38,7 @@ def main():
         t0 = time.time()
         got = api.daligner(blocks[a], [blocks[b] for b in bs], s, stats=stats)
         t_gpu = time.time() - t0
+        api.load_library().damar_dump_profile()
         for st in stats:
             for comp in (0, 1):
                 t = st[f"t{comp}"]
