@@ -62,12 +62,7 @@ static int do_init(int device) {
     }
     CUDA_CHECK(cudaSetDevice(device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    {
-        cudaMemPool_t pool;
-        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = ~0ull;                 // never hand freed blocks back to the driver
-        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
+
     c.device = device;
     // defaults of daligner.c:688-703
     c.opt.minover = 2000; c.opt.symmetric = 1; c.opt.trace_spacing = 100; c.opt.ave_corr = .70;
@@ -76,13 +71,45 @@ static int do_init(int device) {
     return 0;
 }
 
+// ---- caching device allocator ----------------------------------------------------------------
+// A block pair allocates and frees tens of GB of tuple / hit lists; cudaMalloc/cudaFree cost
+// milliseconds per GB and synchronise the device.  All library work is ordered on one stream, so
+// a freed block can be handed to the next request immediately.  Requests are rounded up to a
+// coarse size class and served best-fit from the free list (at most 1.5x the rounded size).
+static std::multimap<size_t, void *> g_free_blocks;
+static std::map<void *, size_t> g_block_size;
+static size_t round_class(size_t b) {
+    size_t q = b >= (256u << 20) ? (64u << 20) : b >= (16u << 20) ? (8u << 20) : b >= (1u << 20) ? (1u << 20) : (64u << 10);
+    return (b + q - 1) / q * q;
+}
+static void release_cached_blocks() {
+    for (auto &kv : g_free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
+    g_free_blocks.clear();
+}
 void *dev_alloc_bytes(size_t bytes) {
+    const size_t r = round_class(bytes ? bytes : 1);
+    auto it = g_free_blocks.lower_bound(r);
+    if (it != g_free_blocks.end() && it->first <= r + r / 2) {
+        void *p = it->second;
+        g_free_blocks.erase(it);
+        return p;
+    }
     void *p = nullptr;
-    CUDA_CHECK(cudaMallocAsync(&p, bytes ? bytes : 16, ctx().stream));
+    cudaError_t e = cudaMalloc(&p, r);
+    if (e != cudaSuccess) {                       // out of memory: drop the cache and retry once
+        cudaGetLastError();
+        CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
+        release_cached_blocks();
+        CUDA_CHECK(cudaMalloc(&p, r));
+    }
+    g_block_size[p] = r;
     return p;
 }
 void dev_free(void *p) {
-    if (p && ctx().ready) cudaFreeAsync(p, ctx().stream);
+    if (!p || !ctx().ready) return;
+    auto it = g_block_size.find(p);
+    if (it == g_block_size.end()) { cudaFree(p); return; }
+    g_free_blocks.emplace(it->second, p);
 }
 
 void ensure_init() {
@@ -115,6 +142,7 @@ void damar_shutdown(void) {
     if (!c.ready) return;
     g_hits.release();
     cudaStreamSynchronize(c.stream);
+    release_cached_blocks();
     cudaStreamDestroy(c.stream);
     c.ready = false;
 }

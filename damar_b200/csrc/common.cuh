@@ -29,9 +29,7 @@ void set_error(const char *fmt, ...);
 constexpr int NUM_SMS_B200 = 148;
 constexpr int PACK_FRONT_PAD = 4;     // words of zero padding in front of every packed base array
 
-// ---- device memory: stream-ordered allocations from the device's default pool, whose release
-//      threshold is raised at init so freed blocks are recycled instead of returned to the driver
-//      (a block pair allocates and frees tens of GB of tuple / hit lists) ----
+// ---- device memory: caching allocator (api.cu); all work is ordered on the context stream ----
 void *dev_alloc_bytes(size_t bytes);
 void dev_free(void *p);
 template <typename T> inline T *dev_alloc(size_t n) { return reinterpret_cast<T *>(dev_alloc_bytes(n * sizeof(T))); }

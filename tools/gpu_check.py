@@ -34,6 +34,9 @@ def main():
     for a, bs in bench.plan(nblocks):
         if only and a not in only:
             continue
+        api.daligner(blocks[a], [blocks[b] for b in bs], s, as_bytes=False)     # warm-up (allocator, kernels)
+        api.load_library().damar_dump_profile()
+        print("  -- second run --", flush=True)
         stats = []
         t0 = time.time()
         got = api.daligner(blocks[a], [blocks[b] for b in bs], s, stats=stats)
