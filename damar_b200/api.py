@@ -55,7 +55,8 @@ class Timings(C.Structure):
                 ("kmers", C.c_int64), ("hits", C.c_int64), ("pairs", C.c_int64), ("la_calls", C.c_int64),
                 ("wave_cells", C.c_int64), ("kernel_launches", C.c_int64),
                 ("scatter_ms", C.c_double), ("scatter_elems", C.c_int64), ("scatter_launches", C.c_int64),
-                ("align_kernel_ms", C.c_double), ("align_launches", C.c_int64)]
+                ("align_kernel_ms", C.c_double), ("align_launches", C.c_int64), ("redo_pairs", C.c_int64),
+                ("redo_kernel_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -207,7 +207,7 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     out->ncheck = out->novl;
     out->limit = g_hits.limit;
     out->multi_la_pairs = (int32_t)g_out.multi;
-    c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs;
+    c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
     c.tm.kernel_launches = c.launches;
     return 0;
 }
@@ -266,7 +266,7 @@ void damar_dump_profile(void) { dump_profile(); }
 void damar_get_timings(damar_timings *t) { *t = ctx().tm; t->kernel_launches = ctx().launches; }
 void damar_reset_kernel_timers(void) {
     damar_timings &t = ctx().tm;
-    t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.align_kernel_ms = 0; t.align_launches = 0;
+    t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
 }
 
 }  // extern "C"

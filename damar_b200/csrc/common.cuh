@@ -182,7 +182,7 @@ struct HostOverlaps {                 // views of pinned staging buffers, valid 
     const void *trace = nullptr;
     int64_t novl = 0, ntrace = 0;
     int tbytes = 2;
-    int64_t nfilt = 0, multi = 0, cells = 0, pairs = 0;
+    int64_t nfilt = 0, multi = 0, cells = 0, pairs = 0, redo = 0;
 };
 void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
                       HostOverlaps &out);

@@ -88,6 +88,8 @@ struct AlignArgs {
     // hits
     const uint64_t *keys; const uint32_t *bpos; int64_t nhits; int pbits, abits;
     const uint32_t *work; uint32_t nwork; unsigned int *next_work;
+    const uint32_t *work_wi;           // optional: original work index of work[i] (second, strided pass)
+    uint32_t *redo_sidx, *redo_wi; unsigned int *redo_count; uint8_t *pair_redo;   // fast pass: pairs handed to the strided pass
     // blocks
     const uint32_t *awords, *bwords; const uint32_t *aboff, *bboff; const int32_t *arlen, *brlen;
     int afirst, bfirst;
@@ -478,7 +480,258 @@ __device__ int emit_chain_rev(int4 *cells, int head, bool isA, int ex, int ey, i
     return -at;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident wave pass: the whole wave front (<= 32 live diagonals) lives in registers, one
+// diagonal per lane (lane = k mod 32), neighbours are fetched with shuffles, and nothing but the
+// pebble cells touches memory.  Same arithmetic and visiting-order semantics as wave_pass; returns
+// false (S.overflow = 2) when the front grows beyond 32 diagonals so that the pair is redone by
+// the strided scratch-memory kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned rotr32(unsigned x, int s) { return __funnelshift_r(x, x, s & 31); }
+
+template <int DIR>
+__device__ void wave_pass_fast(WarpLA &S, const uint32_t *__restrict__ aw, int64_t abase, int alen,
+                               const uint32_t *__restrict__ bw, int64_t bbase, int blen,
+                               int diag, int anti, int minp, int maxp, int aoff, int boff,
+                               int &ex, int &ey, int &ediff, int &eha, int &ehb) {
+    const int lane = threadIdx.x & 31;
+    const int TS = S.TS, PATH_AVE = S.PATH_AVE;
+    const int NEG = (DIR > 0) ? -1 : IMAX;
+    int low = diag, hgh = diag, dif = 0, more = 1;
+    int aclip = (DIR > 0) ? IMAX : -IMAX, bclip = (DIR > 0) ? -IMAX : IMAX;
+    int besta, besty, trima, trimy, trimd = 0, trimha = 0, trimhb = 1;
+    int morea, morey, mored = 0, moreha = 0, morehb = 1, morem = -1, lasta;
+    // per-lane diagonal state
+    int V, HA, HB, HM, HN, NA, NB; uint64_t T;
+    unsigned long long cells_done = 0;
+
+    S.ncell = 0;
+    besta = trima = morea = lasta = anti;
+    besty = trimy = morey = (anti - diag) >> 1;
+
+    {   // ---- wave 0 (uniform) ----
+        const int k = diag;
+        int y = (anti - k) >> 1, x = y + k, na, nb, ha, hb, ham, hbm, n;
+        if (DIR > 0) {
+            na = ((x + (TS - aoff)) / TS - 1) * TS + aoff;
+            nb = ((y + (TS - boff)) / TS - 1) * TS + boff;
+            if (lane == 0) { S.cells[0] = make_int4(-1, k, 0, na); S.cells[1] = make_int4(-1, k, 0, nb); }
+            ha = 0; hb = 1; ham = na; hbm = nb; S.ncell = 2;
+            na += TS; nb += TS;
+            const int ra = alen - x, rb = blen - y;
+            n = slide_fwd(aw, abase + x, bw, bbase + y, ra < rb ? ra : rb);
+            y += n; x += n;
+            if (y == blen) { more = 0; if (bclip < k) bclip = k; }
+            else if (x == alen) { more = 0; aclip = k; }
+            while (x >= na) { if (lane == 0) S.cells[S.ncell] = make_int4(ha, k, 0, na); ha = S.ncell++; ham = na; na += TS; }
+            while (y >= nb) { if (lane == 0) S.cells[S.ncell] = make_int4(hb, k, 0, nb); hb = S.ncell++; hbm = nb; nb += TS; }
+        } else {
+            na = ((x + (TS - aoff) - 1) / TS - 1) * TS + aoff;
+            nb = ((y + (TS - boff) - 1) / TS - 1) * TS + boff;
+            if (lane == 0) { S.cells[0] = make_int4(-1, k, 0, x); S.cells[1] = make_int4(-1, k, 0, y); }
+            ha = 0; hb = 1; ham = x; hbm = y; S.ncell = 2;
+            n = slide_rev(aw, abase + x, bw, bbase + y, x < y ? x : y);
+            y -= n; x -= n;
+            if (y == 0) { more = 0; if (bclip > k) bclip = k; }
+            else if (x == 0) { more = 0; aclip = k; }
+            while (x <= na) { if (lane == 0) S.cells[S.ncell] = make_int4(ha, k, 0, na); ha = S.ncell++; ham = na; na -= TS; }
+            while (y <= nb) { if (lane == 0) S.cells[S.ncell] = make_int4(hb, k, 0, nb); hb = S.ncell++; hbm = nb; nb -= TS; }
+        }
+        const int c = (y << 1) + k;
+        if (DIR > 0 ? (c > besta) : (c < besta)) { besta = trima = lasta = c; besty = trimy = y; trimha = ha; trimhb = hb; }
+        V = c; T = PATH_INT; HA = ha; HB = hb; HM = ham; HN = hbm; NA = na; NB = nb;     // every lane holds a copy; only lane k&31 is live
+    }
+
+    for (;;) {
+        // ---- boundary clipping ----
+        if (more == 0) {
+            bool inside;
+            if (DIR > 0) inside = (besty < blen) && (besta - besty < alen);
+            else inside = (besty > 0) && (besta - besty > 0);
+            if (inside) more = 1;
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int kc = side == 0 ? aclip : bclip;
+                bool hit;
+                if (DIR > 0) hit = side == 0 ? (hgh >= aclip) : (low <= bclip);
+                else         hit = side == 0 ? (low <= aclip) : (hgh >= bclip);
+                if (!hit) continue;
+                if (DIR > 0) { if (side == 0) hgh = kc - 1; else low = kc + 1; }
+                else         { if (side == 0) low = kc + 1; else hgh = kc - 1; }
+                const int sl = kc & 31;
+                const uint64_t tc = __shfl_sync(FULL, T, sl);
+                const int vc = __shfl_sync(FULL, V, sl), hac = __shfl_sync(FULL, HA, sl), hbc = __shfl_sync(FULL, HB, sl);
+                const int mc = __popcll(tc & PATH_MASK61);
+                if (morem <= mc) { morem = mc; morea = vc; morey = (morea - kc) / 2; mored = dif; moreha = hac; morehb = hbc; }
+            }
+            aclip = (DIR > 0) ? IMAX : -IMAX; bclip = (DIR > 0) ? -IMAX : IMAX;
+        }
+        // ---- prune lagging ends ----
+        if (dif > 0 && hgh >= low) {
+            const int k = low + ((lane - low) & 31);
+            const bool keep = (k <= hgh) && (DIR > 0 ? (V >= besta - WAVE_LAG) : (V <= besta + WAVE_LAG));
+            const unsigned km = __ballot_sync(FULL, keep);
+            if (km == 0) hgh = low - 1;
+            else {
+                // bit r of `byrank` <-> diagonal hgh - r
+                const unsigned byrank = rotr32(__brev(km), 31 - (hgh & 31));
+                const int top = __ffs(byrank) - 1, bot = 31 - __clz(byrank);
+                const int nh = hgh - top, nl = hgh - bot;
+                hgh = nh; low = nl;
+            }
+            if (hgh >= low) cells_done += (unsigned)(hgh - low + 1);
+        }
+        if (!(more && (DIR > 0 ? (lasta >= besta - TRIM_MLAG) : (lasta <= besta + TRIM_MLAG)))) break;
+        if (hgh < low) break;
+
+        // ---- widen ----
+        const int plow = low, phgh = hgh;
+        if (low - 1 >= minp) low -= 1;
+        if (hgh + 1 <= maxp) hgh += 1;
+        if (hgh - low + 1 > 32) { S.overflow = 2; break; }
+        dif += 1;
+        const int k = low + ((lane - low) & 31);
+        const bool act = k <= hgh;
+        const int lm = (lane - 1) & 31, lp = (lane + 1) & 31;
+        {   // new end diagonals inherit the trace cursors of their inner neighbour
+            const int naR = __shfl_sync(FULL, NA, lp), nbR = __shfl_sync(FULL, NB, lp);
+            const int naL = __shfl_sync(FULL, NA, lm), nbL = __shfl_sync(FULL, NB, lm);
+            if (act && k < plow) { NA = naR; NB = nbR; }
+            else if (act && k > phgh) { NA = naL; NB = nbL; }
+        }
+        const int vl = __shfl_sync(FULL, V, lm), vr = __shfl_sync(FULL, V, lp);
+        const int vm = (k - 1 >= plow && k - 1 <= phgh) ? vl : NEG;
+        const int vc = (k >= plow && k <= phgh) ? V : NEG;
+        const int vp = (k + 1 >= plow && k + 1 <= phgh) ? vr : NEG;
+        int c, dir;
+        if (DIR > 0) {
+            if (vc < vm) { if (vm < vp) { c = vp + 1; dir = 1; } else { c = vm + 1; dir = -1; } }
+            else if (vc < vp) { c = vp + 1; dir = 1; }
+            else { c = vc + 2; dir = 0; }
+        } else {
+            if (vc > vp) { if (vp > vm) { c = vm - 1; dir = -1; } else { c = vp - 1; dir = 1; } }
+            else if (vc > vm) { c = vm - 1; dir = -1; }
+            else { c = vc - 2; dir = 0; }
+        }
+        const int sl = (lane + dir) & 31;
+        uint64_t b = __shfl_sync(FULL, T, sl) << 1;
+        int ha = __shfl_sync(FULL, HA, sl), hb = __shfl_sync(FULL, HB, sl);
+        int ham = __shfl_sync(FULL, HM, sl), hbm = __shfl_sync(FULL, HN, sl);
+        int y = 0, m = 0;
+        bool clipA = false, clipB = false;
+        if (act) {
+            y = (c - k) >> 1;
+            int x = y + k, n;
+            if (DIR > 0) {
+                const int ra = alen - x, rb = blen - y;
+                n = slide_fwd(aw, abase + x, bw, bbase + y, ra < rb ? ra : rb);
+                y += n; x += n;
+                if (y == blen) clipB = true; else if (x == alen) clipA = true;
+            } else {
+                n = slide_rev(aw, abase + x, bw, bbase + y, x < y ? x : y);
+                y -= n; x -= n;
+                if (y == 0) clipB = true; else if (x == 0) clipA = true;
+            }
+            b = push_matches(b, n);
+            c = (y << 1) + k;
+            m = __popcll(b & PATH_MASK61);
+        } else c = (DIR > 0) ? -IMAX : IMAX;
+        // ---- pebbles ----
+        {
+            const int x = y + k;
+            for (;;) {
+                const bool need = act && (DIR > 0 ? (x >= NA) : (x <= NA));
+                if (!__any_sync(FULL, need)) break;
+                const bool push = need && (DIR > 0 ? (ham < NA) : (ham > NA));
+                const unsigned pm = __ballot_sync(FULL, push);
+                if (push) {
+                    const int id = S.ncell + __popc(pm & ((1u << lane) - 1u));
+                    if (id < S.cells_cap) S.cells[id] = make_int4(ha, k, dif, NA);
+                    ha = id; ham = NA;
+                }
+                S.ncell += __popc(pm);
+                if (need) NA += DIR * TS;
+            }
+            for (;;) {
+                const bool need = act && (DIR > 0 ? (y >= NB) : (y <= NB));
+                if (!__any_sync(FULL, need)) break;
+                const bool push = need && (DIR > 0 ? (hbm < NB) : (hbm > NB));
+                const unsigned pm = __ballot_sync(FULL, push);
+                if (push) {
+                    const int id = S.ncell + __popc(pm & ((1u << lane) - 1u));
+                    if (id < S.cells_cap) S.cells[id] = make_int4(hb, k, dif, NB);
+                    hb = id; hbm = NB;
+                }
+                S.ncell += __popc(pm);
+                if (need) NB += DIR * TS;
+            }
+            if (S.ncell >= S.cells_cap) { S.overflow = 1; break; }
+        }
+        // ---- best / lasta / trim (align.c:911-928 / 1620-1637).  A diagonal is a record setter iff its
+        //      point beats besta and every point visited before it in this wave: exclusive prefix
+        //      extremum over the visiting order (forward hgh -> low, reverse low -> hgh), taken with
+        //      rotating shuffles because lane = k mod 32 ----
+        if (__any_sync(FULL, act && (DIR > 0 ? (c > besta) : (c < besta)))) {
+            const int rank = (DIR > 0) ? (hgh - k) : (k - low);          // visiting rank of this lane (valid if act)
+            int pre = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_sync(FULL, pre, (DIR > 0) ? (lane + o) : (lane - o));   // lane of rank - o
+                if (rank >= o) pre = (DIR > 0) ? max(pre, t) : min(pre, t);
+            }
+            int excl = __shfl_sync(FULL, pre, (DIR > 0) ? (lane + 1) : (lane - 1));
+            excl = (rank == 0) ? besta : ((DIR > 0) ? max(excl, besta) : min(excl, besta));
+            const bool setter = act && (DIR > 0 ? (c > excl) : (c < excl));
+            const bool good = setter && (m >= PATH_AVE);
+            bool trim = false;
+            if (good) {
+                const int lo15 = (int)(b & TRIM_MASK), hi15 = (int)((b >> TRIM_LEN) & TRIM_MASK);
+                trim = (S.table_tab[lo15] >= 0) && (S.table_tab[hi15] + S.score_tab[lo15] >= 0);
+            }
+            // the last setter in visiting order holds the extreme value: pick by value, not by rank
+            const int ext = (DIR > 0) ? __reduce_max_sync(FULL, setter ? c : -IMAX) : __reduce_min_sync(FULL, setter ? c : IMAX);
+            const unsigned sm = __ballot_sync(FULL, setter && c == ext);
+            if (sm) { const int l = __ffs(sm) - 1; besta = ext; besty = __shfl_sync(FULL, y, l); }
+            const unsigned gm = __ballot_sync(FULL, good);
+            if (gm) {
+                const int gext = (DIR > 0) ? __reduce_max_sync(FULL, good ? c : -IMAX) : __reduce_min_sync(FULL, good ? c : IMAX);
+                lasta = gext;
+                const unsigned tm = __ballot_sync(FULL, trim);
+                if (tm) {
+                    const int text = (DIR > 0) ? __reduce_max_sync(FULL, trim ? c : -IMAX) : __reduce_min_sync(FULL, trim ? c : IMAX);
+                    const int l = __ffs(__ballot_sync(FULL, trim && c == text)) - 1;
+                    trima = text; trimy = __shfl_sync(FULL, y, l); trimd = dif;
+                    trimha = __shfl_sync(FULL, ha, l); trimhb = __shfl_sync(FULL, hb, l);
+                }
+            }
+        }
+        // ---- clip bookkeeping in visiting order ----
+        {
+            const unsigned am = __ballot_sync(FULL, clipA), bm = __ballot_sync(FULL, clipB);
+            if (am | bm) {
+                more = 0;
+                if (am) {       // last visited: forward = lowest diagonal, reverse = highest diagonal
+                    const unsigned byrank = (DIR > 0) ? rotr32(__brev(am), 31 - (hgh & 31)) : rotr32(am, low & 31);
+                    const int r = 31 - __clz(byrank);
+                    aclip = (DIR > 0) ? (hgh - r) : (low + r);
+                }
+                if (bm) {       // extreme diagonal = first visited
+                    const unsigned byrank = (DIR > 0) ? rotr32(__brev(bm), 31 - (hgh & 31)) : rotr32(bm, low & 31);
+                    const int r = __ffs(byrank) - 1;
+                    const int kb = (DIR > 0) ? (hgh - r) : (low + r);
+                    if (DIR > 0) { if (bclip < kb) bclip = kb; } else { if (bclip > kb) bclip = kb; }
+                }
+            }
+        }
+        if (act) { V = c; T = b; HA = ha; HB = hb; HM = ham; HN = hbm; }
+    }
+    S.ncells_done += cells_done;
+    if (morem >= 0) { ex = morea - morey; ey = morey; ediff = mored; eha = moreha; ehb = morehb; }
+    else { ex = trima - trimy; ey = trimy; ediff = trimd; eha = trimha; ehb = trimhb; }
+}
+
 // Local_Alignment (align.c:1904-2097) for daligner's call shape.  Warp-collective.
+template <bool FAST>
 __device__ void local_alignment(WarpLA &S, const AlignArgs &P, uint16_t *tbuf, int ar, int br, int alen, int blen,
                                 int diag, int anti, bool selfie, Path &ap, Path &bp) {
     const int lane = threadIdx.x & 31;
@@ -490,7 +743,8 @@ __device__ void local_alignment(WarpLA &S, const AlignArgs &P, uint16_t *tbuf, i
     int ex, ey, ed, ha, hb;
     int flenA = 0, flenB = 0;
 
-    wave_pass<+1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
+    if (FAST) wave_pass_fast<+1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
+    else wave_pass<+1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
     if (S.overflow) return;
     __syncwarp();
     if (lane == 0) {
@@ -501,7 +755,8 @@ __device__ void local_alignment(WarpLA &S, const AlignArgs &P, uint16_t *tbuf, i
     ap.aepos = ex; ap.bepos = ey; ap.diffs = ed;
     __syncwarp();
 
-    wave_pass<-1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
+    if (FAST) wave_pass_fast<-1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
+    else wave_pass<-1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
     if (S.overflow) return;
     __syncwarp();
     int preA = 0, preB = 0;
@@ -558,7 +813,8 @@ __device__ void emit_record(const AlignArgs &P, const Path &p, int aread, int br
     }
 }
 
-__global__ void __launch_bounds__(AL_WARPS * 32) align_pairs(AlignArgs P) {
+template <bool FAST>
+__global__ void __launch_bounds__(AL_WARPS * 32, FAST ? 4 : 3) align_pairs(AlignArgs P) {
     __shared__ int la_low[AL_WARPS][MAX_LA_PER_PAIR], la_hgh[AL_WARPS][MAX_LA_PER_PAIR], la_ae[AL_WARPS][MAX_LA_PER_PAIR];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * AL_WARPS + wib;
@@ -583,11 +839,13 @@ __global__ void __launch_bounds__(AL_WARPS * 32) align_pairs(AlignArgs P) {
     unsigned long long n_la = 0, n_multi = 0, n_pairs = 0;
 
     for (;;) {
-        unsigned wi = 0;
-        if (lane == 0) wi = atomicAdd(P.next_work, 1u);
-        wi = __shfl_sync(FULL, wi, 0);
-        if (wi >= P.nwork) break;
-        const int64_t sidx = P.work[wi];
+        unsigned wslot = 0;
+        if (lane == 0) wslot = atomicAdd(P.next_work, 1u);
+        wslot = __shfl_sync(FULL, wslot, 0);
+        if (wslot >= P.nwork) break;
+        const int64_t sidx = P.work[wslot];
+        const unsigned wi = P.work_wi ? P.work_wi[wslot] : wslot;
+        const unsigned long long la0 = n_la, multi0 = n_multi, cells0 = S.ncells_done;
         const uint64_t pair = P.keys[sidx] >> P.pbits;
         const int ar = (int)(pair & ((1ull << P.abits) - 1ull)), br = (int)(pair >> P.abits);
         const int alen = P.arlen[ar], blen = P.brlen[br];
@@ -670,7 +928,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32) align_pairs(AlignArgs P) {
                     if (__any_sync(FULL, blocked)) continue;
                     Path ap, bp;
                     n_la++;
-                    local_alignment(S, P, tbuf, ar, br, alen, blen, capos - cbpos, capos + cbpos, selfie, ap, bp);
+                    local_alignment<FAST>(S, P, tbuf, ar, br, alen, blen, capos - cbpos, capos + cbpos, selfie, ap, bp);
                     if (S.overflow) break;
                     // Diagonal_Span (filter.c:2079-2110) on the uncompressed A trace
                     int lo, hi;
@@ -724,6 +982,16 @@ __global__ void __launch_bounds__(AL_WARPS * 32) align_pairs(AlignArgs P) {
             if (S.overflow) break;
         }
         if (novl > 1) n_multi++;
+        if (FAST && S.overflow == 2) {
+            // wave front outgrew the warp: hand the whole pair to the strided pass; whatever this pass
+            // emitted for the pair is dropped on the host (pair_redo)
+            if (lane == 0) {
+                const unsigned q = atomicAdd(P.redo_count, 1u);
+                P.redo_sidx[q] = (uint32_t)sidx; P.redo_wi[q] = wi; P.pair_redo[wi] = 1;
+            }
+            n_la = la0; n_multi = multi0; S.ncells_done = cells0; n_pairs--;
+            S.overflow = 0;
+        }
         if (S.overflow) { if (lane == 0) atomicOr(&P.stats[3], 4ull); S.overflow = 0; }
     }
     if (lane == 0) {
@@ -815,7 +1083,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     CUDA_CHECK(cudaMemsetAsync(bscore.p, 0, sizeof(int32_t) * (size_t)nwarps * 2 * nbuck, st));
 
     DevBuf<unsigned long long> counters; counters.reserve(8);
-    DevBuf<unsigned int> next; next.reserve(1);
+    DevBuf<unsigned int> next; next.reserve(4);
+    DevBuf<uint32_t> redo_sidx, redo_wi; DevBuf<uint8_t> pair_redo;
+    redo_sidx.reserve((size_t)nwork + 1); redo_wi.reserve((size_t)nwork + 1); pair_redo.reserve((size_t)nwork + 1);
+    unsigned int nredo = 0; unsigned long long nrec_fast = 0;
     const int tbytes = (TS <= 125) ? 1 : 2;                  // TRACE_XOVR, align.h:58
     unsigned long long rec_cap = 4 * nwork + 1024;
     unsigned long long trace_cap = (unsigned long long)rec_cap * (unsigned long long)(2 * (maxlen / TS + 2)) / 8 + (1ull << 20);
@@ -827,10 +1098,12 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         recs.reserve((size_t)rec_cap); rtoff.reserve((size_t)rec_cap); rseq.reserve((size_t)rec_cap);
         trace.reserve((size_t)trace_cap * tbytes);
         CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 8, st));
-        CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int), st));
+        CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int) * 4, st));
+        CUDA_CHECK(cudaMemsetAsync(pair_redo.p, 0, (size_t)nwork + 1, st));
         AlignArgs P{};
         P.keys = hits.keys; P.bpos = hits.bpos; P.nhits = n; P.pbits = hits.pbits; P.abits = hits.abits;
-        P.work = work.p; P.nwork = (uint32_t)nwork; P.next_work = next.p;
+        P.work = work.p; P.nwork = (uint32_t)nwork; P.next_work = next.p; P.work_wi = nullptr;
+        P.redo_sidx = redo_sidx.p; P.redo_wi = redo_wi.p; P.redo_count = next.p + 1; P.pair_redo = pair_redo.p;
         P.awords = ab->packed[0]; P.bwords = bb->packed[comp ? 1 : 0];
         P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
         P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
@@ -844,9 +1117,20 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         P.trace = trace.p; P.tbytes = tbytes; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
         P.stats = counters.p;
         Timer t_k(st);
-        align_pairs<<<blocks, AL_WARPS * 32, 0, st>>>(P);
+        align_pairs<true><<<blocks, AL_WARPS * 32, 0, st>>>(P);
         KERNEL_CHECK(); count_launch();
         c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
+        CUDA_CHECK(cudaMemcpyAsync(&nredo, next.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&nrec_fast, counters.p + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (nredo > 0) {                               // strided scratch-memory pass for the wide pairs
+            CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int), st));
+            P.work = redo_sidx.p; P.work_wi = redo_wi.p; P.nwork = nredo;
+            Timer t_r(st);
+            align_pairs<false><<<blocks, AL_WARPS * 32, 0, st>>>(P);
+            KERNEL_CHECK(); count_launch();
+            c.tm.redo_kernel_ms += t_r.stop();
+        }
         CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if ((hc[3] & 1ull) && attempt < 4) {            // output buffers too small: grow and rerun
@@ -878,9 +1162,20 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         CUDA_CHECK(cudaMemcpyAsync(h_seq.p, rseq.p, sizeof(uint64_t) * nrec, cudaMemcpyDeviceToHost, st));
     }
     if (ntr) CUDA_CHECK(cudaMemcpyAsync(h_trace.p, trace.p, (size_t)ntr * tbytes, cudaMemcpyDeviceToHost, st));
+    std::vector<uint8_t> h_redo;
+    if (nredo > 0) { h_redo.resize(nwork); CUDA_CHECK(cudaMemcpyAsync(h_redo.data(), pair_redo.p, nwork, cudaMemcpyDeviceToHost, st)); }
     CUDA_CHECK(cudaStreamSynchronize(st));
+    uint64_t nkeep = nrec;
+    if (nredo > 0) {                                   // drop what the fast pass emitted for pairs it gave up on
+        nkeep = 0;
+        for (uint64_t i = 0; i < nrec; i++) {
+            if (i < nrec_fast && h_redo[h_seq.p[i] >> 8]) continue;
+            if (nkeep != i) { h_recs.p[nkeep] = h_recs.p[i]; h_toff.p[nkeep] = h_toff.p[i]; h_seq.p[nkeep] = h_seq.p[i]; }
+            nkeep++;
+        }
+    }
     out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = h_trace.p;
-    out.novl = (int64_t)nrec; out.ntrace = (int64_t)ntr; out.tbytes = tbytes;
+    out.novl = (int64_t)nkeep; out.ntrace = (int64_t)ntr; out.tbytes = tbytes; out.redo = (int64_t)nredo;
     out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)hc[4];
     c.tm.download_ms = t_dl.stop();
 }

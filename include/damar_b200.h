@@ -131,6 +131,8 @@ typedef struct damar_timings {
     /* accumulated since damar_reset_kernel_timers(): the radix-sort scatter kernel (dominant HBM kernel) */
     double  scatter_ms; int64_t scatter_elems; int64_t scatter_launches;
     double  align_kernel_ms; int64_t align_launches;
+    int64_t redo_pairs;          /* pairs whose wave front outgrew one warp (strided second pass) */
+    double  redo_kernel_ms;      /* accumulated like align_kernel_ms */
 } damar_timings;
 void damar_reset_kernel_timers(void);
 void damar_dump_profile(void);   /* host wall-clock breakdown to stderr */

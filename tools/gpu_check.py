@@ -47,7 +47,7 @@ def main():
                 t = st[f"t{comp}"]
                 print(f"  job {a} comp{comp}: hits={st[f'nhits{comp}']} la={st[f'nfilt{comp}']} ovl={st[f'novl{comp}']} multi={st[f'multi{comp}']} "
                       f"| extract {t['extract_ms']:.1f} ksort {t['ksort_ms']:.1f} count {t['count_ms']:.1f} merge {t['merge_ms']:.1f} "
-                      f"hsort {t['hsort_ms']:.1f} pairs {t['pairs_ms']:.1f} align {t['align_ms']:.1f} dl {t['download_ms']:.1f} ms; cells={t['wave_cells']}", flush=True)
+                      f"hsort {t['hsort_ms']:.1f} pairs {t['pairs_ms']:.1f} align {t['align_ms']:.1f} dl {t['download_ms']:.1f} ms; cells={t['wave_cells']} pairs={t['pairs']} redo={t['redo_pairs']} fastk={t['align_kernel_ms']:.1f} redok={t['redo_kernel_ms']:.1f} (cumulative)", flush=True)
         for d in os.listdir(dbdir):
             if d.startswith("d001_"):
                 shutil.rmtree(os.path.join(dbdir, d))
