@@ -31,7 +31,7 @@ class BlockDesc(C.Structure):
     _fields_ = [("nreads", C.c_int32), ("maxlen", C.c_int32), ("totlen", C.c_int64), ("ufirst", C.c_int32),
                 ("part", C.c_int32), ("bases", C.c_void_p), ("boff", C.c_void_p), ("rlen", C.c_void_p),
                 ("mask_anno", C.c_void_p), ("mask_data", C.c_void_p), ("freq", C.c_float * 4),
-                ("sizeof_db", C.c_int64)]
+                ("sizeof_db", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Options(C.Structure):
@@ -69,7 +69,8 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_set_options", "damar_block_upload", "damar_block_free", "damar_sort_kmers", "damar_index_free",
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
-           "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers"]
+           "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
+           "damar_dump_profile"]
 
 _lib = None
 

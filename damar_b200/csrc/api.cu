@@ -1,4 +1,5 @@
 // api.cu -- the C-ABI of include/damar_b200.h on top of the stage implementations.
+#include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <map>
@@ -191,7 +192,7 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
     c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0;
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
-        if (comp) ensure_revcomp(bb);
+        if (comp && !bb->as_is) ensure_revcomp(bb);
         { HostProf hp("mf.seed_hits"); seed_hits(ai, bi, self, comp, g_hits); }
         if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); report_and_align(ab, bb, comp, self, g_hits, g_out); }
     }
@@ -210,6 +211,13 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
     c.tm.kernel_launches = c.launches;
     return 0;
+}
+
+void damar_emission_order(const damar_overlaps *o, int64_t *order) {
+    std::vector<int64_t> idx((size_t)o->novl);
+    for (int64_t i = 0; i < o->novl; i++) idx[i] = i;
+    if (o->seq) std::sort(idx.begin(), idx.end(), [&](int64_t x, int64_t y) { return o->seq[x] < o->seq[y]; });
+    memcpy(order, idx.data(), sizeof(int64_t) * (size_t)o->novl);
 }
 
 // ---- stage read-backs for the parity tests ----

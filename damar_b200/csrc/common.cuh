@@ -132,6 +132,7 @@ struct DeviceBlock {
     uint32_t *boff = nullptr;                   // [nreads+1] (blocks are < 2^31 bases, filter.c:794)
     int32_t *rlen = nullptr;                    // [nreads]
     bool has_mask = false;
+    bool as_is = false;                         // host already complemented the block (DAMAR_BLOCK_AS_IS)
     int64_t *mask_anno[2] = {nullptr, nullptr}; // [nreads+1], forward / mirrored
     int32_t *mask_data[2] = {nullptr, nullptr};
     int64_t mask_len = 0;

@@ -213,6 +213,7 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
     DeviceBlock *b = new DeviceBlock();
     b->nreads = d->nreads; b->maxlen = d->maxlen; b->totlen = d->totlen; b->ufirst = d->ufirst; b->part = d->part;
     b->sizeof_db = d->sizeof_db;
+    b->as_is = (d->flags & DAMAR_BLOCK_AS_IS) != 0;
     memcpy(b->freq, d->freq, sizeof(b->freq));
     b->nbases = d->boff[d->nreads];
     if (b->nbases > 0x7fffffffll) fatal("DB blocks are greater than 2Gbp!");   // filter.c:794-798

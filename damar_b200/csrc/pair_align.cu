@@ -1104,7 +1104,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         P.keys = hits.keys; P.bpos = hits.bpos; P.nhits = n; P.pbits = hits.pbits; P.abits = hits.abits;
         P.work = work.p; P.nwork = (uint32_t)nwork; P.next_work = next.p; P.work_wi = nullptr;
         P.redo_sidx = redo_sidx.p; P.redo_wi = redo_wi.p; P.redo_count = next.p + 1; P.pair_redo = pair_redo.p;
-        P.awords = ab->packed[0]; P.bwords = bb->packed[comp ? 1 : 0];
+        P.awords = ab->packed[0]; P.bwords = bb->packed[(comp && !bb->as_is) ? 1 : 0];
         P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
         P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
         P.K = fp.kmer; P.W = fp.binshift; P.H = fp.hitmin; P.minhit = minhit; P.TS = TS; P.minover = c.opt.minover;

@@ -43,7 +43,13 @@ typedef struct damar_block_desc {
     const int32_t *mask_data;   /* sorted [beg,end) pairs (daligner.c:474-497)               */
     float          freq[4];     /* HITS_DB.freq                                              */
     int64_t        sizeof_db;   /* sizeof_DB(block), db/DB.c:726 (enters the -M rule)        */
+    int32_t        flags;       /* DAMAR_BLOCK_* */
+    int32_t        reserved;
 } damar_block_desc;
+
+/* The host already applied complement_DB (daligner.c:529) where it wanted a complemented block:
+ * damar_match_filter(comp=1) then uses the block as shipped instead of complementing on the device. */
+#define DAMAR_BLOCK_AS_IS 1
 
 /* ---- the globals of daligner.c:131-140 that filter.c reads, plus the Align_Spec fields ---- */
 typedef struct damar_options {
@@ -117,6 +123,10 @@ void         damar_index_free(damar_index *idx);
  * damar_match_filter / damar_shutdown call.  Returns 0 on success.                             */
 int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
                        int self, int comp, damar_overlaps *out);
+
+/* order[0..novl) = record indices sorted by emission rank (the order AddOverlapToBuffer would have
+ * been called in by the reference's report threads)                                              */
+void damar_emission_order(const damar_overlaps *o, int64_t *order);
 
 /* ---- stage-level read-backs (used by the parity tests; not needed by a host) ---- */
 /* sorted k-mer list in the reference's KmerPos layout {u64 code; i32 rpos; i32 read}           */

@@ -104,3 +104,86 @@ def test_sorted_hits_match_oracle(case, comp):
     assert ov.nhits == nh.value and ov.limit == lim.value
     for f in ("bread", "aread", "apos", "diag"):
         assert np.array_equal(got[f], ref[f]), f
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-in: the UNMODIFIED reference host (daligner.c + align.c + DB.c) linked against our library
+# through the filter.h shim (oracle/_ref/daligner_b200, built by oracle/Makefile)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["default", "b2", "dust", "twomasks", "identity", "asym", "k16s200", "memlimit", "notrace"])
+def test_dropin_reference_host(case, tmp_path):
+    import os, shutil, subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "daligner_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/daligner_b200 not built (needs /root/reference at build time)")
+    for fn in os.listdir(TINY):
+        p = os.path.join(TINY, fn)
+        if os.path.isfile(p):
+            shutil.copy(p, tmp_path / fn)
+    r = subprocess.run([exe] + CASES[case]["flags"] + CASES[case]["blocks"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gold = golden_files(case)
+    got = {}
+    for d in os.listdir(tmp_path):
+        if d.startswith("d001_"):
+            for fn in os.listdir(tmp_path / d):
+                got[fn] = open(tmp_path / d / fn, "rb").read()
+    assert sorted(got) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, got[fn])
+        assert ok, f"{case}/{fn}: {why}"
+
+
+def test_sharded_plan_world1(tmp_path):
+    """multi.run_sharded at world size 1 = the whole HPCdaligner plan; files land in d<run>_<blk>/."""
+    import os
+    from damar_b200 import multi
+    o = parse_flags(CASES["default"]["flags"])
+    novl, files = multi.run_sharded(TINY, "T", 2, settings(o), 0, 1, outdir=str(tmp_path))
+    gold = dict(golden_files("default"))
+    gold.update({k: v for k, v in golden_files("b2").items() if k not in gold})
+    assert sorted(files) == sorted(gold)
+    for fn, ref in gold.items():
+        part = int(fn.split(".")[1])
+        got = open(os.path.join(tmp_path, f"d001_{part:05d}", fn), "rb").read()
+        ok, why = dbio.las_equal(ref, got)
+        assert ok, f"{fn}: {why}"
+    assert novl == sum(int.from_bytes(v[:8], "little") for v in gold.values())
+
+
+def test_properties_at_scale():
+    """20 Mbp / 2 blocks: size-independent invariants of the emitted .las (what LAcheck -p -s checks,
+    utils/LAcheck.c:116-221, align.c:3455-3506) plus A/B symmetry, and equality with the reference
+    binary when it is available on the box."""
+    import os, shutil, subprocess, sys
+    from cases import ROOT
+    sys.path.insert(0, ROOT)
+    import bench
+    dbdir, root, nblocks = bench.make_db("small")
+    blks = [dbio.read_block(os.path.join(dbdir, f"{root}.{i}")) for i in (1, 2)]
+    s = api.Settings(mem_limit_gb=32)
+    out = api.daligner(blks[1], [blks[0], blks[1]], s)
+    n12 = int.from_bytes(out[f"{root}.1.{root}.2.las"][:8], "little")
+    n21 = int.from_bytes(out[f"{root}.2.{root}.1.las"][:8], "little")
+    assert n12 == n21 > 1000
+    for fn, buf in out.items():
+        novl, tspace, recs, traces = dbio.parse_las(buf)
+        keys = [(int(r["aread"]), int(r["bread"]), int(r["flags"]) & 1, int(r["abpos"])) for r in recs]
+        assert keys == sorted(keys), fn
+        for r, t in list(zip(recs, traces))[::7]:
+            assert r["tlen"] == 2 * ((r["aepos"] - 1) // tspace - r["abpos"] // tspace + 1)
+            assert sum(t[1::2]) == r["bepos"] - r["bbpos"] and sum(t[0::2]) == r["diffs"]
+            assert (r["aepos"] - r["abpos"]) + (r["bepos"] - r["bbpos"]) >= 2000
+    exe = os.path.join(ROOT, "oracle", "_ref", "daligner")
+    if os.path.exists(exe):
+        for d in os.listdir(dbdir):
+            if d.startswith("d001_"):
+                shutil.rmtree(os.path.join(dbdir, d))
+        subprocess.run([exe, "-j4", "-M32", f"{root}.2", f"{root}.1", f"{root}.2"], cwd=dbdir, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for fn, buf in out.items():
+            part = int(fn.split(".")[1])
+            ref = open(os.path.join(dbdir, f"d001_{part:05d}", fn), "rb").read()
+            ok, why = dbio.las_equal(ref, buf)
+            assert ok, f"{fn}: {why}"

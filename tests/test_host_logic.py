@@ -1,0 +1,189 @@
+"""CPU tests of the host side: DB/track/.las I/O against the reference tools' own files, the
+synthetic DB generator against simulator|FA2db|DBsplit, the plan/sharding logic, the C-ABI surface,
+and the multi-rank block exchange (gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from cases import CASES, GOLDEN, TINY, ROOT, golden_files, load_block
+from damar_b200 import api, dbio, plan
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/*.h is exported by the built library (no compute)."""
+    L = api.load_library()
+    declared = set()
+    for hdr in ("damar_b200.h",):
+        txt = open(os.path.join(ROOT, "include", hdr)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        declared |= set(re.findall(r"\b(damar_[a-z0-9_]+)\s*\(", txt))
+    assert len(declared) >= 20
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert L.damar_abi_version() == 1
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = api.load_library()
+    assert L.damar_init(-1) != 0
+    assert b"no CPU fallback" in L.damar_last_error()
+    with pytest.raises(RuntimeError):
+        api.init()
+
+
+def test_set_filter_params_rejects_illegal():
+    assert api.set_filter_params(1, 6, 0, 35, 4) == 1          # filter.c:173-174
+    assert api.set_filter_params(14, 6, 0, 35, 4) == 0
+
+
+def test_db_block_reader():
+    b1, b2 = load_block(TINY, "T.1", ()), load_block(TINY, "T.2", ())
+    assert b1.ufirst == 0 and b2.ufirst == b1.nreads
+    assert b1.bases[0] == 4 and b1.bases[-1] == 4
+    assert int(b1.boff[-1]) == b1.totlen + b1.nreads
+    assert b1.bases.max() == 4 and set(np.unique(b1.bases[1:1 + int(b1.rlen[0])])) <= {0, 1, 2, 3}
+    assert abs(float(b1.freq.sum()) - 1.0) < 1e-3
+    whole = load_block(TINY, "T", ())
+    assert whole.nreads == b1.nreads + b2.nreads and whole.totlen == b1.totlen + b2.totlen
+    n = int(b2.rlen[0])
+    o2 = 1 + int(whole.boff[b1.nreads])
+    assert np.array_equal(whole.bases[o2:o2 + n], b2.bases[1:1 + n])
+
+
+def test_mask_tracks_and_merge():
+    d = load_block(TINY, "T.2", ("dust",))
+    r = load_block(TINY, "T.2", ("rnd",))
+    both = load_block(TINY, "T.2", ("rnd", "dust"))
+    assert r.mask_anno[-1] == r.mask_data.size and r.mask_data.size % 2 == 0
+    for blk in (d, r, both):
+        for i in range(0, blk.nreads, 37):
+            iv = blk.mask_data[int(blk.mask_anno[i]):int(blk.mask_anno[i + 1])]
+            assert np.all(np.diff(iv) >= 0) and (iv.size == 0 or iv[-1] <= blk.rlen[i])
+    # the union covers exactly the bases either track covers
+    i = int(np.argmax(np.diff(r.mask_anno)))
+    cover = np.zeros(int(r.rlen[i]) + 1, bool)
+    for blk in (d, r):
+        iv = blk.mask_data[int(blk.mask_anno[i]):int(blk.mask_anno[i + 1])]
+        for j in range(0, iv.size, 2):
+            cover[iv[j]:iv[j + 1]] = True
+    cu = np.zeros_like(cover)
+    iv = both.mask_data[int(both.mask_anno[i]):int(both.mask_anno[i + 1])]
+    for j in range(0, iv.size, 2):
+        cu[iv[j]:iv[j + 1]] = True
+    assert np.array_equal(cover, cu)
+
+
+def test_las_equal_masks_padding_only():
+    g = golden_files("default")["T.1.T.1.las"]
+    b = bytearray(g)
+    b[12 + 36] ^= 0xFF                      # padding byte of record 0
+    assert dbio.las_equal(g, bytes(b))[0]
+    b[12 + 8] ^= 0x01                       # abpos of record 0
+    assert not dbio.las_equal(g, bytes(b))[0]
+
+
+def test_simdb_matches_reference_pipeline(tmp_path):
+    """damar_b200/host/simdb == simulator | FA2db -x | DBsplit -s of the reference (bit for bit)."""
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(ref, "simulator")):
+        pytest.skip("oracle/_ref not built")
+    subprocess.run(["make", "-s", "-C", ROOT, "host"], check=True)
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    args = ["0.2", "-c8", "-r5", "-e.13", "-m2500", "-s700", "-x600"]
+    with open(a / "sim.fasta", "w") as f:
+        subprocess.run([os.path.join(ref, "simulator")] + args, stdout=f, check=True)
+    subprocess.run([os.path.join(ref, "FA2db"), "-x", "700", "Q", "sim.fasta"], cwd=a, check=True)
+    subprocess.run([os.path.join(ref, "DBsplit"), "-s1", "Q"], cwd=a, check=True)
+    subprocess.run([os.path.join(ROOT, "damar_b200", "host", "simdb"), str(b), "Q"] + args + ["-X700", "-S1"], check=True,
+                   stdout=subprocess.DEVNULL)
+    assert open(a / ".Q.bps", "rb").read() == open(b / ".Q.bps", "rb").read()
+    assert open(a / "Q.db").read() == open(b / "Q.db").read()
+    x, y = dbio.read_block(str(a / "Q.2")), dbio.read_block(str(b / "Q.2"))
+    assert np.array_equal(x.rlen, y.rlen) and np.array_equal(x.bases, y.bases) and np.array_equal(x.freq, y.freq)
+
+
+def test_plan_matches_hpcdaligner(tmp_path):
+    """Our job list is the reference planner's (HPCdaligner prints `daligner ... R.i R.1 .. R.i`)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "HPCdaligner")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    out = subprocess.run([ref, "-j4", os.path.join(TINY, "T")], capture_output=True, text=True).stdout
+    cmds = [l.split() for l in out.splitlines() if l.startswith("daligner")]
+    ours = plan.hpc_plan(2)
+    got = {(c[-len(j.bs) - 1], tuple(c[-len(j.bs):])) for c, j in zip(sorted(cmds, key=lambda c: c[-1]), ours)}
+    pairs_ref = set()
+    for c in cmds:
+        blocks = [t for t in c[1:] if not t.startswith("-")]
+        a = int(blocks[0].split(".")[-1])
+        pairs_ref |= {(a, int(b.split(".")[-1])) for b in blocks[1:]}
+    pairs_ref = {(max(a, b), min(a, b)) for a, b in pairs_ref}
+    assert pairs_ref == set(plan.block_pairs(2))
+    assert got
+
+
+@pytest.mark.parametrize("nblocks,world", [(1, 1), (4, 1), (4, 2), (4, 4), (4, 8), (21, 8), (7, 3)])
+def test_sharding_covers_every_pair_once(nblocks, world):
+    shards = plan.shard_pairs(nblocks, world)
+    seen = [(j.a, b) for s in shards for j in s for b in j.bs]
+    assert sorted(seen) == sorted(plan.block_pairs(nblocks))
+    assert shards == plan.shard_pairs(nblocks, world)          # deterministic
+    if nblocks * (nblocks + 1) // 2 >= 4 * world:
+        loads = [sum(plan.pair_cost(j.a, b, {i: 1 for i in range(1, nblocks + 1)}) for j in s for b in j.bs) for s in shards]
+        assert max(loads) <= 1.6 * (sum(loads) / world)
+    owners = plan.block_owners(shards)
+    for b, (owner, ranks) in owners.items():
+        assert owner == ranks[0] and all(b in plan.blocks_needed(shards[r]) for r in ranks)
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from damar_b200 import multi
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shards = plan.shard_pairs(2, world)
+    loads = []
+
+    def loader(path, masks):
+        loads.append(os.path.basename(path))
+        return dbio.read_block(path, masks)
+    got = multi.exchange_blocks(TINY, "T", shards, rank, world, dist, "cpu", ["rnd"], loader)
+    q.put((rank, loads, {b: (blk.nreads, int(blk.bases.astype(np.int64).sum()), int(blk.mask_data.astype(np.int64).sum()),
+                             blk.sizeof_db()) for b, blk in got.items()}, [(j.a, j.bs) for j in shards[rank]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_exchange_two_ranks_gloo():
+    """World size 2 on CPU: each block is read from disk by exactly one rank; a rank that needs a block
+    it does not own receives an identical copy through the broadcast."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    truth = {b: dbio.read_block(os.path.join(TINY, f"T.{b}"), ["rnd"]) for b in (1, 2)}
+    loaded = sorted(x for _, loads, _, _ in res for x in loads)
+    assert loaded == ["T.1", "T.2"]                      # every block read from disk exactly once
+    pairs = sorted((a, b) for _, _, _, jobs in res for a, bs in jobs for b in bs)
+    assert pairs == [(1, 1), (2, 1), (2, 2)]
+    for rank, _, blocks, jobs in res:
+        need = {a for a, _ in jobs} | {b for _, bs in jobs for b in bs}
+        assert set(blocks) == need
+        for b, (n, s, ms, sz) in blocks.items():
+            t = truth[b]
+            assert (n, s, ms, sz) == (t.nreads, int(t.bases.astype(np.int64).sum()), int(t.mask_data.astype(np.int64).sum()), t.sizeof_db())
