@@ -141,8 +141,8 @@ def test_sharded_plan_world1(tmp_path):
     from damar_b200 import multi
     o = parse_flags(CASES["default"]["flags"])
     novl, files = multi.run_sharded(TINY, "T", 2, settings(o), 0, 1, outdir=str(tmp_path))
-    gold = dict(golden_files("default"))
-    gold.update({k: v for k, v in golden_files("b2").items() if k not in gold})
+    gold = dict(golden_files("b2"))                       # job `daligner T.2 T.1 T.2`
+    gold["T.1.T.1.las"] = golden_files("default")["T.1.T.1.las"]   # job `daligner T.1 T.1`
     assert sorted(files) == sorted(gold)
     for fn, ref in gold.items():
         part = int(fn.split(".")[1])
