@@ -258,6 +258,7 @@ def main():
 
     sampler = ClockSampler(local_rank)
     # ---- device-resident timing ("value") ----
+    api.load_library().damar_dump_profile() if os.environ.get("DAMAR_PROFILE") else None
     api.reset_kernel_timers()
     l0 = api.timings()["kernel_launches"]
     barrier()
@@ -274,6 +275,9 @@ def main():
     dt = time.perf_counter() - t0
     dt_dev = ev0.elapsed_time(ev1) / 1000.0
     tm = api.timings()
+    if os.environ.get("DAMAR_PROFILE"):
+        print(f"[bench] host profile of {args.steps} resident steps:", file=sys.stderr)
+        api.load_library().damar_dump_profile()
     launches = tm["kernel_launches"] - l0
     for h in resident.values():
         h.free()

@@ -311,6 +311,9 @@ class LasSink:
             self.h = None
 
 
+_shared_sink = None
+
+
 def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list] = None,
              dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
     """`daligner [flags] A B1 B2 ...` (daligner.c:958-1073): returns {las file name: bytes}
@@ -333,7 +336,11 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
 
     da = resident(ablk)
     aidx = sort_kmers(da, 0)
-    sink = LasSink()
+    global _shared_sink
+    if _shared_sink is None:
+        _shared_sink = LasSink()          # kept for the process: its host buffers stay warm between jobs
+    sink = _shared_sink
+    sink.reset()
     for bblk in bblks:
         selfcmp = bblk.name == ablk.name
         db = da if selfcmp else resident(bblk)
@@ -361,7 +368,6 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
                 n1, n2 = n2, n1
             out[n1], out[n2] = conv(b1), conv(b2)
         sink.reset()
-    sink.free()
     if aidx is not None:
         aidx.free()
     if own:

@@ -33,6 +33,38 @@ struct SortKey {                     // SORT_OVL (align.c:6104-6164) flattened i
     }
 };
 
+// .las images are tens to hundreds of MB; glibc serves such requests with fresh mmaps (page faults on
+// first touch dominate the build).  Freed images are kept on a small free list and reused.
+struct ImgHdr { size_t cap; size_t magic; };
+static std::vector<ImgHdr *> g_img_free;
+static const size_t IMG_MAGIC = 0x64616d61726c6173ull;
+static uint8_t *img_alloc(size_t n) {
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < g_img_free.size(); i++)
+        if (g_img_free[i]->cap >= n && (best == (size_t)-1 || g_img_free[i]->cap < g_img_free[best]->cap)) best = i;
+    ImgHdr *h;
+    if (best != (size_t)-1) { h = g_img_free[best]; g_img_free.erase(g_img_free.begin() + best); }
+    else {
+        size_t cap = n + n / 8 + 4096;
+        h = (ImgHdr *)malloc(sizeof(ImgHdr) + cap);
+        if (!h) fatal("out of host memory serialising %zu bytes of .las", n);
+        h->cap = cap; h->magic = IMG_MAGIC;
+    }
+    return reinterpret_cast<uint8_t *>(h + 1);
+}
+static void img_free(void *p) {
+    if (!p) return;
+    ImgHdr *h = reinterpret_cast<ImgHdr *>(p) - 1;
+    if (h->magic != IMG_MAGIC) { free(p); return; }
+    if (g_img_free.size() >= 8) {                         // keep the 8 largest
+        size_t small = 0;
+        for (size_t i = 1; i < g_img_free.size(); i++) if (g_img_free[i]->cap < g_img_free[small]->cap) small = i;
+        if (g_img_free[small]->cap < h->cap) { free(g_img_free[small]); g_img_free[small] = h; } else free(h);
+        return;
+    }
+    g_img_free.push_back(h);
+}
+
 static int host_threads() {
     unsigned n = std::thread::hardware_concurrency();
     if (n == 0) n = 4;
@@ -81,8 +113,7 @@ static int put_range(const LasSink &s, const std::vector<SortKey> &keys, size_t 
     std::vector<size_t> offs(n + 1);
     offs[0] = 12;
     for (size_t i = 0; i < n; i++) offs[i + 1] = offs[i] + 40 + (no_trace ? 0 : (size_t)tbytes * s.ovl[keys[from + i].idx].tlen);
-    uint8_t *buf = (uint8_t *)malloc(offs[n] ? offs[n] : 1);
-    if (!buf) fatal("out of host memory serialising %zu bytes of .las", offs[n]);
+    uint8_t *buf = img_alloc(offs[n] ? offs[n] : 1);
     int64_t n64 = (int64_t)n; int32_t ts = tspace;
     memcpy(buf, &n64, 8); memcpy(buf + 8, &ts, 4);
     auto work = [&](size_t lo, size_t hi) {
@@ -157,6 +188,6 @@ int damar_sink_serialise(damar_las_sink *s_, int trace_spacing, int no_trace, in
     return put_range(*s, keys, lo, keys.size(), trace_spacing, no_trace, buf2, len2);
 }
 
-void damar_free(void *p) { free(p); }
+void damar_free(void *p) { img_free(p); }
 
 }  // extern "C"

@@ -667,62 +667,64 @@ __device__ void wave_pass_fast(WarpLA &S, const uint32_t *__restrict__ aw, int64
             }
             if (S.ncell >= S.cells_cap) { S.overflow = 1; break; }
         }
-        // ---- best / lasta / trim (align.c:911-928 / 1620-1637).  A diagonal is a record setter iff its
-        //      point beats besta and every point visited before it in this wave: exclusive prefix
-        //      extremum over the visiting order (forward hgh -> low, reverse low -> hgh), taken with
-        //      rotating shuffles because lane = k mod 32 ----
-        if (__any_sync(FULL, act && (DIR > 0 ? (c > besta) : (c < besta)))) {
-            const int rank = (DIR > 0) ? (hgh - k) : (k - low);          // visiting rank of this lane (valid if act)
-            int pre = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_sync(FULL, pre, (DIR > 0) ? (lane + o) : (lane - o));   // lane of rank - o
-                if (rank >= o) pre = (DIR > 0) ? max(pre, t) : min(pre, t);
-            }
-            int excl = __shfl_sync(FULL, pre, (DIR > 0) ? (lane + 1) : (lane - 1));
-            excl = (rank == 0) ? besta : ((DIR > 0) ? max(excl, besta) : min(excl, besta));
-            const bool setter = act && (DIR > 0 ? (c > excl) : (c < excl));
-            const bool good = setter && (m >= PATH_AVE);
-            bool trim = false;
-            if (good) {
-                const int lo15 = (int)(b & TRIM_MASK), hi15 = (int)((b >> TRIM_LEN) & TRIM_MASK);
-                trim = (S.table_tab[lo15] >= 0) && (S.table_tab[hi15] + S.score_tab[lo15] >= 0);
-            }
-            // the last setter in visiting order holds the extreme value: pick by value, not by rank
-            const int ext = (DIR > 0) ? __reduce_max_sync(FULL, setter ? c : -IMAX) : __reduce_min_sync(FULL, setter ? c : IMAX);
-            const unsigned sm = __ballot_sync(FULL, setter && c == ext);
-            if (sm) { const int l = __ffs(sm) - 1; besta = ext; besty = __shfl_sync(FULL, y, l); }
-            const unsigned gm = __ballot_sync(FULL, good);
-            if (gm) {
-                const int gext = (DIR > 0) ? __reduce_max_sync(FULL, good ? c : -IMAX) : __reduce_min_sync(FULL, good ? c : IMAX);
-                lasta = gext;
-                const unsigned tm = __ballot_sync(FULL, trim);
-                if (tm) {
-                    const int text = (DIR > 0) ? __reduce_max_sync(FULL, trim ? c : -IMAX) : __reduce_min_sync(FULL, trim ? c : IMAX);
-                    const int l = __ffs(__ballot_sync(FULL, trim && c == text)) - 1;
-                    trima = text; trimy = __shfl_sync(FULL, y, l); trimd = dif;
-                    trimha = __shfl_sync(FULL, ha, l); trimhb = __shfl_sync(FULL, hb, l);
-                }
-            }
-        }
-        // ---- clip bookkeeping in visiting order ----
+        // ---- best / lasta / trim (align.c:911-928 / 1620-1637).  In the reference's visiting order (forward
+        //      hgh -> low, reverse low -> hgh) a diagonal is a record setter iff its point beats besta and every
+        //      point visited before it.  The last setter is the wave's extreme point; lasta / trim come from the
+        //      last setter that also passes the m / table tests, found by walking the few improving candidates
+        //      from the best one down (setters are strictly monotone in visiting order). ----
+#define BYRANK(mask) ((DIR > 0) ? rotr32(__brev(mask), 31 - (hgh & 31)) : rotr32((mask), low & 31))
+#define RANK2LANE(r) ((((DIR > 0) ? (hgh - (r)) : (low + (r)))) & 31)
         {
-            const unsigned am = __ballot_sync(FULL, clipA), bm = __ballot_sync(FULL, clipB);
-            if (am | bm) {
-                more = 0;
-                if (am) {       // last visited: forward = lowest diagonal, reverse = highest diagonal
-                    const unsigned byrank = (DIR > 0) ? rotr32(__brev(am), 31 - (hgh & 31)) : rotr32(am, low & 31);
-                    const int r = 31 - __clz(byrank);
-                    aclip = (DIR > 0) ? (hgh - r) : (low + r);
+            const bool beat = act && (DIR > 0 ? (c > besta) : (c < besta));
+            if (__any_sync(FULL, beat)) {
+                const int ext = (DIR > 0) ? __reduce_max_sync(FULL, beat ? c : -IMAX) : __reduce_min_sync(FULL, beat ? c : IMAX);
+                {
+                    const unsigned em = __ballot_sync(FULL, beat && c == ext);
+                    const int l = RANK2LANE(__ffs(BYRANK(em)) - 1);          // first visited lane holding the extreme
+                    besta = ext; besty = __shfl_sync(FULL, y, l);
                 }
-                if (bm) {       // extreme diagonal = first visited
-                    const unsigned byrank = (DIR > 0) ? rotr32(__brev(bm), 31 - (hgh & 31)) : rotr32(bm, low & 31);
-                    const int r = __ffs(byrank) - 1;
-                    const int kb = (DIR > 0) ? (hgh - r) : (low + r);
-                    if (DIR > 0) { if (bclip < kb) bclip = kb; } else { if (bclip > kb) bclip = kb; }
+                unsigned gm = __ballot_sync(FULL, beat && m >= PATH_AVE);
+                bool have_lasta = false;
+                while (gm) {
+                    const bool ing = (gm >> lane) & 1u;
+                    const int gext = (DIR > 0) ? __reduce_max_sync(FULL, ing ? c : -IMAX) : __reduce_min_sync(FULL, ing ? c : IMAX);
+                    const unsigned gem = __ballot_sync(FULL, ing && c == gext);
+                    const int r = __ffs(BYRANK(gem)) - 1;                    // visiting rank of the candidate
+                    const int l = RANK2LANE(r);
+                    const unsigned geq = __ballot_sync(FULL, act && (DIR > 0 ? (c >= gext) : (c <= gext)));
+                    if ((BYRANK(geq) & ((1u << r) - 1u)) == 0) {             // nothing visited earlier is as good: a setter
+                        if (!have_lasta) { lasta = gext; have_lasta = true; }
+                        int tok = 0;
+                        if (lane == l) {
+                            const int lo15 = (int)(b & TRIM_MASK), hi15 = (int)((b >> TRIM_LEN) & TRIM_MASK);
+                            tok = (S.table_tab[lo15] >= 0) && (S.table_tab[hi15] + S.score_tab[lo15] >= 0);
+                        }
+                        if (__shfl_sync(FULL, tok, l)) {
+                            trima = gext; trimy = __shfl_sync(FULL, y, l); trimd = dif;
+                            trimha = __shfl_sync(FULL, ha, l); trimhb = __shfl_sync(FULL, hb, l);
+                            break;
+                        }
+                    }
+                    gm &= ~gem;
                 }
             }
         }
+        // ---- clip bookkeeping in visiting order (align.c:836-851 / 1545-1560) ----
+        if (__any_sync(FULL, clipA || clipB)) {
+            const unsigned am = __ballot_sync(FULL, clipA), bm = __ballot_sync(FULL, clipB);
+            more = 0;
+            if (am) {       // aclip = last visited clipped diagonal
+                const int r = 31 - __clz(BYRANK(am));
+                aclip = (DIR > 0) ? (hgh - r) : (low + r);
+            }
+            if (bm) {       // bclip = extreme = first visited
+                const int r = __ffs(BYRANK(bm)) - 1;
+                const int kb = (DIR > 0) ? (hgh - r) : (low + r);
+                if (DIR > 0) { if (bclip < kb) bclip = kb; } else { if (bclip > kb) bclip = kb; }
+            }
+        }
+#undef BYRANK
+#undef RANK2LANE
         if (act) { V = c; T = b; HA = ha; HB = hb; HM = ham; HN = hbm; }
     }
     S.ncells_done += cells_done;

@@ -81,33 +81,59 @@ struct GroupArgs {
     unsigned long long *gram;                    // MAXGRAM bins or nullptr
 };
 
+// Each CTA owns a contiguous chunk of A groups and walks it in tiles of MG_TILE groups.  Because both
+// lists are sorted, the B entries that can match a tile lie in one window [lo, hi): two threads
+// locate it with a full binary search, every thread then searches only inside the window
+// (a few hundred entries, resident in L1/L2) instead of the whole B list.
+constexpr int MG_TILE = 2048;
 __global__ void __launch_bounds__(256) match_groups(GroupArgs a) {
     extern __shared__ uint32_t sgram[];
+    __shared__ int64_t win[2];
     const bool histo = (a.gram != nullptr);
-    if (histo) { for (int i = threadIdx.x; i < MAXGRAM; i += blockDim.x) sgram[i] = 0; __syncthreads(); }
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < a.ngroups; g += gridDim.x * blockDim.x) {
-        const uint32_t ja = a.gstart[g];
-        const uint32_t ia = (g + 1 < a.ngroups) ? a.gstart[g + 1] : (uint32_t)a.alen;
-        const uint64_t code = a.acodes[ja];
-        uint32_t jb, ib;
-        if (a.same_list) { jb = ja; ib = ia; }
-        else {
-            jb = (uint32_t)lower_bound_u64(a.bcodes, a.blen, code);
-            ib = jb;
-            if (jb < a.blen && a.bcodes[jb] == code)
-                ib = (code == ~0ull) ? (uint32_t)a.blen : (uint32_t)lower_bound_u64(a.bcodes, a.blen, code + 1);
+    if (histo) { for (int i = threadIdx.x; i < MAXGRAM; i += blockDim.x) sgram[i] = 0; }
+    const uint64_t c0 = (uint64_t)a.ngroups * blockIdx.x / gridDim.x, c1 = (uint64_t)a.ngroups * (blockIdx.x + 1) / gridDim.x;
+    for (uint64_t t0 = c0; t0 < c1; t0 += MG_TILE) {
+        const uint64_t t1 = (t0 + MG_TILE < c1) ? t0 + MG_TILE : c1;
+        __syncthreads();
+        if (!a.same_list && threadIdx.x < 2) {
+            if (threadIdx.x == 0) win[0] = lower_bound_u64(a.bcodes, a.blen, a.acodes[a.gstart[t0]]);
+            else {
+                const uint64_t last = a.acodes[a.gstart[t1 - 1]];
+                win[1] = (last == ~0ull) ? a.blen : lower_bound_u64(a.bcodes, a.blen, last + 1);
+            }
         }
-        unsigned long long ct = 0;
-        if (ib > jb) {
-            if (a.self) {
-                for (uint32_t x = ja; x < ia; x++)
-                    ct += self_partners(a.bgpos, jb, ib, a.agpos[x], a.boff, a.nreads, a.identity, a.comp);
-            } else
-                ct = (unsigned long long)(ia - ja) * (unsigned long long)(ib - jb);
-            if (histo && ct < MAXGRAM) atomicAdd(&sgram[(uint32_t)ct], 1u);
+        __syncthreads();
+        for (uint64_t gg = t0 + threadIdx.x; gg < t1; gg += blockDim.x) {
+            const uint32_t g = (uint32_t)gg;
+            const uint32_t ja = a.gstart[g];
+            const uint32_t ia = (g + 1 < a.ngroups) ? a.gstart[g + 1] : (uint32_t)a.alen;
+            const uint64_t code = a.acodes[ja];
+            uint32_t jb, ib;
+            if (a.same_list) { jb = ja; ib = ia; }
+            else {
+                const int64_t lo = win[0], hi = win[1];
+                jb = (uint32_t)(lo + lower_bound_u64(a.bcodes + lo, hi - lo, code));
+                ib = jb;
+                if ((int64_t)jb < hi && a.bcodes[jb] == code) {      // equal-code runs are short: gallop, then bisect
+                    int64_t step = 1, e = (int64_t)jb + 1;
+                    while (e < hi && a.bcodes[e] == code) { e += step; step <<= 1; }
+                    const int64_t from = e - (step >> 1), to = (e < hi) ? e : hi;
+                    ib = (uint32_t)(from + lower_bound_u64(a.bcodes + from, to - from, code + 1));
+                    if (code == ~0ull) ib = (uint32_t)hi;
+                }
+            }
+            unsigned long long ct = 0;
+            if (ib > jb) {
+                if (a.self) {
+                    for (uint32_t x = ja; x < ia; x++)
+                        ct += self_partners(a.bgpos, jb, ib, a.agpos[x], a.boff, a.nreads, a.identity, a.comp);
+                } else
+                    ct = (unsigned long long)(ia - ja) * (unsigned long long)(ib - jb);
+                if (histo && ct < MAXGRAM) atomicAdd(&sgram[(uint32_t)ct], 1u);
+            }
+            a.gjb[g] = jb; a.gnb[g] = ib - jb;
+            a.gct[g] = (ct > 0xffffffffull) ? 0xffffffffu : (uint32_t)ct;
         }
-        a.gjb[g] = jb; a.gnb[g] = ib - jb;
-        a.gct[g] = (ct > 0xffffffffull) ? 0xffffffffu : (uint32_t)ct;
     }
     if (histo) {
         __syncthreads();
@@ -208,8 +234,8 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     {
         static bool attr = false;
         if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(match_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXGRAM * 4)); attr = true; }
-        unsigned blocks = (ngroups + 255) / 256;
-        if (use_limit && blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
+        unsigned blocks = (ngroups + MG_TILE - 1) / MG_TILE;
+        if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
         if (blocks == 0) blocks = 1;
         match_groups<<<blocks, 256, use_limit ? MAXGRAM * 4 : 0, st>>>(ga);
         KERNEL_CHECK(); count_launch();
