@@ -192,7 +192,7 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
     c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0;
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
-        if (comp && !bb->as_is) ensure_revcomp(bb);
+        ensure_revcomp(ab); ensure_revcomp(bb);               // the reverse wave pass runs on the reverse-complemented reads
         { HostProf hp("mf.seed_hits"); seed_hits(ai, bi, self, comp, g_hits); }
         if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); report_and_align(ab, bb, comp, self, g_hits, g_out); }
     }

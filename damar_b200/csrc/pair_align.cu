@@ -3,20 +3,22 @@
 //
 // Replaces report_thread (reference dalign/filter.c:2128-2511, incl. Diagonal_Span :2079-2110)
 // and Local_Alignment / forward_wave / reverse_wave (dalign/align.c:1904-2097, 409-1122,
-// 1126-1898).  One warp owns one (bread, aread) pair at a time:
-//   * the pair's hits are walked in A-panels of 50 kbp (10 kbp overlap);
-//   * pass 1 accumulates score[diag>>w] (covered bases per 2^w-diagonal bucket) with the
-//     lanes taking 32 hits at a time and resolving same-bucket conflicts by lane order;
-//   * pass 2 evaluates the threshold for 32 hits at once and then consumes candidates in hit
-//     order, each one running a warp-wide local alignment unless an earlier alignment of the
-//     pair already covers it (the `lasta` rule, kept here as a short interval list);
-//   * the wave front lives one diagonal per lane (strided when wider than a warp); the three-way
-//     furthest-reaching recurrence reads the previous wave, so all diagonals update in parallel;
-//     the reference's loop-order tie-breaks (best / trim / clip bookkeeping) are reproduced
-//     with ordered ballots; bases are compared 32 at a time on the 2-bit packed reads.
+// 1126-1898).  Two implementations live here:
+//   * the task pipeline (second half of the file, the default): stage 3 and stage 4 are separate
+//     kernels; every wave pass of every local alignment is one task run by ONE THREAD
+//     (wave_core.cuh), so the reference's sequential tie-breaks need no reformulation and no lane
+//     idles on a narrow front;
+//   * the strided warp kernel (first half): one warp owns one (bread, aread) pair, the wave front is
+//     strided over the lanes in global scratch.  It only sees the pairs whose front outgrows the
+//     task kernel's 64-diagonal ring.
+// Common to both: A-panels of 50 kbp (10 kbp overlap); pass 1 accumulates score[diag>>w] with the
+// lanes taking 32 hits at a time (same-bucket conflicts resolved by lane order); pass 2 evaluates the
+// threshold for 32 hits at once and consumes candidates in hit order unless an earlier alignment of
+// the pair already covers them (the `lasta` rule, kept as a short interval list per pair).
 #include <algorithm>
 
 #include "common.cuh"
+#include "wave_core.cuh"
 
 namespace damar {
 namespace {
@@ -393,347 +395,7 @@ __device__ void wave_pass(WarpLA &S, const uint32_t *__restrict__ aw, int64_t ab
     else { ex = trima - trimy; ey = trimy; ediff = trimd; eha = trimha; ehb = trimhb; }
 }
 
-// Walk a pebble chain from its head back to the root and write the trace pairs
-// (align.c:1001-1111 forward, 1711-1880 reverse).  Lane 0 only.  `isA` selects the A chain
-// (marks are A coordinates) or the B chain.  Forward: pairs are appended at tr[0..); reverse:
-// pairs are prepended before tr[0] and the first partial segment is merged into tr[0], tr[1].
-// Returns the number of values written (forward) or prepended (reverse).
-__device__ int emit_chain_fwd(const int4 *cells, int head, bool isA, int anti, int ex, int ey, int ediff, uint16_t *tr) {
-    // count chain length first so that pairs can be written front to back while walking backwards
-    int n = 0;
-    for (int h = head; h >= 0; h = cells[h].x) n++;
-    // cells in forward order are c_0 (root) .. c_{n-1} (head); pair i (i>=1) = (diff_i - diff_{i-1}, p_i - p_{i-1})
-    int len = 2 * (n - 1);
-    int h = head;
-    int4 cur = cells[h];
-    const int lastk = cur.y;
-    int lastp, laste;
-    {
-        // coordinate "other" of head cell: A chain -> b = mark - diag ; B chain -> a = mark + diag
-        for (int i = n - 1; i >= 1; i--) {
-            const int4 prv = cells[cur.x];
-            const int pc = isA ? (cur.w - cur.y) : (cur.w + cur.y);
-            int pp, pe;
-            if (i == 1) { pp = isA ? ((anti - prv.y) / 2) : ((anti + prv.y) / 2); pe = 0; }
-            else { pp = isA ? (prv.w - prv.y) : (prv.w + prv.y); pe = prv.z; }
-            tr[2 * (i - 1)] = (uint16_t)(cur.z - pe);
-            tr[2 * (i - 1) + 1] = (uint16_t)(pc - pp);
-            cur = prv;
-        }
-        // recompute last logged point from the head cell
-        const int4 hc = cells[head];
-        if (n == 1) { lastp = isA ? ((anti - hc.y) / 2) : ((anti + hc.y) / 2); laste = 0; }
-        else { lastp = isA ? (hc.w - hc.y) : (hc.w + hc.y); laste = hc.z; }
-    }
-    if (isA) {
-        if (lastp + lastk != ex) { tr[len++] = (uint16_t)(ediff - laste); tr[len++] = (uint16_t)(ey - lastp); }
-        else if (lastp != ey) { tr[len - 1] = (uint16_t)(tr[len - 1] + (ey - lastp)); tr[len - 2] = (uint16_t)(tr[len - 2] + (ediff - laste)); }
-    } else {
-        if (lastp - lastk != ey) { tr[len++] = (uint16_t)(ediff - laste); tr[len++] = (uint16_t)(ex - lastp); }
-        else if (lastp != ex) { tr[len - 1] = (uint16_t)(tr[len - 1] + (ex - lastp)); tr[len - 2] = (uint16_t)(tr[len - 2] + (ediff - laste)); }
-    }
-    return len;
-}
-
-// reverse pass: cells in chain order root=c_0 (mark = seed coordinate) .. head.  `flen` = number of
-// values the forward pass left at tr[0..); returns number of values prepended (result starts at tr - ret).
-__device__ int emit_chain_rev(int4 *cells, int head, bool isA, int ex, int ey, int ediff, int TS, int off,
-                              int flen, uint16_t *tr) {
-    int n = 0;
-    for (int h = head; h >= 0; h = cells[h].x) n++;
-    // gather the chain in root->head order is needed because merging happens at the root end;
-    // walk with an index stack emulated by repeated traversal is O(n^2); instead reverse links in place.
-    int a = -1, b;
-    for (int h = head; h >= 0; h = b) { int4 c = cells[h]; b = c.x; c.x = a; cells[h] = c; a = h; }
-    int h = a;                                       // root
-    int4 c = cells[h];
-    int k = c.y;
-    int pb = isA ? (c.w - k) : (c.w + k);            // "other" coordinate of the running point
-    int e = 0, at = 0;
-    const int own = isA ? (pb + k) : (pb - k);       // coordinate on this chain's own axis
-    if (own % TS != off) {                           // seed not on a trace boundary: merge first segment
-        h = c.x;
-        int pa, d;
-        if (h < 0) { pa = isA ? ey : ex; d = ediff; }
-        else { c = cells[h]; k = c.y; pa = isA ? (c.w - k) : (c.w + k); d = c.z; }
-        if (flen == 0) {
-            tr[--at] = (uint16_t)(pb - pa);
-            tr[--at] = isA ? (uint16_t)(d - e) : (uint16_t)(pb - pa);   // sic (align.c:1843-1844)
-        } else { tr[1] = (uint16_t)(tr[1] + (pb - pa)); tr[0] = (uint16_t)(tr[0] + (d - e)); }
-        pb = pa; e = d;
-    }
-    if (h >= 0) {
-        for (h = c.x; h >= 0; h = c.x) {
-            c = cells[h]; k = c.y;
-            const int pa = isA ? (c.w - k) : (c.w + k);
-            tr[--at] = (uint16_t)(pb - pa);
-            tr[--at] = (uint16_t)(c.z - e);
-            pb = pa; e = c.z;
-        }
-        const int endo = isA ? ey : ex;              // end point on the "other" axis
-        const int endown = isA ? ex : ey;
-        const int lastown = isA ? (pb + k) : (pb - k);
-        if (lastown != endown) { tr[--at] = (uint16_t)(pb - endo); tr[--at] = (uint16_t)(ediff - e); }
-        else if (pb != endo) { tr[at + 1] = (uint16_t)(tr[at + 1] + (pb - endo)); tr[at] = (uint16_t)(tr[at] + (ediff - e)); }
-    }
-    (void)n;
-    return -at;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Register-resident wave pass: the whole wave front (<= 32 live diagonals) lives in registers, one
-// diagonal per lane (lane = k mod 32), neighbours are fetched with shuffles, and nothing but the
-// pebble cells touches memory.  Same arithmetic and visiting-order semantics as wave_pass; returns
-// false (S.overflow = 2) when the front grows beyond 32 diagonals so that the pair is redone by
-// the strided scratch-memory kernel.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned rotr32(unsigned x, int s) { return __funnelshift_r(x, x, s & 31); }
-
-template <int DIR>
-__device__ void wave_pass_fast(WarpLA &S, const uint32_t *__restrict__ aw, int64_t abase, int alen,
-                               const uint32_t *__restrict__ bw, int64_t bbase, int blen,
-                               int diag, int anti, int minp, int maxp, int aoff, int boff,
-                               int &ex, int &ey, int &ediff, int &eha, int &ehb) {
-    const int lane = threadIdx.x & 31;
-    const int TS = S.TS, PATH_AVE = S.PATH_AVE;
-    const int NEG = (DIR > 0) ? -1 : IMAX;
-    int low = diag, hgh = diag, dif = 0, more = 1;
-    int aclip = (DIR > 0) ? IMAX : -IMAX, bclip = (DIR > 0) ? -IMAX : IMAX;
-    int besta, besty, trima, trimy, trimd = 0, trimha = 0, trimhb = 1;
-    int morea, morey, mored = 0, moreha = 0, morehb = 1, morem = -1, lasta;
-    // per-lane diagonal state
-    int V, HA, HB, HM, HN, NA, NB; uint64_t T;
-    unsigned long long cells_done = 0;
-
-    S.ncell = 0;
-    besta = trima = morea = lasta = anti;
-    besty = trimy = morey = (anti - diag) >> 1;
-
-    {   // ---- wave 0 (uniform) ----
-        const int k = diag;
-        int y = (anti - k) >> 1, x = y + k, na, nb, ha, hb, ham, hbm, n;
-        if (DIR > 0) {
-            na = ((x + (TS - aoff)) / TS - 1) * TS + aoff;
-            nb = ((y + (TS - boff)) / TS - 1) * TS + boff;
-            if (lane == 0) { S.cells[0] = make_int4(-1, k, 0, na); S.cells[1] = make_int4(-1, k, 0, nb); }
-            ha = 0; hb = 1; ham = na; hbm = nb; S.ncell = 2;
-            na += TS; nb += TS;
-            const int ra = alen - x, rb = blen - y;
-            n = slide_fwd(aw, abase + x, bw, bbase + y, ra < rb ? ra : rb);
-            y += n; x += n;
-            if (y == blen) { more = 0; if (bclip < k) bclip = k; }
-            else if (x == alen) { more = 0; aclip = k; }
-            while (x >= na) { if (lane == 0) S.cells[S.ncell] = make_int4(ha, k, 0, na); ha = S.ncell++; ham = na; na += TS; }
-            while (y >= nb) { if (lane == 0) S.cells[S.ncell] = make_int4(hb, k, 0, nb); hb = S.ncell++; hbm = nb; nb += TS; }
-        } else {
-            na = ((x + (TS - aoff) - 1) / TS - 1) * TS + aoff;
-            nb = ((y + (TS - boff) - 1) / TS - 1) * TS + boff;
-            if (lane == 0) { S.cells[0] = make_int4(-1, k, 0, x); S.cells[1] = make_int4(-1, k, 0, y); }
-            ha = 0; hb = 1; ham = x; hbm = y; S.ncell = 2;
-            n = slide_rev(aw, abase + x, bw, bbase + y, x < y ? x : y);
-            y -= n; x -= n;
-            if (y == 0) { more = 0; if (bclip > k) bclip = k; }
-            else if (x == 0) { more = 0; aclip = k; }
-            while (x <= na) { if (lane == 0) S.cells[S.ncell] = make_int4(ha, k, 0, na); ha = S.ncell++; ham = na; na -= TS; }
-            while (y <= nb) { if (lane == 0) S.cells[S.ncell] = make_int4(hb, k, 0, nb); hb = S.ncell++; hbm = nb; nb -= TS; }
-        }
-        const int c = (y << 1) + k;
-        if (DIR > 0 ? (c > besta) : (c < besta)) { besta = trima = lasta = c; besty = trimy = y; trimha = ha; trimhb = hb; }
-        V = c; T = PATH_INT; HA = ha; HB = hb; HM = ham; HN = hbm; NA = na; NB = nb;     // every lane holds a copy; only lane k&31 is live
-    }
-
-    for (;;) {
-        // ---- boundary clipping ----
-        if (more == 0) {
-            bool inside;
-            if (DIR > 0) inside = (besty < blen) && (besta - besty < alen);
-            else inside = (besty > 0) && (besta - besty > 0);
-            if (inside) more = 1;
-#pragma unroll
-            for (int side = 0; side < 2; side++) {
-                const int kc = side == 0 ? aclip : bclip;
-                bool hit;
-                if (DIR > 0) hit = side == 0 ? (hgh >= aclip) : (low <= bclip);
-                else         hit = side == 0 ? (low <= aclip) : (hgh >= bclip);
-                if (!hit) continue;
-                if (DIR > 0) { if (side == 0) hgh = kc - 1; else low = kc + 1; }
-                else         { if (side == 0) low = kc + 1; else hgh = kc - 1; }
-                const int sl = kc & 31;
-                const uint64_t tc = __shfl_sync(FULL, T, sl);
-                const int vc = __shfl_sync(FULL, V, sl), hac = __shfl_sync(FULL, HA, sl), hbc = __shfl_sync(FULL, HB, sl);
-                const int mc = __popcll(tc & PATH_MASK61);
-                if (morem <= mc) { morem = mc; morea = vc; morey = (morea - kc) / 2; mored = dif; moreha = hac; morehb = hbc; }
-            }
-            aclip = (DIR > 0) ? IMAX : -IMAX; bclip = (DIR > 0) ? -IMAX : IMAX;
-        }
-        // ---- prune lagging ends ----
-        if (dif > 0 && hgh >= low) {
-            const int k = low + ((lane - low) & 31);
-            const bool keep = (k <= hgh) && (DIR > 0 ? (V >= besta - WAVE_LAG) : (V <= besta + WAVE_LAG));
-            const unsigned km = __ballot_sync(FULL, keep);
-            if (km == 0) hgh = low - 1;
-            else {
-                // bit r of `byrank` <-> diagonal hgh - r
-                const unsigned byrank = rotr32(__brev(km), 31 - (hgh & 31));
-                const int top = __ffs(byrank) - 1, bot = 31 - __clz(byrank);
-                const int nh = hgh - top, nl = hgh - bot;
-                hgh = nh; low = nl;
-            }
-            if (hgh >= low) cells_done += (unsigned)(hgh - low + 1);
-        }
-        if (!(more && (DIR > 0 ? (lasta >= besta - TRIM_MLAG) : (lasta <= besta + TRIM_MLAG)))) break;
-        if (hgh < low) break;
-
-        // ---- widen ----
-        const int plow = low, phgh = hgh;
-        if (low - 1 >= minp) low -= 1;
-        if (hgh + 1 <= maxp) hgh += 1;
-        if (hgh - low + 1 > 32) { S.overflow = 2; break; }
-        dif += 1;
-        const int k = low + ((lane - low) & 31);
-        const bool act = k <= hgh;
-        const int lm = (lane - 1) & 31, lp = (lane + 1) & 31;
-        {   // new end diagonals inherit the trace cursors of their inner neighbour
-            const int naR = __shfl_sync(FULL, NA, lp), nbR = __shfl_sync(FULL, NB, lp);
-            const int naL = __shfl_sync(FULL, NA, lm), nbL = __shfl_sync(FULL, NB, lm);
-            if (act && k < plow) { NA = naR; NB = nbR; }
-            else if (act && k > phgh) { NA = naL; NB = nbL; }
-        }
-        const int vl = __shfl_sync(FULL, V, lm), vr = __shfl_sync(FULL, V, lp);
-        const int vm = (k - 1 >= plow && k - 1 <= phgh) ? vl : NEG;
-        const int vc = (k >= plow && k <= phgh) ? V : NEG;
-        const int vp = (k + 1 >= plow && k + 1 <= phgh) ? vr : NEG;
-        int c, dir;
-        if (DIR > 0) {
-            if (vc < vm) { if (vm < vp) { c = vp + 1; dir = 1; } else { c = vm + 1; dir = -1; } }
-            else if (vc < vp) { c = vp + 1; dir = 1; }
-            else { c = vc + 2; dir = 0; }
-        } else {
-            if (vc > vp) { if (vp > vm) { c = vm - 1; dir = -1; } else { c = vp - 1; dir = 1; } }
-            else if (vc > vm) { c = vm - 1; dir = -1; }
-            else { c = vc - 2; dir = 0; }
-        }
-        const int sl = (lane + dir) & 31;
-        uint64_t b = __shfl_sync(FULL, T, sl) << 1;
-        int ha = __shfl_sync(FULL, HA, sl), hb = __shfl_sync(FULL, HB, sl);
-        int ham = __shfl_sync(FULL, HM, sl), hbm = __shfl_sync(FULL, HN, sl);
-        int y = 0, m = 0;
-        bool clipA = false, clipB = false;
-        if (act) {
-            y = (c - k) >> 1;
-            int x = y + k, n;
-            if (DIR > 0) {
-                const int ra = alen - x, rb = blen - y;
-                n = slide_fwd(aw, abase + x, bw, bbase + y, ra < rb ? ra : rb);
-                y += n; x += n;
-                if (y == blen) clipB = true; else if (x == alen) clipA = true;
-            } else {
-                n = slide_rev(aw, abase + x, bw, bbase + y, x < y ? x : y);
-                y -= n; x -= n;
-                if (y == 0) clipB = true; else if (x == 0) clipA = true;
-            }
-            b = push_matches(b, n);
-            c = (y << 1) + k;
-            m = __popcll(b & PATH_MASK61);
-        } else c = (DIR > 0) ? -IMAX : IMAX;
-        // ---- pebbles ----
-        {
-            const int x = y + k;
-            for (;;) {
-                const bool need = act && (DIR > 0 ? (x >= NA) : (x <= NA));
-                if (!__any_sync(FULL, need)) break;
-                const bool push = need && (DIR > 0 ? (ham < NA) : (ham > NA));
-                const unsigned pm = __ballot_sync(FULL, push);
-                if (push) {
-                    const int id = S.ncell + __popc(pm & ((1u << lane) - 1u));
-                    if (id < S.cells_cap) S.cells[id] = make_int4(ha, k, dif, NA);
-                    ha = id; ham = NA;
-                }
-                S.ncell += __popc(pm);
-                if (need) NA += DIR * TS;
-            }
-            for (;;) {
-                const bool need = act && (DIR > 0 ? (y >= NB) : (y <= NB));
-                if (!__any_sync(FULL, need)) break;
-                const bool push = need && (DIR > 0 ? (hbm < NB) : (hbm > NB));
-                const unsigned pm = __ballot_sync(FULL, push);
-                if (push) {
-                    const int id = S.ncell + __popc(pm & ((1u << lane) - 1u));
-                    if (id < S.cells_cap) S.cells[id] = make_int4(hb, k, dif, NB);
-                    hb = id; hbm = NB;
-                }
-                S.ncell += __popc(pm);
-                if (need) NB += DIR * TS;
-            }
-            if (S.ncell >= S.cells_cap) { S.overflow = 1; break; }
-        }
-        // ---- best / lasta / trim (align.c:911-928 / 1620-1637).  In the reference's visiting order (forward
-        //      hgh -> low, reverse low -> hgh) a diagonal is a record setter iff its point beats besta and every
-        //      point visited before it.  The last setter is the wave's extreme point; lasta / trim come from the
-        //      last setter that also passes the m / table tests, found by walking the few improving candidates
-        //      from the best one down (setters are strictly monotone in visiting order). ----
-#define BYRANK(mask) ((DIR > 0) ? rotr32(__brev(mask), 31 - (hgh & 31)) : rotr32((mask), low & 31))
-#define RANK2LANE(r) ((((DIR > 0) ? (hgh - (r)) : (low + (r)))) & 31)
-        {
-            const bool beat = act && (DIR > 0 ? (c > besta) : (c < besta));
-            if (__any_sync(FULL, beat)) {
-                const int ext = (DIR > 0) ? __reduce_max_sync(FULL, beat ? c : -IMAX) : __reduce_min_sync(FULL, beat ? c : IMAX);
-                {
-                    const unsigned em = __ballot_sync(FULL, beat && c == ext);
-                    const int l = RANK2LANE(__ffs(BYRANK(em)) - 1);          // first visited lane holding the extreme
-                    besta = ext; besty = __shfl_sync(FULL, y, l);
-                }
-                unsigned gm = __ballot_sync(FULL, beat && m >= PATH_AVE);
-                bool have_lasta = false;
-                while (gm) {
-                    const bool ing = (gm >> lane) & 1u;
-                    const int gext = (DIR > 0) ? __reduce_max_sync(FULL, ing ? c : -IMAX) : __reduce_min_sync(FULL, ing ? c : IMAX);
-                    const unsigned gem = __ballot_sync(FULL, ing && c == gext);
-                    const int r = __ffs(BYRANK(gem)) - 1;                    // visiting rank of the candidate
-                    const int l = RANK2LANE(r);
-                    const unsigned geq = __ballot_sync(FULL, act && (DIR > 0 ? (c >= gext) : (c <= gext)));
-                    if ((BYRANK(geq) & ((1u << r) - 1u)) == 0) {             // nothing visited earlier is as good: a setter
-                        if (!have_lasta) { lasta = gext; have_lasta = true; }
-                        int tok = 0;
-                        if (lane == l) {
-                            const int lo15 = (int)(b & TRIM_MASK), hi15 = (int)((b >> TRIM_LEN) & TRIM_MASK);
-                            tok = (S.table_tab[lo15] >= 0) && (S.table_tab[hi15] + S.score_tab[lo15] >= 0);
-                        }
-                        if (__shfl_sync(FULL, tok, l)) {
-                            trima = gext; trimy = __shfl_sync(FULL, y, l); trimd = dif;
-                            trimha = __shfl_sync(FULL, ha, l); trimhb = __shfl_sync(FULL, hb, l);
-                            break;
-                        }
-                    }
-                    gm &= ~gem;
-                }
-            }
-        }
-        // ---- clip bookkeeping in visiting order (align.c:836-851 / 1545-1560) ----
-        if (__any_sync(FULL, clipA || clipB)) {
-            const unsigned am = __ballot_sync(FULL, clipA), bm = __ballot_sync(FULL, clipB);
-            more = 0;
-            if (am) {       // aclip = last visited clipped diagonal
-                const int r = 31 - __clz(BYRANK(am));
-                aclip = (DIR > 0) ? (hgh - r) : (low + r);
-            }
-            if (bm) {       // bclip = extreme = first visited
-                const int r = __ffs(BYRANK(bm)) - 1;
-                const int kb = (DIR > 0) ? (hgh - r) : (low + r);
-                if (DIR > 0) { if (bclip < kb) bclip = kb; } else { if (bclip > kb) bclip = kb; }
-            }
-        }
-#undef BYRANK
-#undef RANK2LANE
-        if (act) { V = c; T = b; HA = ha; HB = hb; HM = ham; HN = hbm; }
-    }
-    S.ncells_done += cells_done;
-    if (morem >= 0) { ex = morea - morey; ey = morey; ediff = mored; eha = moreha; ehb = morehb; }
-    else { ex = trima - trimy; ey = trimy; ediff = trimd; eha = trimha; ehb = trimhb; }
-}
-
 // Local_Alignment (align.c:1904-2097) for daligner's call shape.  Warp-collective.
-template <bool FAST>
 __device__ void local_alignment(WarpLA &S, const AlignArgs &P, uint16_t *tbuf, int ar, int br, int alen, int blen,
                                 int diag, int anti, bool selfie, Path &ap, Path &bp) {
     const int lane = threadIdx.x & 31;
@@ -745,26 +407,24 @@ __device__ void local_alignment(WarpLA &S, const AlignArgs &P, uint16_t *tbuf, i
     int ex, ey, ed, ha, hb;
     int flenA = 0, flenB = 0;
 
-    if (FAST) wave_pass_fast<+1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
-    else wave_pass<+1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
+    wave_pass<+1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
     if (S.overflow) return;
     __syncwarp();
     if (lane == 0) {
-        flenA = emit_chain_fwd(S.cells, ha, true, anti, ex, ey, ed, atr);
-        flenB = emit_chain_fwd(S.cells, hb, false, anti, ex, ey, ed, btr);
+        flenA = wc::emit_chain_fwd(reinterpret_cast<const wc::Cell *>(S.cells), ha, true, anti, ex, ey, ed, atr);
+        flenB = wc::emit_chain_fwd(reinterpret_cast<const wc::Cell *>(S.cells), hb, false, anti, ex, ey, ed, btr);
     }
     flenA = __shfl_sync(FULL, flenA, 0); flenB = __shfl_sync(FULL, flenB, 0);
     ap.aepos = ex; ap.bepos = ey; ap.diffs = ed;
     __syncwarp();
 
-    if (FAST) wave_pass_fast<-1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
-    else wave_pass<-1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
+    wave_pass<-1>(S, P.awords, abase, alen, P.bwords, bbase, blen, diag, anti, minp, maxp, aoff, boff, ex, ey, ed, ha, hb);
     if (S.overflow) return;
     __syncwarp();
     int preA = 0, preB = 0;
     if (lane == 0) {
-        preA = emit_chain_rev(S.cells, ha, true, ex, ey, ed, P.TS, aoff, flenA, atr);
-        preB = emit_chain_rev(S.cells, hb, false, ex, ey, ed, P.TS, boff, flenB, btr);
+        preA = wc::emit_chain_rev(reinterpret_cast<wc::Cell *>(S.cells), ha, true, ex, ey, ed, P.TS, aoff, flenA, atr);
+        preB = wc::emit_chain_rev(reinterpret_cast<wc::Cell *>(S.cells), hb, false, ex, ey, ed, P.TS, boff, flenB, btr);
     }
     preA = __shfl_sync(FULL, preA, 0); preB = __shfl_sync(FULL, preB, 0);
     __syncwarp();
@@ -815,8 +475,7 @@ __device__ void emit_record(const AlignArgs &P, const Path &p, int aread, int br
     }
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(AL_WARPS * 32, FAST ? 4 : 3) align_pairs(AlignArgs P) {
+__global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArgs P) {
     __shared__ int la_low[AL_WARPS][MAX_LA_PER_PAIR], la_hgh[AL_WARPS][MAX_LA_PER_PAIR], la_ae[AL_WARPS][MAX_LA_PER_PAIR];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * AL_WARPS + wib;
@@ -847,7 +506,6 @@ __global__ void __launch_bounds__(AL_WARPS * 32, FAST ? 4 : 3) align_pairs(Align
         if (wslot >= P.nwork) break;
         const int64_t sidx = P.work[wslot];
         const unsigned wi = P.work_wi ? P.work_wi[wslot] : wslot;
-        const unsigned long long la0 = n_la, multi0 = n_multi, cells0 = S.ncells_done;
         const uint64_t pair = P.keys[sidx] >> P.pbits;
         const int ar = (int)(pair & ((1ull << P.abits) - 1ull)), br = (int)(pair >> P.abits);
         const int alen = P.arlen[ar], blen = P.brlen[br];
@@ -930,7 +588,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, FAST ? 4 : 3) align_pairs(Align
                     if (__any_sync(FULL, blocked)) continue;
                     Path ap, bp;
                     n_la++;
-                    local_alignment<FAST>(S, P, tbuf, ar, br, alen, blen, capos - cbpos, capos + cbpos, selfie, ap, bp);
+                    local_alignment(S, P, tbuf, ar, br, alen, blen, capos - cbpos, capos + cbpos, selfie, ap, bp);
                     if (S.overflow) break;
                     // Diagonal_Span (filter.c:2079-2110) on the uncompressed A trace
                     int lo, hi;
@@ -984,22 +642,419 @@ __global__ void __launch_bounds__(AL_WARPS * 32, FAST ? 4 : 3) align_pairs(Align
             if (S.overflow) break;
         }
         if (novl > 1) n_multi++;
-        if (FAST && S.overflow == 2) {
-            // wave front outgrew the warp: hand the whole pair to the strided pass; whatever this pass
-            // emitted for the pair is dropped on the host (pair_redo)
-            if (lane == 0) {
-                const unsigned q = atomicAdd(P.redo_count, 1u);
-                P.redo_sidx[q] = (uint32_t)sidx; P.redo_wi[q] = wi; P.pair_redo[wi] = 1;
-            }
-            n_la = la0; n_multi = multi0; S.ncells_done = cells0; n_pairs--;
-            S.overflow = 0;
-        }
         if (S.overflow) { if (lane == 0) atomicOr(&P.stats[3], 4ull); S.overflow = 0; }
     }
     if (lane == 0) {
         atomicAdd(&P.stats[0], n_la); atomicAdd(&P.stats[1], n_multi);
         atomicAdd(&P.stats[2], S.ncells_done); atomicAdd(&P.stats[4], n_pairs);
     }
+}
+
+
+// =============================================================================================
+// Task pipeline (the default path).
+//
+// Stage 3 and stage 4 are separate kernels that meet in small tables:
+//   filter_pairs   one warp per (bread, aread) pair: panel scoring + -h threshold, flags the pairs that
+//                  have at least one seed candidate (filter.c:2251-2290)                     [HBM bound]
+//   scan_round     one warp per active pair: the next candidate that no earlier alignment of the pair
+//                  covers (the `lasta` rule, filter.c:2289, kept as a per-pair interval list)
+//   wave_tasks     ONE THREAD PER TASK, a task being the forward or the reverse wave pass of one local
+//                  alignment (wave_core.cuh); threads refill from a global queue, the wave fronts sit in
+//                  shared memory, pebbles go to a global pool                                [integer bound]
+//   finish_las     one warp per alignment: pebble chains -> trace, B path, Diagonal_Span, lasta update,
+//                  MINOVER, records (align.c:1001-1111, 1711-1895, 2003-2063; filter.c:2318-2395)
+// The alignments of one pair depend on each other through lasta, so a pair contributes one alignment
+// per round; rounds repeat until no pair has a candidate left (almost all pairs need one round).
+// A task whose front outgrows the 32-diagonal ring is rerun with a 64-diagonal ring; beyond that the
+// whole pair goes to the strided warp kernel above.
+// =============================================================================================
+enum : uint32_t { PF_DONE = 1u, PF_REDO = 2u };
+
+struct PairTable {          // one slot per active pair
+    uint32_t *wslot;        // index into the work list = emission rank of the pair
+    int64_t *sidx, *pend, *nidx, *lidx, *pe, *j;
+    int32_t *amark2, *nla, *novl;
+    uint32_t *flags;
+    int32_t *la_low, *la_hgh, *la_ae;     // [slots][MAX_LA_PER_PAIR]
+};
+struct CandTable {          // one slot per local alignment of the current round
+    uint32_t *pair;         // active pair slot
+    int64_t *hidx;          // hit index of the seed
+    int32_t *ar, *br, *apos, *bpos;
+    wc::TaskOut *res;       // [2 * slots]: forward pass, reverse pass
+};
+struct PipeArgs {
+    AlignArgs A;                          // hits, blocks, parameters, output buffers (shared with the strided kernel)
+    const uint32_t *aw[2], *bw[2];        // [0] = the orientation that is aligned, [1] = its reverse complement
+    PairTable pt; CandTable ct;
+    const uint32_t *list_in; uint32_t n_in;
+    uint32_t *flag;                       // filter_pairs: per work pair
+    unsigned int *ctr;                    // device counters, see CTR_*
+    uint32_t *wide_list;
+    wc::Cell *pool; unsigned int pool_cap;
+};
+enum { CTR_NCAND = 0, CTR_NEXT = 1, CTR_NWIDE = 2, CTR_POOL = 3, CTR_NEXT_WIDE = 4, CTR_RETRY = 5, CTR_N = 8 };
+
+struct ScanState { int64_t pend, nidx, lidx, pe, j; int amark2; };
+
+// first index >= from whose pair differs (warp-collective)
+__device__ int64_t pair_extent(const AlignArgs &P, int64_t from, uint64_t pair) {
+    const int lane = threadIdx.x & 31;
+    int64_t pend = from;
+    for (;;) {
+        const int64_t j = pend + lane;
+        const bool same = (j < P.nhits) && ((P.keys[j] >> P.pbits) == pair);
+        const unsigned m = __ballot_sync(FULL, same);
+        if (m == FULL) { pend += 32; continue; }
+        pend += __ffs(~m) - 1;
+        break;
+    }
+    return pend;
+}
+
+// pass 1 of a panel: covered bases per diagonal bucket (filter.c:2268-2277)
+__device__ void panel_score(const AlignArgs &P, int64_t lidx, int64_t pe, int32_t *score, int32_t *lastp) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t pmask = (1ull << P.pbits) - 1ull;
+    for (int64_t j0 = lidx; j0 < pe; j0 += 32) {
+        const int64_t j = j0 + lane;
+        const bool v = j < pe;
+        int apos = 0, d = IMAX - lane;                 // distinct dummies so inactive lanes never match
+        if (v) { apos = (int)(P.keys[j] & pmask); d = (apos - (int)P.bpos[j]) >> P.W; }
+        const unsigned peers = __match_any_sync(FULL, d);
+        const unsigned lower = peers & ((1u << lane) - 1u);
+        int prev = 0;
+        const int src = lower ? (31 - __clz(lower)) : lane;
+        const int prev_peer = __shfl_sync(FULL, apos, src);
+        if (v) prev = lower ? prev_peer : lastp[d];
+        __syncwarp();
+        if (v) {
+            const int add = (apos - prev >= P.K) ? P.K : (apos - prev);
+            atomicAdd(&score[d], add);
+            if ((peers >> lane) == 1u) lastp[d] = apos;   // highest lane of the group
+        }
+        __syncwarp();
+    }
+}
+// pass 3: clear the touched buckets (filter.c:2407-2411)
+__device__ void panel_clear(const AlignArgs &P, int64_t lidx, int64_t pe, int32_t *score, int32_t *lastp) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t pmask = (1ull << P.pbits) - 1ull;
+    for (int64_t j0 = lidx; j0 < pe; j0 += 32) {
+        const int64_t j = j0 + lane;
+        if (j < pe) {
+            const int apos = (int)(P.keys[j] & pmask);
+            const int d = (apos - (int)P.bpos[j]) >> P.W;
+            score[d] = 0; lastp[d] = 0;
+        }
+    }
+    __syncwarp();
+}
+
+// Walks the pair's A-panels (filter.c:2251-2266) from the saved position to the next hit that passes the -h
+// test (filter.c:2289-2290) and is not covered by one of the pair's alignments so far.  Warp-collective; the
+// bucket arrays are left clean.  Returns the hit index, or -1 when the pair is exhausted.
+__device__ int64_t find_candidate(const AlignArgs &P, ScanState &S, int32_t *score, int32_t *lastp,
+                                  int nla, const int32_t *la_low, const int32_t *la_hgh, const int32_t *la_ae) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t pmask = (1ull << P.pbits) - 1ull;
+    bool scored = false;
+    for (;;) {
+        if (S.j < 0) {                                         // open the next panel
+            if (S.nidx >= S.pend) return -1;
+            const int amark = S.amark2 + PANEL_SIZE; S.amark2 = amark - PANEL_OVERLAP;
+            const int64_t lidx = S.nidx;
+            // panel = hits up to and including the first with apos > amark; h2 = first with apos > amark2
+            int64_t pe = S.pend, h2 = S.pend;
+            bool gotpe = false, goth2 = false;
+            for (int64_t j0 = lidx; j0 < S.pend && !(gotpe && goth2); j0 += 32) {
+                const int64_t j = j0 + lane;
+                const int apos = (j < S.pend) ? (int)(P.keys[j] & pmask) : IMAX;
+                const unsigned over = __ballot_sync(FULL, (j < S.pend) && apos > amark);
+                const unsigned over2 = __ballot_sync(FULL, (j < S.pend) && apos > S.amark2);
+                if (!goth2 && over2) { h2 = j0 + __ffs(over2) - 1; goth2 = true; }
+                if (!gotpe && over) { pe = j0 + __ffs(over) - 1 + 1; gotpe = true; }
+            }
+            if (h2 > pe) h2 = pe;
+            S.nidx = h2; S.lidx = lidx; S.pe = pe;
+            if (pe - lidx < P.minhit) continue;
+            S.j = lidx;
+        }
+        if (!scored) { panel_score(P, S.lidx, S.pe, score, lastp); scored = true; }
+        // pass 2 (filter.c:2283-2290) from S.j
+        for (int64_t j0 = S.j; j0 < S.pe; j0 += 32) {
+            const int64_t j = j0 + lane;
+            const bool v = j < S.pe;
+            int apos = 0, d = 0;
+            bool cand = false;
+            if (v) {
+                apos = (int)(P.keys[j] & pmask); d = (apos - (int)P.bpos[j]) >> P.W;
+                const int s = score[d];
+                cand = (s + score[d + 1] >= P.H) || (s + score[d - 1] >= P.H);
+            }
+            unsigned cm = __ballot_sync(FULL, cand);
+            while (cm) {
+                const int l = __ffs(cm) - 1; cm &= cm - 1;
+                const int capos = __shfl_sync(FULL, apos, l), cd = __shfl_sync(FULL, d, l);
+                bool blocked = false;                          // apos > lasta[d] (filter.c:2289)
+                for (int q = lane; q < nla; q += 32)
+                    if (la_low[q] <= cd && cd <= la_hgh[q] && capos <= la_ae[q]) blocked = true;
+                if (__any_sync(FULL, blocked)) continue;
+                panel_clear(P, S.lidx, S.pe, score, lastp);
+                S.j = j0 + l + 1;
+                return j0 + l;
+            }
+        }
+        panel_clear(P, S.lidx, S.pe, score, lastp);
+        scored = false;
+        S.j = -1;
+    }
+}
+
+__device__ __forceinline__ int32_t *warp_buckets(const AlignArgs &P, int gw) {
+    return P.bscore + (size_t)gw * 2 * P.nbuck - P.dmin + 2;          // +2 margin for d-1
+}
+
+// Stage 3 proper: which pairs have any candidate at all?
+__global__ void __launch_bounds__(256) filter_pairs(PipeArgs Q) {
+    const AlignArgs &P = Q.A;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    int32_t *score = warp_buckets(P, gw), *lastp = score + P.nbuck;
+    for (uint32_t w = gw; w < P.nwork; w += nw) {
+        const int64_t sidx = P.work[w];
+        const uint64_t pair = P.keys[sidx] >> P.pbits;
+        ScanState S;
+        S.pend = pair_extent(P, sidx, pair); S.nidx = sidx; S.j = -1; S.amark2 = 0; S.lidx = S.pe = sidx;
+        const int64_t c = find_candidate(P, S, score, lastp, 0, nullptr, nullptr, nullptr);
+        if (lane == 0) Q.flag[w] = (c >= 0) ? 1u : 0u;
+    }
+}
+__global__ void init_pairs(PipeArgs Q, const uint32_t *__restrict__ flag, const uint64_t *__restrict__ off) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= Q.A.nwork || !flag[w]) return;
+    const uint64_t p = off[w];
+    Q.pt.wslot[p] = w;
+    const int64_t sidx = Q.A.work[w];
+    Q.pt.sidx[p] = sidx; Q.pt.pend[p] = -1; Q.pt.nidx[p] = sidx; Q.pt.lidx[p] = sidx; Q.pt.pe[p] = sidx; Q.pt.j[p] = -1;
+    Q.pt.amark2[p] = 0; Q.pt.nla[p] = 0; Q.pt.novl[p] = 0; Q.pt.flags[p] = 0;
+}
+
+// One round of the lasta-ordered candidate walk: every listed pair that is still alive proposes its next seed.
+__global__ void __launch_bounds__(256) scan_round(PipeArgs Q) {
+    const AlignArgs &P = Q.A;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    int32_t *score = warp_buckets(P, gw), *lastp = score + P.nbuck;
+    unsigned long long n_multi = 0;
+    for (uint32_t i = gw; i < Q.n_in; i += nw) {
+        const uint32_t p = Q.list_in ? Q.list_in[i] : i;
+        if (Q.pt.flags[p] & (PF_DONE | PF_REDO)) continue;
+        const int64_t sidx = Q.pt.sidx[p];
+        const uint64_t pair = P.keys[sidx] >> P.pbits;
+        ScanState S;
+        S.pend = Q.pt.pend[p];
+        if (S.pend < 0) S.pend = pair_extent(P, sidx, pair);
+        S.nidx = Q.pt.nidx[p]; S.lidx = Q.pt.lidx[p]; S.pe = Q.pt.pe[p]; S.j = Q.pt.j[p]; S.amark2 = Q.pt.amark2[p];
+        const int nla = Q.pt.nla[p];
+        const size_t lo = (size_t)p * MAX_LA_PER_PAIR;
+        const int64_t c = find_candidate(P, S, score, lastp, nla, Q.pt.la_low + lo, Q.pt.la_hgh + lo, Q.pt.la_ae + lo);
+        if (lane == 0) {
+            Q.pt.pend[p] = S.pend; Q.pt.nidx[p] = S.nidx; Q.pt.lidx[p] = S.lidx; Q.pt.pe[p] = S.pe; Q.pt.j[p] = S.j; Q.pt.amark2[p] = S.amark2;
+            if (c < 0) {
+                Q.pt.flags[p] |= PF_DONE;
+                if (Q.pt.novl[p] > 1) n_multi++;
+            } else {
+                const unsigned slot = atomicAdd(&Q.ctr[CTR_NCAND], 1u);
+                const int apos = (int)(P.keys[c] & ((1ull << P.pbits) - 1ull));
+                Q.ct.pair[slot] = p; Q.ct.hidx[slot] = c;
+                Q.ct.ar[slot] = (int)(pair & ((1ull << P.abits) - 1ull)); Q.ct.br[slot] = (int)(pair >> P.abits);
+                Q.ct.apos[slot] = apos; Q.ct.bpos[slot] = (int)P.bpos[c];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && n_multi) atomicAdd(&P.stats[1], n_multi);
+}
+
+// ---- stage 4: one thread per wave pass ----
+struct DevPool {
+    wc::Cell *cells; unsigned int *top; unsigned int cap;
+    __device__ uint32_t take(int n) {
+        const unsigned int b = atomicAdd(top, (unsigned int)n);
+        return (b + (unsigned int)n <= cap) ? b : wc::NOCELL;
+    }
+    __device__ void store(uint32_t id, const wc::Cell &c) { *reinterpret_cast<int4 *>(cells + id) = make_int4(c.prev, c.diag, c.diff, c.mark); }
+};
+
+template <int RING>
+struct WaveCfg {
+    static constexpr int WARPS = (RING == 32) ? 7 : 3;        // 28 KB (56 KB) of front per warp
+    static constexpr int SMEM = WARPS * wc::FRONT_WORDS * RING * 32 * 4;
+};
+
+// Tasks [0, 2 * ncand) when WIDE == false (task t = pass (t & 1) of alignment t >> 1), the ST_WIDE leftovers of
+// that pass listed in wide_list when WIDE == true.
+template <int RING, bool WIDE>
+__global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeArgs Q) {
+    extern __shared__ uint32_t front_smem[];
+    const AlignArgs &P = Q.A;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    wc::Front<RING, 32> F{front_smem + (size_t)wib * wc::FRONT_WORDS * RING * 32 + lane};
+    DevPool pool{Q.pool, &Q.ctr[CTR_POOL], Q.pool_cap};
+    const unsigned ntasks = WIDE ? Q.ctr[CTR_NWIDE] : 2u * Q.ctr[CTR_NCAND];
+    unsigned int *next = &Q.ctr[WIDE ? CTR_NEXT_WIDE : CTR_NEXT];
+
+    wc::Lane L;
+    L.status = wc::ST_IDLE; L.k = 0; L.low = 0;
+    unsigned task = 0;
+    unsigned long long cells_done = 0;
+    for (;;) {
+        if (L.status != wc::ST_RUN && L.status != wc::ST_EXIT) {
+            if (L.status != wc::ST_IDLE) {                    // retire the finished task
+                wc::TaskOut o;
+                wc::finish(L, o);
+                Q.ct.res[task] = o;
+                cells_done += o.cells;
+                if (!WIDE && L.status == wc::ST_WIDE) Q.wide_list[atomicAdd(&Q.ctr[CTR_NWIDE], 1u)] = task;
+            }
+            // fetch the next task (one atomic per warp-wide batch of idle lanes)
+            const unsigned idle = __activemask();
+            const int leader = __ffs(idle) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(next, (unsigned)__popc(idle));
+            base = __shfl_sync(idle, base, leader);
+            const unsigned t = base + __popc(idle & ((1u << lane) - 1u));
+            if (t >= ntasks) L.status = wc::ST_EXIT;
+            else {
+                task = WIDE ? Q.wide_list[t] : t;
+                const unsigned slot = task >> 1;
+                const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
+                wc::TaskIn in;
+                in.rev = (int)(task & 1u);
+                in.aw = Q.aw[in.rev]; in.bw = Q.bw[in.rev];
+                in.abase = P.aboff[ar]; in.bbase = P.bboff[br];
+                in.alen = P.arlen[ar]; in.blen = P.brlen[br];
+                in.diag = apos - bpos; in.anti = apos + bpos;
+                in.aoff = 0; in.boff = P.comp ? (in.blen % P.TS) : 0;                     // align.c:1970-1984
+                const bool selfie = P.self && !P.comp && ar == br;                       // align.c:1949
+                in.minp = (selfie && in.diag >= 0) ? 1 : -IMAX;                          // align.c:1951-1968
+                in.maxp = (selfie && in.diag <= 0) ? -1 : IMAX;
+                in.TS = P.TS; in.path_ave = P.ave_path; in.score_tab = P.score_tab; in.table_tab = P.table_tab;
+                wc::setup(L, in, F, pool);
+            }
+        }
+        if (__all_sync(FULL, L.status == wc::ST_EXIT)) break;
+        if (L.status == wc::ST_RUN) {
+            if (L.k < L.low) wc::transition<RING>(L, F);
+            if (L.status == wc::ST_RUN && L.k >= L.low) wc::cell(L, F, pool);
+        }
+    }
+    if (cells_done) atomicAdd(&P.stats[2], cells_done);
+}
+
+// ---- stage 4 epilogue: one warp per alignment of the round ----
+__global__ void __launch_bounds__(256) finish_las(PipeArgs Q) {
+    const AlignArgs &P = Q.A;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    uint16_t *tbuf = P.tbuf + (size_t)gw * 8 * P.maxtp;
+    uint16_t *atr = tbuf + 2 * P.maxtp, *btr = tbuf + 6 * P.maxtp;
+    const unsigned ncand = Q.ctr[CTR_NCAND];
+    unsigned long long n_la = 0;
+    for (unsigned slot = gw; slot < ncand; slot += nw) {
+        const uint32_t p = Q.ct.pair[slot];
+        const wc::TaskOut fo = Q.ct.res[2 * slot], ro = Q.ct.res[2 * slot + 1];
+        const uint32_t wi = Q.pt.wslot[p];
+        if (fo.status != wc::ST_DONE || ro.status != wc::ST_DONE) {
+            const bool pool_only = (fo.status == wc::ST_DONE || fo.status == wc::ST_POOL) && (ro.status == wc::ST_DONE || ro.status == wc::ST_POOL);
+            if (lane == 0) {
+                if (pool_only) { Q.pt.j[p] = Q.ct.hidx[slot]; atomicAdd(&Q.ctr[CTR_RETRY], 1u); }     // pebble pool ran dry: same seed next round
+                else {                                                                                 // too wide / out of range: strided kernel
+                    Q.pt.flags[p] |= PF_REDO;
+                    atomicAdd(&P.stats[0], (unsigned long long)(-(long long)Q.pt.nla[p]));              // it recounts the pair's alignments
+                    const unsigned q = atomicAdd(P.redo_count, 1u);
+                    P.redo_sidx[q] = (uint32_t)Q.pt.sidx[p]; P.redo_wi[q] = wi; P.pair_redo[wi] = 1;
+                }
+            }
+            continue;
+        }
+        n_la++;
+        const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
+        const int alen = P.arlen[ar], blen = P.brlen[br];
+        const int anti = apos + bpos;
+        const int aoff = 0, boff = P.comp ? (blen % P.TS) : 0;
+        int flen = 0, pre = 0;
+        if (lane < 2) {                                        // lane 0: A chains, lane 1: B chains
+            const bool isA = lane == 0;
+            uint16_t *tr = isA ? atr : btr;
+            flen = wc::emit_chain_fwd(Q.pool, isA ? fo.ha : fo.hb, isA, anti, fo.ex, fo.ey, fo.ediff, tr);
+            pre = wc::emit_chain_rev(Q.pool, isA ? ro.ha : ro.hb, isA, ro.ex, ro.ey, ro.ediff, P.TS, isA ? aoff : boff, flen, tr);
+        }
+        __syncwarp();
+        const int flenA = __shfl_sync(FULL, flen, 0), flenB = __shfl_sync(FULL, flen, 1);
+        const int preA = __shfl_sync(FULL, pre, 0), preB = __shfl_sync(FULL, pre, 1);
+        Path ap, bp;
+        ap.aepos = fo.ex; ap.bepos = fo.ey; ap.abpos = ro.ex; ap.bbpos = ro.ey; ap.diffs = fo.ediff + ro.ediff;
+        ap.tlen = flenA + preA; ap.trace = atr - preA;
+        bp.tlen = flenB + preB; bp.trace = btr - preB; bp.diffs = ap.diffs;
+        if (P.comp) {                                            // align.c:2033-2055
+            bp.abpos = blen - ap.bepos; bp.bbpos = alen - ap.aepos;
+            bp.aepos = blen - ap.bbpos; bp.bepos = alen - ap.abpos;
+            uint16_t *tr = bp.trace;
+            const int npair = bp.tlen >> 1;
+            for (int i = lane; i < npair / 2; i += 32) {         // reverse the (d, delta) pairs as pairs
+                const int j = npair - 1 - i;
+                const uint16_t d0 = tr[2 * i], d1 = tr[2 * i + 1];
+                tr[2 * i] = tr[2 * j]; tr[2 * i + 1] = tr[2 * j + 1];
+                tr[2 * j] = d0; tr[2 * j + 1] = d1;
+            }
+            __syncwarp();
+        } else {                                                 // align.c:2056-2062
+            bp.aepos = ap.bepos; bp.bepos = ap.aepos; bp.abpos = ap.bbpos; bp.bbpos = ap.abpos;
+        }
+        // Diagonal_Span (filter.c:2079-2110) on the uncompressed A trace, then lasta (filter.c:2318-2333)
+        const int cd = (apos - bpos) >> P.W;
+        int lo, hi;
+        {
+            int dd = ap.abpos - ap.bbpos; lo = hi = dd;
+            dd = ap.aepos - ap.bepos; if (dd < lo) lo = dd; else if (dd > hi) hi = dd;
+            const int nint = (ap.tlen - 2) / 2;
+            int base = (ap.abpos / P.TS) * P.TS - ap.bbpos;
+            for (int q0 = 0; q0 < nint; q0 += 32) {
+                const int q = q0 + lane;
+                int val = (q < nint) ? (P.TS - (int)ap.trace[2 * q + 1]) : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, val, o); if (lane >= o) val += t; }
+                const int dd2 = base + val;
+                int mn = (q < nint) ? dd2 : IMAX, mx = (q < nint) ? dd2 : -IMAX;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { mn = min(mn, __shfl_xor_sync(FULL, mn, o)); mx = max(mx, __shfl_xor_sync(FULL, mx, o)); }
+                if (mn < lo) lo = mn;
+                if (mx > hi) hi = mx;
+                base += __shfl_sync(FULL, val, 31);
+            }
+            lo = (lo >> P.W) - 1; hi = (hi >> P.W) + 1;
+            if (cd < lo) lo = cd; else if (cd > hi) hi = cd;
+        }
+        const int nla = Q.pt.nla[p], novl = Q.pt.novl[p];
+        if (nla < MAX_LA_PER_PAIR) {
+            if (lane == 0) {
+                const size_t o = (size_t)p * MAX_LA_PER_PAIR + nla;
+                Q.pt.la_low[o] = lo; Q.pt.la_hgh[o] = hi; Q.pt.la_ae[o] = ap.aepos; Q.pt.nla[p] = nla + 1;
+            }
+        } else if (lane == 0) atomicOr(&P.stats[3], 2ull);
+        if ((ap.aepos - ap.abpos) + (ap.bepos - ap.bbpos) >= P.minover) {   // filter.c:2335
+            const bool doB = P.symmetric && (ar != br || !P.self || !P.comp);   // filter.c:2301
+            const uint64_t seq = ((uint64_t)wi << 8) | (uint64_t)(novl & 127);
+            emit_record(P, ap, ar + P.afirst, br + P.bfirst, seq);
+            if (doB) emit_record(P, bp, br + P.bfirst, ar + P.afirst, seq | 128ull);
+            if (lane == 0) Q.pt.novl[p] = novl + 1;
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && n_la) atomicAdd(&P.stats[0], n_la);
 }
 
 // New_Align_Spec + set_table (align.c:226-318): floating point only here, evaluated exactly as the
@@ -1024,6 +1079,10 @@ void build_trim_tables(const damar_options &opt, int &ave_path, std::vector<int1
     }
 }
 
+template <typename T> void set_smem(T kernel, int bytes) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
 }  // namespace
 
 void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out) {
@@ -1032,18 +1091,20 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     const FilterParams &fp = c.fp;
     const int64_t n = hits.n;
     const int minhit = (fp.hitmin - 1) / fp.kmer + 1;
+    if (n >= (int64_t)0xffffffffll) fatal("more than 2^32 seed hits in one comparison (%lld): lower -M", (long long)n);
 
-    // ---- work list ----
+    // ---- work list: first hit of every pair with at least minhit hits (filter.c:2210-2221) ----
     HostProf *hp1 = new HostProf("ra.worklist");
     Timer t_pairs(st);
+    const int nslices = fp.nthreads_pow2 > 1024 ? 1024 : fp.nthreads_pow2;
     DevBuf<int64_t> ends; ends.reserve(fp.nthreads_pow2);
     DevBuf<uint32_t> flag; flag.reserve((size_t)n);
     DevBuf<uint64_t> off; off.reserve((size_t)n);
     DevBuf<uint64_t> total; total.reserve(1);
-    slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, fp.nthreads_pow2 > 1024 ? 1024 : fp.nthreads_pow2, fp.nshift, hits.pbits + hits.abits, ends.p);
+    slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits, ends.p);
     KERNEL_CHECK();
     const unsigned hb = (unsigned)((n + 255) / 256);
-    flag_work_pairs<<<hb, 256, 0, st>>>(hits.keys, n, hits.pbits, minhit, ends.p, fp.nthreads_pow2 > 1024 ? 1024 : fp.nthreads_pow2, flag.p);
+    flag_work_pairs<<<hb, 256, 0, st>>>(hits.keys, n, hits.pbits, minhit, ends.p, nslices, flag.p);
     KERNEL_CHECK();
     exclusive_scan_u32_to_u64(flag.p, off.p, n, total.p, st);
     uint64_t nwork = 0;
@@ -1053,13 +1114,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     collect_work_pairs<<<hb, 256, 0, st>>>(flag.p, off.p, n, work.p);
     KERNEL_CHECK();
     count_launch(3);
-    c.tm.pairs_ms = t_pairs.stop();
-    if (nwork == 0) { delete hp1; return; }
+    flag.release(); off.release();
+    if (nwork == 0) { c.tm.pairs_ms = t_pairs.stop(); delete hp1; return; }
 
-    delete hp1;
-    // ---- alignment ----
-    HostProf *hp2 = new HostProf("ra.align_setup");
-    Timer t_align(st);
+    // ---- common arguments ----
     int ave_path; std::vector<int16_t> hs, ht;
     build_trim_tables(c.opt, ave_path, hs, ht);
     DevBuf<int16_t> dscore, dtable; dscore.reserve(hs.size()); dtable.reserve(ht.size());
@@ -1067,69 +1125,159 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     CUDA_CHECK(cudaMemcpyAsync(dtable.p, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice, st));
 
     const int TS = c.opt.trace_spacing;
-    const int blocks = NUM_SMS_B200 * 4;
-    const int nwarps = blocks * AL_WARPS;
+    const int lblocks = NUM_SMS_B200 * 3;                    // strided kernel
+    const int sblocks = NUM_SMS_B200 * 8;                    // scan / filter / finish kernels: 8 warps per CTA
+    const int nwarps = std::max(lblocks * AL_WARPS, sblocks * 8);
     const int ring = 2048;
     const int maxlen = ab->maxlen > bb->maxlen ? ab->maxlen : bb->maxlen;
     const int maxtp = 2 * (maxlen / TS + 2) + 2;
-    int cells_cap = 4 * (2 * (maxlen / TS + 2)) * 24 + 4096;
     const int dmin = (-bb->maxlen) >> fp.binshift, dmax = ab->maxlen >> fp.binshift;
     const int nbuck = dmax - dmin + 1 + 4;
+    const int tbytes = (TS <= 125) ? 1 : 2;                  // TRACE_XOVR, align.h:58
 
-    DevBuf<int32_t> V, HA, HB, HM, HN, NA, NB, bscore; DevBuf<uint64_t> T; DevBuf<int4> cells; DevBuf<uint16_t> tbuf;
-    V.reserve((size_t)nwarps * 2 * ring); HA.reserve((size_t)nwarps * 2 * ring); HB.reserve((size_t)nwarps * 2 * ring);
-    HM.reserve((size_t)nwarps * 2 * ring); HN.reserve((size_t)nwarps * 2 * ring); T.reserve((size_t)nwarps * 2 * ring);
-    NA.reserve((size_t)nwarps * ring); NB.reserve((size_t)nwarps * ring);
-    cells.reserve((size_t)nwarps * cells_cap); tbuf.reserve((size_t)nwarps * 8 * maxtp);
-    bscore.reserve((size_t)nwarps * 2 * nbuck);
+    DevBuf<int32_t> bscore; DevBuf<uint16_t> tbuf;
+    bscore.reserve((size_t)nwarps * 2 * nbuck); tbuf.reserve((size_t)nwarps * 8 * maxtp);
     CUDA_CHECK(cudaMemsetAsync(bscore.p, 0, sizeof(int32_t) * (size_t)nwarps * 2 * nbuck, st));
-
     DevBuf<unsigned long long> counters; counters.reserve(8);
     DevBuf<unsigned int> next; next.reserve(4);
+    DevBuf<unsigned int> ctr; ctr.reserve(CTR_N);
     DevBuf<uint32_t> redo_sidx, redo_wi; DevBuf<uint8_t> pair_redo;
     redo_sidx.reserve((size_t)nwork + 1); redo_wi.reserve((size_t)nwork + 1); pair_redo.reserve((size_t)nwork + 1);
+    DevBuf<uint32_t> pflag; pflag.reserve((size_t)nwork + 1);
+    DevBuf<uint64_t> poff; poff.reserve((size_t)nwork + 1);
+
+    PipeArgs Q{};
+    AlignArgs &P = Q.A;
+    P.keys = hits.keys; P.bpos = hits.bpos; P.nhits = n; P.pbits = hits.pbits; P.abits = hits.abits;
+    P.work = work.p; P.nwork = (uint32_t)nwork; P.next_work = next.p; P.work_wi = nullptr;
+    P.redo_sidx = redo_sidx.p; P.redo_wi = redo_wi.p; P.redo_count = next.p + 1; P.pair_redo = pair_redo.p;
+    const int bsel = (comp && !bb->as_is) ? 1 : 0;
+    P.awords = ab->packed[0]; P.bwords = bb->packed[bsel];
+    Q.aw[0] = ab->packed[0]; Q.aw[1] = ab->packed[1]; Q.bw[0] = bb->packed[bsel]; Q.bw[1] = bb->packed[1 - bsel];
+    if (!Q.aw[1] || !Q.bw[1]) fatal("report_and_align: reverse-complemented reads are not resident");
+    P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
+    P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
+    P.K = fp.kmer; P.W = fp.binshift; P.H = fp.hitmin; P.minhit = minhit; P.TS = TS; P.minover = c.opt.minover;
+    P.comp = comp ? 1 : 0; P.self = self; P.symmetric = c.opt.symmetric;
+    P.ave_path = ave_path; P.score_tab = dscore.p; P.table_tab = dtable.p;
+    P.tbuf = tbuf.p; P.maxtp = maxtp;
+    P.bscore = bscore.p; P.nbuck = nbuck; P.dmin = dmin;
+    P.tbytes = tbytes; P.stats = counters.p;
+    Q.flag = pflag.p; Q.ctr = ctr.p;
+
+    // ---- stage 3: pairs with at least one seed that passes the -h test ----
+    filter_pairs<<<sblocks, 256, 0, st>>>(Q);
+    KERNEL_CHECK();
+    exclusive_scan_u32_to_u64(pflag.p, poff.p, (int64_t)nwork, total.p, st);
+    uint64_t nactive = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nactive, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    count_launch(1);
+    c.tm.pairs_ms = t_pairs.stop();
+    delete hp1;
+
+    HostProf *hp3 = new HostProf("ra.align_run");
+    Timer t_align(st);
+    // pair and alignment tables
+    const size_t na = (size_t)nactive + 1;
+    DevBuf<uint32_t> pt_wslot, pt_flags, ct_pair, list_buf, wide_list;
+    DevBuf<int64_t> pt_i64, ct_hidx;
+    DevBuf<int32_t> pt_i32, pt_la, ct_i32;
+    DevBuf<wc::TaskOut> ct_res;
+    pt_wslot.reserve(na); pt_flags.reserve(na); pt_i64.reserve(6 * na); pt_i32.reserve(3 * na); pt_la.reserve(3 * na * MAX_LA_PER_PAIR);
+    ct_pair.reserve(na); list_buf.reserve(na); wide_list.reserve(2 * na); ct_hidx.reserve(na); ct_i32.reserve(4 * na); ct_res.reserve(2 * na);
+    Q.pt.wslot = pt_wslot.p; Q.pt.flags = pt_flags.p;
+    Q.pt.sidx = pt_i64.p; Q.pt.pend = pt_i64.p + na; Q.pt.nidx = pt_i64.p + 2 * na; Q.pt.lidx = pt_i64.p + 3 * na;
+    Q.pt.pe = pt_i64.p + 4 * na; Q.pt.j = pt_i64.p + 5 * na;
+    Q.pt.amark2 = pt_i32.p; Q.pt.nla = pt_i32.p + na; Q.pt.novl = pt_i32.p + 2 * na;
+    Q.pt.la_low = pt_la.p; Q.pt.la_hgh = pt_la.p + na * MAX_LA_PER_PAIR; Q.pt.la_ae = pt_la.p + 2 * na * MAX_LA_PER_PAIR;
+    Q.ct.pair = ct_pair.p; Q.ct.hidx = ct_hidx.p; Q.ct.res = ct_res.p;
+    Q.ct.ar = ct_i32.p; Q.ct.br = ct_i32.p + na; Q.ct.apos = ct_i32.p + 2 * na; Q.ct.bpos = ct_i32.p + 3 * na;
+    Q.wide_list = wide_list.p;
+
+    // pebble pool: measured need is ~300 cells per alignment on 10 kbp reads; a dry pool only delays alignments a round
+    size_t pool_cells = (size_t)nactive * (size_t)(2 * (maxlen / TS + 2) + 512) + (1u << 16);
+    if (pool_cells > 0x7ffffff0ull) pool_cells = 0x7ffffff0ull;
+    DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
+    Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
+
+    static bool attr = false;
+    if (!attr) {
+        set_smem(wave_tasks<32, false>, WaveCfg<32>::SMEM);
+        set_smem(wave_tasks<64, true>, WaveCfg<64>::SMEM);
+        attr = true;
+    }
+
     unsigned int nredo = 0; unsigned long long nrec_fast = 0;
-    const int tbytes = (TS <= 125) ? 1 : 2;                  // TRACE_XOVR, align.h:58
-    unsigned long long rec_cap = 4 * nwork + 1024;
-    unsigned long long trace_cap = (unsigned long long)rec_cap * (unsigned long long)(2 * (maxlen / TS + 2)) / 8 + (1ull << 20);
+    unsigned long long rec_cap = 4 * nactive + 1024;
+    unsigned long long trace_cap = (unsigned long long)rec_cap * (unsigned long long)(2 * (maxlen / TS + 2)) / 4 + (1ull << 20);
     DevBuf<damar_overlap> recs; DevBuf<uint64_t> rtoff, rseq; DevBuf<uint8_t> trace;
     unsigned long long hc[8];
-    delete hp2;
-    HostProf *hp3 = new HostProf("ra.align_run");
+    int rounds = 0;
     for (int attempt = 0;; attempt++) {
         recs.reserve((size_t)rec_cap); rtoff.reserve((size_t)rec_cap); rseq.reserve((size_t)rec_cap);
         trace.reserve((size_t)trace_cap * tbytes);
         CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 8, st));
         CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int) * 4, st));
         CUDA_CHECK(cudaMemsetAsync(pair_redo.p, 0, (size_t)nwork + 1, st));
-        AlignArgs P{};
-        P.keys = hits.keys; P.bpos = hits.bpos; P.nhits = n; P.pbits = hits.pbits; P.abits = hits.abits;
-        P.work = work.p; P.nwork = (uint32_t)nwork; P.next_work = next.p; P.work_wi = nullptr;
-        P.redo_sidx = redo_sidx.p; P.redo_wi = redo_wi.p; P.redo_count = next.p + 1; P.pair_redo = pair_redo.p;
-        P.awords = ab->packed[0]; P.bwords = bb->packed[(comp && !bb->as_is) ? 1 : 0];
-        P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
-        P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
-        P.K = fp.kmer; P.W = fp.binshift; P.H = fp.hitmin; P.minhit = minhit; P.TS = TS; P.minover = c.opt.minover;
-        P.comp = comp ? 1 : 0; P.self = self; P.symmetric = c.opt.symmetric;
-        P.ave_path = ave_path; P.score_tab = dscore.p; P.table_tab = dtable.p;
-        P.ring = ring; P.V = V.p; P.HA = HA.p; P.HB = HB.p; P.HM = HM.p; P.HN = HN.p; P.NA = NA.p; P.NB = NB.p; P.T = T.p;
-        P.cells = cells.p; P.cells_cap = cells_cap; P.tbuf = tbuf.p; P.maxtp = maxtp;
-        P.bscore = bscore.p; P.nbuck = nbuck; P.dmin = dmin;
         P.recs = recs.p; P.rec_toff = rtoff.p; P.rec_seq = rseq.p; P.rec_cap = rec_cap; P.rec_count = counters.p + 5;
-        P.trace = trace.p; P.tbytes = tbytes; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
-        P.stats = counters.p;
-        Timer t_k(st);
-        align_pairs<true><<<blocks, AL_WARPS * 32, 0, st>>>(P);
-        KERNEL_CHECK(); count_launch();
-        c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
+        P.trace = trace.p; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
+
+        if (nactive > 0) {
+            init_pairs<<<(unsigned)((nwork + 255) / 256), 256, 0, st>>>(Q, pflag.p, poff.p);
+            KERNEL_CHECK(); count_launch();
+        }
+        Q.list_in = nullptr; Q.n_in = (uint32_t)nactive;
+        while (Q.n_in > 0) {
+            rounds++;
+            CUDA_CHECK(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned int) * CTR_N, st));
+            const unsigned sb = (unsigned)std::min<uint64_t>((uint64_t)sblocks, ((uint64_t)Q.n_in + 7) / 8);
+            scan_round<<<sb, 256, 0, st>>>(Q);
+            KERNEL_CHECK(); count_launch();
+            unsigned int ncand = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&ncand, ctr.p + CTR_NCAND, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (ncand == 0) break;
+            Timer t_k(st);
+            {
+                const unsigned per = WaveCfg<32>::WARPS * 32;
+                const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (2 * ncand + per - 1) / per);
+                wave_tasks<32, false><<<wb, per, WaveCfg<32>::SMEM, st>>>(Q);
+                KERNEL_CHECK(); count_launch();
+            }
+            unsigned int nwide = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&nwide, ctr.p + CTR_NWIDE, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            if (nwide > 0) {
+                const unsigned per = WaveCfg<64>::WARPS * 32;
+                const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (nwide + per - 1) / per);
+                wave_tasks<64, true><<<wb, per, WaveCfg<64>::SMEM, st>>>(Q);
+                KERNEL_CHECK(); count_launch();
+            }
+            c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
+            const unsigned fb = (unsigned)std::min<uint64_t>((uint64_t)sblocks, ((uint64_t)ncand + 7) / 8);
+            finish_las<<<fb, 256, 0, st>>>(Q);
+            KERNEL_CHECK(); count_launch();
+            CUDA_CHECK(cudaMemcpyAsync(list_buf.p, ct_pair.p, sizeof(uint32_t) * ncand, cudaMemcpyDeviceToDevice, st));
+            Q.list_in = list_buf.p; Q.n_in = ncand;
+        }
         CUDA_CHECK(cudaMemcpyAsync(&nredo, next.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(&nrec_fast, counters.p + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
-        if (nredo > 0) {                               // strided scratch-memory pass for the wide pairs
+        if (nredo > 0) {                               // strided warp kernel for the pairs with very wide fronts
+            DevBuf<int32_t> V, HA, HB, HM, HN, NA, NB; DevBuf<uint64_t> T; DevBuf<int4> cells;
+            const int lw = lblocks * AL_WARPS;
+            const int cells_cap = 4 * (2 * (maxlen / TS + 2)) * 24 + 4096;
+            V.reserve((size_t)lw * 2 * ring); HA.reserve((size_t)lw * 2 * ring); HB.reserve((size_t)lw * 2 * ring);
+            HM.reserve((size_t)lw * 2 * ring); HN.reserve((size_t)lw * 2 * ring); T.reserve((size_t)lw * 2 * ring);
+            NA.reserve((size_t)lw * ring); NB.reserve((size_t)lw * ring); cells.reserve((size_t)lw * cells_cap);
+            P.ring = ring; P.V = V.p; P.HA = HA.p; P.HB = HB.p; P.HM = HM.p; P.HN = HN.p; P.NA = NA.p; P.NB = NB.p; P.T = T.p;
+            P.cells = cells.p; P.cells_cap = cells_cap;
             CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int), st));
-            P.work = redo_sidx.p; P.work_wi = redo_wi.p; P.nwork = nredo;
+            AlignArgs R = P;
+            R.work = redo_sidx.p; R.work_wi = redo_wi.p; R.nwork = nredo;
             Timer t_r(st);
-            align_pairs<false><<<blocks, AL_WARPS * 32, 0, st>>>(P);
+            align_pairs_strided<<<lblocks, AL_WARPS * 32, 0, st>>>(R);
             KERNEL_CHECK(); count_launch();
             c.tm.redo_kernel_ms += t_r.stop();
         }
@@ -1168,7 +1316,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     if (nredo > 0) { h_redo.resize(nwork); CUDA_CHECK(cudaMemcpyAsync(h_redo.data(), pair_redo.p, nwork, cudaMemcpyDeviceToHost, st)); }
     CUDA_CHECK(cudaStreamSynchronize(st));
     uint64_t nkeep = nrec;
-    if (nredo > 0) {                                   // drop what the fast pass emitted for pairs it gave up on
+    if (nredo > 0) {                                   // drop what the task pipeline emitted for pairs it gave up on
         nkeep = 0;
         for (uint64_t i = 0; i < nrec; i++) {
             if (i < nrec_fast && h_redo[h_seq.p[i] >> 8]) continue;
@@ -1178,8 +1326,9 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     }
     out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = h_trace.p;
     out.novl = (int64_t)nkeep; out.ntrace = (int64_t)ntr; out.tbytes = tbytes; out.redo = (int64_t)nredo;
-    out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)hc[4];
+    out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)nwork;
     c.tm.download_ms = t_dl.stop();
+    (void)rounds;
 }
 
 }  // namespace damar
