@@ -97,7 +97,7 @@ struct AlignArgs {
     int afirst, bfirst;
     // parameters
     int K, W, H, minhit, TS, minover, comp, self, symmetric;
-    int ave_path; const int16_t *score_tab, *table_tab;
+    int ave_path, dscore; const int16_t *score_tab, *table_tab;
     // per-warp scratch
     int ring;                          // power of two
     int32_t *V, *HA, *HB, *HM, *HN, *NA, *NB; uint64_t *T;    // [nwarps][2][ring] except NA/NB [nwarps][ring]
@@ -692,6 +692,7 @@ struct PipeArgs {
     uint32_t *flag;                       // filter_pairs: per work pair
     unsigned int *ctr;                    // device counters, see CTR_*
     uint32_t *wide_list;
+    const uint32_t *task_order;           // tasks of the round, longest expected pass first (or null: index order)
     wc::Cell *pool; unsigned int pool_cap;
 };
 enum { CTR_NCAND = 0, CTR_NEXT = 1, CTR_NWIDE = 2, CTR_POOL = 3, CTR_NEXT_WIDE = 4, CTR_RETRY = 5, CTR_N = 8 };
@@ -878,6 +879,21 @@ __global__ void __launch_bounds__(256) scan_round(PipeArgs Q) {
     if (lane == 0 && n_multi) atomicAdd(&P.stats[1], n_multi);
 }
 
+// Longest-processing-time-first order for the task queue: a pass can run at most to the nearer read end.
+__global__ void task_length_keys(PipeArgs Q, unsigned ntasks, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntasks) return;
+    const unsigned slot = t >> 1;
+    const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
+    int len;
+    if (t & 1u) len = min(apos, bpos);
+    else len = min(Q.A.arlen[ar] - apos, Q.A.brlen[br] - bpos);
+    if (len < 0) len = 0;
+    if (len > 0xffffff) len = 0xffffff;
+    keys[t] = (uint64_t)(0xffffff - len);
+    vals[t] = t;
+}
+
 // ---- stage 4: one thread per wave pass ----
 struct DevPool {
     wc::Cell *cells; unsigned int *top; unsigned int cap;
@@ -890,17 +906,24 @@ struct DevPool {
 
 template <int RING>
 struct WaveCfg {
-    static constexpr int WARPS = (RING == 32) ? 7 : 3;        // 28 KB (56 KB) of front per warp
+    static constexpr int WARPS = (RING == 32) ? 8 : 4;        // 28 KB (56 KB) of front per warp: 224 KB per SM
     static constexpr int SMEM = WARPS * wc::FRONT_WORDS * RING * 32 * 4;
 };
 
 // Tasks [0, 2 * ncand) when WIDE == false (task t = pass (t & 1) of alignment t >> 1), the ST_WIDE leftovers of
 // that pass listed in wide_list when WIDE == true.
-template <int RING, bool WIDE>
+template <int RING, bool WIDE, int NWAY>
 __global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     extern __shared__ uint32_t front_smem[];
+    __shared__ int16_t s_t7[128], s_t8[256];                  // the trim test tables (wave_core.cuh)
     const AlignArgs &P = Q.A;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) {
+        if (i < 128) s_t7[i] = (int16_t)wc::min_suffix_score(i, 7, P.dscore);
+        else s_t8[i - 128] = (int16_t)wc::min_suffix_score(i - 128, 8, P.dscore);
+    }
+    __syncthreads();
+    const wc::TrimTabs tabs{s_t7, s_t8, P.dscore};
     wc::Front<RING, 32> F{front_smem + (size_t)wib * wc::FRONT_WORDS * RING * 32 + lane};
     DevPool pool{Q.pool, &Q.ctr[CTR_POOL], Q.pool_cap};
     const unsigned ntasks = WIDE ? Q.ctr[CTR_NWIDE] : 2u * Q.ctr[CTR_NCAND];
@@ -928,7 +951,7 @@ __global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeA
             const unsigned t = base + __popc(idle & ((1u << lane) - 1u));
             if (t >= ntasks) L.status = wc::ST_EXIT;
             else {
-                task = WIDE ? Q.wide_list[t] : t;
+                task = WIDE ? Q.wide_list[t] : (Q.task_order ? Q.task_order[t] : t);
                 const unsigned slot = task >> 1;
                 const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
                 wc::TaskIn in;
@@ -941,14 +964,14 @@ __global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeA
                 const bool selfie = P.self && !P.comp && ar == br;                       // align.c:1949
                 in.minp = (selfie && in.diag >= 0) ? 1 : -IMAX;                          // align.c:1951-1968
                 in.maxp = (selfie && in.diag <= 0) ? -1 : IMAX;
-                in.TS = P.TS; in.path_ave = P.ave_path; in.score_tab = P.score_tab; in.table_tab = P.table_tab;
+                in.TS = P.TS; in.path_ave = P.ave_path;
                 wc::setup(L, in, F, pool);
             }
         }
         if (__all_sync(FULL, L.status == wc::ST_EXIT)) break;
         if (L.status == wc::ST_RUN) {
             if (L.k < L.low) wc::transition<RING>(L, F);
-            if (L.status == wc::ST_RUN && L.k >= L.low) wc::cell(L, F, pool);
+            if (L.status == wc::ST_RUN && L.k >= L.low) wc::cellsN<NWAY>(L, F, tabs, pool);
         }
     }
     if (cells_done) atomicAdd(&P.stats[2], cells_done);
@@ -1060,7 +1083,7 @@ __global__ void __launch_bounds__(256) finish_las(PipeArgs Q) {
 // New_Align_Spec + set_table (align.c:226-318): floating point only here, evaluated exactly as the
 // reference does (float sum of freq[0]+freq[3], double afterwards).
 double Bias_Factor[10] = {.690, .690, .690, .690, .780, .850, .900, .933, .966, 1.000};
-void build_trim_tables(const damar_options &opt, int &ave_path, std::vector<int16_t> &score, std::vector<int16_t> &table) {
+void build_trim_tables(const damar_options &opt, int &ave_path, int &dscore_out, std::vector<int16_t> &score, std::vector<int16_t> &table) {
     double match = opt.freq[0] + opt.freq[3];
     if (match > .5) match = 1. - match;
     int bias = (int)((match + .025) * 20. - 1.);
@@ -1071,6 +1094,7 @@ void build_trim_tables(const damar_options &opt, int &ave_path, std::vector<int1
     ave_path = (int)(PATH_LEN * (1. - Bias_Factor[bias] * (1. - opt.ave_corr)));
     const int mscore = (int)(FRACTION * Bias_Factor[bias] * (1. - opt.ave_corr));
     const int dscore = FRACTION - mscore;
+    dscore_out = dscore;
     score.resize(TRIM_MASK + 1); table.resize(TRIM_MASK + 1);
     for (int x = 0; x <= TRIM_MASK; x++) {
         int s = 0, mx = 0;
@@ -1118,10 +1142,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     if (nwork == 0) { c.tm.pairs_ms = t_pairs.stop(); delete hp1; return; }
 
     // ---- common arguments ----
-    int ave_path; std::vector<int16_t> hs, ht;
-    build_trim_tables(c.opt, ave_path, hs, ht);
-    DevBuf<int16_t> dscore, dtable; dscore.reserve(hs.size()); dtable.reserve(ht.size());
-    CUDA_CHECK(cudaMemcpyAsync(dscore.p, hs.data(), hs.size() * 2, cudaMemcpyHostToDevice, st));
+    int ave_path, dscore; std::vector<int16_t> hs, ht;
+    build_trim_tables(c.opt, ave_path, dscore, hs, ht);
+    DevBuf<int16_t> dscoret, dtable; dscoret.reserve(hs.size()); dtable.reserve(ht.size());
+    CUDA_CHECK(cudaMemcpyAsync(dscoret.p, hs.data(), hs.size() * 2, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(dtable.p, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice, st));
 
     const int TS = c.opt.trace_spacing;
@@ -1159,7 +1183,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
     P.K = fp.kmer; P.W = fp.binshift; P.H = fp.hitmin; P.minhit = minhit; P.TS = TS; P.minover = c.opt.minover;
     P.comp = comp ? 1 : 0; P.self = self; P.symmetric = c.opt.symmetric;
-    P.ave_path = ave_path; P.score_tab = dscore.p; P.table_tab = dtable.p;
+    P.ave_path = ave_path; P.dscore = dscore; P.score_tab = dscoret.p; P.table_tab = dtable.p;
     P.tbuf = tbuf.p; P.maxtp = maxtp;
     P.bscore = bscore.p; P.nbuck = nbuck; P.dmin = dmin;
     P.tbytes = tbytes; P.stats = counters.p;
@@ -1194,6 +1218,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     Q.ct.pair = ct_pair.p; Q.ct.hidx = ct_hidx.p; Q.ct.res = ct_res.p;
     Q.ct.ar = ct_i32.p; Q.ct.br = ct_i32.p + na; Q.ct.apos = ct_i32.p + 2 * na; Q.ct.bpos = ct_i32.p + 3 * na;
     Q.wide_list = wide_list.p;
+    DevBuf<uint64_t> okeys; DevBuf<uint32_t> ovals;
+    okeys.reserve(4 * na); ovals.reserve(4 * na);
+    static const int nway = getenv("DAMAR_NWAY") ? atoi(getenv("DAMAR_NWAY")) : 4;
+    static const bool lpt = !(getenv("DAMAR_LPT") && atoi(getenv("DAMAR_LPT")) == 0);
 
     // pebble pool: measured need is ~300 cells per alignment on 10 kbp reads; a dry pool only delays alignments a round
     size_t pool_cells = (size_t)nactive * (size_t)(2 * (maxlen / TS + 2) + 512) + (1u << 16);
@@ -1203,8 +1231,9 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
 
     static bool attr = false;
     if (!attr) {
-        set_smem(wave_tasks<32, false>, WaveCfg<32>::SMEM);
-        set_smem(wave_tasks<64, true>, WaveCfg<64>::SMEM);
+        set_smem(wave_tasks<32, false, 2>, WaveCfg<32>::SMEM);
+        set_smem(wave_tasks<32, false, 4>, WaveCfg<32>::SMEM);
+        set_smem(wave_tasks<64, true, 4>, WaveCfg<64>::SMEM);
         attr = true;
     }
 
@@ -1242,7 +1271,17 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             {
                 const unsigned per = WaveCfg<32>::WARPS * 32;
                 const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (2 * ncand + per - 1) / per);
-                wave_tasks<32, false><<<wb, per, WaveCfg<32>::SMEM, st>>>(Q);
+                Q.task_order = nullptr;
+                if (ncand >= 2048 && lpt) {                      // order the queue: longest passes first
+                    const int64_t nt = 2 * (int64_t)ncand;
+                    uint64_t *k0 = okeys.p, *k1 = okeys.p + 2 * na; uint32_t *v0 = ovals.p, *v1 = ovals.p + 2 * na;
+                    task_length_keys<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(Q, (unsigned)nt, k0, v0);
+                    KERNEL_CHECK(); count_launch();
+                    radix_sort_pairs(k0, v0, k1, v1, nt, 24, st);
+                    Q.task_order = v0;
+                }
+                if (nway == 2) wave_tasks<32, false, 2><<<wb, per, WaveCfg<32>::SMEM, st>>>(Q);
+                else wave_tasks<32, false, 4><<<wb, per, WaveCfg<32>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             unsigned int nwide = 0;
@@ -1251,7 +1290,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             if (nwide > 0) {
                 const unsigned per = WaveCfg<64>::WARPS * 32;
                 const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (nwide + per - 1) / per);
-                wave_tasks<64, true><<<wb, per, WaveCfg<64>::SMEM, st>>>(Q);
+                wave_tasks<64, true, 4><<<wb, per, WaveCfg<64>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;

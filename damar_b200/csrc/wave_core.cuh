@@ -21,9 +21,6 @@
 // CPU against the oracle (test infrastructure); the product only ever calls it from kernels.
 #pragma once
 #include <cstdint>
-#ifdef WC_DEBUG
-#include <cstdio>
-#endif
 
 #if defined(__CUDACC__)
 #define WC_HD __host__ __device__ __forceinline__
@@ -109,24 +106,63 @@ WC_HD uint64_t push_matches(uint64_t b, int n) {
 // ---- pebble cell (align.c:399-405): {prev, diag, diff, mark}, original coordinates ----------------
 struct Cell { int32_t prev, diag, diff, mark; };
 
-// chunked bump allocation from the global pool
-struct CellPool {
-    Cell *cells;
-    unsigned int *top;          // next free cell (device: atomic)
-    unsigned int cap;
-};
-
 // ---- per-thread view of its wave-front ring ------------------------------------------------------
 // word arrays: V (furthest anti-diagonal), T lo/hi (match history), HA, HB (chain heads, pool index),
 // HMN (TP index+1 of the heads' marks, A low 16 | B high 16), NAB (next TP index+1 to cross, A | B)
+enum { F_V = 0, F_TLO = 1, F_THI = 2, F_HA = 3, F_HB = 4, F_HMN = 5, F_NAB = 6, FRONT_WORDS = 7 };
 template <int RING, int STRIDE>
 struct Front {
     uint32_t *base;
-    WC_HD uint32_t &at(int arr, int k) const { return base[(arr * RING + (k & (RING - 1))) * STRIDE]; }
-    WC_HD int32_t getV(int k) const { return (int32_t)at(0, k); }
-    WC_HD void setV(int k, int32_t v) const { at(0, k) = (uint32_t)v; }
+    static constexpr int ARR = RING * STRIDE;                   // words between two arrays of one slot
+    WC_HD uint32_t *slot(int k) const { return base + (k & (RING - 1)) * STRIDE; }
 };
-constexpr int FRONT_WORDS = 7;
+
+struct PathState { uint64_t T; uint32_t ha, hb, hmn; };
+template <class FRONT> WC_HD PathState load_path(const uint32_t *s) {
+    PathState p;
+    p.T = (uint64_t)s[F_TLO * FRONT::ARR] | ((uint64_t)s[F_THI * FRONT::ARR] << 32);
+    p.ha = s[F_HA * FRONT::ARR]; p.hb = s[F_HB * FRONT::ARR]; p.hmn = s[F_HMN * FRONT::ARR];
+    return p;
+}
+
+// ---- the trim test tables (align.c:286-318) in 768 bytes ------------------------------------------
+// TABLE[x] (x = 15 match bits, oldest first) is the minimum score over the non-empty suffixes of x and
+// SCORE[x] its total, with +mscore per match and -dscore per difference, mscore + dscore = 1000.  A suffix
+// of x either lies inside the newest 7 bits or is all of them plus a suffix of the older 8, hence
+//   TABLE[x] = min(T7[x & 127], S7(x & 127) + T8[x >> 7]),   S(x) = 1000 * popcount(x) - dscore * bits.
+struct TrimTabs { const int16_t *t7, *t8; int dscore; };
+WC_HD int min_suffix_score(int x, int bits, int dscore) {
+    int best = IMAX;
+    for (int j = 1; j <= bits; j++) {
+        const int ones = popc64((uint64_t)(x & ((1 << j) - 1)));
+        const int v = 1000 * ones - dscore * j;
+        if (v < best) best = v;
+    }
+    return best;
+}
+WC_HD int table15(const TrimTabs &t, int x) {
+    const int a0 = x & 127, a1 = x >> 7;
+    const int u = t.t7[a0], v = t.t8[a1] + 1000 * popc64((uint64_t)a0) - 7 * t.dscore;
+    return u < v ? u : v;
+}
+WC_HD int score15(const TrimTabs &t, int x) { return 1000 * popc64((uint64_t)x) - 15 * t.dscore; }
+// the trim test of align.c:922-925:  TABLE[lo15] >= 0 && TABLE[hi15] + SCORE[lo15] >= 0  for the newest 30 bits of b,
+// i.e. no suffix of the 30-bit window scores below zero; the window is walked in chunks of 7, 8, 7, 8 bits
+WC_HD bool trim_ok(const TrimTabs &t, uint64_t b) {
+    const uint32_t w = (uint32_t)b & 0x3fffffffu;
+    const int a0 = (int)(w & 127u), a1 = (int)((w >> 7) & 255u), a2 = (int)((w >> 15) & 127u), a3 = (int)(w >> 22);
+    const int s0 = 1000 * popc64((uint64_t)a0) - 7 * t.dscore;                    // score of the newest 7
+    const int s1 = 1000 * popc64((uint64_t)(w & 0x7fffu)) - 15 * t.dscore;        // ... newest 15
+    const int s2 = 1000 * popc64((uint64_t)(w & 0x3fffffu)) - 22 * t.dscore;      // ... newest 22
+    int m = t.t7[a0];
+    const int m1 = s0 + t.t8[a1], m2 = s1 + t.t7[a2], m3 = s1 + (1000 * popc64((uint64_t)a2) - 7 * t.dscore) + t.t8[a3];
+    (void)s2;
+    // TABLE[lo15] = min(m, m1); TABLE[hi15] + SCORE[lo15] = min(m2, m3)
+    if (m1 < m) m = m1;
+    if (m2 < m) m = m2;
+    if (m3 < m) m = m3;
+    return m >= 0;
+}
 
 // ---- one task -----------------------------------------------------------------------------------
 struct TaskIn {
@@ -138,7 +174,6 @@ struct TaskIn {
     int minp, maxp;                 // original coordinates (align.c:1951-1968)
     int rev;                        // 0 = forward pass, 1 = reverse pass
     int TS, path_ave;
-    const int16_t *score_tab, *table_tab;
 };
 struct TaskOut {                    // original coordinates
     int32_t ex, ey, ediff;
@@ -153,16 +188,14 @@ struct Lane {
     uint32_t abase, bbase;
     int alen, blen, minp, maxp, TS, path_ave, rev;
     int goffA, goffB;               // trace grid offsets in pass coordinates
-    const int16_t *score_tab, *table_tab;
     // wave state (pass coordinates)
     int low, hgh, k, dif, more, aclip, bclip;
     int besta, besty, lasta, trima, trimy, trimd;
     int morea, morey, mored, morem;
     uint32_t trimha, trimhb, moreha, morehb;
-    // sweep registers: previous-wave values around k
-    int ap, ac, am;                 // V[k+1], V[k], V[k-1] of the previous wave (after the shift at the top of a cell)
-    uint64_t pT, cT;                // T of k+1 / k (previous wave)
-    uint32_t pHA, pHB, pHMN, cHA, cHB, cHMN;
+    // sweep registers: previous-wave values of the diagonals above the cursor
+    int vp, vc;                     // V[k+1], V[k]
+    PathState pp;                   // path state of k+1
     // pebble allocation
     uint32_t cell_next, cell_left;
     int status;
@@ -199,7 +232,6 @@ template <class FRONT, class POOL>
 WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     L.aw = t.aw; L.bw = t.bw; L.abase = t.abase; L.bbase = t.bbase;
     L.alen = t.alen; L.blen = t.blen; L.TS = t.TS; L.path_ave = t.path_ave; L.rev = t.rev;
-    L.score_tab = t.score_tab; L.table_tab = t.table_tab;
     L.cell_left = 0; L.cell_next = 0;
     L.waves = 0; L.cells = 0;
     const int TS = t.TS;
@@ -243,12 +275,24 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     if (naI > 0xfffe || nbI > 0xfffe) { if (L.status == ST_RUN) L.status = ST_RANGE; return; }
     const int c = (y << 1) + k;
     if (c > L.besta) { L.besta = L.trima = L.lasta = c; L.besty = L.trimy = y; L.trimha = ha; L.trimhb = hb; }
-    F.setV(k, c);
-    F.at(1, k) = (uint32_t)PATH_INT; F.at(2, k) = (uint32_t)(PATH_INT >> 32);
-    F.at(3, k) = ha; F.at(4, k) = hb;
-    F.at(5, k) = (uint32_t)(naI - 1) | ((uint32_t)(nbI - 1) << 16);
-    F.at(6, k) = (uint32_t)naI | ((uint32_t)nbI << 16);
+    uint32_t *s = F.slot(k);
+    s[F_V * FRONT::ARR] = (uint32_t)c;
+    s[F_TLO * FRONT::ARR] = (uint32_t)PATH_INT; s[F_THI * FRONT::ARR] = (uint32_t)(PATH_INT >> 32);
+    s[F_HA * FRONT::ARR] = ha; s[F_HB * FRONT::ARR] = hb;
+    s[F_HMN * FRONT::ARR] = (uint32_t)(naI - 1) | ((uint32_t)(nbI - 1) << 16);
+    s[F_NAB * FRONT::ARR] = (uint32_t)naI | ((uint32_t)nbI << 16);
     L.k = k - 1;                                  // wave 0 is complete: next step is a transition
+}
+
+template <class FRONT>
+WC_HD void reach_candidate(Lane &L, const FRONT &F, int kc) {          // align.c:947-974
+    const uint32_t *s = F.slot(kc);
+    const PathState p = load_path<FRONT>(s);
+    const int mc = popc64(p.T & PATH_MASK61);
+    if (L.morem <= mc) {
+        L.morem = mc; L.morea = (int32_t)s[F_V * FRONT::ARR]; L.morey = (L.morea - kc) / 2; L.mored = L.dif;
+        L.moreha = p.ha; L.morehb = p.hb;
+    }
 }
 
 // End of a wave: boundary clipping (align.c:628-658, 943-975), pruning (:977-986), the loop test
@@ -258,115 +302,179 @@ template <int RING, class FRONT>
 WC_HD void transition(Lane &L, const FRONT &F) {
     if (L.more == 0) {
         if (L.besty < L.blen && L.besta - L.besty < L.alen) L.more = 1;
-        if (L.hgh >= L.aclip) {
-            const int kc = L.aclip;
-            L.hgh = kc - 1;
-            const uint64_t tc = (uint64_t)F.at(1, kc) | ((uint64_t)F.at(2, kc) << 32);
-            const int mc = popc64(tc & PATH_MASK61);
-            if (L.morem <= mc) {
-                L.morem = mc; L.morea = F.getV(kc); L.morey = (L.morea - kc) / 2; L.mored = L.dif;
-                L.moreha = F.at(3, kc); L.morehb = F.at(4, kc);
-            }
-        }
-        if (L.low <= L.bclip) {
-            const int kc = L.bclip;
-            L.low = kc + 1;
-            const uint64_t tc = (uint64_t)F.at(1, kc) | ((uint64_t)F.at(2, kc) << 32);
-            const int mc = popc64(tc & PATH_MASK61);
-            if (L.morem <= mc) {
-                L.morem = mc; L.morea = F.getV(kc); L.morey = (L.morea - kc) / 2; L.mored = L.dif;
-                L.moreha = F.at(3, kc); L.morehb = F.at(4, kc);
-            }
-        }
+        if (L.hgh >= L.aclip) { const int kc = L.aclip; L.hgh = kc - 1; reach_candidate(L, F, kc); }
+        if (L.low <= L.bclip) { const int kc = L.bclip; L.low = kc + 1; reach_candidate(L, F, kc); }
         L.aclip = IMAX; L.bclip = -IMAX;
     }
     if (L.dif > 0) {
         const int n = L.besta - WAVE_LAG;
         while (L.hgh >= L.low)
-            if (F.getV(L.hgh) < n) L.hgh -= 1;
-            else { while (F.getV(L.low) < n) L.low += 1; break; }
+            if ((int32_t)F.slot(L.hgh)[F_V * FRONT::ARR] < n) L.hgh -= 1;
+            else { while ((int32_t)F.slot(L.low)[F_V * FRONT::ARR] < n) L.low += 1; break; }
         L.waves += 1;
         if (L.hgh >= L.low) L.cells += (uint32_t)(L.hgh - L.low + 1);
     }
-    if (!(L.more && L.lasta >= L.besta - TRIM_MLAG) || L.hgh < L.low) { L.status = ST_DONE; return; }
     // an empty front (every diagonal ran off a read end) ends the pass; the reference reads stale memory there
+    if (!(L.more && L.lasta >= L.besta - TRIM_MLAG) || L.hgh < L.low) { L.status = ST_DONE; return; }
 
     int low = L.low - 1, hgh = L.hgh + 1;
-#ifdef WC_DEBUG
-    printf("dif %d low %d hgh %d besta %d lasta %d more %d\n", L.dif, L.low, L.hgh, L.besta, L.lasta, L.more);
-#endif
     if (hgh - low + 1 > RING) { L.status = ST_WIDE; return; }
-    if (low >= L.minp) { F.at(6, low) = F.at(6, low + 1); F.setV(low, -1); } else low += 1;
-    if (hgh <= L.maxp) { F.at(6, hgh) = F.at(6, hgh - 1); F.setV(hgh, -1); L.am = -1; } else { hgh -= 1; L.am = F.getV(hgh); }
+    if (low >= L.minp) {
+        uint32_t *s = F.slot(low);
+        s[F_NAB * FRONT::ARR] = F.slot(low + 1)[F_NAB * FRONT::ARR]; s[F_V * FRONT::ARR] = (uint32_t)-1;
+    } else low += 1;
+    if (hgh <= L.maxp) {
+        uint32_t *s = F.slot(hgh);
+        s[F_NAB * FRONT::ARR] = F.slot(hgh - 1)[F_NAB * FRONT::ARR]; s[F_V * FRONT::ARR] = (uint32_t)-1;
+        L.vc = -1;
+    } else { hgh -= 1; L.vc = (int32_t)F.slot(hgh)[F_V * FRONT::ARR]; }
     L.low = low; L.hgh = hgh;
     L.dif += 1;
-    L.ac = -1;
-    L.cT = PATH_INT; L.cHA = L.cHB = NOCELL; L.cHMN = 0;      // becomes the (never chosen) k+1 state of the first cell
+    L.vp = -1;
+    L.pp.T = PATH_INT; L.pp.ha = L.pp.hb = NOCELL; L.pp.hmn = 0;     // the (never chosen) state above hgh
     L.k = hgh;
 }
 
-// One furthest-reaching-point update on diagonal L.k (align.c:789-938).
-template <class FRONT, class POOL>
-WC_HD void cell(Lane &L, const FRONT &F, POOL &pool) {
-    const int k = L.k, TS = L.TS;
-    // shift the sweep window: (ap, ac, am) <- (ac, am, V[k-1]); path state likewise
-    L.ap = L.ac; L.ac = L.am; L.am = (k - 1 >= L.low) ? F.getV(k - 1) : -1;
-    L.pT = L.cT; L.pHA = L.cHA; L.pHB = L.cHB; L.pHMN = L.cHMN;
-    L.cT = (uint64_t)F.at(1, k) | ((uint64_t)F.at(2, k) << 32); L.cHA = F.at(3, k); L.cHB = F.at(4, k); L.cHMN = F.at(5, k);
-    const int ap = L.ap, ac = L.ac, am = L.am;
-    int c; uint64_t b; uint32_t ha, hb, hmn;
-    if (ac < am) {
-        if (am < ap) { c = ap + 1; b = L.pT; ha = L.pHA; hb = L.pHB; hmn = L.pHMN; }
-        else {
-            c = am + 1;
-            b = (uint64_t)F.at(1, k - 1) | ((uint64_t)F.at(2, k - 1) << 32); ha = F.at(3, k - 1); hb = F.at(4, k - 1); hmn = F.at(5, k - 1);
-        }
-    } else if (ac < ap) { c = ap + 1; b = L.pT; ha = L.pHA; hb = L.pHB; hmn = L.pHMN; }
-    else { c = ac + 2; b = L.cT; ha = L.cHA; hb = L.cHB; hmn = L.cHMN; }
-
-    b <<= 1;
-    int y = (c - k) >> 1, x = y + k;
-    {
-        const int ra = L.alen - x, rb = L.blen - y;
-        const int n = slide(L.aw, L.abase + (uint32_t)x, L.bw, L.bbase + (uint32_t)y, ra < rb ? ra : rb);
-        x += n; y += n;
-        b = push_matches(b, n);
+// The three-way furthest-reaching choice (align.c:793-825) with its tie rules.
+WC_HD int choose(int vp, int vc, int vm, int &c) {               // returns +1 / 0 / -1: predecessor diagonal offset
+    if (vc < vm) {
+        if (vm < vp) { c = vp + 1; return 1; }
+        c = vm + 1; return -1;
     }
+    if (vc < vp) { c = vp + 1; return 1; }
+    c = vc + 2; return 0;
+}
+
+// Everything of one cell after the predecessor has been chosen and the slide measured (align.c:836-928):
+// clip bookkeeping, pebbles, best / lasta / trim, and the store of the new front entry.
+template <class FRONT, class POOL>
+WC_HD void settle(Lane &L, const TrimTabs &tabs, POOL &pool, uint32_t *s, int k, int c0, int n, PathState p) {
+    const int TS = L.TS;
+    uint64_t b = push_matches(p.T << 1, n);
+    const int y = ((c0 - k) >> 1) + n, x = y + k;
     if (y == L.blen) { L.more = 0; if (L.bclip < k) L.bclip = k; }
     else if (x == L.alen) { L.more = 0; L.aclip = k; }
-    c = (y << 1) + k;
-    const int m = popc64(b & PATH_MASK61);
-
-    const uint32_t nab = F.at(6, k);
+    const int c = (y << 1) + k;
+    const uint32_t nab = s[F_NAB * FRONT::ARR];
     int naI = (int)(nab & 0xffffu), nbI = (int)(nab >> 16);
-    int hmI = (int)(hmn & 0xffffu), hnI = (int)(hmn >> 16);
+    int hmI = (int)(p.hmn & 0xffffu), hnI = (int)(p.hmn >> 16);
     if (x >= grid(L.goffA, naI, TS) || y >= grid(L.goffB, nbI, TS)) {      // align.c:859-909
         while (x >= grid(L.goffA, naI, TS)) {
-            if (hmI < naI) { ha = push_cell(L, pool, ha, k, L.dif, grid(L.goffA, naI, TS), true); hmI = naI; }
+            if (hmI < naI) { p.ha = push_cell(L, pool, p.ha, k, L.dif, grid(L.goffA, naI, TS), true); hmI = naI; }
             naI++;
         }
         while (y >= grid(L.goffB, nbI, TS)) {
-            if (hnI < nbI) { hb = push_cell(L, pool, hb, k, L.dif, grid(L.goffB, nbI, TS), false); hnI = nbI; }
+            if (hnI < nbI) { p.hb = push_cell(L, pool, p.hb, k, L.dif, grid(L.goffB, nbI, TS), false); hnI = nbI; }
             nbI++;
         }
         if (naI > 0xfffe || nbI > 0xfffe) { if (L.status == ST_RUN) L.status = ST_RANGE; }
     }
     if (c > L.besta) {                                                       // align.c:911-928
         L.besta = c; L.besty = y;
-        if (m >= L.path_ave) {
+        if (popc64(b & PATH_MASK61) >= L.path_ave) {
             L.lasta = c;
-            const int lo15 = (int)(b & TRIM_MASK), hi15 = (int)((b >> TRIM_LEN) & TRIM_MASK);
-            if (ldg16(L.table_tab + lo15) >= 0 && ldg16(L.table_tab + hi15) + ldg16(L.score_tab + lo15) >= 0) {
-                L.trima = c; L.trimy = y; L.trimd = L.dif; L.trimha = ha; L.trimhb = hb;
+            if (trim_ok(tabs, b)) {
+                L.trima = c; L.trimy = y; L.trimd = L.dif; L.trimha = p.ha; L.trimhb = p.hb;
             }
         }
     }
-    F.setV(k, c);
-    F.at(1, k) = (uint32_t)b; F.at(2, k) = (uint32_t)(b >> 32);
-    F.at(3, k) = ha; F.at(4, k) = hb;
-    F.at(5, k) = (uint32_t)hmI | ((uint32_t)hnI << 16);
-    F.at(6, k) = (uint32_t)naI | ((uint32_t)nbI << 16);
-    L.k = k - 1;
+    s[F_V * FRONT::ARR] = (uint32_t)c;
+    s[F_TLO * FRONT::ARR] = (uint32_t)b; s[F_THI * FRONT::ARR] = (uint32_t)(b >> 32);
+    s[F_HA * FRONT::ARR] = p.ha; s[F_HB * FRONT::ARR] = p.hb;
+    s[F_HMN * FRONT::ARR] = (uint32_t)hmI | ((uint32_t)hnI << 16);
+    s[F_NAB * FRONT::ARR] = (uint32_t)naI | ((uint32_t)nbI << 16);
+}
+
+// first probe of a slide: equal bases in the first 32-base window (32 = all equal)
+WC_HD int probe32(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by) {
+    const uint64_t d = window_at(aw, ax) ^ window_at(bw, by);
+    return d ? (clz64(d) >> 1) : 32;
+}
+
+// Two furthest-reaching-point updates per call, on diagonals L.k and L.k - 1 (align.c:789-938).  All cells of a
+// wave read only the previous wave, so the two predecessor choices and the two slides are independent
+// instruction streams (this is where a thread finds its instruction-level parallelism); the bookkeeping that
+// the reference does in visiting order (clips, best, trim) is then applied to k first, k - 1 second.
+template <class FRONT, class POOL>
+WC_HD void cells2(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
+    const int k0 = L.k, k1 = k0 - 1;
+    const bool two = k1 >= L.low;
+    uint32_t *s0 = F.slot(k0), *s1 = F.slot(two ? k1 : k0), *s2 = F.slot((two && k1 - 1 >= L.low) ? k1 - 1 : k0);
+    // previous-wave values (nothing below k0 + 1 has been overwritten yet)
+    const int vm0 = two ? (int32_t)s1[F_V * FRONT::ARR] : -1;                       // V[k0 - 1]
+    const int vm1 = (two && k1 - 1 >= L.low) ? (int32_t)s2[F_V * FRONT::ARR] : -1;  // V[k0 - 2]
+    const PathState pc = load_path<FRONT>(s0), pm = load_path<FRONT>(s1);
+    int c0, c1;
+    const int d0 = choose(L.vp, L.vc, vm0, c0);
+    const int d1 = choose(L.vc, vm0, vm1, c1);
+    PathState q0 = (d0 > 0) ? L.pp : (d0 == 0 ? pc : pm);
+    PathState q1 = (d1 > 0) ? pc : pm;
+    if (two && d1 < 0) q1 = load_path<FRONT>(s2);
+    // slides
+    const int y0 = (c0 - k0) >> 1, x0 = y0 + k0;
+    const int y1 = two ? ((c1 - k1) >> 1) : y0, x1 = two ? (y1 + k1) : x0;
+    const int max0 = (L.alen - x0 < L.blen - y0) ? L.alen - x0 : L.blen - y0;
+    const int max1 = (L.alen - x1 < L.blen - y1) ? L.alen - x1 : L.blen - y1;
+    int n0 = probe32(L.aw, L.abase + (uint32_t)x0, L.bw, L.bbase + (uint32_t)y0);
+    int n1 = probe32(L.aw, L.abase + (uint32_t)x1, L.bw, L.bbase + (uint32_t)y1);
+    if (n0 == 32 && max0 > 32) n0 = 32 + slide(L.aw, L.abase + (uint32_t)(x0 + 32), L.bw, L.bbase + (uint32_t)(y0 + 32), max0 - 32);
+    if (n1 == 32 && max1 > 32) n1 = 32 + slide(L.aw, L.abase + (uint32_t)(x1 + 32), L.bw, L.bbase + (uint32_t)(y1 + 32), max1 - 32);
+    if (n0 > max0) n0 = max0;
+    if (n1 > max1) n1 = max1;
+    // bookkeeping in visiting order
+    settle<FRONT>(L, tabs, pool, s0, k0, c0, n0, q0);
+    if (two) settle<FRONT>(L, tabs, pool, s1, k1, c1, n1, q1);
+    L.vp = vm0; L.vc = vm1; L.pp = pm;
+    L.k = two ? k1 - 1 : k1;
+}
+
+// N furthest-reaching-point updates per call, on diagonals L.k, L.k - 1, ... (the generalisation of cells2 the
+// kernels use: with a few warps per SM the instruction-level parallelism of a thread is what hides latency).
+template <int N, class FRONT, class POOL>
+WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
+    const int k0 = L.k;
+    const int cnt = (k0 - L.low + 1 < N) ? (k0 - L.low + 1) : N;      // cells handled by this call (>= 1)
+    // slot j holds diagonal k0 - j; slots beyond the front alias slot 0 and are never used
+    uint32_t *s[N + 1];
+    int v[N + 2];                                                       // v[j + 1] = V[k0 - j] of the previous wave, v[0] = V[k0 + 1]
+    PathState P[N + 2];                                                 // likewise
+    v[0] = L.vp; v[1] = L.vc; P[0] = L.pp;
+#pragma unroll
+    for (int j = 0; j <= N; j++) {
+        const bool in = (k0 - j >= L.low) && (j <= cnt);
+        s[j] = F.slot(in ? k0 - j : k0);
+        if (j >= 1) v[j + 1] = in ? (int32_t)s[j][F_V * FRONT::ARR] : -1;
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) P[j + 1] = load_path<FRONT>(s[j]);
+    P[N + 1] = P[N];                                                    // loaded below only if it is chosen
+    int c[N], n[N], mx[N];
+    PathState q[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const int d = choose(v[j], v[j + 1], v[j + 2], c[j]);
+        q[j] = (d > 0) ? P[j] : (d == 0 ? P[j + 1] : P[j + 2]);
+        if (j == N - 1 && j < cnt && d < 0) q[j] = load_path<FRONT>(s[N]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const int jj = (j < cnt) ? j : 0;
+        const int kk = k0 - jj, y = ((j < cnt ? c[j] : c[0]) - kk) >> 1, x = y + kk;
+        mx[j] = (L.alen - x < L.blen - y) ? L.alen - x : L.blen - y;
+        n[j] = probe32(L.aw, L.abase + (uint32_t)x, L.bw, L.bbase + (uint32_t)y);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if (j < cnt) {
+            const int kk = k0 - j, y = (c[j] - kk) >> 1, x = y + kk;
+            if (n[j] == 32 && mx[j] > 32) n[j] = 32 + slide(L.aw, L.abase + (uint32_t)(x + 32), L.bw, L.bbase + (uint32_t)(y + 32), mx[j] - 32);
+            if (n[j] > mx[j]) n[j] = mx[j];
+            settle<FRONT>(L, tabs, pool, s[j], kk, c[j], n[j], q[j]);
+        }
+    }
+    // carry the previous-wave values of the diagonal just above the next cursor
+    L.vp = v[N]; L.vc = v[N + 1]; L.pp = P[N];
+    L.k = k0 - cnt;
 }
 
 // end point of the pass in original coordinates (REACH = 1, daligner.c:951; align.c:1001-1012)

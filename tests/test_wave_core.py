@@ -23,8 +23,10 @@ def _lib():
     L = C.CDLL(SO)
     L.wc_local_alignment.restype = C.c_int
     L.wc_local_alignment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.wc_check_trim_tables.restype = C.c_int
+    L.wc_check_trim_tables.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -50,7 +52,7 @@ def trim_tables(ave_corr, freq=(.25, .25, .25, .25)):
             s += mscore if (x >> bit) & 1 else -dscore
         table[x] = s - mx
         score[x] = s
-    return ave_path, score, table
+    return ave_path, score, table, dscore
 
 
 def mutate(rng, s, e):
@@ -71,7 +73,7 @@ def mutate(rng, s, e):
 
 
 def run_both(L, a, b, comp, selfie, diag, anti, ts, ave_corr, tabs, ring=32):
-    ave_path, score, table = tabs
+    ave_path, score, table, dscore = tabs
     alen, blen = len(a), len(b)
     abuf = np.concatenate([[4], a, [4]]).astype(np.int8)
     bbuf = abuf if selfie else np.concatenate([[4], b, [4]]).astype(np.int8)
@@ -86,7 +88,7 @@ def run_both(L, a, b, comp, selfie, diag, anti, ts, ave_corr, tabs, ring=32):
     stats = np.zeros(4, np.int32)
     a8, b8 = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
     st = L.wc_local_alignment(a8.ctypes.data, alen, b8.ctypes.data, blen, comp, selfie, diag, anti, ts, ave_path,
-                              score.ctypes.data, table.ctypes.data, ring, wa.ctypes.data, wta.ctypes.data, wb.ctypes.data,
+                              dscore, ring, wa.ctypes.data, wta.ctypes.data, wb.ctypes.data,
                               wtb.ctypes.data, stats.ctypes.data)
     return st, (oa, ota[:oa[5]], ob, otb[:ob[5]]), (wa, wta[:wa[5]], wb, wtb[:wb[5]])
 
@@ -100,8 +102,16 @@ def lib():
     return _lib()
 
 
+@pytest.mark.parametrize("ave_corr", [.65, .70, .75, .85, .95])
+def test_small_trim_tables_equal_the_reference_tables(lib, ave_corr):
+    ave_path, score, table, dscore = trim_tables(ave_corr)
+    assert lib.wc_check_trim_tables(dscore, score.ctypes.data, table.ctypes.data) == 0
+
+
+@pytest.mark.parametrize("nway", [2, 3, 4])
 @pytest.mark.parametrize("ts,ave_corr,err", [(100, .70, .12), (100, .70, .06), (126, .75, .10), (50, .70, .12), (100, .65, .15), (100, .95, .004)])
-def test_wave_core_matches_oracle_on_overlaps(lib, ts, ave_corr, err):
+def test_wave_core_matches_oracle_on_overlaps(lib, ts, ave_corr, err, nway):
+    lib.wc_set_nway(nway)
     rng = np.random.default_rng(1234 + ts + int(err * 1000))
     tabs = trim_tables(ave_corr)
     G = rng.integers(0, 4, 40000).astype(np.uint8)
@@ -139,6 +149,7 @@ def test_wave_core_matches_oracle_on_overlaps(lib, ts, ave_corr, err):
 
 def test_wave_core_self_alignment(lib):
     """A read against itself off the main diagonal (align.c:1949-1968: the wave may not cross diagonal 0)."""
+    lib.wc_set_nway(4)
     rng = np.random.default_rng(99)
     tabs = trim_tables(.70)
     done = 0
@@ -166,6 +177,7 @@ def test_wave_core_self_alignment(lib):
 
 def test_wave_core_read_ends_and_short_reads(lib):
     """Seeds at the very ends, tiny reads, reads shorter than a trace spacing."""
+    lib.wc_set_nway(4)
     rng = np.random.default_rng(7)
     tabs = trim_tables(.70)
     done = 0

@@ -24,8 +24,20 @@ std::vector<uint32_t> pack(const std::vector<uint8_t> &s) {
     return w;
 }
 
+struct HostTabs {
+    int16_t t7[128], t8[256];
+    TrimTabs tabs;
+    explicit HostTabs(int dscore) {
+        for (int x = 0; x < 128; x++) t7[x] = (int16_t)min_suffix_score(x, 7, dscore);
+        for (int x = 0; x < 256; x++) t8[x] = (int16_t)min_suffix_score(x, 8, dscore);
+        tabs = TrimTabs{t7, t8, dscore};
+    }
+};
+
+int g_nway = 2;
+
 template <int RING>
-int run_pass(const TaskIn &t, HostPool &pool, TaskOut &out) {
+int run_pass(const TaskIn &t, const TrimTabs &tabs, HostPool &pool, TaskOut &out) {
     uint32_t store[FRONT_WORDS * RING];
     memset(store, 0xee, sizeof(store));
     Front<RING, 1> F{store};
@@ -33,7 +45,11 @@ int run_pass(const TaskIn &t, HostPool &pool, TaskOut &out) {
     setup(L, t, F, pool);
     while (L.status == ST_RUN) {
         if (L.k < L.low) transition<RING>(L, F);
-        if (L.status == ST_RUN && L.k >= L.low) cell(L, F, pool);
+        if (L.status == ST_RUN && L.k >= L.low) {
+            if (g_nway == 2) cells2(L, F, tabs, pool);
+            else if (g_nway == 4) cellsN<4>(L, F, tabs, pool);
+            else cellsN<3>(L, F, tabs, pool);
+        }
     }
     finish(L, out);
     return L.status;
@@ -43,11 +59,29 @@ int run_pass(const TaskIn &t, HostPool &pool, TaskOut &out) {
 
 extern "C" {
 
+// the 768-byte decomposition of the trim tables against the full 2 x 32768 tables of align.c:286-318
+int wc_check_trim_tables(int dscore, const int16_t *score_tab, const int16_t *table_tab) {
+    HostTabs ht(dscore);
+    int bad = 0;
+    for (int x = 0; x < 32768; x++)
+        if (table15(ht.tabs, x) != table_tab[x] || score15(ht.tabs, x) != score_tab[x]) bad++;
+    // the fused 30-bit test on a pseudo-random sample of windows (plus garbage above bit 29)
+    uint64_t r = 88172645463325252ull;
+    for (int i = 0; i < 2000000; i++) {
+        r ^= r << 13; r ^= r >> 7; r ^= r << 17;
+        const int lo = (int)(r & 0x7fff), hi = (int)((r >> 15) & 0x7fff);
+        const bool want = table_tab[lo] >= 0 && table_tab[hi] + score_tab[lo] >= 0;
+        if (trim_ok(ht.tabs, r) != want) bad++;
+    }
+    return bad;
+}
+void wc_set_nway(int n) { g_nway = n; }
+
 // Local_Alignment for daligner's call shape on unpacked sequences (values 0..3).  `bseq` is the B read in the
 // orientation that is aligned (already complemented when comp).  Returns 0, or the failing pass status.
 // aout/bout = {abpos, bbpos, aepos, bepos, diffs, tlen}; traces are written from index 0.
 int wc_local_alignment(const uint8_t *aseq, int alen, const uint8_t *bseq, int blen, int comp, int selfie, int diag, int anti,
-                       int TS, int path_ave, const int16_t *score_tab, const int16_t *table_tab, int ring,
+                       int TS, int path_ave, int dscore, int ring,
                        int32_t *aout, uint16_t *atrace, int32_t *bout, uint16_t *btrace, int32_t *stats) {
     std::vector<uint8_t> a(aseq, aseq + alen), b(bseq, bseq + blen), arc(alen), brc(blen);
     for (int i = 0; i < alen; i++) arc[i] = 3 - a[alen - 1 - i];
@@ -66,15 +100,16 @@ int wc_local_alignment(const uint8_t *aseq, int alen, const uint8_t *bseq, int b
     t.abase = abase; t.bbase = bbase; t.alen = alen; t.blen = blen; t.diag = diag; t.anti = anti;
     t.aoff = 0; t.boff = comp ? blen % TS : 0;
     t.minp = (selfie && diag >= 0) ? 1 : -IMAX; t.maxp = (selfie && diag <= 0) ? -1 : IMAX;
-    t.TS = TS; t.path_ave = path_ave; t.score_tab = score_tab; t.table_tab = table_tab;
+    t.TS = TS; t.path_ave = path_ave;
+    HostTabs ht(dscore);
 
     HostPool pool;
     TaskOut fo{}, ro{};
     t.rev = 0; t.aw = aw.data(); t.bw = bw.data();
-    int st = (ring == 64) ? run_pass<64>(t, pool, fo) : run_pass<32>(t, pool, fo);
+    int st = (ring == 64) ? run_pass<64>(t, ht.tabs, pool, fo) : run_pass<32>(t, ht.tabs, pool, fo);
     if (st != ST_DONE) return st;
     t.rev = 1; t.aw = awr.data(); t.bw = bwr.data();
-    st = (ring == 64) ? run_pass<64>(t, pool, ro) : run_pass<32>(t, pool, ro);
+    st = (ring == 64) ? run_pass<64>(t, ht.tabs, pool, ro) : run_pass<32>(t, ht.tabs, pool, ro);
     if (st != ST_DONE) return st + 100;
     if (stats) { stats[0] = fo.waves + ro.waves; stats[1] = fo.cells + ro.cells; stats[2] = (int32_t)pool.cells.size(); }
 
