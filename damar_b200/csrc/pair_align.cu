@@ -692,6 +692,7 @@ struct PipeArgs {
     uint32_t *flag;                       // filter_pairs: per work pair
     unsigned int *ctr;                    // device counters, see CTR_*
     uint32_t *wide_list;
+    wc::Lane *wide_lane; uint32_t *wide_ring;   // state of the passes that outgrew the 32-diagonal ring: [task][32][FRONT_WORDS]
     const uint32_t *task_order;           // tasks of the round, longest expected pass first (or null: index order)
     wc::Cell *pool; unsigned int pool_cap;
 };
@@ -939,8 +940,18 @@ __global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeA
                 wc::TaskOut o;
                 wc::finish(L, o);
                 Q.ct.res[task] = o;
-                cells_done += o.cells;
-                if (!WIDE && L.status == wc::ST_WIDE) Q.wide_list[atomicAdd(&Q.ctr[CTR_NWIDE], 1u)] = task;
+                if (WIDE || L.status != wc::ST_WIDE) cells_done += o.cells;
+                if (!WIDE && L.status == wc::ST_WIDE) {         // park the pass: the 64-diagonal kernel resumes it where it stands
+                    const unsigned w = atomicAdd(&Q.ctr[CTR_NWIDE], 1u);
+                    Q.wide_list[w] = task;
+                    Q.wide_lane[w] = L;
+                    uint32_t *dst = Q.wide_ring + (size_t)w * 32 * wc::FRONT_WORDS;
+                    for (int k = L.low; k <= L.hgh; k++) {
+                        const uint32_t *sl = F.slot(k);
+#pragma unroll
+                        for (int a = 0; a < wc::FRONT_WORDS; a++) dst[(k - L.low) * wc::FRONT_WORDS + a] = sl[a * wc::Front<RING, 32>::ARR];
+                    }
+                }
             }
             // fetch the next task (one atomic per warp-wide batch of idle lanes)
             const unsigned idle = __activemask();
@@ -950,8 +961,20 @@ __global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeA
             base = __shfl_sync(idle, base, leader);
             const unsigned t = base + __popc(idle & ((1u << lane) - 1u));
             if (t >= ntasks) L.status = wc::ST_EXIT;
-            else {
-                task = WIDE ? Q.wide_list[t] : (Q.task_order ? Q.task_order[t] : t);
+            else if (WIDE) {                                  // resume a parked pass at its wave boundary
+                task = Q.wide_list[t];
+                L = Q.wide_lane[t];
+                const uint32_t *src = Q.wide_ring + (size_t)t * 32 * wc::FRONT_WORDS;
+                for (int k = L.low; k <= L.hgh; k++) {
+                    uint32_t *sl = F.slot(k);
+#pragma unroll
+                    for (int a = 0; a < wc::FRONT_WORDS; a++) sl[a * wc::Front<RING, 32>::ARR] = src[(k - L.low) * wc::FRONT_WORDS + a];
+                }
+                // transition() runs again from the top: clipping and pruning are idempotent, only its counters are not
+                L.waves -= 1; L.cells -= (uint32_t)(L.hgh - L.low + 1);
+                L.k = L.low - 1; L.status = wc::ST_RUN;
+            } else {
+                task = Q.task_order ? Q.task_order[t] : t;
                 const unsigned slot = task >> 1;
                 const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
                 wc::TaskIn in;
@@ -1218,6 +1241,9 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     Q.ct.pair = ct_pair.p; Q.ct.hidx = ct_hidx.p; Q.ct.res = ct_res.p;
     Q.ct.ar = ct_i32.p; Q.ct.br = ct_i32.p + na; Q.ct.apos = ct_i32.p + 2 * na; Q.ct.bpos = ct_i32.p + 3 * na;
     Q.wide_list = wide_list.p;
+    DevBuf<wc::Lane> wide_lane; DevBuf<uint32_t> wide_ring;
+    wide_lane.reserve(2 * na); wide_ring.reserve(2 * na * 32 * wc::FRONT_WORDS);
+    Q.wide_lane = wide_lane.p; Q.wide_ring = wide_ring.p;
     DevBuf<uint64_t> okeys; DevBuf<uint32_t> ovals;
     okeys.reserve(4 * na); ovals.reserve(4 * na);
     static const int nway = getenv("DAMAR_NWAY") ? atoi(getenv("DAMAR_NWAY")) : 4;
