@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -70,7 +72,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
-           "damar_dump_profile"]
+           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at"]
 
 _lib = None
 
@@ -105,6 +107,8 @@ def load_library():
     L.damar_sink_free.argtypes = [C.c_void_p]
     L.damar_sink_reset.argtypes = [C.c_void_p]
     L.damar_sink_add.argtypes = [C.c_void_p, C.POINTER(Overlaps)]
+    L.damar_sink_add_at.argtypes = [C.c_void_p, C.POINTER(Overlaps), C.c_int64]
+    L.damar_worker_bind.argtypes = [C.c_int]
     L.damar_sink_count.restype = C.c_int64
     L.damar_sink_count.argtypes = [C.c_void_p]
     L.damar_sink_serialise.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
@@ -284,8 +288,11 @@ class LasSink:
     def __init__(self):
         self.h = load_library().damar_sink_new()
 
-    def add(self, ov: Overlaps):
-        load_library().damar_sink_add(self.h, C.byref(ov))
+    def add(self, ov: Overlaps, ordinal: Optional[int] = None):
+        if ordinal is None:
+            load_library().damar_sink_add(self.h, C.byref(ov))
+        else:
+            load_library().damar_sink_add_at(self.h, C.byref(ov), ordinal)
 
     def reset(self):
         load_library().damar_sink_reset(self.h)
@@ -311,7 +318,35 @@ class LasSink:
             self.h = None
 
 
-_shared_sink = None
+# ---- worker pool: independent comparisons (B block x orientation) in flight at once ----------------
+# Every pool thread binds its own library context (stream, device-memory cache, result slots), so the serial
+# tail of one comparison (a few long wave passes, later lasta rounds) overlaps the bulk kernels of the next and
+# the host-side .las sort/serialisation overlaps GPU work.  DAMAR_WORKERS=1 runs everything on the caller's thread.
+_pool = None
+_pool_lock = threading.Lock()
+_pool_next = [0]
+_free_sinks: List["LasSink"] = []
+
+
+def _bind_worker():
+    L = load_library()
+    with _pool_lock:
+        _pool_next[0] += 1
+        idx = _pool_next[0]
+    if L.damar_worker_bind(idx) != 0:
+        raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
+
+
+def workers() -> int:
+    n = int(os.environ.get("DAMAR_WORKERS", "3"))
+    return max(1, min(n, load_library().damar_worker_count() - 1))
+
+
+def _get_pool():
+    global _pool
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=workers(), thread_name_prefix="damar", initializer=_bind_worker)
+    return _pool
 
 
 def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list] = None,
@@ -336,24 +371,38 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
 
     da = resident(ablk)
     aidx = sort_kmers(da, 0)
-    global _shared_sink
-    if _shared_sink is None:
-        _shared_sink = LasSink()          # kept for the process: its host buffers stay warm between jobs
-    sink = _shared_sink
-    sink.reset()
+    inline = workers() == 1
+
+    def compare(bblk, db, selfcmp, comp, sink, st):
+        """one Match_Filter call (daligner.c:1041 / 1053) on the calling thread's worker context"""
+        bidx = aidx if (selfcmp and comp == 0) else sort_kmers(db, comp)
+        ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
+        sink.add(ov, comp)
+        st[f"nhits{comp}"], st[f"nfilt{comp}"], st[f"novl{comp}"] = ov.nhits, ov.nfilt, ov.novl
+        st[f"multi{comp}"] = ov.multi_la_pairs
+        st[f"t{comp}"] = timings()
+        if bidx is not None and bidx is not aidx:
+            bidx.free()
+
+    jobs = []
     for bblk in bblks:
         selfcmp = bblk.name == ablk.name
         db = da if selfcmp else resident(bblk)
+        sink = _free_sinks.pop() if _free_sinks else LasSink()   # kept for the process: host buffers stay warm
+        sink.reset()
         st = {}
-        for comp in (0, 1):
-            bidx = aidx if (selfcmp and comp == 0) else sort_kmers(db, comp)
-            ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
-            sink.add(ov)
-            st[f"nhits{comp}"], st[f"nfilt{comp}"], st[f"novl{comp}"] = ov.nhits, ov.nfilt, ov.novl
-            st[f"multi{comp}"] = ov.multi_la_pairs
-            st[f"t{comp}"] = timings()
-            if bidx is not None and bidx is not aidx:
-                bidx.free()
+        if inline:
+            futs = None
+            for comp in (0, 1):
+                compare(bblk, db, selfcmp, comp, sink, st)
+        else:
+            futs = [_get_pool().submit(compare, bblk, db, selfcmp, comp, sink, st) for comp in (0, 1)]
+        jobs.append((bblk, selfcmp, sink, st, futs))
+
+    for bblk, selfcmp, sink, st, futs in jobs:
+        if futs is not None:
+            for f in futs:
+                f.result()
         if stats is not None:
             stats.append(st)
         an, bn = ablk.name, bblk.name
@@ -368,6 +417,7 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
                 n1, n2 = n2, n1
             out[n1], out[n2] = conv(b1), conv(b2)
         sink.reset()
+        _free_sinks.append(sink)
     if aidx is not None:
         aidx.free()
     if own:

@@ -25,13 +25,23 @@ void fatal(const char *fmt, ...) {
     exit(1);                                   // reference behaviour: message + exit(1), db/DB.h:84-86
 }
 
-Context &ctx() { static Context c; return c; }
+// ---- worker contexts ----
+constexpr int MAX_WORKERS = 8;
+static Context g_ctx[MAX_WORKERS];
+static thread_local Context *tl_ctx = &g_ctx[0];
+static std::mutex g_mu;                           // guards the process-wide settings, size map and profile
+static FilterParams g_fp;
+static damar_options g_opt{};
+static bool g_opt_set = false;
+static int g_device = -1;
+Context &ctx() { return *tl_ctx; }
 
 static std::map<std::string, std::pair<double, long>> g_prof;
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 HostProf::HostProf(const char *n) : name(n), t0(now_s()) {}
-HostProf::~HostProf() { auto &e = g_prof[name]; e.first += now_s() - t0; e.second++; }
+HostProf::~HostProf() { std::lock_guard<std::mutex> lock(g_mu); auto &e = g_prof[name]; e.first += now_s() - t0; e.second++; }
 void dump_profile() {
+    std::lock_guard<std::mutex> lock(g_mu);
     for (auto &kv : g_prof) fprintf(stderr, "[damar profile] %-28s %9.1f ms  (%ld calls)\n", kv.first.c_str(), kv.second.first * 1e3, kv.second.second);
     g_prof.clear();
 }
@@ -47,27 +57,34 @@ static int pick_device() {
 static int do_init(int device) {
     Context &c = ctx();
     if (c.ready) return 0;
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n <= 0) {
-        set_error("no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
-        return 1;
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (g_device < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= 0) {
+            set_error("no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+            return 1;
+        }
+        if (device < 0) device = pick_device();
+        if (device >= n) device = device % n;
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) {
+            set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name, prop.major, prop.minor);
+            return 1;
+        }
+        g_device = device;
+        if (!g_opt_set) {                         // defaults of daligner.c:688-703
+            g_opt.minover = 2000; g_opt.symmetric = 1; g_opt.trace_spacing = 100; g_opt.ave_corr = .70;
+            g_opt.freq[0] = g_opt.freq[1] = g_opt.freq[2] = g_opt.freq[3] = .25f;
+        }
     }
-    if (device < 0) device = pick_device();
-    if (device >= n) device = device % n;
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", device, prop.name, prop.major, prop.minor);
-        return 1;
-    }
-    CUDA_CHECK(cudaSetDevice(device));
+    CUDA_CHECK(cudaSetDevice(g_device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-
-    c.device = device;
-    // defaults of daligner.c:688-703
-    c.opt.minover = 2000; c.opt.symmetric = 1; c.opt.trace_spacing = 100; c.opt.ave_corr = .70;
-    c.opt.freq[0] = c.opt.freq[1] = c.opt.freq[2] = c.opt.freq[3] = .25f;
+    c.index = (int)(&c - g_ctx);
+    c.device = g_device;
+    if (!c.ws) c.ws = new WorkerScratch();
+    c.fp = g_fp; c.opt = g_opt;
     c.ready = true;
     return 0;
 }
@@ -77,50 +94,64 @@ static int do_init(int device) {
 // milliseconds per GB and synchronise the device.  All library work is ordered on one stream, so
 // a freed block can be handed to the next request immediately.  Requests are rounded up to a
 // coarse size class and served best-fit from the free list (at most 1.5x the rounded size).
-static std::multimap<size_t, void *> g_free_blocks;
 static std::map<void *, size_t> g_block_size;
 static size_t round_class(size_t b) {
     size_t q = b >= (256u << 20) ? (64u << 20) : b >= (16u << 20) ? (8u << 20) : b >= (1u << 20) ? (1u << 20) : (64u << 10);
     return (b + q - 1) / q * q;
 }
-static void release_cached_blocks() {
-    for (auto &kv : g_free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
-    g_free_blocks.clear();
+static void release_cached_blocks(Context &c) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &kv : c.free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
+    c.free_blocks.clear();
 }
 void *dev_alloc_bytes(size_t bytes) {
+    Context &c = ctx();
     const size_t r = round_class(bytes ? bytes : 1);
-    auto it = g_free_blocks.lower_bound(r);
-    if (it != g_free_blocks.end() && it->first <= r + r / 2) {
+    auto it = c.free_blocks.lower_bound(r);
+    if (it != c.free_blocks.end() && it->first <= r + r / 2) {
         void *p = it->second;
-        g_free_blocks.erase(it);
+        c.free_blocks.erase(it);
         return p;
     }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, r);
-    if (e != cudaSuccess) {                       // out of memory: drop the cache and retry once
+    if (e != cudaSuccess) {                       // out of memory: drop this worker's cache and retry once
         cudaGetLastError();
-        CUDA_CHECK(cudaStreamSynchronize(ctx().stream));
-        release_cached_blocks();
+        CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        release_cached_blocks(c);
         CUDA_CHECK(cudaMalloc(&p, r));
     }
+    std::lock_guard<std::mutex> lock(g_mu);
     g_block_size[p] = r;
     return p;
 }
+// A block freed by a worker goes to THAT worker's cache: the caller guarantees that no other stream still
+// uses it (blocks and indices shared between workers are freed only after the workers have been joined).
 void dev_free(void *p) {
-    if (!p || !ctx().ready) return;
-    auto it = g_block_size.find(p);
-    if (it == g_block_size.end()) { cudaFree(p); return; }
-    g_free_blocks.emplace(it->second, p);
+    Context &c = ctx();
+    if (!p || !c.ready) return;
+    size_t sz = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = g_block_size.find(p);
+        if (it != g_block_size.end()) sz = it->second;
+    }
+    if (sz == 0) { cudaFree(p); return; }
+    c.free_blocks.emplace(sz, p);
 }
 
 void ensure_init() {
-    if (!ctx().ready && do_init(-1) != 0) fatal("%s", g_last_error.c_str());
+    Context &c = ctx();
+    if (!c.ready && do_init(-1) != 0) fatal("%s", g_last_error.c_str());
+    std::lock_guard<std::mutex> lock(g_mu);
+    c.fp = g_fp; c.opt = g_opt;
 }
 
-// ---- results of the last match_filter call ----
-static HostOverlaps g_out;
-static SeedHits g_hits;
-static const DeviceBlock *g_hits_a = nullptr, *g_hits_b = nullptr;
+// ---- results of the last match_filter call live in the worker's scratch ----
+#define g_out (scratch().out)
+#define g_hits (scratch().hits)
+#define g_hits_a (scratch().hits_a)
+#define g_hits_b (scratch().hits_b)
 
 void SeedHits::release() {
     if (keys) dev_free(keys);
@@ -139,27 +170,46 @@ int damar_init(int device) { return do_init(device); }
 const char *damar_last_error(void) { return g_last_error.c_str(); }
 
 void damar_shutdown(void) {
-    Context &c = ctx();
-    if (!c.ready) return;
-    g_hits.release();
-    cudaStreamSynchronize(c.stream);
-    release_cached_blocks();
-    cudaStreamDestroy(c.stream);
-    c.ready = false;
+    Context *saved = tl_ctx;
+    for (int i = 0; i < MAX_WORKERS; i++) {
+        Context &c = g_ctx[i];
+        if (!c.ready) continue;
+        tl_ctx = &c;
+        c.ws->hits.release();
+        cudaStreamSynchronize(c.stream);
+        release_cached_blocks(c);
+        cudaStreamDestroy(c.stream);
+        c.ready = false;
+    }
+    tl_ctx = saved;
+    g_device = -1;
 }
+
+/* Binds the calling host thread to worker context `index` (0 = the default context).  Every context has its
+ * own stream, device-memory cache and result slots, so independent comparisons can be in flight at once. */
+int damar_worker_bind(int index) {
+    if (index < 0 || index >= MAX_WORKERS) return 1;
+    tl_ctx = &g_ctx[index];
+    const int rc = do_init(-1);
+    if (rc == 0) CUDA_CHECK(cudaSetDevice(g_device));        // the context may have been created by another thread
+    return rc;
+}
+int damar_worker_count(void) { return MAX_WORKERS; }
 
 int damar_set_filter_params(int kmer, int binshift, int suppress, int hitmin, int nthreads) {
     if (kmer <= 1 || kmer > 32) return 1;                     // filter.c:173-174 (+ u64 code limit)
-    FilterParams &fp = ctx().fp;
+    std::lock_guard<std::mutex> lock(g_mu);
+    FilterParams &fp = g_fp;
     fp.kmer = kmer; fp.binshift = binshift; fp.suppress = suppress; fp.hitmin = hitmin; fp.nthreads = nthreads;
     fp.kmask = (kmer == 32) ? ~0ull : ((1ull << (2 * kmer)) - 1);
     fp.nthreads_pow2 = 1; fp.nshift = 0;
     while (2 * fp.nthreads_pow2 <= nthreads) { fp.nthreads_pow2 *= 2; fp.nshift++; }   // filter.c:192-198
     fp.set = true;
+    ctx().fp = fp;
     return 0;
 }
 
-void damar_set_options(const damar_options *opt) { ctx().opt = *opt; }
+void damar_set_options(const damar_options *opt) { std::lock_guard<std::mutex> lock(g_mu); g_opt = *opt; g_opt_set = true; ctx().opt = *opt; }
 
 damar_block *damar_block_upload(const damar_block_desc *desc) {
     ensure_init();
@@ -271,10 +321,22 @@ int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
 }
 
 void damar_dump_profile(void) { dump_profile(); }
-void damar_get_timings(damar_timings *t) { *t = ctx().tm; t->kernel_launches = ctx().launches; }
+void damar_get_timings(damar_timings *t) {
+    *t = ctx().tm;                                            // per-call fields of the calling worker ...
+    t->kernel_launches = 0; t->scatter_ms = 0; t->scatter_elems = 0; t->scatter_launches = 0;
+    t->align_kernel_ms = 0; t->align_launches = 0; t->redo_kernel_ms = 0;
+    for (int i = 0; i < MAX_WORKERS; i++) {                   // ... accumulators summed over all workers
+        const Context &c = g_ctx[i];
+        t->kernel_launches += c.launches;
+        t->scatter_ms += c.tm.scatter_ms; t->scatter_elems += c.tm.scatter_elems; t->scatter_launches += c.tm.scatter_launches;
+        t->align_kernel_ms += c.tm.align_kernel_ms; t->align_launches += c.tm.align_launches; t->redo_kernel_ms += c.tm.redo_kernel_ms;
+    }
+}
 void damar_reset_kernel_timers(void) {
-    damar_timings &t = ctx().tm;
-    t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
+    for (int i = 0; i < MAX_WORKERS; i++) {
+        damar_timings &t = g_ctx[i].tm;
+        t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
+    }
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -105,8 +106,16 @@ struct HostProf {
 };
 void dump_profile();
 
-// ---- process-wide context ----
+// ---- per-worker context ----
+// Independent comparisons (block pair x orientation) may run concurrently: each host thread binds one
+// worker context (damar_worker_bind) with its own stream, device-memory cache, pinned staging and result
+// slots; context 0 is the default one.  Filter parameters and options are process-wide and copied into
+// the context at every API entry.
+struct SeedHits;
+struct HostOverlaps;
+struct WorkerScratch;
 struct Context {
+    int index = 0;
     int device = -1;
     cudaStream_t stream = nullptr;
     FilterParams fp;
@@ -114,6 +123,8 @@ struct Context {
     damar_timings tm{};
     int64_t launches = 0;
     bool ready = false;
+    std::multimap<size_t, void *> free_blocks;   // caching allocator (api.cu)
+    WorkerScratch *ws = nullptr;                 // buffers that outlive a call (api.cu)
 };
 Context &ctx();
 void ensure_init();
@@ -185,6 +196,19 @@ struct HostOverlaps {                 // views of pinned staging buffers, valid 
     int tbytes = 2;
     int64_t nfilt = 0, multi = 0, cells = 0, pairs = 0, redo = 0;
 };
+// buffers that used to be function statics, one set per worker context
+struct WorkerScratch {
+    DevBuf<uint32_t> tile_hist;                  // radix_sort.cu
+    cudaEvent_t rs_ev[16][2]; bool rs_ev_init = false;
+    DevBuf<uint64_t> scan_tot;                   // scan.cu
+    DevBuf<uint32_t> tot32_index, tot32_merge;   // kmer_index.cu, seed_merge.cu
+    PinnedBuf<damar_overlap> h_recs; PinnedBuf<uint64_t> h_toff, h_seq; PinnedBuf<uint8_t> h_trace;   // pair_align.cu
+    HostOverlaps out;                            // results of the last match_filter call
+    SeedHits hits;
+    const DeviceBlock *hits_a = nullptr, *hits_b = nullptr;
+};
+inline WorkerScratch &scratch() { return *ctx().ws; }
+
 void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
                       HostOverlaps &out);
 

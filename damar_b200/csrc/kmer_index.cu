@@ -9,6 +9,7 @@
 // A k-mer entry is (code, gpos): gpos indexes the reference's unpacked `bases` array and names
 // the k-mer's LAST base, so (read, rpos) = (r, gpos - boff[r]).  Sorting stably on code with
 // entries generated in gpos order reproduces the reference's (code, read, rpos) order.
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -255,6 +256,8 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
 }
 
 void ensure_revcomp(DeviceBlock *b) {
+    static std::mutex mu;                        // several workers may want the same block's complement at once
+    std::lock_guard<std::mutex> lock(mu);
     if (b->packed[1]) return;
     Context &c = ctx();
     b->packed[1] = alloc_packed(b->npacked_words, c.stream);
@@ -268,6 +271,7 @@ void ensure_revcomp(DeviceBlock *b) {
         mirror_mask<<<(b->nreads + 255) / 256, 256, 0, c.stream>>>(b->mask_anno[0], b->mask_data[0], b->mask_data[1], b->rlen, b->nreads);
         KERNEL_CHECK(); count_launch();
     }
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));  // other workers' streams may read it as soon as the lock drops
 }
 
 DeviceIndex *build_index(DeviceBlock *b, int comp) {
@@ -293,7 +297,7 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     // kbase[r] = exclusive prefix of per-read counts (32-bit is enough: kmers < 2^31, filter.c:762)
     uint32_t total32 = 0;
     {
-        static DevBuf<uint32_t> tot32; tot32.reserve(1);
+        DevBuf<uint32_t> &tot32 = scratch().tot32_index; tot32.reserve(1);
         exclusive_scan_u32_inplace(per_read.p, b->nreads, tot32.p, st);
         CUDA_CHECK(cudaMemcpyAsync(&total32, tot32.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));

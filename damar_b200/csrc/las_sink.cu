@@ -4,6 +4,7 @@
 // (align.c:3375-3396).  Host-only code; nothing here touches the device.  The final sort and the
 // image build are spread over host threads (the reference does both single-threaded).
 #include <algorithm>
+#include <mutex>
 #include <thread>
 
 #include "common.cuh"
@@ -17,6 +18,7 @@ struct LasSink {
     std::vector<uint8_t> trace;      // raw trace bytes (uint8 or uint16 values)
     int tbytes = 0;
     uint64_t calls = 0;
+    std::mutex mu;                   // damar_sink_add_at may be called from several worker threads
 };
 
 struct SortKey {                     // SORT_OVL (align.c:6104-6164) flattened into integers
@@ -37,8 +39,10 @@ struct SortKey {                     // SORT_OVL (align.c:6104-6164) flattened i
 // first touch dominate the build).  Freed images are kept on a small free list and reused.
 struct ImgHdr { size_t cap; size_t magic; };
 static std::vector<ImgHdr *> g_img_free;
+static std::mutex g_img_mu;
 static const size_t IMG_MAGIC = 0x64616d61726c6173ull;
 static uint8_t *img_alloc(size_t n) {
+    std::lock_guard<std::mutex> lock(g_img_mu);
     size_t best = (size_t)-1;
     for (size_t i = 0; i < g_img_free.size(); i++)
         if (g_img_free[i]->cap >= n && (best == (size_t)-1 || g_img_free[i]->cap < g_img_free[best]->cap)) best = i;
@@ -56,6 +60,7 @@ static void img_free(void *p) {
     if (!p) return;
     ImgHdr *h = reinterpret_cast<ImgHdr *>(p) - 1;
     if (h->magic != IMG_MAGIC) { free(p); return; }
+    std::lock_guard<std::mutex> lock(g_img_mu);
     if (g_img_free.size() >= 8) {                         // keep the 8 largest
         size_t small = 0;
         for (size_t i = 1; i < g_img_free.size(); i++) if (g_img_free[i]->cap < g_img_free[small]->cap) small = i;
@@ -152,10 +157,14 @@ void damar_sink_reset(damar_las_sink *s_) {
 }
 int64_t damar_sink_count(const damar_las_sink *s) { return (int64_t) reinterpret_cast<const LasSink *>(s)->ovl.size(); }
 
-void damar_sink_add(damar_las_sink *s_, const damar_overlaps *o) {
+// `ordinal` = position of this Match_Filter call in the job (0 = first B block normal, 1 = its complement, ...):
+// the reference buffers the calls in that order, which breaks full SORT_OVL ties.
+void damar_sink_add_at(damar_las_sink *s_, const damar_overlaps *o, int64_t ordinal) {
     HostProf hp("sink_add");
     LasSink *s = reinterpret_cast<LasSink *>(s_);
-    if (o->novl == 0) { s->calls++; return; }
+    std::lock_guard<std::mutex> lock(s->mu);
+    if ((uint64_t)ordinal >= s->calls) s->calls = (uint64_t)ordinal + 1;
+    if (o->novl == 0) return;
     if (s->tbytes == 0) s->tbytes = o->trace_bytes;
     if (s->tbytes != o->trace_bytes) fatal("damar_sink_add: mixed trace widths in one sink");
     const uint64_t base = s->trace.size();
@@ -164,11 +173,13 @@ void damar_sink_add(damar_las_sink *s_, const damar_overlaps *o) {
     s->toff.resize(n0 + o->novl); s->seq.resize(n0 + o->novl);
     for (int64_t i = 0; i < o->novl; i++) {
         s->toff[n0 + i] = base + o->trace_off[i] * (uint64_t)o->trace_bytes;
-        s->seq[n0 + i] = (s->calls << 48) | (o->seq ? o->seq[i] : (uint64_t)i);
+        s->seq[n0 + i] = ((uint64_t)ordinal << 48) | (o->seq ? o->seq[i] : (uint64_t)i);
     }
     const uint8_t *tb = reinterpret_cast<const uint8_t *>(o->trace);
     s->trace.insert(s->trace.end(), tb, tb + (size_t)o->ntrace * o->trace_bytes);
-    s->calls++;
+}
+void damar_sink_add(damar_las_sink *s_, const damar_overlaps *o) {
+    damar_sink_add_at(s_, o, (int64_t)reinterpret_cast<LasSink *>(s_)->calls);
 }
 
 int damar_sink_serialise(damar_las_sink *s_, int trace_spacing, int no_trace, int only_identity, int split_read,

@@ -1368,7 +1368,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     //      order the reference's thread buffers would have had ----
     HostProf hp4("ra.download");
     Timer t_dl(st);
-    static PinnedBuf<damar_overlap> h_recs; static PinnedBuf<uint64_t> h_toff, h_seq; static PinnedBuf<uint8_t> h_trace;
+    WorkerScratch &ws = scratch();
+    PinnedBuf<damar_overlap> &h_recs = ws.h_recs; PinnedBuf<uint64_t> &h_toff = ws.h_toff, &h_seq = ws.h_seq; PinnedBuf<uint8_t> &h_trace = ws.h_trace;
     const uint64_t nrec = hc[5], ntr = hc[6];
     h_recs.reserve(nrec + 1); h_toff.reserve(nrec + 1); h_seq.reserve(nrec + 1); h_trace.reserve(ntr * tbytes + 16);
     if (nrec) {

@@ -114,8 +114,6 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
     }
 }
 
-DevBuf<uint32_t> g_tile_hist;
-
 }  // namespace
 
 // Sorts on key bits [0, nbits).  On return keys/vals point at the sorted data and
@@ -125,6 +123,8 @@ void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uin
     if (n <= 1 || nbits <= 0) return;
     if (n >= (int64_t)0xffffffffll) fatal("radix_sort_pairs: %lld elements exceed the 32-bit offset range", (long long)n);
     const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    WorkerScratch &ws = scratch();
+    DevBuf<uint32_t> &g_tile_hist = ws.tile_hist;
     g_tile_hist.reserve((size_t)ntiles * 256);
     static bool attr_set = false;
     const size_t dyn = (sizeof(uint64_t) + sizeof(uint32_t)) * RS_TILE;
@@ -132,9 +132,8 @@ void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uin
         CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         attr_set = true;
     }
-    static cudaEvent_t ev[16][2];
-    static bool ev_init = false;
-    if (!ev_init) { for (auto &e : ev) { CUDA_CHECK(cudaEventCreate(&e[0])); CUDA_CHECK(cudaEventCreate(&e[1])); } ev_init = true; }
+    cudaEvent_t (&ev)[16][2] = ws.rs_ev;
+    if (!ws.rs_ev_init) { for (auto &e : ev) { CUDA_CHECK(cudaEventCreate(&e[0])); CUDA_CHECK(cudaEventCreate(&e[1])); } ws.rs_ev_init = true; }
     int npass = 0;
     for (int shift = 0; shift < nbits; shift += 8, npass++) {
         rs_hist<<<ntiles, RS_THREADS, 0, st>>>(keys, n, shift, g_tile_hist.p, ntiles);

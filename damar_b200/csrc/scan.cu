@@ -115,7 +115,7 @@ void exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int64_t n, uin
 
 // total_dev (optional) receives the low 32 bits of the sum
 void exclusive_scan_u32_inplace(uint32_t *data, int64_t n, uint32_t *total_dev, cudaStream_t st) {
-    static DevBuf<uint64_t> tot;
+    DevBuf<uint64_t> &tot = scratch().scan_tot;
     tot.reserve(1);
     scan_impl<uint32_t>(data, data, n, tot.p, st);
     if (total_dev) CUDA_CHECK(cudaMemcpyAsync(total_dev, tot.p, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));

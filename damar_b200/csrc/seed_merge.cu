@@ -209,7 +209,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     DevBuf<uint64_t> off, total;
     DevBuf<unsigned long long> gram;
     gid.reserve((size_t)alen); total.reserve(1);
-    static DevBuf<uint32_t> tot32; tot32.reserve(1);
+    DevBuf<uint32_t> &tot32 = scratch().tot32_merge; tot32.reserve(1);
     const unsigned eb = (unsigned)((alen + 255) / 256);
     mark_heads<<<eb, 256, 0, st>>>(ai->codes, alen, gid.p);
     KERNEL_CHECK();

@@ -104,6 +104,13 @@ int         damar_init(int device);
 void        damar_shutdown(void);
 const char *damar_last_error(void);
 
+/* Worker contexts: independent comparisons (block pair x orientation) may be in flight at once, one per
+ * host thread.  A thread binds itself to context `index` (0 .. damar_worker_count()-1; 0 is the default
+ * every thread starts with); each context has its own CUDA stream, device-memory cache and result slots.
+ * Blocks and indices may be shared read-only between contexts once the call that created them returned. */
+int damar_worker_bind(int index);
+int damar_worker_count(void);
+
 /* Set_Filter_Params (filter.c:171-201).  Returns 1 for an illegal combination. */
 int  damar_set_filter_params(int kmer, int binshift, int suppress, int hitmin, int nthreads);
 void damar_set_options(const damar_options *opt);
@@ -154,6 +161,8 @@ damar_las_sink *damar_sink_new(void);
 void            damar_sink_free(damar_las_sink *s);
 void            damar_sink_reset(damar_las_sink *s);                         /* Reset_Overlap_Buffer */
 void            damar_sink_add(damar_las_sink *s, const damar_overlaps *o);  /* AddOverlapToBuffer x novl */
+/* same, for calls that complete out of order: `ordinal` = position of the Match_Filter call in the job */
+void            damar_sink_add_at(damar_las_sink *s, const damar_overlaps *o, int64_t ordinal);
 int64_t         damar_sink_count(const damar_las_sink *s);
 /* Sort by SORT_OVL (align.c:6104) and serialise to malloc'd .las images (header int64 novl,
  * int32 tspace; 40-byte records; u8 traces when trace_spacing <= 125).  split_read >= 0 writes
