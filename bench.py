@@ -307,7 +307,10 @@ def main():
     alg_bytes = 32.0 * sc_el / max(sc_n, 1)                       # per launch: 16 B read + 16 B write per record
     achieved = (32.0 * sc_el) / (sc_ms / 1000.0) / 1e9 if sc_ms > 0 else 0.0
     roofline = {"kernel": "rs_scatter (radix sort pass: stable rank + scatter)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak,
+                # measured dram bytes per launch: 23.94 B/element (12 B SoA records in + out) in profiles/r01_rs_scatter_ncu.txt
+                "traffic": 23.94 * sc_el / max(sc_n, 1), "traffic_source": "ncu --set full dram__bytes_read+write per element x elements per launch",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launches": sc_n, "avg_launch_ms": sc_ms / max(sc_n, 1),
                 "share_of_step": (sc_ms / 1000.0) / dt if world == 1 else None}
     line = {"metric": "daligner overlaps/s", "value": value, "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,

@@ -338,7 +338,7 @@ def _bind_worker():
 
 
 def workers() -> int:
-    n = int(os.environ.get("DAMAR_WORKERS", "3"))
+    n = int(os.environ.get("DAMAR_WORKERS", "4"))
     return max(1, min(n, load_library().damar_worker_count() - 1))
 
 

@@ -200,7 +200,7 @@ struct HostOverlaps {                 // views of pinned staging buffers, valid 
 struct WorkerScratch {
     DevBuf<uint32_t> tile_hist;                  // radix_sort.cu
     cudaEvent_t rs_ev[16][2]; bool rs_ev_init = false;
-    DevBuf<uint64_t> scan_tot;                   // scan.cu
+    DevBuf<uint64_t> scan_tot, scan_sums;        // scan.cu
     DevBuf<uint32_t> tot32_index, tot32_merge;   // kmer_index.cu, seed_merge.cu
     PinnedBuf<damar_overlap> h_recs; PinnedBuf<uint64_t> h_toff, h_seq; PinnedBuf<uint8_t> h_trace;   // pair_align.cu
     HostOverlaps out;                            // results of the last match_filter call

@@ -16,6 +16,7 @@
 // threshold for 32 hits at once and consumes candidates in hit order unless an earlier alignment of
 // the pair already covers them (the `lasta` rule, kept as a short interval list per pair).
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 #include "wave_core.cuh"
@@ -1255,13 +1256,12 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
-    static bool attr = false;
-    if (!attr) {
+    static std::once_flag attr;
+    std::call_once(attr, [] {
         set_smem(wave_tasks<32, false, 2>, WaveCfg<32>::SMEM);
         set_smem(wave_tasks<32, false, 4>, WaveCfg<32>::SMEM);
         set_smem(wave_tasks<64, true, 4>, WaveCfg<64>::SMEM);
-        attr = true;
-    }
+    });
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0;
     unsigned long long rec_cap = 4 * nactive + 1024;

@@ -6,6 +6,8 @@
 //   scan       : exclusive scan of the digit-major [256][tiles] table
 //   rs_scatter : warp match_any ranking (stable), tile-local reorder in shared memory, then
 //                coalesced runs to global memory.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace damar {
@@ -126,12 +128,9 @@ void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uin
     WorkerScratch &ws = scratch();
     DevBuf<uint32_t> &g_tile_hist = ws.tile_hist;
     g_tile_hist.reserve((size_t)ntiles * 256);
-    static bool attr_set = false;
+    static std::once_flag attr_set;
     const size_t dyn = (sizeof(uint64_t) + sizeof(uint32_t)) * RS_TILE;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-        attr_set = true;
-    }
+    std::call_once(attr_set, [dyn] { CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); });
     cudaEvent_t (&ev)[16][2] = ws.rs_ev;
     if (!ws.rs_ev_init) { for (auto &e : ev) { CUDA_CHECK(cudaEventCreate(&e[0])); CUDA_CHECK(cudaEventCreate(&e[1])); } ws.rs_ev_init = true; }
     int npass = 0;

@@ -89,7 +89,6 @@ __global__ void __launch_bounds__(SC_THREADS) k_tile_downsweep(const uint32_t *i
     }
 }
 
-DevBuf<uint64_t> g_sums;
 
 template <typename OutT>
 void scan_impl(const uint32_t *in, OutT *out, int64_t n, uint64_t *total_dev, cudaStream_t st) {
@@ -98,6 +97,7 @@ void scan_impl(const uint32_t *in, OutT *out, int64_t n, uint64_t *total_dev, cu
         return;
     }
     int64_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    DevBuf<uint64_t> &g_sums = scratch().scan_sums;
     g_sums.reserve((size_t)tiles + 1);
     k_tile_reduce<<<(unsigned)tiles, SC_THREADS, 0, st>>>(in, n, g_sums.p);
     KERNEL_CHECK();

@@ -18,6 +18,8 @@
 //      order report_thread depends on.
 #include <type_traits>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace damar {
@@ -232,8 +234,8 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     ga.self = self; ga.comp = comp; ga.identity = c.opt.identity; ga.same_list = same_list;
     ga.gjb = gjb.p; ga.gnb = gnb.p; ga.gct = gct.p; ga.gram = use_limit ? gram.p : nullptr;
     {
-        static bool attr = false;
-        if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(match_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXGRAM * 4)); attr = true; }
+        static std::once_flag attr;
+        std::call_once(attr, [] { CUDA_CHECK(cudaFuncSetAttribute(match_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXGRAM * 4)); });
         unsigned blocks = (ngroups + MG_TILE - 1) / MG_TILE;
         if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
         if (blocks == 0) blocks = 1;
