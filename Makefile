@@ -16,7 +16,7 @@ damar_b200/host/simdb: damar_b200/host/simdb.cpp
 
 lib: $(LIB)
 
-$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/damar_b200.h
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh $(CSRC)/wave_core.cuh include/damar_b200.h
 	$(NVCC) $(NVFLAGS) -c -o $@ $< 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
 
 $(LIB): $(OBJS)

@@ -906,16 +906,16 @@ struct DevPool {
     __device__ void store(uint32_t id, const wc::Cell &c) { *reinterpret_cast<int4 *>(cells + id) = make_int4(c.prev, c.diag, c.diff, c.mark); }
 };
 
-template <int RING>
+template <int RING, int WARPS_>
 struct WaveCfg {
-    static constexpr int WARPS = (RING == 32) ? 8 : 4;        // 28 KB (56 KB) of front per warp: 224 KB per SM
+    static constexpr int WARPS = WARPS_;                      // 20 KB (RING 32) / 40 KB (RING 64) of front per warp
     static constexpr int SMEM = WARPS * wc::FRONT_WORDS * RING * 32 * 4;
 };
 
 // Tasks [0, 2 * ncand) when WIDE == false (task t = pass (t & 1) of alignment t >> 1), the ST_WIDE leftovers of
 // that pass listed in wide_list when WIDE == true.
-template <int RING, bool WIDE, int NWAY>
-__global__ void __launch_bounds__(WaveCfg<RING>::WARPS * 32, 1) wave_tasks(PipeArgs Q) {
+template <int RING, bool WIDE, int NWAY, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     extern __shared__ uint32_t front_smem[];
     __shared__ int16_t s_t7[128], s_t8[256];                  // the trim test tables (wave_core.cuh)
     const AlignArgs &P = Q.A;
@@ -1256,11 +1256,14 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
+    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 11;
     static std::once_flag attr;
     std::call_once(attr, [] {
-        set_smem(wave_tasks<32, false, 2>, WaveCfg<32>::SMEM);
-        set_smem(wave_tasks<32, false, 4>, WaveCfg<32>::SMEM);
-        set_smem(wave_tasks<64, true, 4>, WaveCfg<64>::SMEM);
+        set_smem(wave_tasks<32, false, 4, 8>, WaveCfg<32, 8>::SMEM);
+        set_smem(wave_tasks<32, false, 4, 10>, WaveCfg<32, 10>::SMEM);
+        set_smem(wave_tasks<32, false, 4, 11>, WaveCfg<32, 11>::SMEM);
+        set_smem(wave_tasks<32, false, 2, 11>, WaveCfg<32, 11>::SMEM);
+        set_smem(wave_tasks<64, true, 4, 5>, WaveCfg<64, 5>::SMEM);
     });
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0;
@@ -1295,7 +1298,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             if (ncand == 0) break;
             Timer t_k(st);
             {
-                const unsigned per = WaveCfg<32>::WARPS * 32;
+                const unsigned per = (unsigned)wwarps * 32;
                 const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (2 * ncand + per - 1) / per);
                 Q.task_order = nullptr;
                 if (ncand >= 2048 && lpt) {                      // order the queue: longest passes first
@@ -1306,17 +1309,19 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
                     radix_sort_pairs(k0, v0, k1, v1, nt, 24, st);
                     Q.task_order = v0;
                 }
-                if (nway == 2) wave_tasks<32, false, 2><<<wb, per, WaveCfg<32>::SMEM, st>>>(Q);
-                else wave_tasks<32, false, 4><<<wb, per, WaveCfg<32>::SMEM, st>>>(Q);
+                if (nway == 2) wave_tasks<32, false, 2, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
+                else if (wwarps == 8) wave_tasks<32, false, 4, 8><<<wb, per, WaveCfg<32, 8>::SMEM, st>>>(Q);
+                else if (wwarps == 10) wave_tasks<32, false, 4, 10><<<wb, per, WaveCfg<32, 10>::SMEM, st>>>(Q);
+                else wave_tasks<32, false, 4, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             unsigned int nwide = 0;
             CUDA_CHECK(cudaMemcpyAsync(&nwide, ctr.p + CTR_NWIDE, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(cudaStreamSynchronize(st));
             if (nwide > 0) {
-                const unsigned per = WaveCfg<64>::WARPS * 32;
+                const unsigned per = WaveCfg<64, 5>::WARPS * 32;
                 const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (nwide + per - 1) / per);
-                wave_tasks<64, true, 4><<<wb, per, WaveCfg<64>::SMEM, st>>>(Q);
+                wave_tasks<64, true, 4, 5><<<wb, per, WaveCfg<64, 5>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;

@@ -24,8 +24,10 @@
 
 #if defined(__CUDACC__)
 #define WC_HD __host__ __device__ __forceinline__
+#define WC_RARE __host__ __device__ __noinline__       // one copy of the code paths only few cells take
 #else
 #define WC_HD inline
+#define WC_RARE inline
 #endif
 
 namespace damar {
@@ -90,7 +92,7 @@ WC_HD uint64_t window_at(const uint32_t *__restrict__ words, uint32_t s) {
     return ((uint64_t)funnel_l(x1, x0, o) << 32) | funnel_l(x2, x1, o);
 }
 // number of equal bases A[ax+i] == B[by+i], i = 0.., capped at maxn
-WC_HD int slide(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by, int maxn) {
+WC_RARE int slide(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by, int maxn) {
     int n = 0;
     while (n < maxn) {
         const uint64_t d = window_at(aw, ax + (uint32_t)n) ^ window_at(bw, by + (uint32_t)n);
@@ -107,9 +109,10 @@ WC_HD uint64_t push_matches(uint64_t b, int n) {
 struct Cell { int32_t prev, diag, diff, mark; };
 
 // ---- per-thread view of its wave-front ring ------------------------------------------------------
-// word arrays: V (furthest anti-diagonal), T lo/hi (match history), HA, HB (chain heads, pool index),
-// HMN (TP index+1 of the heads' marks, A low 16 | B high 16), NAB (next TP index+1 to cross, A | B)
-enum { F_V = 0, F_TLO = 1, F_THI = 2, F_HA = 3, F_HB = 4, F_HMN = 5, F_NAB = 6, FRONT_WORDS = 7 };
+// word arrays: V (furthest anti-diagonal), T lo/hi (match history), HA, HB (chain heads, pool index).
+// The reference also keeps, per diagonal, the next trace point to cross (NA, NB) and relies on the mark of a
+// path's head pebble; both are functions of the previous wave here (see settle): 20 bytes per diagonal.
+enum { F_V = 0, F_TLO = 1, F_THI = 2, F_HA = 3, F_HB = 4, FRONT_WORDS = 5 };
 template <int RING, int STRIDE>
 struct Front {
     uint32_t *base;
@@ -117,11 +120,11 @@ struct Front {
     WC_HD uint32_t *slot(int k) const { return base + (k & (RING - 1)) * STRIDE; }
 };
 
-struct PathState { uint64_t T; uint32_t ha, hb, hmn; };
+struct PathState { uint64_t T; uint32_t ha, hb; };
 template <class FRONT> WC_HD PathState load_path(const uint32_t *s) {
     PathState p;
     p.T = (uint64_t)s[F_TLO * FRONT::ARR] | ((uint64_t)s[F_THI * FRONT::ARR] << 32);
-    p.ha = s[F_HA * FRONT::ARR]; p.hb = s[F_HB * FRONT::ARR]; p.hmn = s[F_HMN * FRONT::ARR];
+    p.ha = s[F_HA * FRONT::ARR]; p.hb = s[F_HB * FRONT::ARR];
     return p;
 }
 
@@ -148,7 +151,7 @@ WC_HD int table15(const TrimTabs &t, int x) {
 WC_HD int score15(const TrimTabs &t, int x) { return 1000 * popc64((uint64_t)x) - 15 * t.dscore; }
 // the trim test of align.c:922-925:  TABLE[lo15] >= 0 && TABLE[hi15] + SCORE[lo15] >= 0  for the newest 30 bits of b,
 // i.e. no suffix of the 30-bit window scores below zero; the window is walked in chunks of 7, 8, 7, 8 bits
-WC_HD bool trim_ok(const TrimTabs &t, uint64_t b) {
+WC_RARE bool trim_ok(const TrimTabs t, uint64_t b) {
     const uint32_t w = (uint32_t)b & 0x3fffffffu;
     const int a0 = (int)(w & 127u), a1 = (int)((w >> 7) & 255u), a2 = (int)((w >> 15) & 127u), a3 = (int)(w >> 22);
     const int s0 = 1000 * popc64((uint64_t)a0) - 7 * t.dscore;                    // score of the newest 7
@@ -188,6 +191,7 @@ struct Lane {
     uint32_t abase, bbase;
     int alen, blen, minp, maxp, TS, path_ave, rev;
     int goffA, goffB;               // trace grid offsets in pass coordinates
+    uint64_t magic;                 // ceil(2^40 / TS)
     // wave state (pass coordinates)
     int low, hgh, k, dif, more, aclip, bclip;
     int besta, besty, lasta, trima, trimy, trimd;
@@ -204,28 +208,39 @@ struct Lane {
 
 WC_HD int grid(int goff, int idx1, int TS) { return goff + (idx1 - 1) * TS; }   // idx1 = TP index + 1
 
+// The one copy of the pebble store: takes a fresh chunk from the pool when the thread's current one is used up.
+// Returns the cell's pool index, or NOCELL when the pool is dry.  Everything is passed by value so that the
+// caller's state stays in registers across the call.
+template <class POOL>
+WC_RARE uint32_t push_raw(POOL pool, uint32_t next, uint32_t left, uint32_t prev, int diag, int diff, int mark) {
+    if (left == 0) {
+        next = pool.take(CELL_CHUNK);
+        if (next == NOCELL) return NOCELL;
+    }
+    Cell c;
+    c.prev = (int32_t)prev; c.diag = diag; c.diff = diff; c.mark = mark;
+    pool.store(next, c);
+    return next;
+}
 template <class POOL>
 WC_HD uint32_t push_cell(Lane &L, POOL &pool, uint32_t prev, int k, int dif, int markA_or_B_pass, bool isA) {
-    if (L.cell_left == 0) {
-        const uint32_t b = pool.take(CELL_CHUNK);
-        if (b == NOCELL) { L.status = ST_POOL; return prev; }
-        L.cell_next = b; L.cell_left = CELL_CHUNK;
-    }
-    const uint32_t id = L.cell_next++;
-    L.cell_left--;
-    Cell c;
-    c.prev = (int32_t)prev;
-    c.diff = dif;
-    if (L.rev) {                       // back to original coordinates
-        c.diag = (L.alen - L.blen) - k;
-        c.mark = (isA ? L.alen : L.blen) - markA_or_B_pass;
-    } else { c.diag = k; c.mark = markA_or_B_pass; }
-    pool.store(id, c);
+    // back to original coordinates
+    const int diag = L.rev ? (L.alen - L.blen) - k : k;
+    const int mark = L.rev ? (isA ? L.alen : L.blen) - markA_or_B_pass : markA_or_B_pass;
+    const uint32_t id = push_raw(pool, L.cell_next, L.cell_left, prev, diag, dif, mark);
+    if (id == NOCELL) { L.status = ST_POOL; return prev; }
+    L.cell_left = (L.cell_left ? L.cell_left : (uint32_t)CELL_CHUNK) - 1u;
+    L.cell_next = id + 1u;
     return id;
 }
 
 // floor((v - goff) / TS) + 1 for v - goff >= -TS
 WC_HD int tp_index1(int v, int goff, int TS) { return (v - goff + TS) / TS; }
+// the same with the lane's reciprocal ceil(2^40 / TS): exact for reads shorter than 2^24 bases
+WC_HD int tp_index1(const Lane &L, int v, int goff) {
+    const uint32_t u = (uint32_t)(v - goff + L.TS);
+    return (int)(((uint64_t)u * L.magic) >> 40);
+}
 
 // Wave 0 (align.c:491-626 forward, 1206-1340 reverse) and the lane's constants.
 template <class FRONT, class POOL>
@@ -235,6 +250,7 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     L.cell_left = 0; L.cell_next = 0;
     L.waves = 0; L.cells = 0;
     const int TS = t.TS;
+    L.magic = ((1ull << 40) + (uint64_t)TS - 1) / (uint64_t)TS;
     const int y0 = (t.anti - t.diag) >> 1, x0 = y0 + t.diag;
     int x, y, k;
     if (!t.rev) {
@@ -261,8 +277,6 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     uint32_t hb = push_cell(L, pool, NOCELL, k, 0, t.rev ? y : grid(L.goffB, nbI, TS), false);
     L.trimha = L.moreha = ha; L.trimhb = L.morehb = hb;
     naI += 1; nbI += 1;
-    if (naI > 0xfffe || nbI > 0xfffe) { L.status = ST_RANGE; return; }
-
     {
         const int ra = L.alen - x, rb = L.blen - y;
         const int n = slide(L.aw, L.abase + (uint32_t)x, L.bw, L.bbase + (uint32_t)y, ra < rb ? ra : rb);
@@ -272,15 +286,12 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     else if (x == L.alen) { L.more = 0; L.aclip = k; }
     while (x >= grid(L.goffA, naI, TS)) { ha = push_cell(L, pool, ha, k, 0, grid(L.goffA, naI, TS), true); naI++; }
     while (y >= grid(L.goffB, nbI, TS)) { hb = push_cell(L, pool, hb, k, 0, grid(L.goffB, nbI, TS), false); nbI++; }
-    if (naI > 0xfffe || nbI > 0xfffe) { if (L.status == ST_RUN) L.status = ST_RANGE; return; }
     const int c = (y << 1) + k;
     if (c > L.besta) { L.besta = L.trima = L.lasta = c; L.besty = L.trimy = y; L.trimha = ha; L.trimhb = hb; }
     uint32_t *s = F.slot(k);
     s[F_V * FRONT::ARR] = (uint32_t)c;
     s[F_TLO * FRONT::ARR] = (uint32_t)PATH_INT; s[F_THI * FRONT::ARR] = (uint32_t)(PATH_INT >> 32);
     s[F_HA * FRONT::ARR] = ha; s[F_HB * FRONT::ARR] = hb;
-    s[F_HMN * FRONT::ARR] = (uint32_t)(naI - 1) | ((uint32_t)(nbI - 1) << 16);
-    s[F_NAB * FRONT::ARR] = (uint32_t)naI | ((uint32_t)nbI << 16);
     L.k = k - 1;                                  // wave 0 is complete: next step is a transition
 }
 
@@ -319,19 +330,13 @@ WC_HD void transition(Lane &L, const FRONT &F) {
 
     int low = L.low - 1, hgh = L.hgh + 1;
     if (hgh - low + 1 > RING) { L.status = ST_WIDE; return; }
-    if (low >= L.minp) {
-        uint32_t *s = F.slot(low);
-        s[F_NAB * FRONT::ARR] = F.slot(low + 1)[F_NAB * FRONT::ARR]; s[F_V * FRONT::ARR] = (uint32_t)-1;
-    } else low += 1;
-    if (hgh <= L.maxp) {
-        uint32_t *s = F.slot(hgh);
-        s[F_NAB * FRONT::ARR] = F.slot(hgh - 1)[F_NAB * FRONT::ARR]; s[F_V * FRONT::ARR] = (uint32_t)-1;
-        L.vc = -1;
-    } else { hgh -= 1; L.vc = (int32_t)F.slot(hgh)[F_V * FRONT::ARR]; }
+    if (low >= L.minp) F.slot(low)[F_V * FRONT::ARR] = (uint32_t)-1; else low += 1;
+    if (hgh <= L.maxp) { F.slot(hgh)[F_V * FRONT::ARR] = (uint32_t)-1; L.vc = -1; }
+    else { hgh -= 1; L.vc = (int32_t)F.slot(hgh)[F_V * FRONT::ARR]; }
     L.low = low; L.hgh = hgh;
     L.dif += 1;
     L.vp = -1;
-    L.pp.T = PATH_INT; L.pp.ha = L.pp.hb = NOCELL; L.pp.hmn = 0;     // the (never chosen) state above hgh
+    L.pp.T = PATH_INT; L.pp.ha = L.pp.hb = NOCELL;                    // the (never chosen) state above hgh
     L.k = hgh;
 }
 
@@ -346,28 +351,32 @@ WC_HD int choose(int vp, int vc, int vm, int &c) {               // returns +1 /
 }
 
 // Everything of one cell after the predecessor has been chosen and the slide measured (align.c:836-928):
-// clip bookkeeping, pebbles, best / lasta / trim, and the store of the new front entry.
+// clip bookkeeping, pebbles, best / lasta / trim, and the store of the new front entry.  `d` is the chosen
+// predecessor's diagonal offset (choose()).
+//
+// Trace points.  The reference keeps NA[k] / NB[k] = first trace point beyond diagonal k's previous furthest
+// point, and logs a pebble for every NA[k] <= x that the arriving path has not logged yet (its head pebble's
+// mark < NA[k]).  A path has always logged every trace point up to its own previous position (xp, yp), and the
+// chosen predecessor is never behind diagonal k's previous point on either axis (the three-way rule picks the
+// larger anti-diagonal), so the pebbles logged are exactly the trace points in (xp, x] and (yp, y]: nothing
+// but the previous wave's V is needed.  One step from the predecessor costs x and/or y one base:
+// d = +1 (from k + 1): y only; d = -1 (from k - 1): x only; d = 0: both.
 template <class FRONT, class POOL>
-WC_HD void settle(Lane &L, const TrimTabs &tabs, POOL &pool, uint32_t *s, int k, int c0, int n, PathState p) {
+WC_HD void settle(Lane &L, const TrimTabs &tabs, POOL &pool, uint32_t *s, int k, int c0, int n, int d, PathState p) {
     const int TS = L.TS;
     uint64_t b = push_matches(p.T << 1, n);
-    const int y = ((c0 - k) >> 1) + n, x = y + k;
+    const int y0 = (c0 - k) >> 1, x0 = y0 + k;
+    const int y = y0 + n, x = x0 + n;
     if (y == L.blen) { L.more = 0; if (L.bclip < k) L.bclip = k; }
     else if (x == L.alen) { L.more = 0; L.aclip = k; }
     const int c = (y << 1) + k;
-    const uint32_t nab = s[F_NAB * FRONT::ARR];
-    int naI = (int)(nab & 0xffffu), nbI = (int)(nab >> 16);
-    int hmI = (int)(p.hmn & 0xffffu), hnI = (int)(p.hmn >> 16);
-    if (x >= grid(L.goffA, naI, TS) || y >= grid(L.goffB, nbI, TS)) {      // align.c:859-909
-        while (x >= grid(L.goffA, naI, TS)) {
-            if (hmI < naI) { p.ha = push_cell(L, pool, p.ha, k, L.dif, grid(L.goffA, naI, TS), true); hmI = naI; }
-            naI++;
-        }
-        while (y >= grid(L.goffB, nbI, TS)) {
-            if (hnI < nbI) { p.hb = push_cell(L, pool, p.hb, k, L.dif, grid(L.goffB, nbI, TS), false); hnI = nbI; }
-            nbI++;
-        }
-        if (naI > 0xfffe || nbI > 0xfffe) { if (L.status == ST_RUN) L.status = ST_RANGE; }
+    const int xp = x0 - (d <= 0 ? 1 : 0), yp = y0 - (d >= 0 ? 1 : 0);
+    int ia = tp_index1(L, xp, L.goffA);
+    int ib = tp_index1(L, yp, L.goffB);
+    const int ja = tp_index1(L, x, L.goffA), jb = tp_index1(L, y, L.goffB);
+    if (ja > ia || jb > ib) {                                                // align.c:859-909
+        while (ia < ja) { ia++; p.ha = push_cell(L, pool, p.ha, k, L.dif, grid(L.goffA, ia, TS), true); }
+        while (ib < jb) { ib++; p.hb = push_cell(L, pool, p.hb, k, L.dif, grid(L.goffB, ib, TS), false); }
     }
     if (c > L.besta) {                                                       // align.c:911-928
         L.besta = c; L.besty = y;
@@ -381,8 +390,6 @@ WC_HD void settle(Lane &L, const TrimTabs &tabs, POOL &pool, uint32_t *s, int k,
     s[F_V * FRONT::ARR] = (uint32_t)c;
     s[F_TLO * FRONT::ARR] = (uint32_t)b; s[F_THI * FRONT::ARR] = (uint32_t)(b >> 32);
     s[F_HA * FRONT::ARR] = p.ha; s[F_HB * FRONT::ARR] = p.hb;
-    s[F_HMN * FRONT::ARR] = (uint32_t)hmI | ((uint32_t)hnI << 16);
-    s[F_NAB * FRONT::ARR] = (uint32_t)naI | ((uint32_t)nbI << 16);
 }
 
 // first probe of a slide: equal bases in the first 32-base window (32 = all equal)
@@ -391,45 +398,10 @@ WC_HD int probe32(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *
     return d ? (clz64(d) >> 1) : 32;
 }
 
-// Two furthest-reaching-point updates per call, on diagonals L.k and L.k - 1 (align.c:789-938).  All cells of a
-// wave read only the previous wave, so the two predecessor choices and the two slides are independent
-// instruction streams (this is where a thread finds its instruction-level parallelism); the bookkeeping that
-// the reference does in visiting order (clips, best, trim) is then applied to k first, k - 1 second.
-template <class FRONT, class POOL>
-WC_HD void cells2(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
-    const int k0 = L.k, k1 = k0 - 1;
-    const bool two = k1 >= L.low;
-    uint32_t *s0 = F.slot(k0), *s1 = F.slot(two ? k1 : k0), *s2 = F.slot((two && k1 - 1 >= L.low) ? k1 - 1 : k0);
-    // previous-wave values (nothing below k0 + 1 has been overwritten yet)
-    const int vm0 = two ? (int32_t)s1[F_V * FRONT::ARR] : -1;                       // V[k0 - 1]
-    const int vm1 = (two && k1 - 1 >= L.low) ? (int32_t)s2[F_V * FRONT::ARR] : -1;  // V[k0 - 2]
-    const PathState pc = load_path<FRONT>(s0), pm = load_path<FRONT>(s1);
-    int c0, c1;
-    const int d0 = choose(L.vp, L.vc, vm0, c0);
-    const int d1 = choose(L.vc, vm0, vm1, c1);
-    PathState q0 = (d0 > 0) ? L.pp : (d0 == 0 ? pc : pm);
-    PathState q1 = (d1 > 0) ? pc : pm;
-    if (two && d1 < 0) q1 = load_path<FRONT>(s2);
-    // slides
-    const int y0 = (c0 - k0) >> 1, x0 = y0 + k0;
-    const int y1 = two ? ((c1 - k1) >> 1) : y0, x1 = two ? (y1 + k1) : x0;
-    const int max0 = (L.alen - x0 < L.blen - y0) ? L.alen - x0 : L.blen - y0;
-    const int max1 = (L.alen - x1 < L.blen - y1) ? L.alen - x1 : L.blen - y1;
-    int n0 = probe32(L.aw, L.abase + (uint32_t)x0, L.bw, L.bbase + (uint32_t)y0);
-    int n1 = probe32(L.aw, L.abase + (uint32_t)x1, L.bw, L.bbase + (uint32_t)y1);
-    if (n0 == 32 && max0 > 32) n0 = 32 + slide(L.aw, L.abase + (uint32_t)(x0 + 32), L.bw, L.bbase + (uint32_t)(y0 + 32), max0 - 32);
-    if (n1 == 32 && max1 > 32) n1 = 32 + slide(L.aw, L.abase + (uint32_t)(x1 + 32), L.bw, L.bbase + (uint32_t)(y1 + 32), max1 - 32);
-    if (n0 > max0) n0 = max0;
-    if (n1 > max1) n1 = max1;
-    // bookkeeping in visiting order
-    settle<FRONT>(L, tabs, pool, s0, k0, c0, n0, q0);
-    if (two) settle<FRONT>(L, tabs, pool, s1, k1, c1, n1, q1);
-    L.vp = vm0; L.vc = vm1; L.pp = pm;
-    L.k = two ? k1 - 1 : k1;
-}
-
-// N furthest-reaching-point updates per call, on diagonals L.k, L.k - 1, ... (the generalisation of cells2 the
-// kernels use: with a few warps per SM the instruction-level parallelism of a thread is what hides latency).
+// N furthest-reaching-point updates per call, on diagonals L.k, L.k - 1, ... (align.c:789-938).  All cells of a
+// wave read only the previous wave, so the N predecessor choices and slides are independent instruction streams:
+// with a few warps per SM this instruction-level parallelism is what hides latency.  The bookkeeping that the
+// reference does in visiting order (clips, best, trim) is then applied to k, k - 1, ... in turn.
 template <int N, class FRONT, class POOL>
 WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
     const int k0 = L.k;
@@ -448,11 +420,12 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
 #pragma unroll
     for (int j = 0; j < N; j++) P[j + 1] = load_path<FRONT>(s[j]);
     P[N + 1] = P[N];                                                    // loaded below only if it is chosen
-    int c[N], n[N], mx[N];
+    int c[N], n[N], mx[N], dd[N];
     PathState q[N];
 #pragma unroll
     for (int j = 0; j < N; j++) {
         const int d = choose(v[j], v[j + 1], v[j + 2], c[j]);
+        dd[j] = d;
         q[j] = (d > 0) ? P[j] : (d == 0 ? P[j + 1] : P[j + 2]);
         if (j == N - 1 && j < cnt && d < 0) q[j] = load_path<FRONT>(s[N]);
     }
@@ -469,7 +442,7 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
             const int kk = k0 - j, y = (c[j] - kk) >> 1, x = y + kk;
             if (n[j] == 32 && mx[j] > 32) n[j] = 32 + slide(L.aw, L.abase + (uint32_t)(x + 32), L.bw, L.bbase + (uint32_t)(y + 32), mx[j] - 32);
             if (n[j] > mx[j]) n[j] = mx[j];
-            settle<FRONT>(L, tabs, pool, s[j], kk, c[j], n[j], q[j]);
+            settle<FRONT>(L, tabs, pool, s[j], kk, c[j], n[j], dd[j], q[j]);
         }
     }
     // carry the previous-wave values of the diagonal just above the next cursor

@@ -11,10 +11,10 @@ using namespace damar::wc;
 
 namespace {
 
-struct HostPool {
-    std::vector<Cell> cells;
-    uint32_t take(int n) { uint32_t b = (uint32_t)cells.size(); cells.resize(cells.size() + n); return b; }
-    void store(uint32_t id, const Cell &c) { cells[id] = c; }
+struct HostPool {                      // copied by value into push_raw like the device pool: shares the vector
+    std::vector<Cell> *v;
+    uint32_t take(int n) { uint32_t b = (uint32_t)v->size(); v->resize(v->size() + n); return b; }
+    void store(uint32_t id, const Cell &c) { (*v)[id] = c; }
 };
 
 // 2 bit/base, 16 bases per word, first base in the top bits; `pad` slack words at the end
@@ -46,7 +46,7 @@ int run_pass(const TaskIn &t, const TrimTabs &tabs, HostPool &pool, TaskOut &out
     while (L.status == ST_RUN) {
         if (L.k < L.low) transition<RING>(L, F);
         if (L.status == ST_RUN && L.k >= L.low) {
-            if (g_nway == 2) cells2(L, F, tabs, pool);
+            if (g_nway == 2) cellsN<2>(L, F, tabs, pool);
             else if (g_nway == 4) cellsN<4>(L, F, tabs, pool);
             else cellsN<3>(L, F, tabs, pool);
         }
@@ -103,7 +103,8 @@ int wc_local_alignment(const uint8_t *aseq, int alen, const uint8_t *bseq, int b
     t.TS = TS; t.path_ave = path_ave;
     HostTabs ht(dscore);
 
-    HostPool pool;
+    std::vector<Cell> cellvec;
+    HostPool pool{&cellvec};
     TaskOut fo{}, ro{};
     t.rev = 0; t.aw = aw.data(); t.bw = bw.data();
     int st = (ring == 64) ? run_pass<64>(t, ht.tabs, pool, fo) : run_pass<32>(t, ht.tabs, pool, fo);
@@ -111,15 +112,15 @@ int wc_local_alignment(const uint8_t *aseq, int alen, const uint8_t *bseq, int b
     t.rev = 1; t.aw = awr.data(); t.bw = bwr.data();
     st = (ring == 64) ? run_pass<64>(t, ht.tabs, pool, ro) : run_pass<32>(t, ht.tabs, pool, ro);
     if (st != ST_DONE) return st + 100;
-    if (stats) { stats[0] = fo.waves + ro.waves; stats[1] = fo.cells + ro.cells; stats[2] = (int32_t)pool.cells.size(); }
+    if (stats) { stats[0] = fo.waves + ro.waves; stats[1] = fo.cells + ro.cells; stats[2] = (int32_t)cellvec.size(); }
 
     const int maxtp = 2 * ((alen > blen ? alen : blen) / TS + 2) + 2;
     std::vector<uint16_t> tbuf(8 * maxtp, 0);
     uint16_t *atr = tbuf.data() + 2 * maxtp, *btr = tbuf.data() + 6 * maxtp;
-    const int flenA = emit_chain_fwd(pool.cells.data(), fo.ha, true, anti, fo.ex, fo.ey, fo.ediff, atr);
-    const int flenB = emit_chain_fwd(pool.cells.data(), fo.hb, false, anti, fo.ex, fo.ey, fo.ediff, btr);
-    const int preA = emit_chain_rev(pool.cells.data(), ro.ha, true, ro.ex, ro.ey, ro.ediff, TS, t.aoff, flenA, atr);
-    const int preB = emit_chain_rev(pool.cells.data(), ro.hb, false, ro.ex, ro.ey, ro.ediff, TS, t.boff, flenB, btr);
+    const int flenA = emit_chain_fwd(cellvec.data(), fo.ha, true, anti, fo.ex, fo.ey, fo.ediff, atr);
+    const int flenB = emit_chain_fwd(cellvec.data(), fo.hb, false, anti, fo.ex, fo.ey, fo.ediff, btr);
+    const int preA = emit_chain_rev(cellvec.data(), ro.ha, true, ro.ex, ro.ey, ro.ediff, TS, t.aoff, flenA, atr);
+    const int preB = emit_chain_rev(cellvec.data(), ro.hb, false, ro.ex, ro.ey, ro.ediff, TS, t.boff, flenB, btr);
     const int atlen = flenA + preA, btlen = flenB + preB;
     uint16_t *at = atr - preA, *bt = btr - preB;
     const int abpos = ro.ex, bbpos = ro.ey, aepos = fo.ex, bepos = fo.ey, diffs = fo.ediff + ro.ediff;
