@@ -19,6 +19,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "path_fuse.h"
 #include "wave_core.cuh"
 
 namespace damar {
@@ -1133,6 +1134,96 @@ template <typename T> void set_smem(T kernel, int bytes) {
 
 }  // namespace
 
+
+// ---- Handle_Redundancies glue (filter.c:2438-2449): host post-pass over the pairs with several alignments ----
+namespace {
+
+// the two reads of a pair, unpacked from the device copies only when a bridge has to realign them
+struct PairSeqs : FuseSeqs {
+    const DeviceBlock *ab, *bb; int bsel, ar, br; cudaStream_t st;
+    mutable std::vector<uint8_t> a, b; mutable bool have = false;
+    static void pull(const uint32_t *words, uint32_t base, int len, std::vector<uint8_t> &dst, cudaStream_t st) {
+        const uint32_t w0 = base >> 4, w1 = (base + (uint32_t)len + 15u) >> 4;
+        std::vector<uint32_t> w(w1 - w0 + 1);
+        CUDA_CHECK(cudaMemcpyAsync(w.data(), words + w0, sizeof(uint32_t) * w.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        dst.resize((size_t)len + 1);
+        for (int i = 0; i < len; i++) {
+            const uint32_t p = base + (uint32_t)i;
+            dst[i] = (uint8_t)((w[(p >> 4) - w0] >> (30 - 2 * (int)(p & 15u))) & 3u);
+        }
+        dst[len] = 4;
+    }
+    void fetch() const override {
+        if (have) return;
+        pull(ab->packed[0], (uint32_t)ab->h_boff[ar], ab->h_rlen[ar], a, st);
+        pull(bb->packed[bsel], (uint32_t)bb->h_boff[br], bb->h_rlen[br], b, st);
+        have = true;
+    }
+    const uint8_t *aseq() const override { return a.data(); }
+    const uint8_t *bseq() const override { return b.data(); }
+    int alen() const override { return ab->h_rlen[ar]; }
+    int blen() const override { return bb->h_rlen[br]; }
+};
+
+// Rewrites the record arrays in place; new traces go to `extra` (values, not bytes) and get offsets >= ntr.
+// Returns the new record count.
+uint64_t fuse_pass(damar_overlap *recs, uint64_t *toff, uint64_t *seq, const void *trace, uint64_t nrec, uint64_t ntr, int tbytes,
+                   std::vector<uint16_t> &extra, const DeviceBlock *ab, const DeviceBlock *bb, int bsel, int comp, int ts, cudaStream_t st,
+                   int64_t *nfused) {
+    // pairs with more than one A record
+    std::vector<uint64_t> order(nrec);
+    for (uint64_t i = 0; i < nrec; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return seq[x] < seq[y]; });
+    std::vector<uint8_t> dead(nrec, 0);
+    auto load = [&](uint64_t i) {
+        FusePath p;
+        const damar_overlap &r = recs[i];
+        p.abpos = r.abpos; p.bbpos = r.bbpos; p.aepos = r.aepos; p.bepos = r.bepos; p.diffs = r.diffs;
+        p.trace.resize((size_t)r.tlen);
+        if (tbytes == 1) { const uint8_t *t = reinterpret_cast<const uint8_t *>(trace) + toff[i]; for (int k = 0; k < r.tlen; k++) p.trace[k] = t[k]; }
+        else { const uint16_t *t = reinterpret_cast<const uint16_t *>(trace) + toff[i]; for (int k = 0; k < r.tlen; k++) p.trace[k] = t[k]; }
+        return p;
+    };
+    auto store = [&](uint64_t i, const FusePath &p, uint64_t sq) {
+        damar_overlap &r = recs[i];
+        r.abpos = p.abpos; r.bbpos = p.bbpos; r.aepos = p.aepos; r.bepos = p.bepos; r.diffs = p.diffs; r.tlen = (int32_t)p.trace.size();
+        toff[i] = ntr + extra.size();
+        extra.insert(extra.end(), p.trace.begin(), p.trace.end());
+        seq[i] = sq;
+    };
+    for (uint64_t g0 = 0; g0 < nrec;) {
+        uint64_t g1 = g0;
+        const uint64_t wi = seq[order[g0]] >> 8;
+        while (g1 < nrec && (seq[order[g1]] >> 8) == wi) g1++;
+        std::vector<uint64_t> ia, ib;                     // record indices, emission order
+        for (uint64_t g = g0; g < g1; g++) ((seq[order[g]] & 128ull) ? ib : ia).push_back(order[g]);
+        g0 = g1;
+        if (ia.size() < 2 && ib.size() < 2) continue;
+        std::vector<FusePath> am, bm;
+        for (uint64_t i : ia) am.push_back(load(i));
+        for (uint64_t i : ib) bm.push_back(load(i));
+        PairSeqs sq;
+        sq.ab = ab; sq.bb = bb; sq.bsel = bsel; sq.st = st;
+        sq.ar = recs[ia[0]].aread - ab->ufirst; sq.br = recs[ia[0]].bread - bb->ufirst;
+        const bool both = ia.size() > 1 && ib.size() > 1;
+        if (ia.size() > 1) handle_redundancies(am, both ? &bm : nullptr, comp, ts, sq);
+        else handle_redundancies(bm, nullptr, comp, ts, sq);
+        if (am.size() != ia.size() || bm.size() != ib.size()) (*nfused)++;
+        for (size_t k = 0; k < ia.size(); k++) { if (k < am.size()) store(ia[k], am[k], (wi << 8) | k); else dead[ia[k]] = 1; }
+        for (size_t k = 0; k < ib.size(); k++) { if (k < bm.size()) store(ib[k], bm[k], (wi << 8) | 128ull | k); else dead[ib[k]] = 1; }
+    }
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < nrec; i++) {
+        if (dead[i]) continue;
+        if (n != i) { recs[n] = recs[i]; toff[n] = toff[i]; seq[n] = seq[i]; }
+        n++;
+    }
+    return n;
+}
+
+}  // namespace
+
 void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
@@ -1395,8 +1486,28 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             nkeep++;
         }
     }
-    out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = h_trace.p;
-    out.novl = (int64_t)nkeep; out.ntrace = (int64_t)ntr; out.tbytes = tbytes; out.redo = (int64_t)nredo;
+    uint64_t ntr_out = ntr;
+    const void *trace_out = h_trace.p;
+    int64_t nfused = 0;
+    if (hc[1] > 0 && nkeep > 0) {            // pairs with several alignments: Handle_Redundancies
+        HostProf hpf("ra.fuse");
+        std::vector<uint16_t> extra;
+        nkeep = fuse_pass(h_recs.p, h_toff.p, h_seq.p, h_trace.p, nkeep, ntr, tbytes, extra, ab, bb, bsel, comp ? 1 : 0, TS, st, &nfused);
+        if (!extra.empty()) {                                    // rewritten traces live behind the downloaded ones
+            std::vector<uint8_t> &all = ws.fused_trace;
+            all.resize((size_t)(ntr + extra.size()) * tbytes);
+            memcpy(all.data(), h_trace.p, (size_t)ntr * tbytes);
+            if (tbytes == 1) {
+                for (size_t i = 0; i < extra.size(); i++) {
+                    if (extra[i] > 255) fatal("Compression of trace to bytes fails, value too big");   // align.c:3385-3388
+                    all[(size_t)ntr + i] = (uint8_t)extra[i];
+                }
+            } else memcpy(all.data() + (size_t)ntr * 2, extra.data(), extra.size() * 2);
+            trace_out = all.data(); ntr_out = ntr + extra.size();
+        }
+    }
+    out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = trace_out;
+    out.novl = (int64_t)nkeep; out.ntrace = (int64_t)ntr_out; out.tbytes = tbytes; out.redo = (int64_t)nredo;
     out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)nwork;
     c.tm.download_ms = t_dl.stop();
     (void)rounds;

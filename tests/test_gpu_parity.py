@@ -2,11 +2,14 @@
   (1) the committed reference .las files of every golden case, bit for bit (padding bytes masked),
   (2) the oracle, stage by stage: sorted k-mer list (Sort_Kmers contract) and sorted seed hits.
 """
+import json
+import os
+
 import numpy as np
 import pytest
 
 import oracle_ffi as O
-from cases import CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from cases import CASES, GOLDEN, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
 from damar_b200 import api, dbio
 
 pytestmark = pytest.mark.gpu
@@ -26,6 +29,28 @@ def test_las_matches_reference(case):
     out = api.daligner(blks[0], blks[1:], settings(o), stats=stats)
     gold = golden_files(case)
     assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+REP = os.path.join(GOLDEN, "rep")
+with open(os.path.join(REP, "cases.json")) as _f:
+    REP_CASES = json.load(_f)
+
+
+@pytest.mark.parametrize("case", sorted(REP_CASES))
+def test_las_matches_reference_with_redundant_alignments(case):
+    """Read pairs with several local alignments: Handle_Redundancies (filter.c:1804-2077) fuses alignments that share
+    a trace point, drops contained ones and bridges narrowly parallel ones (tests/golden/make_repeats.py)."""
+    o = parse_flags(REP_CASES[case]["flags"])
+    blks = [load_block(REP, n, ()) for n in REP_CASES[case]["blocks"]]
+    stats = []
+    out = api.daligner(blks[0], blks[1:], settings(o), stats=stats)
+    d = os.path.join(REP, "ref", case)
+    gold = {fn: open(os.path.join(d, fn), "rb").read() for fn in sorted(os.listdir(d))}
+    assert sorted(out) == sorted(gold)
+    assert sum(st["multi0"] + st["multi1"] for st in stats) > 0          # the post-pass had work
     for fn, ref in gold.items():
         ok, why = dbio.las_equal(ref, out[fn])
         assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
