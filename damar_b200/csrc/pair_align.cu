@@ -1348,6 +1348,9 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
     static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 11;
+    // CTAs (= SMs, one CTA fills an SM's shared memory) of one comparison's wave kernel; fewer than 148 lets the kernels of
+    // concurrent comparisons run side by side so that the tail of one overlaps the bulk of another
+    static const int wave_ctas = getenv("DAMAR_WAVE_CTAS") ? std::max(1, std::min(NUM_SMS_B200, atoi(getenv("DAMAR_WAVE_CTAS")))) : NUM_SMS_B200;
     static std::once_flag attr;
     std::call_once(attr, [] {
         set_smem(wave_tasks<32, false, 4, 8>, WaveCfg<32, 8>::SMEM);
@@ -1390,7 +1393,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             Timer t_k(st);
             {
                 const unsigned per = (unsigned)wwarps * 32;
-                const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (2 * ncand + per - 1) / per);
+                const unsigned wb = std::min<unsigned>((unsigned)wave_ctas, (2 * ncand + per - 1) / per);
                 Q.task_order = nullptr;
                 if (ncand >= 2048 && lpt) {                      // order the queue: longest passes first
                     const int64_t nt = 2 * (int64_t)ncand;
