@@ -72,7 +72,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
-           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at"]
+           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased"]
 
 _lib = None
 
@@ -91,6 +91,8 @@ def load_library():
     L.damar_last_error.restype = C.c_char_p
     L.damar_set_filter_params.argtypes = [C.c_int] * 5
     L.damar_set_options.argtypes = [C.POINTER(Options)]
+    L.damar_set_biased.argtypes = [C.c_int]
+    L.damar_set_biased.restype = None
     L.damar_block_upload.restype = C.c_void_p
     L.damar_block_upload.argtypes = [C.POINTER(BlockDesc)]
     L.damar_block_free.argtypes = [C.c_void_p]
@@ -142,6 +144,7 @@ class Settings:
     only_identity: bool = False  # -O
     no_trace: bool = False    # -T
     verbose: bool = False     # -v
+    biased: bool = False      # -b  (variable-length k-mers by base log-frequency, filter.c:549)
     run_id: int = 1           # -r
 
 
@@ -212,6 +215,7 @@ def set_options(s: Settings, freq: Sequence[float]) -> None:
         o.freq[i] = float(freq[i])
     o.mem_limit = int(s.mem_limit_gb) * (1 << 30)
     load_library().damar_set_options(C.byref(o))
+    load_library().damar_set_biased(int(s.biased))
 
 
 def sort_kmers(dblock: DeviceBlockHandle, comp: int = 0) -> Optional[KmerIndex]:

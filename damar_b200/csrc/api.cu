@@ -1,6 +1,7 @@
 // api.cu -- the C-ABI of include/damar_b200.h on top of the stage implementations.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <map>
 #include <mutex>
@@ -33,6 +34,8 @@ static std::mutex g_mu;                           // guards the process-wide set
 static FilterParams g_fp;
 static damar_options g_opt{};
 static bool g_opt_set = false;
+static bool g_bias_latched = false;
+static int g_log_base[4];
 static int g_device = -1;
 Context &ctx() { return *tl_ctx; }
 
@@ -147,6 +150,18 @@ void ensure_init() {
     c.fp = g_fp; c.opt = g_opt;
 }
 
+// filter.c:774-789: NormShift/LogBase are built once per process, from the freq of the block of the first
+// Sort_Kmers call (the forward A block, daligner.c:982) and reused for every later block and orientation.
+void bias_log_base(const float freq[4], int out[4]) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    if (!g_bias_latched) {
+        const double scale = -10000. / log(4.);
+        for (int i = 0; i < 4; i++) g_log_base[i] = (int)ceil(scale * log(freq[i]));
+        g_bias_latched = true;
+    }
+    for (int i = 0; i < 4; i++) out[i] = g_log_base[i];
+}
+
 // ---- results of the last match_filter call live in the worker's scratch ----
 #define g_out (scratch().out)
 #define g_hits (scratch().hits)
@@ -205,8 +220,17 @@ int damar_set_filter_params(int kmer, int binshift, int suppress, int hitmin, in
     fp.nthreads_pow2 = 1; fp.nshift = 0;
     while (2 * fp.nthreads_pow2 <= nthreads) { fp.nthreads_pow2 *= 2; fp.nshift++; }   // filter.c:192-198
     fp.set = true;
+    g_bias_latched = false;
     ctx().fp = fp;
     return 0;
+}
+
+/* BIASED (daligner.c:132, set by -b).  Call before the first damar_sort_kmers of a job. */
+void damar_set_biased(int biased) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_fp.biased = biased != 0;
+    g_bias_latched = false;
+    ctx().fp.biased = g_fp.biased;
 }
 
 void damar_set_options(const damar_options *opt) { std::lock_guard<std::mutex> lock(g_mu); g_opt = *opt; g_opt_set = true; ctx().opt = *opt; }

@@ -80,7 +80,10 @@ struct FilterParams {
     int nthreads_pow2 = 4, nshift = 2;
     uint64_t kmask = (1ull << 28) - 1;
     bool set = false;
+    bool biased = false;                        // BIASED (-b, daligner.c:729)
 };
+// LogBase of filter.c:774-789: fixed by the FIRST Sort_Kmers call after Set_Filter_Params (api.cu)
+void bias_log_base(const float freq[4], int out[4]);
 
 struct Timer {
     cudaEvent_t a, b;

@@ -24,6 +24,7 @@ static int g_nthreads = 4;
 int Set_Filter_Params(int kmer, int binshift, int suppress, int hitmin, int nthreads)
 {
     g_nthreads = nthreads;
+    damar_set_biased(BIASED);                        /* daligner.c parses -b before this call (:729, :862) */
     return damar_set_filter_params(kmer, binshift, suppress, hitmin, nthreads);
 }
 

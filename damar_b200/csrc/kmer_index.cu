@@ -176,6 +176,70 @@ __global__ void __launch_bounds__(256) extract_tuples(const uint32_t *__restrict
     gpos[idx] = (uint32_t)p;
 }
 
+// -b: variable-length k-mers whose summed -log4 base frequency reaches K "bases" of information
+// (biased_tuple_thread, filter.c:549-688).  The window's left edge depends on where the previous window of the
+// same stretch ended, so a stretch (a whole read, or a gap between mask intervals) is walked by ONE thread, first
+// to count, then to emit.  A masked stretch that reaches q while still growing emits at p == q with the code of
+// the bases before it (filter.c:598-599 leaves only the inner loop) -- kept, the unmasked variant leaves the read.
+struct BiasTable { int lb0, lb1, lb2, lb3, lognorm, logthresh; };
+__device__ __forceinline__ int bias_of(const BiasTable &t, uint32_t x) { return (x & 2u) ? ((x & 1u) ? t.lb3 : t.lb2) : ((x & 1u) ? t.lb1 : t.lb0); }
+
+template <bool EMIT>
+__device__ uint32_t biased_stretch(const uint32_t *__restrict__ words, int64_t g0, int p0, int q, bool masked, int K, uint64_t kmask,
+                                   const BiasTable &bt, uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos, uint32_t n) {
+    uint64_t c = 0;
+    int a = 0, k = 1, p = p0;
+    uint32_t cnt = 0;
+    while (p < q) {
+        uint32_t x = base_at(words, g0 + p);
+        a += bias_of(bt, x); c = (c << 2) | x;
+        while (a < bt.lognorm && k < K) {
+            if (++p >= q) {
+                if (!masked) return cnt;
+                break;
+            }
+            x = base_at(words, g0 + p);
+            k++; a += bias_of(bt, x); c = (c << 2) | x;
+        }
+        for (;;) {
+            const int u = a - bias_of(bt, base_at(words, g0 + p - k + 1));
+            if (u < bt.lognorm) break;
+            a = u; k--;
+        }
+        if (a > bt.logthresh) {
+            if (EMIT) { codes[n + cnt] = (c << (2 * (K - k))) & kmask; gpos[n + cnt] = (uint32_t)(g0 + p); }
+            cnt++;
+        }
+        p++;
+        a -= bias_of(bt, base_at(words, g0 + p - k));
+    }
+    return cnt;
+}
+
+// one thread per read; EMIT=false fills per_read, EMIT=true writes from kbase[r] on
+template <bool EMIT>
+__global__ void biased_tuples(const uint32_t *__restrict__ words, const uint32_t *__restrict__ boff, const int32_t *__restrict__ rlen,
+                              int nreads, int K, uint64_t kmask, const int64_t *__restrict__ anno, const int32_t *__restrict__ data,
+                              BiasTable bt, uint32_t *__restrict__ per_read, const uint32_t *__restrict__ kbase,
+                              uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nreads) return;
+    const int len = rlen[r];
+    const int64_t g0 = boff[r];
+    uint32_t n = EMIT ? kbase[r] : 0u, n0 = n;
+    if (anno == nullptr) {
+        n += biased_stretch<EMIT>(words, g0, 0, len, false, K, kmask, bt, codes, gpos, n);
+    } else {
+        const int64_t b = anno[r], f = anno[r + 1];
+        for (int64_t j = b; j <= f; j += 2) {
+            const int p = (j == b) ? 0 : data[j - 1];
+            const int q = (j == f) ? len : data[j];
+            if (p + K <= q) n += biased_stretch<EMIT>(words, g0, p, q, true, K, kmask, bt, codes, gpos, n);
+        }
+    }
+    if (!EMIT) per_read[r] = n - n0;
+}
+
 // -t suppression (compsize_thread / compress_thread, filter.c:700-751): keep[i] = 1 iff the
 // run of equal codes containing i is shorter than `too_frequent`.  A thread only needs to look
 // `too_frequent` entries to either side.
@@ -291,8 +355,17 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     DevBuf<uint64_t> total;
     per_read.reserve((size_t)b->nreads + 1);
     total.reserve(1);
-    if (b->has_mask) gap_pref.reserve((size_t)(b->mask_len / 2 + b->nreads + 1));
-    count_tuples<<<(b->nreads + 255) / 256, 256, 0, st>>>(b->rlen, b->nreads, K, anno, data, per_read.p, gap_pref.p);
+    if (b->has_mask && !fp.biased) gap_pref.reserve((size_t)(b->mask_len / 2 + b->nreads + 1));
+    BiasTable bt{};
+    if (fp.biased) {
+        int lb[4];
+        bias_log_base(b->freq, lb);              // latched at the first Sort_Kmers after Set_Filter_Params (filter.c:774)
+        bt = BiasTable{lb[0], lb[1], lb[2], lb[3], 10000 * K, 10000 * (K - 2)};   // MAX_BIAS = 2 (filter.c:69)
+        biased_tuples<false><<<(b->nreads + 63) / 64, 64, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, K, fp.kmask, anno, data,
+                                                                    bt, per_read.p, nullptr, nullptr, nullptr);
+    } else {
+        count_tuples<<<(b->nreads + 255) / 256, 256, 0, st>>>(b->rlen, b->nreads, K, anno, data, per_read.p, gap_pref.p);
+    }
     KERNEL_CHECK(); count_launch();
     // kbase[r] = exclusive prefix of per-read counts (32-bit is enough: kmers < 2^31, filter.c:762)
     uint32_t total32 = 0;
@@ -312,8 +385,12 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
     g0 = (std::remove_reference<decltype(g0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 2));
     g1 = (std::remove_reference<decltype(g1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 2));
-    extract_tuples<<<(unsigned)((b->nbases + 255) / 256), 256, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, b->nbases, K,
-                                                                        anno, data, per_read.p, gap_pref.p, k0, g0);
+    if (fp.biased)
+        biased_tuples<true><<<(b->nreads + 63) / 64, 64, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, K, fp.kmask, anno, data,
+                                                                   bt, nullptr, per_read.p, k0, g0);
+    else
+        extract_tuples<<<(unsigned)((b->nbases + 255) / 256), 256, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, b->nbases, K,
+                                                                            anno, data, per_read.p, gap_pref.p, k0, g0);
     KERNEL_CHECK(); count_launch();
     c.tm.extract_ms = t_ex.stop();
 

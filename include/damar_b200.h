@@ -114,6 +114,10 @@ int damar_worker_count(void);
 /* Set_Filter_Params (filter.c:171-201).  Returns 1 for an illegal combination. */
 int  damar_set_filter_params(int kmer, int binshift, int suppress, int hitmin, int nthreads);
 void damar_set_options(const damar_options *opt);
+/* BIASED (-b, daligner.c:132/729): variable-length k-mers by base log-frequency (biased_tuple_thread,
+ * filter.c:549-688).  The per-base weights are fixed from the freq of the block of the FIRST
+ * damar_sort_kmers call that follows damar_set_filter_params / damar_set_biased (filter.c:774-789). */
+void damar_set_biased(int biased);
 
 /* block residency: ships the block to HBM and packs it to 2 bit/base.                          */
 damar_block *damar_block_upload(const damar_block_desc *desc);

@@ -14,6 +14,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 #include <limits.h>
 #include "daligner_oracle.h"
@@ -78,6 +79,35 @@ static uint64_t key_pair(const rec16 *r) { return r->hi; }                      
  * compaction (filter.c:700-751, 890-939).  Result: every admissible k-mer, stably sorted by
  * code (ties in (read,rpos) order), followed by the sentinels {~0},{0} (filter.c:941-942).
  * ------------------------------------------------------------------------------------------ */
+/* biased_tuple_thread (filter.c:549-688) for one stretch [p0, q) of a read: variable-length k-mers whose summed
+ * -log4 frequency reaches Kmer "bases" of information; `masked` selects the interval-gap variant (:571-631), whose
+ * inner growth loop stops at q WITHOUT leaving the outer step, else the whole-read variant (:633-676), which
+ * leaves the read at its terminator.  Emits into list (may be NULL: count only); returns the count.             */
+static int64_t biased_stretch(const int8_t *s, int p0, int q, int masked, int K, uint64_t kmask, const int *LogBase,
+                              int LogNorm, int LogThresh, ora_kmer *list, int read)
+{
+    const int8_t *t = s + 1;
+    uint64_t c = 0; int a = 0, k = 1, p = p0, x; int64_t n = 0;
+    const int Kshift = 2 * K;
+    while (masked ? (p < q) : (s[p] != 4)) {
+        x = s[p];
+        a += LogBase[x]; c = (c << 2) | (uint64_t)x;
+        while (a < LogNorm && k < K) {
+            if (masked) { if (++p >= q) break; x = s[p]; }
+            else { if ((x = s[++p]) == 4) return n; }
+            k += 1; a += LogBase[x]; c = (c << 2) | (uint64_t)x;
+        }
+        for (;;) { int u = a - LogBase[(int)t[p - k]]; if (u < LogNorm) break; a = u; k -= 1; }
+        if (a > LogThresh) {
+            if (list) { list[n].code = (c << (Kshift - 2 * k)) & kmask; list[n].read = read; list[n].rpos = p; }
+            n++;
+        }
+        p += 1;
+        a -= LogBase[(int)s[p - k]];
+    }
+    return n;
+}
+
 ora_kmer *ora_sort_kmers(const ora_block *blk, const ora_params *p, int64_t *len)
 {
     const int K = p->kmer;
@@ -85,16 +115,31 @@ ora_kmer *ora_sort_kmers(const ora_block *blk, const ora_params *p, int64_t *len
     int64_t total = 0, n = 0;
     int i;
     ora_kmer *list, *tmp, *rez;
+    int LogBase[4] = {0, 0, 0, 0}, LogNorm = 0, LogThresh = 0;
+
+    if (p->biased) {                               /* filter.c:774-789; MAX_BIAS = 2 (:69).  The reference fills LogBase
+                                                      ONCE, at the first Sort_Kmers call of the process = the forward A block
+                                                      (daligner.c:982), and reuses it for every later block and orientation. */
+        const float *fq = p->freq;
+        double scale = -10000. / log(4.);
+        LogNorm = 10000 * K; LogThresh = 10000 * (K - 2);
+        for (i = 0; i < 4; i++) LogBase[i] = (int)ceil(scale * log(fq[i]));
+    }
 
     for (i = 0; i < blk->nreads; i++) {
+        const int8_t *s = blk->bases + blk->boff[i];
         if (blk->manno == NULL) {
-            if (blk->rlen[i] >= K) total += blk->rlen[i] - K + 1;
+            if (p->biased) total += biased_stretch(s, 0, blk->rlen[i], 0, K, kmask, LogBase, LogNorm, LogThresh, NULL, i);
+            else if (blk->rlen[i] >= K) total += blk->rlen[i] - K + 1;
         } else {                                   /* gaps between mask intervals, filter.c:483-515 */
             int64_t b = blk->manno[i], f = blk->manno[i + 1], a;
             for (a = b; a <= f; a += 2) {
                 int pp = (a == b) ? 0 : blk->mdata[a - 1];
                 int q  = (a == f) ? blk->rlen[i] : blk->mdata[a];
-                if (pp + K <= q) total += q - (pp + K - 1);
+                if (pp + K <= q) {
+                    if (p->biased) total += biased_stretch(s, pp, q, 1, K, kmask, LogBase, LogNorm, LogThresh, NULL, i);
+                    else total += q - (pp + K - 1);
+                }
             }
         }
     }
@@ -108,6 +153,7 @@ ora_kmer *ora_sort_kmers(const ora_block *blk, const ora_params *p, int64_t *len
         const int8_t *s = blk->bases + blk->boff[i];
         if (blk->manno == NULL) {                  /* filter.c:529-544 */
             uint64_t c = 0; int x, pos = 0;
+            if (p->biased) { n += biased_stretch(s, 0, blk->rlen[i], 0, K, kmask, LogBase, LogNorm, LogThresh, list + n, i); continue; }
             if (blk->rlen[i] < K) continue;
             for (x = 1; x < K; x++) c = (c << 2) | (uint64_t)s[pos++];
             while (s[pos] != 4) {
@@ -121,6 +167,7 @@ ora_kmer *ora_sort_kmers(const ora_block *blk, const ora_params *p, int64_t *len
                 int q   = (a == f) ? blk->rlen[i] : blk->mdata[a];
                 if (pos + K <= q) {
                     uint64_t c = 0; int x;
+                    if (p->biased) { n += biased_stretch(s, pos, q, 1, K, kmask, LogBase, LogNorm, LogThresh, list + n, i); continue; }
                     for (x = 1; x < K; x++) c = (c << 2) | (uint64_t)s[pos++];
                     while (pos < q) {
                         c = ((c << 2) | (uint64_t)s[pos]) & kmask;

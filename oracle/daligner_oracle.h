@@ -49,6 +49,7 @@ typedef struct {
     float    freq[4];                                     /* A block base frequencies         */
     uint64_t mem_limit;                                   /* MEM_LIMIT in bytes; 0 == -M0     */
     int64_t  sizeof_a, sizeof_b;                          /* sizeof_DB() of the two blocks    */
+    int32_t  biased;                                      /* -b (BIASED, daligner.c:729)       */
 } ora_params;
 
 /* One .las record as it reaches Write_Overlap (align.c:3365): 36 meaningful bytes. */

@@ -15,9 +15,14 @@ with open(os.path.join(GOLDEN, "cases.json")) as f:
     CASES = json.load(f)
 
 
+BIAS = os.path.join(GOLDEN, "bias")        # AT-rich DB for -b (tests/golden/make_biased.py)
+with open(os.path.join(BIAS, "cases.json")) as f:
+    BIAS_CASES = json.load(f)
+
+
 def parse_flags(flags):
     """daligner flags -> dict(k,w,h,t,e,l,s,j,M,masks,I,O,A,T) (daligner.c:721-808)."""
-    o = dict(k=14, w=6, h=35, t=0, e=0.70, l=1000, s=100, j=4, M=None, masks=[], I=False, O=False, A=False, T=False)
+    o = dict(k=14, w=6, h=35, t=0, e=0.70, l=1000, s=100, j=4, M=None, masks=[], I=False, O=False, A=False, T=False, b=False)
     for f in flags:
         c, v = f[1], f[2:]
         if c in "kwhtlsjM":
@@ -26,7 +31,7 @@ def parse_flags(flags):
             o["e"] = float(v)
         elif c == "m":
             o["masks"].append(v)
-        elif c in "IOAT":
+        elif c in "IOATb":
             o[c] = True
         elif c == "v":
             pass
@@ -38,14 +43,14 @@ def parse_flags(flags):
 def oracle_kwargs(o):
     return dict(k=o["k"], w=o["w"], h=o["h"], t=o["t"], nthreads=o["j"], identity=int(o["I"] or o["O"]),
                 symmetric=int(not o["A"]), minlen=o["l"], tspace=o["s"], no_trace=int(o["T"]), ave_corr=o["e"],
-                mem_limit=(o["M"] or 0) << 30)
+                mem_limit=(o["M"] or 0) << 30, biased=int(o.get("b", False)))
 
 
 def settings(o):
     from damar_b200.api import Settings
     return Settings(kmer=o["k"], binshift=o["w"], hitmin=o["h"], suppress=o["t"], ave_corr=o["e"], minlen=o["l"],
                     trace_spacing=o["s"], nthreads=o["j"], mem_limit_gb=o["M"] or 0, symmetric=not o["A"],
-                    identity=o["I"], only_identity=o["O"], no_trace=o["T"])
+                    identity=o["I"], only_identity=o["O"], no_trace=o["T"], biased=o.get("b", False))
 
 
 @lru_cache(maxsize=None)
@@ -53,6 +58,6 @@ def load_block(dbdir, name, masks):
     return dbio.read_block(os.path.join(dbdir, name), list(masks) if masks else None)
 
 
-def golden_files(case):
-    d = os.path.join(TINY, "ref", case)
+def golden_files(case, dbdir=TINY):
+    d = os.path.join(dbdir, "ref", case)
     return {fn: open(os.path.join(d, fn), "rb").read() for fn in sorted(os.listdir(d))}

@@ -27,7 +27,8 @@ class OraParams(C.Structure):
                 ("hitmin", C.c_int32), ("nthreads", C.c_int32), ("identity", C.c_int32),
                 ("symmetric", C.c_int32), ("minover", C.c_int32), ("tspace", C.c_int32),
                 ("no_trace", C.c_int32), ("ave_corr", C.c_double), ("freq", C.c_float * 4),
-                ("mem_limit", C.c_uint64), ("sizeof_a", C.c_int64), ("sizeof_b", C.c_int64)]
+                ("mem_limit", C.c_uint64), ("sizeof_a", C.c_int64), ("sizeof_b", C.c_int64),
+                ("biased", C.c_int32)]
 
 
 class OraOvl(C.Structure):
@@ -112,7 +113,7 @@ class HostBlock:
 
 
 def make_params(k=14, w=6, h=35, t=0, nthreads=4, identity=0, symmetric=1, minlen=1000, tspace=100,
-                no_trace=0, ave_corr=0.70, freq=(.25, .25, .25, .25), mem_limit=0, sizeof_a=0, sizeof_b=0):
+                no_trace=0, ave_corr=0.70, freq=(.25, .25, .25, .25), mem_limit=0, sizeof_a=0, sizeof_b=0, biased=0):
     p = OraParams()
     p.kmer, p.binshift, p.suppress, p.hitmin, p.nthreads = k, w, t, h, nthreads
     p.identity, p.symmetric, p.minover, p.tspace, p.no_trace = identity, symmetric, 2 * minlen, tspace, no_trace
@@ -120,6 +121,7 @@ def make_params(k=14, w=6, h=35, t=0, nthreads=4, identity=0, symmetric=1, minle
     for i in range(4):
         p.freq[i] = float(freq[i])
     p.mem_limit, p.sizeof_a, p.sizeof_b = mem_limit, sizeof_a, sizeof_b
+    p.biased = biased
     return p
 
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
-from cases import CASES, GOLDEN, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from cases import BIAS, BIAS_CASES, CASES, GOLDEN, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
 from damar_b200 import api, dbio
 
 pytestmark = pytest.mark.gpu
@@ -56,12 +56,30 @@ def test_las_matches_reference_with_redundant_alignments(case):
         assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
 
 
-@pytest.mark.parametrize("case,comp", [("default", 0), ("default", 1), ("rndmask", 0), ("rndmask", 1),
-                                       ("k16s200", 0), ("twomasks", 1)])
-def test_sorted_kmers_match_oracle(case, comp):
-    o = parse_flags(CASES[case]["flags"])
-    blk = load_block(TINY, CASES[case]["blocks"][0], tuple(o["masks"]))
-    p = O.make_params(**oracle_kwargs(o))
+@pytest.mark.parametrize("case", sorted(BIAS_CASES))
+def test_las_matches_reference_biased(case):
+    """-b: variable-length k-mers (biased_tuple_thread, filter.c:549-688) on the AT-rich fixture."""
+    o = parse_flags(BIAS_CASES[case]["flags"])
+    blks = [load_block(BIAS, n, tuple(o["masks"])) for n in BIAS_CASES[case]["blocks"]]
+    out = api.daligner(blks[0], blks[1:], settings(o))
+    gold = golden_files(case, BIAS)
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+KMER_CASES = [(TINY, CASES, c, comp) for c, comp in [("default", 0), ("default", 1), ("rndmask", 0), ("rndmask", 1),
+                                                     ("k16s200", 0), ("twomasks", 1)]] + \
+             [(BIAS, BIAS_CASES, c, comp) for c, comp in [("bias_b", 0), ("bias_b", 1), ("bias_b_dust", 0),
+                                                          ("bias_b_dust", 1), ("bias_b_k16", 1)]]
+
+
+@pytest.mark.parametrize("dbdir,table,case,comp", KMER_CASES, ids=[f"{c}-{comp}" for _, _, c, comp in KMER_CASES])
+def test_sorted_kmers_match_oracle(dbdir, table, case, comp):
+    o = parse_flags(table[case]["flags"])
+    blk = load_block(dbdir, table[case]["blocks"][0], tuple(o["masks"]))
+    p = O.make_params(**{**oracle_kwargs(o), "freq": tuple(float(x) for x in blk.freq)})
     hb = O.HostBlock(blk)
     L = O.lib()
     if comp:
@@ -78,6 +96,8 @@ def test_sorted_kmers_match_oracle(case, comp):
     assert api.set_filter_params(o["k"], o["w"], o["t"], o["h"], o["j"]) == 0
     api.set_options(settings(o), blk.freq)
     d = api.DeviceBlockHandle(blk)
+    if comp and o["b"]:
+        api.sort_kmers(d, 0).free()        # -b weights are fixed by the first (forward) Sort_Kmers call of a job
     idx = api.sort_kmers(d, comp)
     got = idx.download()
     idx.free(); d.free()
@@ -135,20 +155,22 @@ def test_sorted_hits_match_oracle(case, comp):
 # drop-in: the UNMODIFIED reference host (daligner.c + align.c + DB.c) linked against our library
 # through the filter.h shim (oracle/_ref/daligner_b200, built by oracle/Makefile)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["default", "b2", "dust", "twomasks", "identity", "asym", "k16s200", "memlimit", "notrace"])
+@pytest.mark.parametrize("case", ["default", "b2", "dust", "twomasks", "identity", "asym", "k16s200", "memlimit", "notrace",
+                                  "bias_b", "bias_b_dust"])
 def test_dropin_reference_host(case, tmp_path):
     import os, shutil, subprocess
     from cases import ROOT
     exe = os.path.join(ROOT, "oracle", "_ref", "daligner_b200")
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/daligner_b200 not built (needs /root/reference at build time)")
-    for fn in os.listdir(TINY):
-        p = os.path.join(TINY, fn)
+    dbdir, table = (BIAS, BIAS_CASES) if case.startswith("bias") else (TINY, CASES)
+    for fn in os.listdir(dbdir):
+        p = os.path.join(dbdir, fn)
         if os.path.isfile(p):
             shutil.copy(p, tmp_path / fn)
-    r = subprocess.run([exe] + CASES[case]["flags"] + CASES[case]["blocks"], cwd=tmp_path, capture_output=True, text=True)
+    r = subprocess.run([exe] + table[case]["flags"] + table[case]["blocks"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
-    gold = golden_files(case)
+    gold = golden_files(case, dbdir)
     got = {}
     for d in os.listdir(tmp_path):
         if d.startswith("d001_"):

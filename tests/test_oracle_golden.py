@@ -4,7 +4,7 @@ The golden files were written by the UNMODIFIED reference binary (tests/golden/m
 import pytest
 
 import oracle_ffi as O
-from cases import CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
+from cases import BIAS, BIAS_CASES, CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
 from damar_b200 import dbio
 
 
@@ -21,6 +21,25 @@ def test_oracle_matches_reference(case):
         assert ok, f"{case}/{fn}: {why}"
     # pairs with >1 surviving alignment enter Handle_Redundancies (filter.c:2442) in the reference; the
     # golden comparison above shows that it left them unchanged on these fixtures
+
+
+@pytest.mark.parametrize("case", sorted(BIAS_CASES))
+def test_oracle_matches_reference_biased(case):
+    """-b (biased_tuple_thread, filter.c:549-688) on an AT-rich DB (simulator -b.7); the *_h90 pair shows that the
+    option changes the records on this DB (the two reference outputs differ)."""
+    o = parse_flags(BIAS_CASES[case]["flags"])
+    blks = [load_block(BIAS, n, tuple(o["masks"])) for n in BIAS_CASES[case]["blocks"]]
+    out = O.daligner(blks[0], blks[1:], oracle_kwargs(o), only_identity=int(o["O"]))
+    gold = golden_files(case, BIAS)
+    assert sorted(k for k in out if k != "_stats") == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why}"
+
+
+def test_biased_option_changes_output():
+    a, b = golden_files("bias_b_h90", BIAS), golden_files("bias_plain_h90", BIAS)
+    assert any(a[fn] != b[fn] for fn in a)
 
 
 def test_las_roundtrip_parse():
