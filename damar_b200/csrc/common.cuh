@@ -29,6 +29,7 @@ void set_error(const char *fmt, ...);
 
 constexpr int NUM_SMS_B200 = 148;
 constexpr int PACK_FRONT_PAD = 4;     // words of zero padding in front of every packed base array
+constexpr int RTAB_SHIFT = 9;         // one read-lookup entry per 512 base slots (reads are mostly longer than that)
 
 // ---- device memory: caching allocator (api.cu); all work is ordered on the context stream ----
 void *dev_alloc_bytes(size_t bytes);
@@ -145,6 +146,7 @@ struct DeviceBlock {
     int64_t npacked_words = 0;
     uint32_t *boff = nullptr;                   // [nreads+1] (blocks are < 2^31 bases, filter.c:794)
     int32_t *rlen = nullptr;                    // [nreads]
+    uint32_t *rtab = nullptr;                   // read holding gpos (i << RTAB_SHIFT): starting point of read_of_tab()
     bool has_mask = false;
     bool as_is = false;                         // host already complemented the block (DAMAR_BLOCK_AS_IS)
     int64_t *mask_anno[2] = {nullptr, nullptr}; // [nreads+1], forward / mirrored

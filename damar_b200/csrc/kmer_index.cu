@@ -24,6 +24,7 @@ DeviceBlock::~DeviceBlock() {
     }
     if (boff) dev_free(boff);
     if (rlen) dev_free(rlen);
+    if (rtab) dev_free(rtab);
 }
 DeviceIndex::~DeviceIndex() {
     if (codes) dev_free(codes);
@@ -69,6 +70,15 @@ __device__ __forceinline__ int read_of(const uint32_t *__restrict__ boff, int nr
         if (boff[mid] <= p) lo = mid; else hi = mid;
     }
     return lo;
+}
+
+// rtab[i] = read whose slot range holds gpos i << RTAB_SHIFT: turns the per-entry binary search over boff of the
+// merge kernels (seed_merge.cu) into one table load plus a step or two
+__global__ void build_rtab(const uint32_t *__restrict__ boff, int nreads, int64_t nbases, uint32_t *__restrict__ rtab, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = i << RTAB_SHIFT;
+    rtab[i] = (uint32_t)read_of(boff, nreads, (uint32_t)(p < nbases ? p : nbases - 1));
 }
 
 // reverse-complement every read in packed form (daligner.c:511-527): one thread per output word
@@ -302,6 +312,12 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
     {
         int64_t nw = b->npacked_words;
         pack_bases<<<(unsigned)((nw + 255) / 256), 256, 0, c.stream>>>(dbytes, nbytes, b->packed[0], nw);
+        KERNEL_CHECK(); count_launch();
+    }
+    {
+        const int64_t nt = (b->nbases >> RTAB_SHIFT) + 1;
+        b->rtab = (std::remove_reference<decltype(b->rtab)>::type)dev_alloc_bytes(sizeof(uint32_t) * nt);
+        build_rtab<<<(unsigned)((nt + 255) / 256), 256, 0, c.stream>>>(b->boff, b->nreads, b->nbases, b->rtab, nt);
         KERNEL_CHECK(); count_launch();
     }
     if (d->mask_anno != nullptr) {

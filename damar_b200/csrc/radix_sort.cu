@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist(const uint64_t *__restrict
     tile_hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+__global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                         uint64_t *__restrict__ kout, uint32_t *__restrict__ vout,
                                                         int64_t n, int shift, const uint32_t *__restrict__ tile_off,
                                                         int ntiles) {
@@ -50,14 +50,14 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
     const int64_t base = (int64_t)blockIdx.x * RS_TILE;
     const int nvalid = (int)((n - base < RS_TILE) ? (n - base) : RS_TILE);
 
+    // keys stay in registers for the whole pass; the values are only fetched when their slot is known, which keeps
+    // the kernel at 80 registers = 3 CTAs (24 warps) per SM
     uint64_t key[RS_ITEMS];
-    uint32_t val[RS_ITEMS];
     uint16_t rank[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; i++) {
         int t = w * RS_WTILE + i * 32 + lane;
-        if (t < nvalid) { key[i] = kin[base + t]; val[i] = vin[base + t]; }
-        else { key[i] = ~0ull; val[i] = 0; }
+        key[i] = (t < nvalid) ? kin[base + t] : ~0ull;
     }
     for (int d = tid; d < RS_WARPS * 256; d += RS_THREADS) (&whist[0][0])[d] = 0;
     __syncthreads();
@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
     for (int i = 0; i < RS_ITEMS; i++) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
         const uint32_t p = dstart[d] + whist[w][d] + rank[i];
-        if (p < (uint32_t)RS_TILE) { skeys[p] = key[i]; svals[p] = val[i]; }
+        const int t = w * RS_WTILE + i * 32 + lane;
+        if (t < nvalid) { skeys[p] = key[i]; svals[p] = vin[base + t]; }
     }
     __syncthreads();
 

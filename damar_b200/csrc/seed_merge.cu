@@ -51,10 +51,12 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__
     while (l < r) { uint32_t m = (l + r) >> 1; if (a[m] < x) l = m + 1; else r = m; }
     return l;
 }
-__device__ __forceinline__ int read_of(const uint32_t *__restrict__ boff, int nreads, uint32_t p) {
-    int lo = 0, hi = nreads;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (boff[mid] <= p) lo = mid; else hi = mid; }
-    return lo;
+// the read whose slot range [boff[r], boff[r+1]) holds gpos p, from the block's lookup table (kmer_index.cu::build_rtab)
+struct ReadMap { const uint32_t *boff, *rtab; };
+__device__ __forceinline__ int read_of(const ReadMap m, uint32_t p) {
+    int r = (int)m.rtab[p >> RTAB_SHIFT];
+    while (m.boff[r + 1] <= p) r++;
+    return r;
 }
 
 // Number of B-group entries admitted for A entry (gpos ga) in a self comparison:
@@ -63,12 +65,12 @@ __device__ __forceinline__ int read_of(const uint32_t *__restrict__ boff, int nr
 //   -I, C        : b.read <= a.read                          (filter.c:1092-1096)
 // All three are "gposB < threshold" because the group is in gpos order and both blocks share boff.
 __device__ __forceinline__ uint32_t self_partners(const uint32_t *__restrict__ bgpos, uint32_t jb, uint32_t ib, uint32_t ga,
-                                                  const uint32_t *__restrict__ boff, int nreads, int identity, int comp) {
+                                                  const ReadMap m, int identity, int comp) {
     uint32_t thr;
     if (identity && !comp) thr = ga;
     else {
-        int r = read_of(boff, nreads, ga);
-        thr = (identity && comp) ? boff[r + 1] : boff[r];
+        int r = read_of(m, ga);
+        thr = (identity && comp) ? m.boff[r + 1] : m.boff[r];
     }
     return lower_bound_u32(bgpos, jb, ib, thr) - jb;
 }
@@ -77,19 +79,37 @@ struct GroupArgs {
     const uint64_t *acodes; const uint32_t *agpos; int64_t alen;
     const uint64_t *bcodes; const uint32_t *bgpos; int64_t blen;
     const uint32_t *gstart; uint32_t ngroups;
-    const uint32_t *boff; int nreads;            // of the A block (== B block when self)
+    ReadMap amap;                                // of the A block (== B block when self)
     int self, comp, identity, same_list;
     uint32_t *gjb, *gnb, *gct;                   // per group: B run start, B run length, min(ct, 2^32-1)
     unsigned long long *gram;                    // MAXGRAM bins or nullptr
 };
 
+// [jb, ib) = the run of `code` inside the sorted window w[0, n)
+__device__ __forceinline__ void equal_run(const uint64_t *w, int64_t n, uint64_t code, int64_t &jb, int64_t &ib) {
+    jb = lower_bound_u64(w, n, code);
+    ib = jb;
+    if (jb < n && w[jb] == code) {                               // equal-code runs are short: gallop, then bisect
+        int64_t step = 1, e = jb + 1;
+        while (e < n && w[e] == code) { e += step; step <<= 1; }
+        const int64_t from = e - (step >> 1), to = (e < n) ? e : n;
+        ib = (code == ~0ull) ? n : from + lower_bound_u64(w + from, to - from, code + 1);
+    }
+}
+
 // Each CTA owns a contiguous chunk of A groups and walks it in tiles of MG_TILE groups.  Because both
 // lists are sorted, the B entries that can match a tile lie in one window [lo, hi): two threads
-// locate it with a full binary search, every thread then searches only inside the window
-// (a few hundred entries, resident in L1/L2) instead of the whole B list.
+// locate it with a full binary search; the window's codes are then staged in shared memory (coalesced
+// stream of the B list, read once) and every thread bisects there.  Windows larger than MG_WIN entries
+// (a tile that spans a very frequent code) are searched in place.
+// Self comparison of a list with itself (N orientation): the B run IS the A run and the partners of an entry
+// are the entries of the run that belong to earlier reads -- a run of one k-mer (most of them: any k-mer with
+// a sequencing error in it) has none and needs no search at all.
 constexpr int MG_TILE = 2048;
+constexpr int MG_WIN = 4096;
 __global__ void __launch_bounds__(256) match_groups(GroupArgs a) {
     extern __shared__ uint32_t sgram[];
+    __shared__ uint64_t swin[MG_WIN];
     __shared__ int64_t win[2];
     const bool histo = (a.gram != nullptr);
     if (histo) { for (int i = threadIdx.x; i < MAXGRAM; i += blockDim.x) sgram[i] = 0; }
@@ -105,34 +125,46 @@ __global__ void __launch_bounds__(256) match_groups(GroupArgs a) {
             }
         }
         __syncthreads();
+        const int64_t lo = a.same_list ? 0 : win[0], hi = a.same_list ? 0 : win[1];
+        const bool staged = !a.same_list && (hi - lo <= MG_WIN);
+        if (staged) {
+            for (int i = threadIdx.x; i < (int)(hi - lo); i += blockDim.x) swin[i] = a.bcodes[lo + i];
+            __syncthreads();
+        }
         for (uint64_t gg = t0 + threadIdx.x; gg < t1; gg += blockDim.x) {
             const uint32_t g = (uint32_t)gg;
             const uint32_t ja = a.gstart[g];
             const uint32_t ia = (g + 1 < a.ngroups) ? a.gstart[g + 1] : (uint32_t)a.alen;
-            const uint64_t code = a.acodes[ja];
             uint32_t jb, ib;
-            if (a.same_list) { jb = ja; ib = ia; }
-            else {
-                const int64_t lo = win[0], hi = win[1];
-                jb = (uint32_t)(lo + lower_bound_u64(a.bcodes + lo, hi - lo, code));
-                ib = jb;
-                if ((int64_t)jb < hi && a.bcodes[jb] == code) {      // equal-code runs are short: gallop, then bisect
-                    int64_t step = 1, e = (int64_t)jb + 1;
-                    while (e < hi && a.bcodes[e] == code) { e += step; step <<= 1; }
-                    const int64_t from = e - (step >> 1), to = (e < hi) ? e : hi;
-                    ib = (uint32_t)(from + lower_bound_u64(a.bcodes + from, to - from, code + 1));
-                    if (code == ~0ull) ib = (uint32_t)hi;
+            unsigned long long ct = 0;
+            if (a.same_list) {
+                jb = ja; ib = ia;
+                const unsigned long long n = ia - ja;
+                if (!a.self) ct = n * n;
+                else if (a.identity) ct = n * (n - 1) / 2;          // partners of the x-th entry: the x before it (filter.c:1097-1104)
+                else if (n > 1) {                                    // entries of earlier reads (filter.c:1108-1112)
+                    uint32_t rs = ja, bhi = 0;
+                    for (uint32_t x = ja; x < ia; x++) {
+                        const uint32_t gp = a.agpos[x];
+                        if (gp >= bhi) { rs = x; bhi = a.amap.boff[read_of(a.amap, gp) + 1]; }
+                        ct += rs - ja;
+                    }
+                }
+            } else {
+                const uint64_t code = a.acodes[ja];
+                int64_t rj, ri;
+                if (staged) equal_run(swin, hi - lo, code, rj, ri);
+                else equal_run(a.bcodes + lo, hi - lo, code, rj, ri);
+                jb = (uint32_t)(lo + rj); ib = (uint32_t)(lo + ri);
+                if (ib > jb) {
+                    if (a.self) {
+                        for (uint32_t x = ja; x < ia; x++)
+                            ct += self_partners(a.bgpos, jb, ib, a.agpos[x], a.amap, a.identity, a.comp);
+                    } else
+                        ct = (unsigned long long)(ia - ja) * (unsigned long long)(ib - jb);
                 }
             }
-            unsigned long long ct = 0;
-            if (ib > jb) {
-                if (a.self) {
-                    for (uint32_t x = ja; x < ia; x++)
-                        ct += self_partners(a.bgpos, jb, ib, a.agpos[x], a.boff, a.nreads, a.identity, a.comp);
-                } else
-                    ct = (unsigned long long)(ia - ja) * (unsigned long long)(ib - jb);
-                if (histo && ct < MAXGRAM) atomicAdd(&sgram[(uint32_t)ct], 1u);
-            }
+            if (histo && ib > jb && ct < MAXGRAM) atomicAdd(&sgram[(uint32_t)ct], 1u);
             a.gjb[g] = jb; a.gnb[g] = ib - jb;
             a.gct[g] = (ct > 0xffffffffull) ? 0xffffffffu : (uint32_t)ct;
         }
@@ -147,8 +179,8 @@ __global__ void __launch_bounds__(256) match_groups(GroupArgs a) {
 struct EntryArgs {
     const uint32_t *agpos; int64_t alen; const uint32_t *bgpos;
     const uint32_t *gid, *gjb, *gnb, *gct;
-    const uint32_t *aboff; int anreads; const uint32_t *bboff; int bnreads;
-    int self, comp, identity; uint32_t limit;
+    ReadMap amap, bmap;
+    int self, comp, identity, same_list; uint32_t limit;
     uint32_t *cnt; const uint64_t *off;
     uint64_t *keys; uint32_t *bpos; int pbits, abits;
 };
@@ -159,8 +191,8 @@ __global__ void __launch_bounds__(256) count_entries(EntryArgs e) {
     const uint32_t g = e.gid[i];
     uint32_t c = 0;
     const uint32_t nb = e.gnb[g];
-    if (nb > 0 && e.gct[g] < e.limit) {
-        if (e.self) c = self_partners(e.bgpos, e.gjb[g], e.gjb[g] + nb, e.agpos[i], e.aboff, e.anreads, e.identity, e.comp);
+    if (nb > 0 && e.gct[g] < e.limit && !(e.same_list && e.self && nb == 1)) {   // a run of one k-mer of the list itself has no partner
+        if (e.self) c = self_partners(e.bgpos, e.gjb[g], e.gjb[g] + nb, e.agpos[i], e.amap, e.identity, e.comp);
         else c = nb;
     }
     e.cnt[i] = c;
@@ -174,14 +206,14 @@ __global__ void __launch_bounds__(256) emit_hits(EntryArgs e) {
     const uint32_t g = e.gid[i];
     const uint32_t jb = e.gjb[g];
     const uint32_t ga = e.agpos[i];
-    const int ar = read_of(e.aboff, e.anreads, ga);
-    const uint32_t apos = ga - e.aboff[ar];
+    const int ar = read_of(e.amap, ga);
+    const uint32_t apos = ga - e.amap.boff[ar];
     const uint64_t klow = ((uint64_t)ar << e.pbits) | apos;
     uint64_t o = e.off[i];
     int br = -1; uint32_t blo = 0, bhi = 0;
     for (uint32_t x = 0; x < c; x++, o++) {
         const uint32_t gb = e.bgpos[jb + x];
-        if (br < 0 || gb < blo || gb >= bhi) { br = read_of(e.bboff, e.bnreads, gb); blo = e.bboff[br]; bhi = e.bboff[br + 1]; }
+        if (br < 0 || gb < blo || gb >= bhi) { br = read_of(e.bmap, gb); blo = e.bmap.boff[br]; bhi = e.bmap.boff[br + 1]; }
         e.keys[o] = ((uint64_t)br << (e.pbits + e.abits)) | klow;
         e.bpos[o] = gb - blo;
     }
@@ -230,7 +262,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     GroupArgs ga{};
     ga.acodes = ai->codes; ga.agpos = ai->gpos; ga.alen = alen;
     ga.bcodes = bi->codes; ga.bgpos = bi->gpos; ga.blen = blen;
-    ga.gstart = gstart.p; ga.ngroups = ngroups; ga.boff = ab->boff; ga.nreads = ab->nreads;
+    ga.gstart = gstart.p; ga.ngroups = ngroups; ga.amap = ReadMap{ab->boff, ab->rtab};
     ga.self = self; ga.comp = comp; ga.identity = c.opt.identity; ga.same_list = same_list;
     ga.gjb = gjb.p; ga.gnb = gnb.p; ga.gct = gct.p; ga.gram = use_limit ? gram.p : nullptr;
     {
@@ -271,8 +303,8 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     EntryArgs ea{};
     ea.agpos = ai->gpos; ea.alen = alen; ea.bgpos = bi->gpos;
     ea.gid = gid.p; ea.gjb = gjb.p; ea.gnb = gnb.p; ea.gct = gct.p;
-    ea.aboff = ab->boff; ea.anreads = ab->nreads; ea.bboff = bb->boff; ea.bnreads = bb->nreads;
-    ea.self = self; ea.comp = comp; ea.identity = c.opt.identity; ea.limit = (uint32_t)limit;
+    ea.amap = ReadMap{ab->boff, ab->rtab}; ea.bmap = ReadMap{bb->boff, bb->rtab};
+    ea.self = self; ea.comp = comp; ea.identity = c.opt.identity; ea.same_list = same_list; ea.limit = (uint32_t)limit;
     ea.cnt = cnt.p; ea.off = off.p;
     count_entries<<<eb, 256, 0, st>>>(ea);
     KERNEL_CHECK(); count_launch();

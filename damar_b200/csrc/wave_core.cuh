@@ -101,8 +101,8 @@ WC_RARE int slide(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *
     }
     return n < maxn ? n : maxn;
 }
-WC_HD uint64_t push_matches(uint64_t b, int n) {
-    return (n >= 64) ? ~0ull : ((b << n) | ((1ull << n) - 1ull));
+WC_HD uint64_t push_matches(uint64_t b, int n) {             // b << n with n ones shifted in
+    return (n >= 64) ? ~0ull : ~(~b << n);
 }
 
 // ---- pebble cell (align.c:399-405): {prev, diag, diff, mark}, original coordinates ----------------
@@ -151,7 +151,7 @@ WC_HD int table15(const TrimTabs &t, int x) {
 WC_HD int score15(const TrimTabs &t, int x) { return 1000 * popc64((uint64_t)x) - 15 * t.dscore; }
 // the trim test of align.c:922-925:  TABLE[lo15] >= 0 && TABLE[hi15] + SCORE[lo15] >= 0  for the newest 30 bits of b,
 // i.e. no suffix of the 30-bit window scores below zero; the window is walked in chunks of 7, 8, 7, 8 bits
-WC_RARE bool trim_ok(const TrimTabs t, uint64_t b) {
+WC_HD bool trim_ok(const TrimTabs t, uint64_t b) {
     const uint32_t w = (uint32_t)b & 0x3fffffffu;
     const int a0 = (int)(w & 127u), a1 = (int)((w >> 7) & 255u), a2 = (int)((w >> 15) & 127u), a3 = (int)(w >> 22);
     const int s0 = 1000 * popc64((uint64_t)a0) - 7 * t.dscore;                    // score of the newest 7
@@ -192,6 +192,7 @@ struct Lane {
     int alen, blen, minp, maxp, TS, path_ave, rev;
     int goffA, goffB;               // trace grid offsets in pass coordinates
     uint64_t magic;                 // ceil(2^40 / TS)
+    uint32_t magic32;               // ceil(2^32 / TS), or 0 when that is not exact for these reads
     // wave state (pass coordinates)
     int low, hgh, k, dif, more, aclip, bclip;
     int besta, besty, lasta, trima, trimy, trimd;
@@ -237,9 +238,17 @@ WC_HD uint32_t push_cell(Lane &L, POOL &pool, uint32_t prev, int k, int dif, int
 // floor((v - goff) / TS) + 1 for v - goff >= -TS
 WC_HD int tp_index1(int v, int goff, int TS) { return (v - goff + TS) / TS; }
 // the same with the lane's reciprocal ceil(2^40 / TS): exact for reads shorter than 2^24 bases
+WC_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+// magic32 = ceil(2^32 / TS) is exact while u * TS < 2^32, which setup() checks against the read lengths
 WC_HD int tp_index1(const Lane &L, int v, int goff) {
     const uint32_t u = (uint32_t)(v - goff + L.TS);
-    return (int)(((uint64_t)u * L.magic) >> 40);
+    return L.magic32 ? (int)umulhi32(u, L.magic32) : (int)(((uint64_t)u * L.magic) >> 40);
 }
 
 // Wave 0 (align.c:491-626 forward, 1206-1340 reverse) and the lane's constants.
@@ -251,6 +260,10 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     L.waves = 0; L.cells = 0;
     const int TS = t.TS;
     L.magic = ((1ull << 40) + (uint64_t)TS - 1) / (uint64_t)TS;
+    {
+        const uint64_t umax = (uint64_t)(t.alen > t.blen ? t.alen : t.blen) + 2 * (uint64_t)TS;
+        L.magic32 = (TS > 1 && umax * (uint64_t)TS < (1ull << 32)) ? (uint32_t)(((1ull << 32) + (uint64_t)TS - 1) / (uint64_t)TS) : 0u;
+    }
     const int y0 = (t.anti - t.diag) >> 1, x0 = y0 + t.diag;
     int x, y, k;
     if (!t.rev) {
@@ -318,10 +331,29 @@ WC_HD void transition(Lane &L, const FRONT &F) {
         L.aclip = IMAX; L.bclip = -IMAX;
     }
     if (L.dif > 0) {
+        // align.c:977-986: drop lagging diagonals from the top, then from the bottom.  Mostly 0 - 2 go on either side:
+        // the four front values that decide that are fetched at once instead of one dependent load per test.
         const int n = L.besta - WAVE_LAG;
-        while (L.hgh >= L.low)
-            if ((int32_t)F.slot(L.hgh)[F_V * FRONT::ARR] < n) L.hgh -= 1;
-            else { while ((int32_t)F.slot(L.low)[F_V * FRONT::ARR] < n) L.low += 1; break; }
+        int hgh = L.hgh, low = L.low;
+        int vh[4], vl[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { vh[i] = (int32_t)F.slot(hgh - i)[F_V * FRONT::ARR]; vl[i] = (int32_t)F.slot(low + i)[F_V * FRONT::ARR]; }
+        {
+            const int w = hgh - low + 1;
+            int cut = 0;
+#pragma unroll
+            for (int i = 3; i >= 0; i--) cut = (i < w && vh[i] < n) ? cut + 1 : 0;      // leading run of lagging diagonals
+            hgh -= cut;
+            if (cut == 4) while (hgh >= low && (int32_t)F.slot(hgh)[F_V * FRONT::ARR] < n) hgh -= 1;
+        }
+        if (hgh >= low) {                                 // V[hgh] >= n stops the walk at the latest
+            int cut = 0;
+#pragma unroll
+            for (int i = 3; i >= 0; i--) cut = (vl[i] < n && low + i < hgh) ? cut + 1 : 0;
+            low += cut;
+            if (cut == 4) while ((int32_t)F.slot(low)[F_V * FRONT::ARR] < n) low += 1;
+        }
+        L.hgh = hgh; L.low = low;
         L.waves += 1;
         if (L.hgh >= L.low) L.cells += (uint32_t)(L.hgh - L.low + 1);
     }
@@ -342,17 +374,17 @@ WC_HD void transition(Lane &L, const FRONT &F) {
 
 // The three-way furthest-reaching choice (align.c:793-825) with its tie rules.
 WC_HD int choose(int vp, int vc, int vm, int &c) {               // returns +1 / 0 / -1: predecessor diagonal offset
-    if (vc < vm) {
-        if (vm < vp) { c = vp + 1; return 1; }
-        c = vm + 1; return -1;
-    }
-    if (vc < vp) { c = vp + 1; return 1; }
-    c = vc + 2; return 0;
+    const bool low = vc < vm;                                     // k - 1 beats k (ties go to k)
+    const int m = low ? vm : vc;
+    const bool up = m < vp;                                       // k + 1 beats both (ties go to the lower diagonal)
+    c = up ? vp + 1 : (low ? vm + 1 : vc + 2);
+    return up ? 1 : (low ? -1 : 0);
 }
 
-// Everything of one cell after the predecessor has been chosen and the slide measured (align.c:836-928):
-// clip bookkeeping, pebbles, best / lasta / trim, and the store of the new front entry.  `d` is the chosen
-// predecessor's diagonal offset (choose()).
+// What follows a cell's predecessor choice and slide (align.c:836-928) is done for the N cells of a cellsN call in
+// three converged phases instead of cell by cell: (1) clips, best / lasta and the trace points crossed, (2) the
+// pebbles, (3) the trim test.  Pebbles and the trim test are rare per cell but not per warp: inlined per cell they
+// made the warp run 4 x 32 mostly idle copies of that code per call.
 //
 // Trace points.  The reference keeps NA[k] / NB[k] = first trace point beyond diagonal k's previous furthest
 // point, and logs a pebble for every NA[k] <= x that the arriving path has not logged yet (its head pebble's
@@ -361,36 +393,10 @@ WC_HD int choose(int vp, int vc, int vm, int &c) {               // returns +1 /
 // larger anti-diagonal), so the pebbles logged are exactly the trace points in (xp, x] and (yp, y]: nothing
 // but the previous wave's V is needed.  One step from the predecessor costs x and/or y one base:
 // d = +1 (from k + 1): y only; d = -1 (from k - 1): x only; d = 0: both.
-template <class FRONT, class POOL>
-WC_HD void settle(Lane &L, const TrimTabs &tabs, POOL &pool, uint32_t *s, int k, int c0, int n, int d, PathState p) {
-    const int TS = L.TS;
-    uint64_t b = push_matches(p.T << 1, n);
-    const int y0 = (c0 - k) >> 1, x0 = y0 + k;
-    const int y = y0 + n, x = x0 + n;
-    if (y == L.blen) { L.more = 0; if (L.bclip < k) L.bclip = k; }
-    else if (x == L.alen) { L.more = 0; L.aclip = k; }
-    const int c = (y << 1) + k;
-    const int xp = x0 - (d <= 0 ? 1 : 0), yp = y0 - (d >= 0 ? 1 : 0);
-    int ia = tp_index1(L, xp, L.goffA);
-    int ib = tp_index1(L, yp, L.goffB);
-    const int ja = tp_index1(L, x, L.goffA), jb = tp_index1(L, y, L.goffB);
-    if (ja > ia || jb > ib) {                                                // align.c:859-909
-        while (ia < ja) { ia++; p.ha = push_cell(L, pool, p.ha, k, L.dif, grid(L.goffA, ia, TS), true); }
-        while (ib < jb) { ib++; p.hb = push_cell(L, pool, p.hb, k, L.dif, grid(L.goffB, ib, TS), false); }
-    }
-    if (c > L.besta) {                                                       // align.c:911-928
-        L.besta = c; L.besty = y;
-        if (popc64(b & PATH_MASK61) >= L.path_ave) {
-            L.lasta = c;
-            if (trim_ok(tabs, b)) {
-                L.trima = c; L.trimy = y; L.trimd = L.dif; L.trimha = p.ha; L.trimhb = p.hb;
-            }
-        }
-    }
-    s[F_V * FRONT::ARR] = (uint32_t)c;
-    s[F_TLO * FRONT::ARR] = (uint32_t)b; s[F_THI * FRONT::ARR] = (uint32_t)(b >> 32);
-    s[F_HA * FRONT::ARR] = p.ha; s[F_HB * FRONT::ARR] = p.hb;
-}
+//
+// Trim point.  The reference tests every new best point in visiting order and keeps the last one that passes
+// (align.c:918-927); the candidates of a call are therefore tested newest first until one passes.
+struct CellOut { uint64_t b; int c, y, ia, ja, ib, jb; bool cand; };
 
 // first probe of a slide: equal bases in the first 32-base window (32 = all equal)
 WC_HD int probe32(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by) {
@@ -436,15 +442,96 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
         mx[j] = (L.alen - x < L.blen - y) ? L.alen - x : L.blen - y;
         n[j] = probe32(L.aw, L.abase + (uint32_t)x, L.bw, L.bbase + (uint32_t)y);
     }
+    // phase 1: end of the slide, clips, best / lasta, trace points crossed (visiting order)
+    CellOut o[N];
+    uint32_t pm = 0, slow = 0;                   // bit 2j / 2j+1: cell j crosses exactly one A / B trace point; slow: more than one
+    int nj = -1, ncand = 0;                      // newest trim candidate of the call
+    uint64_t nb = 0; int nc = 0, ny = 0;
 #pragma unroll
     for (int j = 0; j < N; j++) {
+        o[j].cand = false; o[j].ia = o[j].ja = o[j].ib = o[j].jb = 0; o[j].b = 0; o[j].c = 0; o[j].y = 0;
         if (j < cnt) {
-            const int kk = k0 - j, y = (c[j] - kk) >> 1, x = y + kk;
-            if (n[j] == 32 && mx[j] > 32) n[j] = 32 + slide(L.aw, L.abase + (uint32_t)(x + 32), L.bw, L.bbase + (uint32_t)(y + 32), mx[j] - 32);
+            const int kk = k0 - j, y0 = (c[j] - kk) >> 1, x0 = y0 + kk;
+            if (n[j] == 32 && mx[j] > 32) n[j] = 32 + slide(L.aw, L.abase + (uint32_t)(x0 + 32), L.bw, L.bbase + (uint32_t)(y0 + 32), mx[j] - 32);
             if (n[j] > mx[j]) n[j] = mx[j];
-            settle<FRONT>(L, tabs, pool, s[j], kk, c[j], n[j], dd[j], q[j]);
+            const int d = dd[j];
+            const uint64_t b = push_matches(q[j].T << 1, n[j]);
+            const int y = y0 + n[j], x = x0 + n[j];
+            if (y == L.blen) { L.more = 0; if (L.bclip < kk) L.bclip = kk; }
+            else if (x == L.alen) { L.more = 0; L.aclip = kk; }
+            const int cc = (y << 1) + kk;
+            // trace points in (xp, x]: the last one at or below x lies rem below it, so it is crossed iff x - xp > rem
+            // and a second one iff x - xp > rem + TS (long slides only: counted exactly there)
+            const int ja = tp_index1(L, x, L.goffA), jb = tp_index1(L, y, L.goffB);
+            const int rema = x - grid(L.goffA, ja, L.TS), remb = y - grid(L.goffB, jb, L.TS);
+            const int sa = n[j] + (d <= 0 ? 1 : 0), sb = n[j] + (d >= 0 ? 1 : 0);          // x - xp, y - yp
+            o[j].ja = ja; o[j].jb = jb;
+            if (sa > rema) pm |= 1u << (2 * j);
+            if (sb > remb) pm |= 2u << (2 * j);
+            if (sa > rema + L.TS || sb > remb + L.TS) {
+                slow |= 1u << j;
+                o[j].ia = tp_index1(L, x - sa, L.goffA); o[j].ib = tp_index1(L, y - sb, L.goffB);
+            }
+            o[j].b = b; o[j].c = cc; o[j].y = y;
+            if (cc > L.besta) {                                                  // align.c:911-917
+                L.besta = cc; L.besty = y;
+                if (popc64(b & PATH_MASK61) >= L.path_ave) { L.lasta = cc; o[j].cand = true; nj = j; nb = b; nc = cc; ny = y; ncand++; }
+            }
         }
     }
+    // phase 2: pebbles (align.c:859-909), one at a time through the single copy of the store
+    while (slow) {                               // cells that crossed several trace points of one axis in one slide: A chain, then B chain
+        const int js = 63 - clz64((uint64_t)(slow & (0u - slow)));
+        slow &= slow - 1u;
+        pm &= ~(3u << (2 * js));
+        int ia = 0, ja = 0, ib = 0, jb = 0; uint32_t ha = 0, hb = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) if (j == js) { ia = o[j].ia; ja = o[j].ja; ib = o[j].ib; jb = o[j].jb; ha = q[j].ha; hb = q[j].hb; }
+        for (int i = ia + 1; i <= ja; i++) ha = push_cell(L, pool, ha, k0 - js, L.dif, grid(L.goffA, i, L.TS), true);
+        for (int i = ib + 1; i <= jb; i++) hb = push_cell(L, pool, hb, k0 - js, L.dif, grid(L.goffB, i, L.TS), false);
+#pragma unroll
+        for (int j = 0; j < N; j++) if (j == js) { q[j].ha = ha; q[j].hb = hb; }
+    }
+    while (pm) {
+        const int bit = 63 - clz64((uint64_t)(pm & (0u - pm)));
+        pm &= pm - 1u;
+        const int js = bit >> 1;
+        const bool isA = (bit & 1) == 0;
+        int idx = 0; uint32_t head = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) if (j == js) { idx = isA ? o[j].ja : o[j].jb; head = isA ? q[j].ha : q[j].hb; }
+        const uint32_t id = push_cell(L, pool, head, k0 - js, L.dif, grid(isA ? L.goffA : L.goffB, idx, L.TS), isA);
+#pragma unroll
+        for (int j = 0; j < N; j++) if (j == js) { if (isA) q[j].ha = id; else q[j].hb = id; }
+    }
+    // phase 3: the trim point = the newest candidate that passes the test (align.c:918-927)
+    if (nj >= 0) {
+        bool ok = trim_ok(tabs, nb);
+        while (!ok && ncand > 1) {               // rare: fall back to the next older candidate
+            int pj = -1;
+#pragma unroll
+            for (int j = 0; j < N; j++) if (j < nj && o[j].cand) pj = j;
+            nj = pj; ncand--;
+#pragma unroll
+            for (int j = 0; j < N; j++) if (j == nj) { nb = o[j].b; nc = o[j].c; ny = o[j].y; }
+            ok = trim_ok(tabs, nb);
+        }
+        if (ok) {
+            uint32_t ha = 0, hb = 0;
+#pragma unroll
+            for (int j = 0; j < N; j++) if (j == nj) { ha = q[j].ha; hb = q[j].hb; }
+            L.trima = nc; L.trimy = ny; L.trimd = L.dif; L.trimha = ha; L.trimhb = hb;
+        }
+    }
+    // the new front entries
+#pragma unroll
+    for (int j = 0; j < N; j++)
+        if (j < cnt) {
+            uint32_t *t = s[j];
+            t[F_V * FRONT::ARR] = (uint32_t)o[j].c;
+            t[F_TLO * FRONT::ARR] = (uint32_t)o[j].b; t[F_THI * FRONT::ARR] = (uint32_t)(o[j].b >> 32);
+            t[F_HA * FRONT::ARR] = q[j].ha; t[F_HB * FRONT::ARR] = q[j].hb;
+        }
     // carry the previous-wave values of the diagonal just above the next cursor
     L.vp = v[N]; L.vc = v[N + 1]; L.pp = P[N];
     L.k = k0 - cnt;
