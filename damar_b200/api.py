@@ -353,28 +353,36 @@ def _get_pool():
     return _pool
 
 
-def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list] = None,
-             dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
-    """`daligner [flags] A B1 B2 ...` (daligner.c:958-1073): returns {las file name: bytes}
-    (or LasImage objects with as_bytes=False, which avoids one host copy per file)."""
+class _Job:
+    """One `daligner A B1 B2 ...` job between submit() and collect()."""
+    __slots__ = ("ablk", "s", "symmetric", "da", "aidx", "cmps", "own", "dcache")
+
+
+def _job_options(ablk: Block, bblks: List[Block], s: Settings):
+    symmetric = s.symmetric and all(b.root == ablk.root for b in bblks)     # daligner.c:911-946
+    return Settings(**{**s.__dict__, "symmetric": symmetric}), tuple(float(x) for x in ablk.freq)
+
+
+def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[str, DeviceBlockHandle]] = None) -> _Job:
+    """First half of a job (daligner.c:958-1060): ships the blocks, sorts the A k-mers and queues every Match_Filter
+    call (B block x orientation) on the worker pool.  collect() waits for them and writes the .las images."""
     init()
     if set_filter_params(s.kmer, s.binshift, s.suppress, s.hitmin, s.nthreads):
         raise ValueError("Illegal combination of filter parameters")       # daligner.c:862-866
-    symmetric = s.symmetric and all(b.root == ablk.root for b in bblks)     # daligner.c:911-946
-    s = Settings(**{**s.__dict__, "symmetric": symmetric})
-    set_options(s, ablk.freq)
-    own = dcache is None
-    dcache = {} if dcache is None else dcache
-    out: Dict[str, bytes] = {}
-    conv = (lambda im: im.tobytes()) if as_bytes else (lambda im: im)
+    s, freq = _job_options(ablk, bblks, s)
+    set_options(s, freq)
+    J = _Job()
+    J.ablk, J.s, J.symmetric = ablk, s, s.symmetric
+    J.own = dcache is None
+    J.dcache = dcache = {} if dcache is None else dcache
 
     def resident(b: Block) -> DeviceBlockHandle:
         if b.name not in dcache:
             dcache[b.name] = DeviceBlockHandle(b)
         return dcache[b.name]
 
-    da = resident(ablk)
-    aidx = sort_kmers(da, 0)
+    J.da = da = resident(ablk)
+    J.aidx = aidx = sort_kmers(da, 0)
     inline = workers() == 1
 
     def compare(bblk, db, selfcmp, comp, sink, st):
@@ -388,7 +396,7 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
         if bidx is not None and bidx is not aidx:
             bidx.free()
 
-    jobs = []
+    J.cmps = []
     for bblk in bblks:
         selfcmp = bblk.name == ablk.name
         db = da if selfcmp else resident(bblk)
@@ -401,16 +409,23 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
                 compare(bblk, db, selfcmp, comp, sink, st)
         else:
             futs = [_get_pool().submit(compare, bblk, db, selfcmp, comp, sink, st) for comp in (0, 1)]
-        jobs.append((bblk, selfcmp, sink, st, futs))
+        J.cmps.append((bblk, selfcmp, sink, st, futs))
+    return J
 
-    for bblk, selfcmp, sink, st, futs in jobs:
+
+def collect(J: _Job, stats: Optional[list] = None, as_bytes: bool = True) -> Dict[str, bytes]:
+    """Second half of a job: Write_Overlap_Buffer for every B block (align.c:6166-6367)."""
+    out: Dict[str, bytes] = {}
+    conv = (lambda im: im.tobytes()) if as_bytes else (lambda im: im)
+    ablk, s = J.ablk, J.s
+    for bblk, selfcmp, sink, st, futs in J.cmps:
         if futs is not None:
             for f in futs:
                 f.result()
         if stats is not None:
             stats.append(st)
         an, bn = ablk.name, bblk.name
-        if selfcmp or not symmetric:                                        # align.c:6235
+        if selfcmp or not J.symmetric:                                      # align.c:6235
             b1, _ = sink.serialise(s, -1)
             out[f"{an}.{bn}.las"] = conv(b1)
         else:
@@ -422,8 +437,42 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
             out[n1], out[n2] = conv(b1), conv(b2)
         sink.reset()
         _free_sinks.append(sink)
-    if aidx is not None:
-        aidx.free()
+    if J.aidx is not None:
+        J.aidx.free()
+    if J.own:
+        for h in J.dcache.values():
+            h.free()
+    return out
+
+
+def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list] = None,
+             dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
+    """`daligner [flags] A B1 B2 ...` (daligner.c:958-1073): returns {las file name: bytes}
+    (or LasImage objects with as_bytes=False, which avoids one host copy per file)."""
+    return collect(submit(ablk, bblks, s, dcache), stats, as_bytes)
+
+
+def daligner_plan(jobs: List[tuple], s: Settings, stats: Optional[list] = None,
+                  dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
+    """The jobs of an HPCdaligner plan (dalign/HPCdaligner.c:709-788), [(A block, [B blocks]), ...], one after the other
+    like the script would run them -- except that job i+1 is submitted (its A block shipped and indexed, its comparisons
+    queued) BEFORE job i is collected, so the GPU does not idle while the host sorts and serialises job i's records.
+    Jobs whose process-wide options differ (base frequencies of another DB, -b) are not overlapped."""
+    own = dcache is None
+    dcache = {} if dcache is None else dcache
+    out: Dict[str, bytes] = {}
+    pend, pend_key = None, None
+    for ablk, bblks in jobs:
+        key = _job_options(ablk, bblks, s)
+        if pend is not None and (key != pend_key or s.biased):
+            out.update(collect(pend, stats, as_bytes))
+            pend = None
+        nxt = submit(ablk, bblks, s, dcache)
+        if pend is not None:
+            out.update(collect(pend, stats, as_bytes))
+        pend, pend_key = nxt, key
+    if pend is not None:
+        out.update(collect(pend, stats, as_bytes))
     if own:
         for h in dcache.values():
             h.free()

@@ -120,7 +120,7 @@ void *dev_alloc_bytes(size_t bytes) {
     cudaError_t e = cudaMalloc(&p, r);
     if (e != cudaSuccess) {                       // out of memory: drop this worker's cache and retry once
         cudaGetLastError();
-        CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        CUDA_CHECK(stream_wait(c.stream));
         release_cached_blocks(c);
         CUDA_CHECK(cudaMalloc(&p, r));
     }
@@ -148,6 +148,21 @@ void ensure_init() {
     if (!c.ready && do_init(-1) != 0) fatal("%s", g_last_error.c_str());
     std::lock_guard<std::mutex> lock(g_mu);
     c.fp = g_fp; c.opt = g_opt;
+}
+
+bool blocking_sync() {
+    static const bool on = [] {
+        const char *e = getenv("DAMAR_BLOCKING_SYNC");
+        return (e && *e) ? atoi(e) != 0 : true;
+    }();
+    return on;
+}
+cudaError_t stream_wait(cudaStream_t st) {
+    if (!blocking_sync()) return cudaStreamSynchronize(st);
+    Context &c = ctx();
+    if (!c.wait_ev) { cudaError_t e = cudaEventCreateWithFlags(&c.wait_ev, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    cudaError_t e = cudaEventRecord(c.wait_ev, st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c.wait_ev);
 }
 
 // filter.c:774-789: NormShift/LogBase are built once per process, from the freq of the block of the first
@@ -327,7 +342,7 @@ int damar_index_download(const damar_index *idx_, void *kmerpos_out, int64_t cap
                                                                          idx->blk->nreads, tmp.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(kmerpos_out, tmp.p, sizeof(uint4) * idx->len, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    CUDA_CHECK(stream_wait(c.stream));
     return 0;
 }
 
@@ -340,7 +355,7 @@ int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
                                                                          g_hits.abits, tmp.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(seedpair_out, tmp.p, sizeof(int4) * g_hits.n, cudaMemcpyDeviceToHost, c.stream));
-    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    CUDA_CHECK(stream_wait(c.stream));
     return g_hits.n;
 }
 

@@ -86,11 +86,18 @@ struct FilterParams {
 // LogBase of filter.c:774-789: fixed by the FIRST Sort_Kmers call after Set_Filter_Params (api.cu)
 void bias_log_base(const float freq[4], int out[4]);
 
+// Host waits.  With several ranks per host (one process per GPU, a few worker threads each) spinning waits would
+// oversubscribe the cores, and even one rank's four spinning workers slowed the end-to-end pass (1220 vs 1120 ms on
+// C2, the main thread copies blocks meanwhile), so the waits block: DAMAR_BLOCKING_SYNC=0 spins instead.
+bool blocking_sync();
+cudaError_t stream_wait(cudaStream_t st);
+inline unsigned timing_event_flags() { return blocking_sync() ? cudaEventBlockingSync : cudaEventDefault; }
+
 struct Timer {
     cudaEvent_t a, b;
     cudaStream_t s;
     explicit Timer(cudaStream_t st) : s(st) {
-        CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+        CUDA_CHECK(cudaEventCreateWithFlags(&a, timing_event_flags())); CUDA_CHECK(cudaEventCreateWithFlags(&b, timing_event_flags()));
         CUDA_CHECK(cudaEventRecord(a, s));
     }
     float stop() {
@@ -127,6 +134,7 @@ struct Context {
     damar_timings tm{};
     int64_t launches = 0;
     bool ready = false;
+    cudaEvent_t wait_ev = nullptr;               // blocking-sync event of stream_wait()
     std::multimap<size_t, void *> free_blocks;   // caching allocator (api.cu)
     WorkerScratch *ws = nullptr;                 // buffers that outlive a call (api.cu)
 };
@@ -207,6 +215,7 @@ struct WorkerScratch {
     cudaEvent_t rs_ev[16][2]; bool rs_ev_init = false;
     DevBuf<uint64_t> scan_tot, scan_sums;        // scan.cu
     DevBuf<uint32_t> tot32_index, tot32_merge;   // kmer_index.cu, seed_merge.cu
+    PinnedBuf<uint8_t> h_up[2]; cudaEvent_t up_ev[2] = {nullptr, nullptr};   // upload_block: pinned double buffer
     PinnedBuf<damar_overlap> h_recs; PinnedBuf<uint64_t> h_toff, h_seq; PinnedBuf<uint8_t> h_trace;   // pair_align.cu
     std::vector<uint8_t> fused_trace;            // downloaded + rewritten traces when Handle_Redundancies fired
     HostOverlaps out;                            // results of the last match_filter call

@@ -1146,7 +1146,7 @@ struct PairSeqs : FuseSeqs {
         const uint32_t w0 = base >> 4, w1 = (base + (uint32_t)len + 15u) >> 4;
         std::vector<uint32_t> w(w1 - w0 + 1);
         CUDA_CHECK(cudaMemcpyAsync(w.data(), words + w0, sizeof(uint32_t) * w.size(), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_wait(st));
         dst.resize((size_t)len + 1);
         for (int i = 0; i < len; i++) {
             const uint32_t p = base + (uint32_t)i;
@@ -1248,7 +1248,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     exclusive_scan_u32_to_u64(flag.p, off.p, n, total.p, st);
     uint64_t nwork = 0;
     CUDA_CHECK(cudaMemcpyAsync(&nwork, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_wait(st));
     DevBuf<uint32_t> work; work.reserve((size_t)nwork + 1);
     collect_work_pairs<<<hb, 256, 0, st>>>(flag.p, off.p, n, work.p);
     KERNEL_CHECK();
@@ -1310,7 +1310,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     exclusive_scan_u32_to_u64(pflag.p, poff.p, (int64_t)nwork, total.p, st);
     uint64_t nactive = 0;
     CUDA_CHECK(cudaMemcpyAsync(&nactive, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_wait(st));
     count_launch(1);
     c.tm.pairs_ms = t_pairs.stop();
     delete hp1;
@@ -1357,6 +1357,9 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         set_smem(wave_tasks<32, false, 4, 10>, WaveCfg<32, 10>::SMEM);
         set_smem(wave_tasks<32, false, 4, 11>, WaveCfg<32, 11>::SMEM);
         set_smem(wave_tasks<32, false, 2, 11>, WaveCfg<32, 11>::SMEM);
+        set_smem(wave_tasks<32, false, 3, 11>, WaveCfg<32, 11>::SMEM);
+        set_smem(wave_tasks<32, false, 5, 11>, WaveCfg<32, 11>::SMEM);
+        set_smem(wave_tasks<32, false, 6, 11>, WaveCfg<32, 11>::SMEM);
         set_smem(wave_tasks<64, true, 4, 5>, WaveCfg<64, 5>::SMEM);
     });
 
@@ -1388,7 +1391,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             KERNEL_CHECK(); count_launch();
             unsigned int ncand = 0;
             CUDA_CHECK(cudaMemcpyAsync(&ncand, ctr.p + CTR_NCAND, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(stream_wait(st));
             if (ncand == 0) break;
             Timer t_k(st);
             {
@@ -1404,6 +1407,9 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
                     Q.task_order = v0;
                 }
                 if (nway == 2) wave_tasks<32, false, 2, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
+                else if (nway == 3) wave_tasks<32, false, 3, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
+                else if (nway == 5) wave_tasks<32, false, 5, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
+                else if (nway == 6) wave_tasks<32, false, 6, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
                 else if (wwarps == 8) wave_tasks<32, false, 4, 8><<<wb, per, WaveCfg<32, 8>::SMEM, st>>>(Q);
                 else if (wwarps == 10) wave_tasks<32, false, 4, 10><<<wb, per, WaveCfg<32, 10>::SMEM, st>>>(Q);
                 else wave_tasks<32, false, 4, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
@@ -1411,7 +1417,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             }
             unsigned int nwide = 0;
             CUDA_CHECK(cudaMemcpyAsync(&nwide, ctr.p + CTR_NWIDE, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(cudaStreamSynchronize(st));
+            CUDA_CHECK(stream_wait(st));
             if (nwide > 0) {
                 const unsigned per = WaveCfg<64, 5>::WARPS * 32;
                 const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (nwide + per - 1) / per);
@@ -1427,7 +1433,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         }
         CUDA_CHECK(cudaMemcpyAsync(&nredo, next.p + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaMemcpyAsync(&nrec_fast, counters.p + 5, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_wait(st));
         if (nredo > 0) {                               // strided warp kernel for the pairs with very wide fronts
             DevBuf<int32_t> V, HA, HB, HM, HN, NA, NB; DevBuf<uint64_t> T; DevBuf<int4> cells;
             const int lw = lblocks * AL_WARPS;
@@ -1446,7 +1452,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             c.tm.redo_kernel_ms += t_r.stop();
         }
         CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_wait(st));
         if ((hc[3] & 1ull) && attempt < 4) {            // output buffers too small: grow and rerun
             if (hc[5] > rec_cap) rec_cap = hc[5] + 1024;
             if (hc[6] > trace_cap) trace_cap = hc[6] + 1024;
@@ -1479,7 +1485,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     if (ntr) CUDA_CHECK(cudaMemcpyAsync(h_trace.p, trace.p, (size_t)ntr * tbytes, cudaMemcpyDeviceToHost, st));
     std::vector<uint8_t> h_redo;
     if (nredo > 0) { h_redo.resize(nwork); CUDA_CHECK(cudaMemcpyAsync(h_redo.data(), pair_redo.p, nwork, cudaMemcpyDeviceToHost, st)); }
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_wait(st));
     uint64_t nkeep = nrec;
     if (nredo > 0) {                                   // drop what the task pipeline emitted for pairs it gave up on
         nkeep = 0;

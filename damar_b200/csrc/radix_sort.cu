@@ -133,7 +133,7 @@ void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uin
     const size_t dyn = (sizeof(uint64_t) + sizeof(uint32_t)) * RS_TILE;
     std::call_once(attr_set, [dyn] { CUDA_CHECK(cudaFuncSetAttribute(rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); });
     cudaEvent_t (&ev)[16][2] = ws.rs_ev;
-    if (!ws.rs_ev_init) { for (auto &e : ev) { CUDA_CHECK(cudaEventCreate(&e[0])); CUDA_CHECK(cudaEventCreate(&e[1])); } ws.rs_ev_init = true; }
+    if (!ws.rs_ev_init) { for (auto &e : ev) { CUDA_CHECK(cudaEventCreateWithFlags(&e[0], timing_event_flags())); CUDA_CHECK(cudaEventCreateWithFlags(&e[1], timing_event_flags())); } ws.rs_ev_init = true; }
     int npass = 0;
     for (int shift = 0; shift < nbits; shift += 8, npass++) {
         rs_hist<<<ntiles, RS_THREADS, 0, st>>>(keys, n, shift, g_tile_hist.p, ntiles);

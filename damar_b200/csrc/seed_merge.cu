@@ -250,7 +250,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     exclusive_scan_u32_inplace(gid.p, alen, tot32.p, st);
     uint32_t ngroups = 0;
     CUDA_CHECK(cudaMemcpyAsync(&ngroups, tot32.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_wait(st));
     gstart.reserve((size_t)ngroups + 1); gjb.reserve(ngroups); gnb.reserve(ngroups); gct.reserve(ngroups);
     finish_groups<<<eb, 256, 0, st>>>(ai->codes, alen, gid.p, gstart.p);
     KERNEL_CHECK();
@@ -280,7 +280,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     if (use_limit) {
         std::vector<unsigned long long> histo(MAXGRAM);
         CUDA_CHECK(cudaMemcpyAsync(histo.data(), gram.p, sizeof(unsigned long long) * MAXGRAM, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+        CUDA_CHECK(stream_wait(st));
         int64_t avail = (int64_t)(((int64_t)(c.opt.mem_limit - (uint64_t)(ab->sizeof_db + bb->sizeof_db))) / (uint64_t)16);
         if (same_list || avail > alen + 2 * blen) avail = (avail - alen) / 2;
         else avail = avail - (alen + blen);
@@ -311,7 +311,7 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     exclusive_scan_u32_to_u64(cnt.p, off.p, alen, total.p, st);
     uint64_t nhits = 0;
     CUDA_CHECK(cudaMemcpyAsync(&nhits, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    CUDA_CHECK(stream_wait(st));
     if (c.opt.verbose) { printf("   Hit count = %lld\n", (long long)nhits); fflush(stdout); }
     if (nhits == 0) { c.tm.merge_ms = t_merge.stop(); delete hp2; return; }
 

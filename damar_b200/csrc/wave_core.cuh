@@ -396,7 +396,7 @@ WC_HD int choose(int vp, int vc, int vm, int &c) {               // returns +1 /
 //
 // Trim point.  The reference tests every new best point in visiting order and keeps the last one that passes
 // (align.c:918-927); the candidates of a call are therefore tested newest first until one passes.
-struct CellOut { uint64_t b; int c, y, ia, ja, ib, jb; bool cand; };
+struct CellOut { uint64_t b; int c, y, ia, ja, ib, jb; };
 
 // first probe of a slide: equal bases in the first 32-base window (32 = all equal)
 WC_HD int probe32(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by) {
@@ -445,11 +445,10 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
     // phase 1: end of the slide, clips, best / lasta, trace points crossed (visiting order)
     CellOut o[N];
     uint32_t pm = 0, slow = 0;                   // bit 2j / 2j+1: cell j crosses exactly one A / B trace point; slow: more than one
-    int nj = -1, ncand = 0;                      // newest trim candidate of the call
-    uint64_t nb = 0; int nc = 0, ny = 0;
+    uint32_t cm = 0;                             // bit j: cell j is a trim candidate (new best with a dense enough history)
 #pragma unroll
     for (int j = 0; j < N; j++) {
-        o[j].cand = false; o[j].ia = o[j].ja = o[j].ib = o[j].jb = 0; o[j].b = 0; o[j].c = 0; o[j].y = 0;
+        o[j].ia = o[j].ja = o[j].ib = o[j].jb = 0; o[j].b = 0; o[j].c = 0; o[j].y = 0;
         if (j < cnt) {
             const int kk = k0 - j, y0 = (c[j] - kk) >> 1, x0 = y0 + kk;
             if (n[j] == 32 && mx[j] > 32) n[j] = 32 + slide(L.aw, L.abase + (uint32_t)(x0 + 32), L.bw, L.bbase + (uint32_t)(y0 + 32), mx[j] - 32);
@@ -475,7 +474,7 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
             o[j].b = b; o[j].c = cc; o[j].y = y;
             if (cc > L.besta) {                                                  // align.c:911-917
                 L.besta = cc; L.besty = y;
-                if (popc64(b & PATH_MASK61) >= L.path_ave) { L.lasta = cc; o[j].cand = true; nj = j; nb = b; nc = cc; ny = y; ncand++; }
+                if (popc64(b & PATH_MASK61) >= L.path_ave) { L.lasta = cc; cm |= 1u << j; }
             }
         }
     }
@@ -504,24 +503,14 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
 #pragma unroll
         for (int j = 0; j < N; j++) if (j == js) { if (isA) q[j].ha = id; else q[j].hb = id; }
     }
-    // phase 3: the trim point = the newest candidate that passes the test (align.c:918-927)
-    if (nj >= 0) {
-        bool ok = trim_ok(tabs, nb);
-        while (!ok && ncand > 1) {               // rare: fall back to the next older candidate
-            int pj = -1;
+    // phase 3: the trim point = the newest candidate that passes the test (align.c:918-927); it is nearly always the first tried
+    while (cm) {
+        const int nj = 63 - clz64((uint64_t)cm);
+        cm &= ~(1u << nj);
+        uint64_t nb = 0; int nc = 0, ny = 0; uint32_t ha = 0, hb = 0;
 #pragma unroll
-            for (int j = 0; j < N; j++) if (j < nj && o[j].cand) pj = j;
-            nj = pj; ncand--;
-#pragma unroll
-            for (int j = 0; j < N; j++) if (j == nj) { nb = o[j].b; nc = o[j].c; ny = o[j].y; }
-            ok = trim_ok(tabs, nb);
-        }
-        if (ok) {
-            uint32_t ha = 0, hb = 0;
-#pragma unroll
-            for (int j = 0; j < N; j++) if (j == nj) { ha = q[j].ha; hb = q[j].hb; }
-            L.trima = nc; L.trimy = ny; L.trimd = L.dif; L.trimha = ha; L.trimhb = hb;
-        }
+        for (int j = 0; j < N; j++) if (j == nj) { nb = o[j].b; nc = o[j].c; ny = o[j].y; ha = q[j].ha; hb = q[j].hb; }
+        if (trim_ok(tabs, nb)) { L.trima = nc; L.trimy = ny; L.trimd = L.dif; L.trimha = ha; L.trimhb = hb; break; }
     }
     // the new front entries
 #pragma unroll

@@ -76,13 +76,22 @@ def run_sharded(dbdir: str, root: str, nblocks: int, settings, rank: int, world:
     blocks = exchange_blocks(dbdir, root, shards, rank, world, dist, device, masks)
     cache: Dict[str, api.DeviceBlockHandle] = {}
     novl, files = 0, {}
-    for job in shards[rank]:
-        out = api.daligner(blocks[job.a], [blocks[b] for b in job.bs], settings, dcache=cache, as_bytes=False)
-        for name, im in out.items():
+    def finish(pending):
+        nonlocal novl
+        for name, im in api.collect(pending, as_bytes=False).items():
             novl += im.novl
             if outdir is not None:
                 api.write_outputs(outdir, {name: im}, settings.run_id)
             files[name] = len(im)
+
+    pend = None                                   # job i+1 is queued on the GPU before job i's records are sorted and written
+    for job in shards[rank]:
+        nxt = api.submit(blocks[job.a], [blocks[b] for b in job.bs], settings, dcache=cache)
+        if pend is not None:
+            finish(pend)
+        pend = nxt
+    if pend is not None:
+        finish(pend)
     for h in cache.values():
         h.free()
     return novl, files

@@ -199,6 +199,19 @@ def test_sharded_plan_world1(tmp_path):
     assert novl == sum(int.from_bytes(v[:8], "little") for v in gold.values())
 
 
+def test_pipelined_plan_matches_reference():
+    """api.daligner_plan overlaps job i+1 (upload, A index, queued comparisons) with the collection of job i: same files."""
+    o = parse_flags(CASES["default"]["flags"])
+    b1, b2 = load_block(TINY, "T.1", ()), load_block(TINY, "T.2", ())
+    out = api.daligner_plan([(b1, [b1]), (b2, [b1, b2])], settings(o))
+    gold = dict(golden_files("b2"))                       # job `daligner T.2 T.1 T.2`
+    gold["T.1.T.1.las"] = golden_files("default")["T.1.T.1.las"]   # job `daligner T.1 T.1`
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{fn}: {why}"
+
+
 def test_properties_at_scale():
     """20 Mbp / 2 blocks: size-independent invariants of the emitted .las (what LAcheck -p -s checks,
     utils/LAcheck.c:116-221, align.c:3455-3506) plus A/B symmetry, and equality with the reference
