@@ -307,11 +307,12 @@ def main():
     clocks = sampler.stop()
 
     if world > 1:
-        t = torch.tensor([dt, dt_e, float(novl), float(novl_e), float(launches)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dt, dt_e, float(novl), float(novl_e), float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         dt, dt_e = float(tmax[0]), float(tmax[1])
         novl, novl_e, launches = int(tsum[2]), int(tsum[3]), int(tsum[4])
+        h2d, d2h = int(tsum[5]), int(tsum[6])                      # whole job, like value
     value = novl / dt
     e2e = novl_e / dt_e
 
