@@ -72,7 +72,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
-           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased"]
+           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs"]
 
 _lib = None
 
@@ -91,6 +91,9 @@ def load_library():
     L.damar_last_error.restype = C.c_char_p
     L.damar_set_filter_params.argtypes = [C.c_int] * 5
     L.damar_set_options.argtypes = [C.POINTER(Options)]
+    L.damar_trace_point_diffs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                          C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    L.damar_trace_point_diffs.restype = C.c_int
     L.damar_set_biased.argtypes = [C.c_int]
     L.damar_set_biased.restype = None
     L.damar_block_upload.restype = C.c_void_p
@@ -477,6 +480,32 @@ def daligner_plan(jobs: List[tuple], s: Settings, stats: Optional[list] = None,
         for h in dcache.values():
             h.free()
     return out
+
+
+def trace_point_diffs(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las: bytes, segments: bool = False):
+    """Compute_Trace_PTS (align.c:5577-5692) in its cost form over a whole .las image whose A reads lie in `ablock` and B
+    reads in `bblock`: returns the per-record sums of the exact segment edit distances (what the reference leaves in
+    path->diffs; -1 for a rejected record) and, with segments=True, also one value per trace-point segment plus the
+    offset of every record's first segment."""
+    from . import dbio
+    novl, tspace, recs, traces = dbio.parse_las(las)
+    tbytes = 1 if tspace <= 125 else 2
+    toff = np.zeros(novl + 1, np.uint64)
+    toff[1:] = np.cumsum(recs["tlen"].astype(np.uint64))
+    trace = np.frombuffer(b"".join(traces), dtype=np.uint8).copy() if novl else np.zeros(1, np.uint8)
+    if trace.size == 0:
+        trace = np.zeros(1, np.uint8)
+    recs = np.ascontiguousarray(recs)
+    rec = np.zeros(max(novl, 1), np.int32)
+    ntrace = int(toff[novl])
+    seg = np.zeros(max(ntrace // 2, 1), np.uint16) if segments else None
+    rc = load_library().damar_trace_point_diffs(ablock.handle, bblock.handle, recs.ctypes.data, toff.ctypes.data, trace.ctypes.data,
+                                                tbytes, novl, ntrace, tspace, rec.ctypes.data,
+                                                seg.ctypes.data if seg is not None else None)
+    if rc not in (0, 1):
+        raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
+    rec = rec[:novl]
+    return (rec, seg[: ntrace // 2], (toff[:novl] // 2).astype(np.int64)) if segments else rec
 
 
 def las_dir(run_id: int, part: int) -> str:

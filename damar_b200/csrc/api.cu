@@ -302,6 +302,15 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     return 0;
 }
 
+int damar_trace_point_diffs(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
+                            const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
+                            int32_t *rec_diffs, uint16_t *seg_diffs) {
+    ensure_init();
+    if (trace_spacing <= 0 || (trace_bytes != 1 && trace_bytes != 2)) { set_error("damar_trace_point_diffs: bad trace spacing / width"); return 1; }
+    return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
+                                  trace_bytes, novl, ntrace, trace_spacing, rec_diffs, seg_diffs);
+}
+
 void damar_emission_order(const damar_overlaps *o, int64_t *order) {
     std::vector<int64_t> idx((size_t)o->novl);
     for (int64_t i = 0; i < o->novl; i++) idx[i] = i;

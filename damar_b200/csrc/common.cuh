@@ -224,6 +224,10 @@ struct WorkerScratch {
 };
 inline WorkerScratch &scratch() { return *ctx().ws; }
 
+// trace_pts.cu
+int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap *ovl, const uint64_t *toff, const void *trace,
+                           int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs);
+
 void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
                       HostOverlaps &out);
 

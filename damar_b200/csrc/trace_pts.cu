@@ -1,0 +1,162 @@
+// trace_pts.cu -- Compute_Trace_PTS in its cost form: the exact edit distance of every trace-point segment.
+//
+// Replaces, for the numbers it produces, Compute_Trace_PTS + iter_np (reference dalign/align.c:5577-5692,
+// 4892-5230): the consumers of a .las file (LAshow utils/LAshow.c:261, LAcorrect, LAstitch ...) re-align every
+// segment between two trace points -- A[ab, ae) with ae on the trace grid, against B[bb, bb + b_i) -- and leave
+// the sum of the segment distances in path->diffs.  iter_np counts a substitution, an insertion and a deletion
+// as one difference each (it returns D + |M - N| with steps toward the end diagonal free, steps away from it 2
+// and mismatches 1), i.e. the unit-cost edit distance, which does not depend on its tie-breaking; the edit
+// script it also writes does, and is not produced here.
+//
+// One warp per record, one lane per segment (the B start of a segment is a warp prefix sum of the b_i), each
+// lane running the furthest-reaching recurrence over its own diagonals with 32-base packed compares:
+//     F[e][k] = slide(max(F[e-1][k] + 1, F[e-1][k-1] + 1, F[e-1][k+1])),   k = x - y,  done when F[e][M-N] = M.
+// Doubles as the on-device validator of the wave kernel's output: every emitted (d_i, b_i) is realisable, and
+// optimal unless the record went through bridging (tests/test_gpu_parity.py).
+#include "common.cuh"
+#include "wave_core.cuh"
+
+namespace damar {
+namespace {
+
+constexpr int TP_EMAX = 1023;                 // largest segment distance handled (8-bit traces hold 255 at most)
+
+struct TpArgs {
+    const uint32_t *aw, *bw[2];               // packed A reads; B reads forward / reverse-complemented
+    const uint32_t *aboff, *bboff; const int32_t *arlen, *brlen;
+    int afirst, bfirst, anreads, bnreads;
+    const damar_overlap *ovl; const uint64_t *toff; const void *trace; int tbytes; int64_t novl; int TS;
+    int32_t *rec; uint16_t *seg; int *err;
+};
+
+__device__ __forceinline__ int trace_at(const TpArgs &P, uint64_t i) {
+    return P.tbytes == 1 ? (int)((const uint8_t *)P.trace)[i] : (int)((const uint16_t *)P.trace)[i];
+}
+
+// unit-cost edit distance of A[0, M) (base index ax) and B[0, N) (base index bx); -1 beyond TP_EMAX
+__device__ int segment_distance(const uint32_t *__restrict__ aw, uint32_t ax, int M, const uint32_t *__restrict__ bw, uint32_t bx, int N,
+                                int16_t *F0, int16_t *F1) {
+    const int del = M - N;
+    // e = 0
+    {
+        const int lim = M < N ? M : N;
+        const int x = wc::slide(aw, ax, bw, bx, lim);
+        if (x == M && del == 0) return 0;
+        F0[TP_EMAX + 1] = (int16_t)x;
+    }
+    int16_t *prev = F0, *cur = F1;
+    for (int e = 1; e <= TP_EMAX; e++) {
+        const int klo = (-e < -N) ? -N : -e, khi = (e > M) ? M : e;
+        for (int k = klo; k <= khi; k++) {
+            // predecessors live on diagonals within [-(e-1), e-1] and inside the box
+            const int plo = (-(e - 1) < -N) ? -N : -(e - 1), phi = ((e - 1) > M) ? M : (e - 1);
+            int x = -1;
+            if (k >= plo && k <= phi) x = prev[TP_EMAX + 1 + k] + 1;                       // substitution
+            if (k - 1 >= plo && k - 1 <= phi) { const int v = prev[TP_EMAX + 1 + k - 1] + 1; if (v > x) x = v; }   // A base alone
+            if (k + 1 >= plo && k + 1 <= phi) { const int v = prev[TP_EMAX + 1 + k + 1]; if (v > x) x = v; }       // B base alone
+            // clamp to the box: x <= M, y = x - k <= N, and y >= 0
+            if (x > M) x = M;
+            if (x - k > N) x = N + k;
+            if (x < k) x = k;
+            if (x < 0) x = 0;
+            const int y = x - k;
+            const int lim = (M - x < N - y) ? M - x : N - y;
+            if (lim > 0) x += wc::slide(aw, ax + (uint32_t)x, bw, bx + (uint32_t)y, lim);
+            cur[TP_EMAX + 1 + k] = (int16_t)x;
+        }
+        if (del >= klo && del <= khi && cur[TP_EMAX + 1 + del] >= M) return e;
+        int16_t *t = prev; prev = cur; cur = t;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(128) trace_point_diffs(TpArgs P, int16_t *__restrict__ scratch) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    int16_t *F0 = scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * 2 * (2 * TP_EMAX + 3);
+    int16_t *F1 = F0 + (2 * TP_EMAX + 3);
+    for (int64_t r = gw; r < P.novl; r += nw) {
+        const damar_overlap o = P.ovl[r];
+        const int ar = o.aread - P.afirst, br = o.bread - P.bfirst;
+        if (ar < 0 || ar >= P.anreads || br < 0 || br >= P.bnreads) { if (lane == 0) { atomicExch(P.err, 1); P.rec[r] = -1; } continue; }
+        const int comp = (int)(o.flags & 1u);
+        const uint32_t *bw = P.bw[comp];
+        const uint32_t abase = P.aboff[ar], bbase = P.bboff[br];
+        const int alen = P.arlen[ar], blen = P.brlen[br];
+        const int nseg = o.tlen / 2;
+        const uint64_t t0 = P.toff[r];
+        int total = 0, bb0 = o.bbpos;
+        bool bad = (o.aepos > alen || o.bepos > blen || o.abpos < 0 || o.bbpos < 0);      // TP_Error, align.c:5667
+        if (nseg == 0) bad = true;                                                        // -T records carry no trace points
+        for (int s0 = 0; s0 < nseg; s0 += 32) {
+            const int s = s0 + lane;
+            const bool v = s < nseg;
+            const int bi = v ? trace_at(P, t0 + 2 * (uint64_t)s + 1) : 0;
+            int inc = bi;                                                                 // inclusive prefix of the b_i
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            const int bb = bb0 + inc - bi;
+            int dist = 0;
+            if (v && !bad) {
+                const int grid0 = (o.abpos / P.TS) * P.TS;
+                const int ab = (s == 0) ? o.abpos : grid0 + s * P.TS;
+                const int ae = (s == nseg - 1) ? o.aepos : grid0 + (s + 1) * P.TS;
+                const int be = (s == nseg - 1) ? o.bepos : bb + bi;
+                if (ae > alen || be > blen || ae < ab || be < bb) bad = true;
+                else {
+                    dist = segment_distance(P.aw, abase + (uint32_t)ab, ae - ab, bw, bbase + (uint32_t)bb, be - bb, F0, F1);
+                    if (dist < 0) { bad = true; dist = 0; }
+                    if (P.seg) P.seg[t0 / 2 + (uint64_t)s] = (uint16_t)dist;
+                }
+            }
+            bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) dist += __shfl_xor_sync(0xffffffffu, dist, d);
+            total += dist;
+            bb0 += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) { P.rec[r] = bad ? -1 : total; if (bad) atomicExch(P.err, 1); }
+    }
+}
+
+}  // namespace
+
+// rec_diffs[novl]: what Compute_Trace_PTS leaves in path->diffs (-1: trace point out of bounds, align.c:5667);
+// seg_diffs (optional): one value per segment, segment i of record r at trace_off[r] / 2 + i.  Returns 0, or 1 if any
+// record was out of bounds.
+int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap *ovl, const uint64_t *toff, const void *trace,
+                           int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    if (novl <= 0) return 0;
+    bool any_comp = false;
+    for (int64_t i = 0; i < novl; i++) if (ovl[i].flags & 1u) { any_comp = true; break; }
+    if (any_comp) ensure_revcomp(bb);
+    DevBuf<damar_overlap> d_ovl; DevBuf<uint64_t> d_toff; DevBuf<uint8_t> d_trace; DevBuf<int32_t> d_rec; DevBuf<uint16_t> d_seg; DevBuf<int> d_err;
+    DevBuf<int16_t> d_scr;
+    d_ovl.reserve((size_t)novl); d_toff.reserve((size_t)novl); d_trace.reserve((size_t)ntrace * tbytes + 16); d_rec.reserve((size_t)novl);
+    d_err.reserve(1);
+    if (seg_diffs) d_seg.reserve((size_t)ntrace / 2 + 1);
+    CUDA_CHECK(cudaMemcpyAsync(d_ovl.p, ovl, sizeof(damar_overlap) * novl, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(d_toff.p, toff, sizeof(uint64_t) * novl, cudaMemcpyHostToDevice, st));
+    if (ntrace > 0) CUDA_CHECK(cudaMemcpyAsync(d_trace.p, trace, (size_t)ntrace * tbytes, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemsetAsync(d_err.p, 0, sizeof(int), st));
+    const int blocks = NUM_SMS_B200 * 4, threads = 128;
+    d_scr.reserve((size_t)blocks * threads * 2 * (2 * TP_EMAX + 3));
+    TpArgs P{};
+    P.aw = ab->packed[0]; P.bw[0] = bb->packed[0]; P.bw[1] = any_comp ? bb->packed[1] : bb->packed[0];
+    P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
+    P.afirst = ab->ufirst; P.bfirst = bb->ufirst; P.anreads = ab->nreads; P.bnreads = bb->nreads;
+    P.ovl = d_ovl.p; P.toff = d_toff.p; P.trace = d_trace.p; P.tbytes = tbytes; P.novl = novl; P.TS = TS;
+    P.rec = d_rec.p; P.seg = seg_diffs ? d_seg.p : nullptr; P.err = d_err.p;
+    trace_point_diffs<<<blocks, threads, 0, st>>>(P, d_scr.p);
+    KERNEL_CHECK(); count_launch();
+    int err = 0;
+    CUDA_CHECK(cudaMemcpyAsync(rec_diffs, d_rec.p, sizeof(int32_t) * novl, cudaMemcpyDeviceToHost, st));
+    if (seg_diffs && ntrace > 0) CUDA_CHECK(cudaMemcpyAsync(seg_diffs, d_seg.p, sizeof(uint16_t) * (size_t)(ntrace / 2), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(stream_wait(st));
+    return err;
+}
+
+}  // namespace damar

@@ -24,7 +24,7 @@
 
 #if defined(__CUDACC__)
 #define WC_HD __host__ __device__ __forceinline__
-#define WC_RARE __host__ __device__ __noinline__       // one copy of the code paths only few cells take
+#define WC_RARE inline __host__ __device__ __noinline__      // one copy of the code paths only few cells take
 #else
 #define WC_HD inline
 #define WC_RARE inline

@@ -139,6 +139,17 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
  * been called in by the reference's report threads)                                              */
 void damar_emission_order(const damar_overlaps *o, int64_t *order);
 
+/* Compute_Trace_PTS (align.c:5577-5692, called by the consumers of a .las file: utils/LAshow.c:261, LAcorrect, LAstitch)
+ * in its cost form: the exact edit distance of every trace-point segment of every record, i.e. what iter_np returns
+ * per segment (align.c:5230) and what Compute_Trace_PTS leaves in path->diffs per record -- not the edit script.
+ * Records and traces are given as damar_match_filter / a .las file hold them (aread of ablk, bread of bblk, DB-global
+ * ids; B coordinates of COMP records in the complemented read).  rec_diffs[novl] receives the per-record sums (-1:
+ * "trace point out of bounds", align.c:5667, or a record without trace points); seg_diffs (may be NULL) one value per
+ * segment, segment i of record r at trace_off[r] / 2 + i.  Returns 0, or 1 when any record was rejected.            */
+int damar_trace_point_diffs(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
+                            const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
+                            int32_t *rec_diffs, uint16_t *seg_diffs);
+
 /* ---- stage-level read-backs (used by the parity tests; not needed by a host) ---- */
 /* sorted k-mer list in the reference's KmerPos layout {u64 code; i32 rpos; i32 read}           */
 int damar_index_download(const damar_index *idx, void *kmerpos_out, int64_t capacity);

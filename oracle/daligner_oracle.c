@@ -1051,3 +1051,57 @@ void ora_serialise_las(ora_result *r, const ora_params *p, int only_identity, in
     }
     free(idx);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Compute_Trace_PTS, cost form (align.c:5577-5692).  Segment i of a record is A[ab, ae) x B[bb, bb + b_i) with
+ * ae = the next multiple of the trace spacing (the last segment ends at aepos, bepos; align.c:5655-5688); iter_np
+ * (align.c:4892-5230) returns D + |M - N| where D counts mismatches 1, steps away from the end diagonal 2 and steps
+ * toward it 0, i.e. the unit-cost edit distance of the two strings.  Restated as the plain dynamic program.
+ * ------------------------------------------------------------------------------------------ */
+static int edit_distance(const int8_t *a, int m, const int8_t *b, int n, int *row)
+{
+    int i, j;
+    for (j = 0; j <= n; j++) row[j] = j;
+    for (i = 1; i <= m; i++) {
+        int diag = row[0], v;
+        row[0] = i;
+        for (j = 1; j <= n; j++) {
+            v = diag + (a[i - 1] != b[j - 1]);
+            diag = row[j];
+            if (row[j] + 1 < v) v = row[j] + 1;
+            if (row[j - 1] + 1 < v) v = row[j - 1] + 1;
+            row[j] = v;
+        }
+    }
+    return row[n];
+}
+
+void ora_trace_point_diffs(const ora_block *ablk, const ora_block *bblk, const ora_block *cblk, const int32_t *recs,
+                           const uint64_t *toff, const uint16_t *trace, int64_t novl, int tspace,
+                           int32_t *rec_diffs, uint16_t *seg)
+{
+    int64_t r;
+    int *row = (int *)malloc(sizeof(int) * ((size_t)bblk->maxlen + 2));
+    for (r = 0; r < novl; r++) {
+        const int32_t *o = recs + 10 * r;
+        const int tlen = o[0], abpos = o[2], bbpos = o[3], aepos = o[4], bepos = o[5], comp = o[6] & 1;
+        const int ar = o[7] - ablk->ufirst, br = o[8] - bblk->ufirst;
+        const ora_block *bsrc = comp ? cblk : bblk;
+        const int8_t *aseq = ablk->bases + ablk->boff[ar], *bseq = bsrc->bases + bsrc->boff[br];
+        const uint16_t *t = trace + toff[r];
+        const int nseg = tlen / 2;
+        int i, ab = abpos, bb = bbpos, ae = (abpos / tspace) * tspace, be, total = 0;
+        for (i = 0; i < nseg; i++) {
+            if (i == nseg - 1) { ae = aepos; be = bepos; }
+            else { ae += tspace; be = bb + t[2 * i + 1]; }
+            {
+                const int d = edit_distance(aseq + ab, ae - ab, bseq + bb, be - bb, row);
+                if (seg) seg[toff[r] / 2 + i] = (uint16_t)d;
+                total += d;
+            }
+            ab = ae; bb = be;
+        }
+        rec_diffs[r] = total;
+    }
+    free(row);
+}

@@ -91,6 +91,15 @@ void ora_match_filter(const ora_block *ab, const ora_block *bb,
 
 /* complement_DB (daligner.c:529): returns a malloc'd mirror (bases+mask); free with ora_free_block */
 ora_block *ora_complement_block(const ora_block *blk);
+
+/* Compute_Trace_PTS in its cost form (align.c:5577-5692; iter_np returns the unit-cost edit distance, :5230): the exact
+ * edit distance of every trace-point segment of every record, by the textbook O(M*N) recurrence.  `recs` are raw 40-byte
+ * .las records (tlen, diffs, abpos, bbpos, aepos, bepos, flags, aread, bread, pad), `toff[r]` the index of record r's
+ * first trace value in `trace` (uint16 values), cblk = ora_complement_block(bblk) for the comp records (or NULL).
+ * rec_diffs[r] = sum over the segments (path->diffs after the call), seg (may be NULL) one value per segment at toff[r]/2 + i. */
+void ora_trace_point_diffs(const ora_block *ablk, const ora_block *bblk, const ora_block *cblk, const int32_t *recs,
+                           const uint64_t *toff, const uint16_t *trace, int64_t novl, int tspace,
+                           int32_t *rec_diffs, uint16_t *seg);
 void       ora_free_block(ora_block *blk);
 
 /* one Local_Alignment call (align.c:1904) on raw sequences; for unit tests.

@@ -90,6 +90,9 @@ def lib():
         L.ora_local_alignment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.POINTER(OraParams), C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]
+        L.ora_trace_point_diffs.restype = None
+        L.ora_trace_point_diffs.argtypes = [C.POINTER(OraBlock), C.POINTER(OraBlock), C.POINTER(OraBlock), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.ora_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
@@ -211,3 +214,26 @@ def daligner(ablk, bblks, p_kwargs, only_identity=0):
     if aptr:
         L.ora_free(aptr)
     return out
+
+
+def trace_point_diffs(ablk, bblk, las: bytes, every: int = 1):
+    """ora_trace_point_diffs over (every `every`-th record of) a .las image: (record indices, per-record sums,
+    per-segment values, first-segment offsets into the per-segment array of the SELECTED records)."""
+    from damar_b200 import dbio
+    novl, tspace, recs, traces = dbio.parse_las(las)
+    idx = np.arange(0, novl, every)
+    tbytes = 1 if tspace <= 125 else 2
+    sel = np.ascontiguousarray(recs[idx])
+    tr = [np.frombuffer(traces[i], dtype=np.uint8 if tbytes == 1 else np.uint16).astype(np.uint16) for i in idx]
+    toff = np.zeros(len(idx) + 1, np.uint64)
+    toff[1:] = np.cumsum([len(t) for t in tr])
+    trace = np.concatenate(tr) if tr else np.zeros(1, np.uint16)
+    ha, hb = HostBlock(ablk), HostBlock(bblk)
+    L = lib()
+    cb = L.ora_complement_block(C.byref(hb.c))
+    rec = np.zeros(max(len(idx), 1), np.int32)
+    seg = np.zeros(max(int(toff[-1]) // 2, 1), np.uint16)
+    L.ora_trace_point_diffs(C.byref(ha.c), C.byref(hb.c), cb, sel.ctypes.data, toff.ctypes.data, trace.ctypes.data,
+                            len(idx), tspace, rec.ctypes.data, seg.ctypes.data)
+    L.ora_free_block(cb)
+    return idx, rec[: len(idx)], seg[: int(toff[-1]) // 2], (toff[:-1] // 2).astype(np.int64)

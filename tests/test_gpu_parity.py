@@ -235,6 +235,22 @@ def test_properties_at_scale():
             assert r["tlen"] == 2 * ((r["aepos"] - 1) // tspace - r["abpos"] // tspace + 1)
             assert sum(t[1::2]) == r["bepos"] - r["bbpos"] and sum(t[0::2]) == r["diffs"]
             assert (r["aepos"] - r["abpos"]) + (r["bepos"] - r["bbpos"]) >= 2000
+    # Compute_Trace_PTS on the device (trace_pts.cu): every trace-point segment the wave kernel emitted is realisable with at
+    # most its recorded differences, and the per-record sums equal the records' own diffs except after bridging
+    import time
+    dh = {n: api.DeviceBlockHandle(blks[i]) for i, n in enumerate((f"{root}.1", f"{root}.2"))}
+    for fn, buf in out.items():
+        an, bn = ".".join(fn.split(".")[0:2]), ".".join(fn.split(".")[2:4])
+        novl, tspace, recs, traces = dbio.parse_las(buf)
+        t0 = time.perf_counter()
+        rec, seg, soff = api.trace_point_diffs(dh[an], dh[bn], buf, segments=True)
+        dt = time.perf_counter() - t0
+        d_rec = np.concatenate([np.frombuffer(t, dtype=np.uint8)[0::2].astype(np.int64) for t in traces])
+        assert np.all(rec >= 0) and np.all(seg <= d_rec), fn
+        assert np.all(rec <= recs["diffs"]) and (rec == recs["diffs"]).mean() > 0.99, fn
+        print(f"trace_point_diffs {fn}: {novl} records, {len(seg)} segments in {dt * 1e3:.1f} ms (incl. parse + copies)")
+    for h in dh.values():
+        h.free()
     exe = os.path.join(ROOT, "oracle", "_ref", "daligner")
     if os.path.exists(exe):
         for d in os.listdir(dbdir):
