@@ -107,25 +107,26 @@ __device__ __forceinline__ void equal_run(const uint64_t *w, int64_t n, uint64_t
 // a sequencing error in it) has none and needs no search at all.
 constexpr int MG_TILE = 2048;
 constexpr int MG_WIN = 4096;
-__global__ void __launch_bounds__(256) match_groups(GroupArgs a) {
+// window of B entries that can match tile t of A groups: one thread per tile, so the two 27-step bisections of the whole
+// B list (DRAM latency each step) of all tiles run side by side instead of one tile after the other inside a CTA
+__global__ void tile_windows(GroupArgs a, int64_t *__restrict__ wlo, int64_t *__restrict__ whi, uint32_t ntiles) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint64_t t0 = (uint64_t)t * MG_TILE, t1 = (t0 + MG_TILE < a.ngroups) ? t0 + MG_TILE : a.ngroups;
+    const uint64_t first = a.acodes[a.gstart[t0]], last = a.acodes[a.gstart[t1 - 1]];
+    wlo[t] = lower_bound_u64(a.bcodes, a.blen, first);
+    whi[t] = (last == ~0ull) ? a.blen : lower_bound_u64(a.bcodes, a.blen, last + 1);
+}
+
+__global__ void __launch_bounds__(256) match_groups(GroupArgs a, const int64_t *__restrict__ wlo, const int64_t *__restrict__ whi, uint32_t ntiles) {
     extern __shared__ uint32_t sgram[];
     __shared__ uint64_t swin[MG_WIN];
-    __shared__ int64_t win[2];
     const bool histo = (a.gram != nullptr);
     if (histo) { for (int i = threadIdx.x; i < MAXGRAM; i += blockDim.x) sgram[i] = 0; }
-    const uint64_t c0 = (uint64_t)a.ngroups * blockIdx.x / gridDim.x, c1 = (uint64_t)a.ngroups * (blockIdx.x + 1) / gridDim.x;
-    for (uint64_t t0 = c0; t0 < c1; t0 += MG_TILE) {
-        const uint64_t t1 = (t0 + MG_TILE < c1) ? t0 + MG_TILE : c1;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t t0 = (uint64_t)tile * MG_TILE, t1 = (t0 + MG_TILE < a.ngroups) ? t0 + MG_TILE : a.ngroups;
         __syncthreads();
-        if (!a.same_list && threadIdx.x < 2) {
-            if (threadIdx.x == 0) win[0] = lower_bound_u64(a.bcodes, a.blen, a.acodes[a.gstart[t0]]);
-            else {
-                const uint64_t last = a.acodes[a.gstart[t1 - 1]];
-                win[1] = (last == ~0ull) ? a.blen : lower_bound_u64(a.bcodes, a.blen, last + 1);
-            }
-        }
-        __syncthreads();
-        const int64_t lo = a.same_list ? 0 : win[0], hi = a.same_list ? 0 : win[1];
+        const int64_t lo = a.same_list ? 0 : wlo[tile], hi = a.same_list ? 0 : whi[tile];
         const bool staged = !a.same_list && (hi - lo <= MG_WIN);
         if (staged) {
             for (int i = threadIdx.x; i < (int)(hi - lo); i += blockDim.x) swin[i] = a.bcodes[lo + i];
@@ -268,10 +269,17 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
     {
         static std::once_flag attr;
         std::call_once(attr, [] { CUDA_CHECK(cudaFuncSetAttribute(match_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXGRAM * 4)); });
-        unsigned blocks = (ngroups + MG_TILE - 1) / MG_TILE;
+        const unsigned ntiles = (ngroups + MG_TILE - 1) / MG_TILE;
+        unsigned blocks = ntiles;
         if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
         if (blocks == 0) blocks = 1;
-        match_groups<<<blocks, 256, use_limit ? MAXGRAM * 4 : 0, st>>>(ga);
+        DevBuf<int64_t> wlo, whi;
+        if (!same_list && ntiles > 0) {
+            wlo.reserve(ntiles); whi.reserve(ntiles);
+            tile_windows<<<(ntiles + 127) / 128, 128, 0, st>>>(ga, wlo.p, whi.p, ntiles);
+            KERNEL_CHECK(); count_launch();
+        }
+        match_groups<<<blocks, 256, use_limit ? MAXGRAM * 4 : 0, st>>>(ga, wlo.p, whi.p, ntiles);
         KERNEL_CHECK(); count_launch();
     }
 
