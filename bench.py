@@ -306,6 +306,30 @@ def main():
     dt_e = time.perf_counter() - t1
     clocks = sampler.stop()
 
+    # ---- N > 1: one all-vs-all of ONE DB (rank 0's) with its block pairs sharded over the ranks (plan.shard_pairs) and the
+    # blocks that several ranks need broadcast over NCCL (multi.exchange_blocks): the wall time BASELINE.json's metric asks for.
+    # Strong scaling of a 10-pair plan, reported beside the weak-scaling `value`; DAMAR_BENCH_AVA=0 skips it.
+    ava = None
+    if world > 1 and os.environ.get("DAMAR_BENCH_AVA", "1") != "0":
+        try:
+            from damar_b200 import multi
+            dbdir0, root0, nb0 = make_db(args.workload, seed_shift=0)
+            multi.run_sharded(dbdir0, root0, nb0, s, rank, world, dist=dist, device=f"cuda:{local_rank}")      # warm-up (NCCL groups)
+            barrier()
+            t2 = time.perf_counter()
+            n_ava, _ = multi.run_sharded(dbdir0, root0, nb0, s, rank, world, dist=dist, device=f"cuda:{local_rank}")
+            barrier()
+            dt_ava = time.perf_counter() - t2
+            ta = torch.tensor([dt_ava, float(n_ava)], dtype=torch.float64, device="cuda")
+            tm_ = ta.clone(); dist.all_reduce(tm_, op=dist.ReduceOp.MAX)
+            ts_ = ta.clone(); dist.all_reduce(ts_, op=dist.ReduceOp.SUM)
+            ava = {"wall_ms": 1000 * float(tm_[0]), "overlaps": int(ts_[1]), "block_pairs": nb0 * (nb0 + 1) // 2, "n_gpus": world,
+                   "scaling": "strong", "overlaps_per_s": int(ts_[1]) / float(tm_[0]),
+                   "what": "whole HPCdaligner plan of one DB from block files on disk to sorted .las images in host memory: "
+                           "pairs sharded over the ranks, shared blocks broadcast over NCCL"}
+        except Exception as e:  # noqa: BLE001
+            ava = {"error": str(e)[:300]}
+
     if world > 1:
         t = torch.tensor([dt, dt_e, float(novl), float(novl_e), float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -348,6 +372,8 @@ def main():
             "device_event_ms_per_step_rank0": 1000 * dt_dev / args.steps,
             "align_kernel_ms_per_step": tm["align_kernel_ms"] / max(args.steps, 1)}
 
+    if ava is not None:
+        line["all_vs_all"] = ava
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             P = pow2_floor(cores)

@@ -125,12 +125,16 @@ def read_block(path: str, tracks: Optional[List[str]] = None) -> Block:
     np.cumsum(rlen.astype(np.int64) + 1, out=boff[1:])
     bases = np.full(int(boff[nreads]) + 1, 4, dtype=np.uint8)
     bps = np.memmap(hidden + ".bps", dtype=np.uint8, mode="r")
-    disk = recs["boff"]
-    for i in range(nreads):
-        n = int(rlen[i])
-        clen = (n + 3) >> 2
-        o = 1 + int(boff[i])
-        bases[o: o + n] = unpack_2bit(np.asarray(bps[int(disk[i]): int(disk[i]) + clen]), n)
+    disk = recs["boff"].astype(np.int64)
+    if nreads:
+        # the reads of a block are contiguous in .bps, each starting on a byte: unpack the whole range in one go, then
+        # copy every read's bases to its slot (unpacking read by read cost 0.25 s per 70 Mbp block)
+        lo, hi = int(disk.min()), int((disk + ((rlen.astype(np.int64) + 3) >> 2)).max())
+        flat = unpack_2bit(np.asarray(bps[lo:hi]), 4 * (hi - lo))
+        for i in range(nreads):
+            n = int(rlen[i])
+            o, q = 1 + int(boff[i]), 4 * (int(disk[i]) - lo)
+            bases[o: o + n] = flat[q: q + n]
     blk = Block(name=f"{root}.{part}" if part > 0 else root, root=root, path=hidden, part=part,
                 ufirst=ufirst, nreads=nreads, maxlen=maxlen, totlen=totlen, ureads=ureads, freq=freq,
                 rlen=rlen, boff=boff, bases=bases)

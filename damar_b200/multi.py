@@ -22,6 +22,20 @@ def _pack_meta(blk: dbio.Block) -> np.ndarray:
                        int(has_mask), blk.mask_data.size if has_mask else 0], dtype=np.int64)
 
 
+_GROUPS: Dict[tuple, object] = {}
+
+
+def _group_for(dist, ranks, world):
+    """Process group of exactly `ranks`, created once per process (an NCCL communicator takes seconds to set up);
+    None = the default group when every rank takes part."""
+    key = tuple(ranks)
+    if len(key) == world:
+        return None
+    if key not in _GROUPS:
+        _GROUPS[key] = dist.new_group(ranks=list(key))
+    return _GROUPS[key]
+
+
 def exchange_blocks(dbdir: str, root: str, shards: Sequence[Sequence[Job]], rank: int, world: int,
                     dist=None, device: str = "cpu", masks: Optional[List[str]] = None,
                     loader: Callable[[str, Optional[List[str]]], dbio.Block] = dbio.read_block) -> Dict[int, dbio.Block]:
@@ -35,7 +49,7 @@ def exchange_blocks(dbdir: str, root: str, shards: Sequence[Sequence[Job]], rank
         if rank == owner:
             blk = loader(os.path.join(dbdir, f"{root}.{b}"), masks)
         if len(ranks) > 1 and world > 1:
-            group = dist.new_group(ranks=ranks)             # every rank must create every group
+            group = _group_for(dist, ranks, world)          # every rank must create every group
             if rank in ranks:
                 meta = torch.from_numpy(_pack_meta(blk) if blk is not None else np.zeros(9, np.int64)).to(device)
                 dist.broadcast(meta, src=owner, group=group)

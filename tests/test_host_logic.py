@@ -162,14 +162,15 @@ def _exchange_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_block_exchange_two_ranks_gloo():
-    """World size 2 on CPU: each block is read from disk by exactly one rank; a rank that needs a block
-    it does not own receives an identical copy through the broadcast."""
+@pytest.mark.parametrize("world", [2, 4])
+def test_block_exchange_two_ranks_gloo(world):
+    """World size 2 (and 4: more ranks than units, one rank idles) on CPU: each block is read from disk by exactly one
+    rank; a rank that needs a block it does not own receives an identical copy through the broadcast."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    ps = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    ps = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
     for p in ps:
         p.start()
     res = [q.get(timeout=120) for _ in ps]
