@@ -217,7 +217,6 @@ struct WorkerScratch {
     DevBuf<uint32_t> tot32_index, tot32_merge;   // kmer_index.cu, seed_merge.cu
     PinnedBuf<uint8_t> h_up[2]; cudaEvent_t up_ev[2] = {nullptr, nullptr};   // upload_block: pinned double buffer
     PinnedBuf<damar_overlap> h_recs; PinnedBuf<uint64_t> h_toff, h_seq; PinnedBuf<uint8_t> h_trace;   // pair_align.cu
-    std::vector<uint8_t> fused_trace;            // downloaded + rewritten traces when Handle_Redundancies fired
     HostOverlaps out;                            // results of the last match_filter call
     SeedHits hits;
     const DeviceBlock *hits_a = nullptr, *hits_b = nullptr;

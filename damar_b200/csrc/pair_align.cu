@@ -19,7 +19,7 @@
 #include <mutex>
 
 #include "common.cuh"
-#include "path_fuse.h"
+#include "path_fuse_core.cuh"
 #include "wave_core.cuh"
 
 namespace damar {
@@ -1135,91 +1135,120 @@ template <typename T> void set_smem(T kernel, int bytes) {
 }  // namespace
 
 
-// ---- Handle_Redundancies glue (filter.c:2438-2449): host post-pass over the pairs with several alignments ----
+// ---- Handle_Redundancies (filter.c:1804-2077, called at :2438-2449) on the device ----
+// Runs after the last round over the finished record arrays: records are sorted by emission rank (= pair, A before B,
+// alignment order), one THREAD per pair with more than one alignment applies path_fuse_core.cuh to the pair's paths and
+// rewrites the pair's records in place (new traces are appended to the trace pool, dropped records are flagged dead).
 namespace {
 
-// the two reads of a pair, unpacked from the device copies only when a bridge has to realign them
-struct PairSeqs : FuseSeqs {
-    const DeviceBlock *ab, *bb; int bsel, ar, br; cudaStream_t st;
-    mutable std::vector<uint8_t> a, b; mutable bool have = false;
-    static void pull(const uint32_t *words, uint32_t base, int len, std::vector<uint8_t> &dst, cudaStream_t st) {
-        const uint32_t w0 = base >> 4, w1 = (base + (uint32_t)len + 15u) >> 4;
-        std::vector<uint32_t> w(w1 - w0 + 1);
-        CUDA_CHECK(cudaMemcpyAsync(w.data(), words + w0, sizeof(uint32_t) * w.size(), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(stream_wait(st));
-        dst.resize((size_t)len + 1);
-        for (int i = 0; i < len; i++) {
-            const uint32_t p = base + (uint32_t)i;
-            dst[i] = (uint8_t)((w[(p >> 4) - w0] >> (30 - 2 * (int)(p & 15u))) & 3u);
-        }
-        dst[len] = 4;
-    }
-    void fetch() const override {
-        if (have) return;
-        pull(ab->packed[0], (uint32_t)ab->h_boff[ar], ab->h_rlen[ar], a, st);
-        pull(bb->packed[bsel], (uint32_t)bb->h_boff[br], bb->h_rlen[br], b, st);
-        have = true;
-    }
-    const uint8_t *aseq() const override { return a.data(); }
-    const uint8_t *bseq() const override { return b.data(); }
-    int alen() const override { return ab->h_rlen[ar]; }
-    int blen() const override { return bb->h_rlen[br]; }
+struct HrArgs {
+    damar_overlap *recs; uint64_t *toff, *seq; uint8_t *dead; unsigned long long nrec, nrec_fast;
+    const uint8_t *pair_redo;                 // pairs the task pipeline gave up on: what it had emitted for them is void
+    const uint32_t *order;                    // record indices sorted by emission rank
+    void *trace; int tbytes; unsigned long long trace_cap; unsigned long long *trace_count;
+    const uint32_t *aw, *bw; const uint32_t *aboff, *bboff; const int32_t *arlen, *brlen; int afirst, bfirst;
+    int comp, ts;
+    uint32_t *pool; unsigned long long pool_cap; unsigned long long *pool_top;
+    unsigned long long *stats;                // [3] |= 1 trace pool full, |= 8 value > 255 in an 8-bit trace, |= 16 scratch pool dry
+    unsigned long long *nfused;
 };
 
-// Rewrites the record arrays in place; new traces go to `extra` (values, not bytes) and get offsets >= ntr.
-// Returns the new record count.
-uint64_t fuse_pass(damar_overlap *recs, uint64_t *toff, uint64_t *seq, const void *trace, uint64_t nrec, uint64_t ntr, int tbytes,
-                   std::vector<uint16_t> &extra, const DeviceBlock *ab, const DeviceBlock *bb, int bsel, int comp, int ts, cudaStream_t st,
-                   int64_t *nfused) {
-    // pairs with more than one A record
-    std::vector<uint64_t> order(nrec);
-    for (uint64_t i = 0; i < nrec; i++) order[i] = i;
-    std::sort(order.begin(), order.end(), [&](uint64_t x, uint64_t y) { return seq[x] < seq[y]; });
-    std::vector<uint8_t> dead(nrec, 0);
-    auto load = [&](uint64_t i) {
-        FusePath p;
-        const damar_overlap &r = recs[i];
-        p.abpos = r.abpos; p.bbpos = r.bbpos; p.aepos = r.aepos; p.bepos = r.bepos; p.diffs = r.diffs;
-        p.trace.resize((size_t)r.tlen);
-        if (tbytes == 1) { const uint8_t *t = reinterpret_cast<const uint8_t *>(trace) + toff[i]; for (int k = 0; k < r.tlen; k++) p.trace[k] = t[k]; }
-        else { const uint16_t *t = reinterpret_cast<const uint16_t *>(trace) + toff[i]; for (int k = 0; k < r.tlen; k++) p.trace[k] = t[k]; }
-        return p;
-    };
-    auto store = [&](uint64_t i, const FusePath &p, uint64_t sq) {
-        damar_overlap &r = recs[i];
-        r.abpos = p.abpos; r.bbpos = p.bbpos; r.aepos = p.aepos; r.bepos = p.bepos; r.diffs = p.diffs; r.tlen = (int32_t)p.trace.size();
-        toff[i] = ntr + extra.size();
-        extra.insert(extra.end(), p.trace.begin(), p.trace.end());
-        seq[i] = sq;
-    };
-    for (uint64_t g0 = 0; g0 < nrec;) {
-        uint64_t g1 = g0;
-        const uint64_t wi = seq[order[g0]] >> 8;
-        while (g1 < nrec && (seq[order[g1]] >> 8) == wi) g1++;
-        std::vector<uint64_t> ia, ib;                     // record indices, emission order
-        for (uint64_t g = g0; g < g1; g++) ((seq[order[g]] & 128ull) ? ib : ia).push_back(order[g]);
-        g0 = g1;
-        if (ia.size() < 2 && ib.size() < 2) continue;
-        std::vector<FusePath> am, bm;
-        for (uint64_t i : ia) am.push_back(load(i));
-        for (uint64_t i : ib) bm.push_back(load(i));
-        PairSeqs sq;
-        sq.ab = ab; sq.bb = bb; sq.bsel = bsel; sq.st = st;
-        sq.ar = recs[ia[0]].aread - ab->ufirst; sq.br = recs[ia[0]].bread - bb->ufirst;
-        const bool both = ia.size() > 1 && ib.size() > 1;
-        if (ia.size() > 1) handle_redundancies(am, both ? &bm : nullptr, comp, ts, sq);
-        else handle_redundancies(bm, nullptr, comp, ts, sq);
-        if (am.size() != ia.size() || bm.size() != ib.size()) (*nfused)++;
-        for (size_t k = 0; k < ia.size(); k++) { if (k < am.size()) store(ia[k], am[k], (wi << 8) | k); else dead[ia[k]] = 1; }
-        for (size_t k = 0; k < ib.size(); k++) { if (k < bm.size()) store(ib[k], bm[k], (wi << 8) | 128ull | k); else dead[ib[k]] = 1; }
+struct PackedSeq {                            // base i of one read of a packed block
+    const uint32_t *words; uint32_t base;
+    __device__ int operator()(int i) const { const uint32_t p = base + (uint32_t)i; return (int)((words[p >> 4] >> (30 - 2 * (int)(p & 15u))) & 3u); }
+};
+struct PoolArena {                            // bump allocation from one global pool, 4-byte units
+    uint32_t *pool; unsigned long long cap; unsigned long long *top; bool dry;
+    __device__ uint32_t *grab(unsigned long long words) {
+        words = (words + 1ull) & ~1ull;                     // 8-byte granules: Path arrays hold pointers
+        const unsigned long long o = atomicAdd(top, words);
+        if (o + words > cap) { dry = true; return nullptr; }
+        return pool + o;
     }
-    uint64_t n = 0;
-    for (uint64_t i = 0; i < nrec; i++) {
-        if (dead[i]) continue;
-        if (n != i) { recs[n] = recs[i]; toff[n] = toff[i]; seq[n] = seq[i]; }
-        n++;
+    __device__ uint16_t *take(int n) { return reinterpret_cast<uint16_t *>(grab((unsigned long long)(n + 1) / 2 + 1)); }
+    __device__ int *take_ints(int n) { return reinterpret_cast<int *>(grab((unsigned long long)n + 1)); }
+};
+
+__global__ void hr_sort_keys(HrArgs H, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H.nrec) return;
+    const uint64_t sq = H.seq[i];
+    const bool dead = (i < H.nrec_fast) && H.pair_redo != nullptr && H.pair_redo[sq >> 8];
+    H.dead[i] = dead ? 1 : 0;
+    keys[i] = dead ? ~0ull : sq;
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(64) handle_redundancies_pairs(HrArgs H) {
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= H.nrec) return;
+    const uint32_t i0 = H.order[j];
+    if (H.dead[i0]) return;
+    const uint64_t wi = H.seq[i0] >> 8;
+    if (j > 0) { const uint32_t ip = H.order[j - 1]; if (!H.dead[ip] && (H.seq[ip] >> 8) == wi) return; }   // not the pair's first record
+    uint32_t ia[MAX_LA_PER_PAIR], ib[MAX_LA_PER_PAIR];
+    int na = 0, nb = 0;
+    for (unsigned long long q = j; q < H.nrec; q++) {
+        const uint32_t i = H.order[q];
+        if (H.dead[i] || (H.seq[i] >> 8) != wi) break;
+        if (H.seq[i] & 128ull) { if (nb < MAX_LA_PER_PAIR) ib[nb++] = i; }
+        else if (na < MAX_LA_PER_PAIR) ia[na++] = i;
     }
-    return n;
+    if (na < 2 && nb < 2) return;
+
+    PoolArena al{H.pool, H.pool_cap, H.pool_top, false};
+    pf::Path *am = reinterpret_cast<pf::Path *>(al.grab((unsigned long long)(na + nb + 2) * (sizeof(pf::Path) / 4)));
+    if (am == nullptr) { atomicOr(H.stats + 3, 16ull); return; }
+    pf::Path *bm = am + na + 1;
+    auto load = [&](uint32_t i, pf::Path &p) {
+        const damar_overlap r = H.recs[i];
+        p.abpos = r.abpos; p.bbpos = r.bbpos; p.aepos = r.aepos; p.bepos = r.bepos; p.diffs = r.diffs; p.tlen = r.tlen;
+        p.trace = al.take(r.tlen);
+        if (p.trace == nullptr) return;
+        const uint64_t o = H.toff[i];
+        if (H.tbytes == 1) { const uint8_t *t = reinterpret_cast<const uint8_t *>(H.trace) + o; for (int k = 0; k < r.tlen; k++) p.trace[k] = t[k]; }
+        else { const uint16_t *t = reinterpret_cast<const uint16_t *>(H.trace) + o; for (int k = 0; k < r.tlen; k++) p.trace[k] = t[k]; }
+    };
+    for (int k = 0; k < na; k++) load(ia[k], am[k]);
+    for (int k = 0; k < nb; k++) load(ib[k], bm[k]);
+    if (al.dry) { atomicOr(H.stats + 3, 16ull); return; }
+
+    const damar_overlap first = H.recs[na > 0 ? ia[0] : ib[0]];
+    const int ar = (na > 0 ? first.aread - H.afirst : first.bread - H.afirst);
+    const int br = (na > 0 ? first.bread - H.bfirst : first.aread - H.bfirst);
+    const PackedSeq sa{H.aw, H.aboff[ar]}, sb{H.bw, H.bboff[br]};
+    const int alen = H.arlen[ar], blen = H.brlen[br];
+    int sa_n = na, sb_n = nb;
+    if (na > 1) {
+        const bool both = nb > 1;
+        const int no = pf::handle_redundancies(am, both ? bm : nullptr, na, H.comp, H.ts, sa, alen, sb, blen, al);
+        if (no < 0) { atomicOr(H.stats + 3, 16ull); return; }
+        sa_n = no; if (both) sb_n = no;
+    } else {
+        const int no = pf::handle_redundancies(bm, (pf::Path *)nullptr, nb, H.comp, H.ts, sa, alen, sb, blen, al);
+        if (no < 0) { atomicOr(H.stats + 3, 16ull); return; }
+        sb_n = no;
+    }
+    if (sa_n != na || sb_n != nb) atomicAdd(H.nfused, 1ull);
+
+    auto store = [&](uint32_t i, const pf::Path &p, uint64_t sq) {
+        const unsigned long long to = atomicAdd(H.trace_count, (unsigned long long)p.tlen);
+        if (to + (unsigned long long)p.tlen > H.trace_cap) { atomicOr(H.stats + 3, 1ull); return; }
+        damar_overlap r = H.recs[i];
+        r.abpos = p.abpos; r.bbpos = p.bbpos; r.aepos = p.aepos; r.bepos = p.bepos; r.diffs = p.diffs; r.tlen = p.tlen;
+        H.recs[i] = r; H.toff[i] = to; H.seq[i] = sq;
+        if (H.tbytes == 1) {                                 // Compress_TraceTo8 (align.c:3375-3396)
+            uint8_t *t = reinterpret_cast<uint8_t *>(H.trace) + to;
+            bool big = false;
+            for (int k = 0; k < p.tlen; k++) { big |= p.trace[k] > 255; t[k] = (uint8_t)p.trace[k]; }
+            if (big) atomicOr(H.stats + 3, 8ull);
+        } else {
+            uint16_t *t = reinterpret_cast<uint16_t *>(H.trace) + to;
+            for (int k = 0; k < p.tlen; k++) t[k] = p.trace[k];
+        }
+    };
+    for (int k = 0; k < na; k++) { if (k < sa_n) store(ia[k], am[k], (wi << 8) | (uint64_t)k); else H.dead[ia[k]] = 1; }
+    for (int k = 0; k < nb; k++) { if (k < sb_n) store(ib[k], bm[k], (wi << 8) | 128ull | (uint64_t)k); else H.dead[ib[k]] = 1; }
 }
 
 }  // namespace
@@ -1364,6 +1393,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     });
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0;
+    DevBuf<uint8_t> dead; DevBuf<uint64_t> hr_keys; DevBuf<uint32_t> hr_vals, hr_pool; DevBuf<unsigned long long> hr_top;
+    bool have_dead = false;
     unsigned long long rec_cap = 4 * nactive + 1024;
     unsigned long long trace_cap = (unsigned long long)rec_cap * (unsigned long long)(2 * (maxlen / TS + 2)) / 4 + (1ull << 20);
     DevBuf<damar_overlap> recs; DevBuf<uint64_t> rtoff, rseq; DevBuf<uint8_t> trace;
@@ -1453,6 +1484,40 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         }
         CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(stream_wait(st));
+        have_dead = false;
+        if (!(hc[3] & 1ull) && hc[5] > 0 && (hc[1] > 0 || nredo > 0)) {
+            // records the task pipeline emitted for pairs it later handed to the strided kernel are void; pairs with several
+            // alignments go through Handle_Redundancies (filter.c:2438-2449), one thread per pair
+            HostProf hpf("ra.fuse");
+            const unsigned long long nrec = hc[5];
+            dead.reserve((size_t)nrec + 1);
+            hr_keys.reserve(2 * (size_t)nrec + 4); hr_vals.reserve(2 * (size_t)nrec + 4);
+            HrArgs H{};
+            H.recs = recs.p; H.toff = rtoff.p; H.seq = rseq.p; H.dead = dead.p; H.nrec = nrec; H.nrec_fast = nrec_fast;
+            H.pair_redo = nredo > 0 ? pair_redo.p : nullptr;
+            H.trace = trace.p; H.tbytes = tbytes; H.trace_cap = trace_cap; H.trace_count = counters.p + 6;
+            H.aw = ab->packed[0]; H.bw = bb->packed[bsel]; H.aboff = ab->boff; H.bboff = bb->boff; H.arlen = ab->rlen; H.brlen = bb->rlen;
+            H.afirst = ab->ufirst; H.bfirst = bb->ufirst; H.comp = comp ? 1 : 0; H.ts = TS;
+            H.stats = counters.p; H.nfused = counters.p + 7;
+            uint64_t *k0 = hr_keys.p, *k1 = hr_keys.p + nrec + 2; uint32_t *v0 = hr_vals.p, *v1 = hr_vals.p + nrec + 2;
+            hr_sort_keys<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(H, k0, v0);
+            KERNEL_CHECK(); count_launch();
+            have_dead = true;
+            if (hc[1] > 0) {
+                static const size_t pool_mb = getenv("DAMAR_HR_POOL_MB") ? (size_t)atoll(getenv("DAMAR_HR_POOL_MB")) : 0;
+                size_t pool_words = pool_mb ? (pool_mb << 18) : std::min<size_t>((size_t)2 << 30, ((size_t)hc[1] << 16) + ((size_t)16 << 20));
+                hr_pool.reserve(pool_words); hr_top.reserve(1);
+                CUDA_CHECK(cudaMemsetAsync(hr_top.p, 0, sizeof(unsigned long long), st));
+                int kb = 9;                                                      // rank = pair << 8 | B flag | alignment number
+                while ((1ull << (kb - 8)) < (unsigned long long)nwork + 2) kb++;
+                radix_sort_pairs(k0, v0, k1, v1, (int64_t)nrec, kb, st);
+                H.order = v0; H.pool = hr_pool.p; H.pool_cap = pool_words; H.pool_top = hr_top.p;
+                handle_redundancies_pairs<<<(unsigned)((nrec + 63) / 64), 64, 0, st>>>(H);
+                KERNEL_CHECK(); count_launch();
+            }
+            CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(stream_wait(st));
+        }
         if ((hc[3] & 1ull) && attempt < 4) {            // output buffers too small: grow and rerun
             if (hc[5] > rec_cap) rec_cap = hc[5] + 1024;
             if (hc[6] > trace_cap) trace_cap = hc[6] + 1024;
@@ -1467,6 +1532,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         fatal("alignment scratch overflow (flags %llu): wave wider than %d diagonals, pebble arena or per-pair alignment list exhausted",
               hc[3], ring);
     if (hc[3] & 1ull) fatal("alignment output buffers overflowed repeatedly");
+    if (hc[3] & 16ull) fatal("Handle_Redundancies scratch pool exhausted; raise DAMAR_HR_POOL_MB");
     if (hc[3] & 8ull) fatal("Compression of trace to bytes fails, value too big");   // align.c:3385-3388
 
     // ---- download into pinned staging; records stay in device emission order, `seq` carries the
@@ -1483,38 +1549,20 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         CUDA_CHECK(cudaMemcpyAsync(h_seq.p, rseq.p, sizeof(uint64_t) * nrec, cudaMemcpyDeviceToHost, st));
     }
     if (ntr) CUDA_CHECK(cudaMemcpyAsync(h_trace.p, trace.p, (size_t)ntr * tbytes, cudaMemcpyDeviceToHost, st));
-    std::vector<uint8_t> h_redo;
-    if (nredo > 0) { h_redo.resize(nwork); CUDA_CHECK(cudaMemcpyAsync(h_redo.data(), pair_redo.p, nwork, cudaMemcpyDeviceToHost, st)); }
+    std::vector<uint8_t> h_dead;
+    if (have_dead && nrec) { h_dead.resize(nrec); CUDA_CHECK(cudaMemcpyAsync(h_dead.data(), dead.p, nrec, cudaMemcpyDeviceToHost, st)); }
     CUDA_CHECK(stream_wait(st));
     uint64_t nkeep = nrec;
-    if (nredo > 0) {                                   // drop what the task pipeline emitted for pairs it gave up on
+    if (have_dead) {                                   // drop the flagged records (pure bookkeeping; the decisions were made on the device)
         nkeep = 0;
         for (uint64_t i = 0; i < nrec; i++) {
-            if (i < nrec_fast && h_redo[h_seq.p[i] >> 8]) continue;
+            if (h_dead[i]) continue;
             if (nkeep != i) { h_recs.p[nkeep] = h_recs.p[i]; h_toff.p[nkeep] = h_toff.p[i]; h_seq.p[nkeep] = h_seq.p[i]; }
             nkeep++;
         }
     }
-    uint64_t ntr_out = ntr;
+    const uint64_t ntr_out = ntr;
     const void *trace_out = h_trace.p;
-    int64_t nfused = 0;
-    if (hc[1] > 0 && nkeep > 0) {            // pairs with several alignments: Handle_Redundancies
-        HostProf hpf("ra.fuse");
-        std::vector<uint16_t> extra;
-        nkeep = fuse_pass(h_recs.p, h_toff.p, h_seq.p, h_trace.p, nkeep, ntr, tbytes, extra, ab, bb, bsel, comp ? 1 : 0, TS, st, &nfused);
-        if (!extra.empty()) {                                    // rewritten traces live behind the downloaded ones
-            std::vector<uint8_t> &all = ws.fused_trace;
-            all.resize((size_t)(ntr + extra.size()) * tbytes);
-            memcpy(all.data(), h_trace.p, (size_t)ntr * tbytes);
-            if (tbytes == 1) {
-                for (size_t i = 0; i < extra.size(); i++) {
-                    if (extra[i] > 255) fatal("Compression of trace to bytes fails, value too big");   // align.c:3385-3388
-                    all[(size_t)ntr + i] = (uint8_t)extra[i];
-                }
-            } else memcpy(all.data() + (size_t)ntr * 2, extra.data(), extra.size() * 2);
-            trace_out = all.data(); ntr_out = ntr + extra.size();
-        }
-    }
     out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = trace_out;
     out.novl = (int64_t)nkeep; out.ntrace = (int64_t)ntr_out; out.tbytes = tbytes; out.redo = (int64_t)nredo;
     out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)nwork;

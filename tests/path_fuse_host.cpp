@@ -1,23 +1,30 @@
-// path_fuse_host.cpp -- TEST INFRASTRUCTURE: applies the product's host-side Handle_Redundancies
-// (damar_b200/csrc/path_fuse.cu) to the UNFUSED alignments the oracle buffered for one Match_Filter call, so that
+// path_fuse_host.cpp -- TEST INFRASTRUCTURE: applies the product's Handle_Redundancies (damar_b200/csrc/path_fuse_core.cuh,
+// the very code the handle_redundancies kernel runs one pair per thread) on the CPU to the UNFUSED alignments the oracle buffered for one Match_Filter call, so that
 // "oracle + path_fuse" can be compared with the reference's .las files on the CPU (tests/test_path_fuse.py).
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <vector>
 
-#include "../damar_b200/csrc/path_fuse.cu"
+#include "../damar_b200/csrc/path_fuse_core.cuh"
 #include "../oracle/daligner_oracle.h"
 
 using namespace damar;
 
 namespace {
-struct OraSeqs : FuseSeqs {
-    const ora_block *ab, *bb; int ar, br;
-    void fetch() const override {}
-    const uint8_t *aseq() const override { return reinterpret_cast<const uint8_t *>(ab->bases + ab->boff[ar]); }
-    const uint8_t *bseq() const override { return reinterpret_cast<const uint8_t *>(bb->bases + bb->boff[br]); }
-    int alen() const override { return ab->rlen[ar]; }
-    int blen() const override { return bb->rlen[br]; }
+// the CPU stand-ins of what the kernel provides: reads as bytes, an arena that grows
+struct ByteSeq {
+    const uint8_t *p;
+    int operator()(int i) const { return p[i]; }
+};
+struct HostArena {
+    std::vector<std::unique_ptr<uint32_t[]>> chunks;
+    uint16_t *take(int n) { chunks.emplace_back(new uint32_t[(size_t)n / 2 + 2]); return reinterpret_cast<uint16_t *>(chunks.back().get()); }
+    int *take_ints(int n) { chunks.emplace_back(new uint32_t[(size_t)n + 2]); return reinterpret_cast<int *>(chunks.back().get()); }
+};
+struct FusePath {
+    int abpos = 0, bbpos = 0, aepos = 0, bepos = 0, diffs = 0;
+    std::vector<uint16_t> trace;
 };
 FusePath load(const ora_result *r, int64_t i) {
     FusePath p;
@@ -25,6 +32,31 @@ FusePath load(const ora_result *r, int64_t i) {
     p.abpos = o.abpos; p.bbpos = o.bbpos; p.aepos = o.aepos; p.bepos = o.bepos; p.diffs = o.diffs;
     p.trace.assign(r->trace + o.toff, r->trace + o.toff + o.tlen);
     return p;
+}
+// runs the product's post-pass (path_fuse_core.cuh) on vector-backed lists
+void handle_redundancies(std::vector<FusePath> &am, std::vector<FusePath> *bm, int comp, int ts, const ora_block *ab, int ar,
+                         const ora_block *bb, int br) {
+    HostArena al;
+    auto view = [](std::vector<FusePath> &v) {
+        std::vector<pf::Path> o(v.size());
+        for (size_t i = 0; i < v.size(); i++)
+            o[i] = pf::Path{v[i].abpos, v[i].bbpos, v[i].aepos, v[i].bepos, v[i].diffs, (int)v[i].trace.size(), v[i].trace.data()};
+        return o;
+    };
+    std::vector<pf::Path> pa = view(am), pb;
+    if (bm) pb = view(*bm);
+    const ByteSeq sa{reinterpret_cast<const uint8_t *>(ab->bases + ab->boff[ar])}, sb{reinterpret_cast<const uint8_t *>(bb->bases + bb->boff[br])};
+    const int no = pf::handle_redundancies(pa.data(), bm ? pb.data() : nullptr, (int)am.size(), comp, ts, sa, ab->rlen[ar], sb, bb->rlen[br], al);
+    auto back = [&](std::vector<pf::Path> &v, std::vector<FusePath> &dst) {
+        std::vector<FusePath> o((size_t)no);
+        for (int i = 0; i < no; i++) {
+            o[i].abpos = v[i].abpos; o[i].bbpos = v[i].bbpos; o[i].aepos = v[i].aepos; o[i].bepos = v[i].bepos; o[i].diffs = v[i].diffs;
+            o[i].trace.assign(v[i].trace, v[i].trace + v[i].tlen);
+        }
+        dst.swap(o);
+    };
+    back(pa, am);
+    if (bm) back(pb, *bm);
 }
 }  // namespace
 
@@ -57,9 +89,8 @@ extern "C" int64_t pf_fuse_result(ora_result *r, int64_t from, const ora_block *
         std::vector<FusePath> am, bm;
         for (int64_t q = 0; q < na; q++) am.push_back(load(r, i + q));
         for (int64_t q = 0; q < nb; q++) bm.push_back(load(r, i + na + q));
-        OraSeqs sq; sq.ab = ab; sq.bb = bb; sq.ar = ar; sq.br = br;
-        if (na > 1) handle_redundancies(am, nb > 1 ? &bm : nullptr, comp, ts, sq);
-        else if (nb > 1) handle_redundancies(bm, nullptr, comp, ts, sq);
+        if (na > 1) handle_redundancies(am, nb > 1 ? &bm : nullptr, comp, ts, ab, ar, bb, br);
+        else if (nb > 1) handle_redundancies(bm, nullptr, comp, ts, ab, ar, bb, br);
         if ((int64_t)am.size() != na || (int64_t)bm.size() != nb) changed++;
         for (size_t q = 0; q < am.size(); q++) emit(r->ovl[i], am[q]);
         for (size_t q = 0; q < bm.size(); q++) emit(r->ovl[i + na], bm[q]);

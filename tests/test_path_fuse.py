@@ -1,4 +1,4 @@
-"""CPU check of the host-side Handle_Redundancies (damar_b200/csrc/path_fuse.cu): the oracle buffers the UNFUSED
+"""CPU check of Handle_Redundancies (damar_b200/csrc/path_fuse_core.cuh, the code the CUDA kernel runs one pair per thread): the oracle buffers the UNFUSED
 alignments of every pair (it restates the path up to filter.c:2436), tests/path_fuse_host.cpp applies the
 product's post-pass to them, and the serialised result must equal the reference daligner's .las files of the
 `rep` fixture (tests/golden/make_repeats.py: containments, fusions and bridges)."""
@@ -16,8 +16,7 @@ from damar_b200 import dbio
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "_build", "libpathfuse_host.so")
-SRC = [os.path.join(HERE, "path_fuse_host.cpp"), os.path.join(ROOT, "damar_b200", "csrc", "path_fuse.cu"),
-       os.path.join(ROOT, "damar_b200", "csrc", "path_fuse.h")]
+SRC = [os.path.join(HERE, "path_fuse_host.cpp"), os.path.join(ROOT, "damar_b200", "csrc", "path_fuse_core.cuh")]
 REP = os.path.join(GOLDEN, "rep")
 with open(os.path.join(REP, "cases.json")) as _f:
     REP_CASES = json.load(_f)
