@@ -24,20 +24,59 @@ CONFIGS = {
 
 
 def settings(flags):
-    o = dict(k=14, w=6, h=35, e=.70, l=1000, s=100, M=32)
+    o = dict(k=14, w=6, h=35, e=.70, l=1000, s=100, M=32, t=0)
+    sw = set()
     for f in flags:
-        if f[1] in "kwhlsM":
+        if f[1] in "kwhlsMt":
             o[f[1]] = int(f[2:])
         elif f[1] == "e":
             o["e"] = float(f[2:])
+        elif f[1] in "IATOb":
+            sw.add(f[1])
     return api.Settings(kmer=o["k"], binshift=o["w"], hitmin=o["h"], ave_corr=o["e"], minlen=o["l"], trace_spacing=o["s"],
-                        mem_limit_gb=o["M"], nthreads=4)
+                        mem_limit_gb=o["M"], nthreads=4, suppress=o["t"], identity="I" in sw, symmetric="A" not in sw,
+                        no_trace="T" in sw, only_identity="O" in sw, biased="b" in sw)
+
+
+# the option space at 2 x 10 Mbp (bench workload "small"): job `daligner [flags] S.2 S.1 S.2` against the reference binary
+FLAG_SETS = [[], ["-t12"], ["-I"], ["-A"], ["-T"], ["-s200"], ["-s50"], ["-k16", "-h50"], ["-k12", "-w5", "-h28"], ["-e.85"],
+             ["-l2500"], ["-b"], ["-M1"], ["-k20", "-h60", "-e.8"], ["-w7", "-h40"]]
+
+
+def flag_sweep():
+    dbdir, root, nblocks = bench.make_db("small")
+    blocks = {i: dbio.read_block(os.path.join(dbdir, f"{root}.{i}")) for i in (1, 2)}
+    allok = True
+    for fl in FLAG_SETS:
+        flags = ["-M32"] + fl if not any(f.startswith("-M") for f in fl) else list(fl)
+        s = settings(flags)
+        got = api.daligner(blocks[2], [blocks[1], blocks[2]], s)
+        for d in os.listdir(dbdir):
+            if d.startswith("d001_"):
+                shutil.rmtree(os.path.join(dbdir, d))
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "daligner"), "-j4"] + flags + [f"{root}.2", f"{root}.1", f"{root}.2"],
+                       cwd=dbdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        ok_all, novl = True, 0
+        for fn, v in got.items():
+            part = int(fn.split(".")[1])
+            ref = open(os.path.join(dbdir, f"d001_{part:05d}", fn), "rb").read()
+            ok, why = dbio.las_equal(ref, v)
+            ok_all &= ok
+            novl += int.from_bytes(v[:8], "little")
+            if not ok:
+                print(f"    {fn}: DIFF {why}", flush=True)
+        allok &= ok_all
+        print(f"  flags {' '.join(flags):28s} {len(got)} files, {novl:7d} overlaps: {'OK' if ok_all else 'DIFF'}", flush=True)
+    return allok
 
 
 def main():
     names = sys.argv[1:] or list(CONFIGS)
     api.init()
     allok = True
+    if "flags" in names:
+        names.remove("flags")
+        allok &= flag_sweep()
     for name in names:
         cfg = CONFIGS[name]
         bench.WORKLOADS[name] = dict(sim=cfg["sim"], split=cfg["split"], root=cfg["root"], desc=name)
