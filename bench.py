@@ -280,7 +280,7 @@ def main():
     launches = tm["kernel_launches"] - l0
 
     # ---- the dominant HBM kernel on its own: Sort_Kmers of every block and orientation of the workload, one at a
-    # time.  Inside a step four comparisons are in flight, and the event interval around a sort launch then also
+    # time.  Inside a step six comparisons are in flight, and the event interval around a sort launch then also
     # counts the time its CTAs wait for SMs held by another comparison's wave kernel; both figures are reported.
     api.reset_kernel_timers()
     barrier()
@@ -352,7 +352,7 @@ def main():
                 "in_step": {"achieved": in_step, "frac": in_step / peak, "launches": tm["scatter_launches"],
                             "avg_launch_ms": tm["scatter_ms"] / max(tm["scatter_launches"], 1),
                             "share_of_step": (tm["scatter_ms"] / 1000.0) / dt if world == 1 else None,
-                            "note": "event intervals inside the timed steps, 4 comparisons in flight: a launch also waits for "
+                            "note": "event intervals inside the timed steps, several comparisons in flight: a launch also waits for "
                                     "SMs held by other comparisons' wave kernels"},
                 # measured dram bytes per launch: 23.94 B/element (12 B SoA records in + out) in profiles/r01_rs_scatter_ncu.txt
                 "traffic": 23.94 * sc_el / max(sc_n, 1), "traffic_source": "ncu --set full dram__bytes_read+write per element x elements per launch",

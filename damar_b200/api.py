@@ -345,7 +345,7 @@ def _bind_worker():
 
 
 def workers() -> int:
-    n = int(os.environ.get("DAMAR_WORKERS", "4"))
+    n = int(os.environ.get("DAMAR_WORKERS", "6"))
     return max(1, min(n, load_library().damar_worker_count() - 1))
 
 

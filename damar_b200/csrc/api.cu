@@ -27,7 +27,7 @@ void fatal(const char *fmt, ...) {
 }
 
 // ---- worker contexts ----
-constexpr int MAX_WORKERS = 8;
+constexpr int MAX_WORKERS = 13;
 static Context g_ctx[MAX_WORKERS];
 static thread_local Context *tl_ctx = &g_ctx[0];
 static std::mutex g_mu;                           // guards the process-wide settings, size map and profile
