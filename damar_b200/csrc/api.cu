@@ -1,5 +1,7 @@
 // api.cu -- the C-ABI of include/damar_b200.h on top of the stage implementations.
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -103,26 +105,48 @@ static size_t round_class(size_t b) {
     return (b + q - 1) / q * q;
 }
 static void release_cached_blocks(Context &c) {
+    std::lock_guard<std::mutex> lk(c.cache_mu);
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto &kv : c.free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
     c.free_blocks.clear();
 }
+// Memory pressure between workers: a worker whose cudaMalloc fails frees the cached blocks of EVERY worker (cudaFree waits
+// for the device, so blocks whose last kernels are still queued on another stream are safe to give back) and then retries
+// for a while -- the other comparisons in flight finish and hand their lists back.
+static void release_all_caches() {
+    for (int i = 0; i < MAX_WORKERS; i++) {
+        Context &o = g_ctx[i];
+        std::lock_guard<std::mutex> lk(o.cache_mu);
+        std::lock_guard<std::mutex> lock(g_mu);
+        for (auto &kv : o.free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
+        o.free_blocks.clear();
+    }
+}
 void *dev_alloc_bytes(size_t bytes) {
     Context &c = ctx();
     const size_t r = round_class(bytes ? bytes : 1);
-    auto it = c.free_blocks.lower_bound(r);
-    if (it != c.free_blocks.end() && it->first <= r + r / 2) {
-        void *p = it->second;
-        c.free_blocks.erase(it);
-        return p;
+    {
+        std::lock_guard<std::mutex> lk(c.cache_mu);
+        auto it = c.free_blocks.lower_bound(r);
+        if (it != c.free_blocks.end() && it->first <= r + r / 2) {
+            void *p = it->second;
+            c.free_blocks.erase(it);
+            return p;
+        }
     }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, r);
-    if (e != cudaSuccess) {                       // out of memory: drop this worker's cache and retry once
+    if (e != cudaSuccess) {
         cudaGetLastError();
         CUDA_CHECK(stream_wait(c.stream));
-        release_cached_blocks(c);
-        CUDA_CHECK(cudaMalloc(&p, r));
+        for (int attempt = 0;; attempt++) {
+            release_all_caches();
+            e = cudaMalloc(&p, r);
+            if (e == cudaSuccess) break;
+            cudaGetLastError();
+            if (attempt >= 600) fatal("out of device memory: %zu bytes requested (%s)", r, cudaGetErrorString(e));
+            std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        }
     }
     std::lock_guard<std::mutex> lock(g_mu);
     g_block_size[p] = r;
@@ -140,6 +164,7 @@ void dev_free(void *p) {
         if (it != g_block_size.end()) sz = it->second;
     }
     if (sz == 0) { cudaFree(p); return; }
+    std::lock_guard<std::mutex> lk(c.cache_mu);
     c.free_blocks.emplace(sz, p);
 }
 

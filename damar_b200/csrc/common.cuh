@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -135,6 +136,7 @@ struct Context {
     int64_t launches = 0;
     bool ready = false;
     cudaEvent_t wait_ev = nullptr;               // blocking-sync event of stream_wait()
+    std::mutex cache_mu;                         // guards free_blocks: another worker may trim it under memory pressure
     std::multimap<size_t, void *> free_blocks;   // caching allocator (api.cu)
     WorkerScratch *ws = nullptr;                 // buffers that outlive a call (api.cu)
 };
