@@ -35,7 +35,7 @@ constexpr int TRIM_MASK = 0x7fff;
 constexpr int TRIM_MLAG = 200;
 constexpr int WAVE_LAG = 30;
 constexpr int FRACTION = 1000;
-constexpr int MAX_LA_PER_PAIR = 64;
+constexpr int MAX_LA_PER_PAIR = 127;   // the emission rank keeps the alignment number of a pair in 7 bits
 constexpr int IMAX = 0x7fffffff;
 
 constexpr int AL_WARPS = 4;            // warps per CTA of the alignment kernel
@@ -425,8 +425,8 @@ __device__ void local_alignment(WarpLA &S, const AlignArgs &P, uint16_t *tbuf, i
     __syncwarp();
     int preA = 0, preB = 0;
     if (lane == 0) {
-        preA = wc::emit_chain_rev(reinterpret_cast<wc::Cell *>(S.cells), ha, true, ex, ey, ed, P.TS, aoff, flenA, atr);
-        preB = wc::emit_chain_rev(reinterpret_cast<wc::Cell *>(S.cells), hb, false, ex, ey, ed, P.TS, boff, flenB, btr);
+        preA = wc::emit_chain_rev(reinterpret_cast<wc::Cell *>(S.cells), wc::reverse_chain(reinterpret_cast<wc::Cell *>(S.cells), ha), true, ex, ey, ed, P.TS, aoff, flenA, atr);
+        preB = wc::emit_chain_rev(reinterpret_cast<wc::Cell *>(S.cells), wc::reverse_chain(reinterpret_cast<wc::Cell *>(S.cells), hb), false, ex, ey, ed, P.TS, boff, flenB, btr);
     }
     preA = __shfl_sync(FULL, preA, 0); preB = __shfl_sync(FULL, preB, 0);
     __syncwarp();
@@ -909,7 +909,7 @@ struct DevPool {
 
 template <int RING, int WARPS_>
 struct WaveCfg {
-    static constexpr int WARPS = WARPS_;                      // 20 KB (RING 32) / 40 KB (RING 64) of front per warp
+    static constexpr int WARPS = WARPS_;                      // 16 KB (RING 32) / 32 KB (RING 64) of front per warp
     static constexpr int SMEM = WARPS * wc::FRONT_WORDS * RING * 32 * 4;
 };
 
@@ -1033,13 +1033,14 @@ __global__ void __launch_bounds__(256) finish_las(PipeArgs Q) {
         const int alen = P.arlen[ar], blen = P.brlen[br];
         const int anti = apos + bpos;
         const int aoff = 0, boff = P.comp ? (blen % P.TS) : 0;
-        int flen = 0, pre = 0;
-        if (lane < 2) {                                        // lane 0: A chains, lane 1: B chains
-            const bool isA = lane == 0;
-            uint16_t *tr = isA ? atr : btr;
-            flen = wc::emit_chain_fwd(Q.pool, isA ? fo.ha : fo.hb, isA, anti, fo.ex, fo.ey, fo.ediff, tr);
-            pre = wc::emit_chain_rev(Q.pool, isA ? ro.ha : ro.hb, isA, ro.ex, ro.ey, ro.ediff, P.TS, isA ? aoff : boff, flen, tr);
-        }
+        int flen = 0, pre = 0, rroot = -1;
+        if (lane < 2)                                          // lane 0: the A trace points of the chains, lane 1: the B trace points
+            flen = wc::emit_chain_fwd<true>(Q.pool, fo.ha, lane == 0, anti, fo.ex, fo.ey, fo.ediff, lane == 0 ? atr : btr);
+        if (lane == 0) rroot = wc::reverse_chain(Q.pool, ro.ha);
+        __syncwarp();
+        rroot = __shfl_sync(FULL, rroot, 0);
+        if (lane < 2)
+            pre = wc::emit_chain_rev<true>(Q.pool, rroot, lane == 0, ro.ex, ro.ey, ro.ediff, P.TS, lane == 0 ? aoff : boff, flen, lane == 0 ? atr : btr);
         __syncwarp();
         const int flenA = __shfl_sync(FULL, flen, 0), flenB = __shfl_sync(FULL, flen, 1);
         const int preA = __shfl_sync(FULL, pre, 0), preB = __shfl_sync(FULL, pre, 1);
@@ -1376,20 +1377,17 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
-    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 11;
+    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 12;
     // CTAs (= SMs, one CTA fills an SM's shared memory) of one comparison's wave kernel; fewer than 148 lets the kernels of
     // concurrent comparisons run side by side so that the tail of one overlaps the bulk of another
     static const int wave_ctas = getenv("DAMAR_WAVE_CTAS") ? std::max(1, std::min(NUM_SMS_B200, atoi(getenv("DAMAR_WAVE_CTAS")))) : NUM_SMS_B200;
     static std::once_flag attr;
     std::call_once(attr, [] {
-        set_smem(wave_tasks<32, false, 4, 8>, WaveCfg<32, 8>::SMEM);
-        set_smem(wave_tasks<32, false, 4, 10>, WaveCfg<32, 10>::SMEM);
         set_smem(wave_tasks<32, false, 4, 11>, WaveCfg<32, 11>::SMEM);
-        set_smem(wave_tasks<32, false, 2, 11>, WaveCfg<32, 11>::SMEM);
-        set_smem(wave_tasks<32, false, 3, 11>, WaveCfg<32, 11>::SMEM);
-        set_smem(wave_tasks<32, false, 5, 11>, WaveCfg<32, 11>::SMEM);
-        set_smem(wave_tasks<32, false, 6, 11>, WaveCfg<32, 11>::SMEM);
-        set_smem(wave_tasks<64, true, 4, 5>, WaveCfg<64, 5>::SMEM);
+        set_smem(wave_tasks<32, false, 4, 12>, WaveCfg<32, 12>::SMEM);
+        set_smem(wave_tasks<32, false, 4, 14>, WaveCfg<32, 14>::SMEM);
+        set_smem(wave_tasks<32, false, 3, 14>, WaveCfg<32, 14>::SMEM);
+        set_smem(wave_tasks<64, true, 4, 7>, WaveCfg<64, 7>::SMEM);
     });
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0;
@@ -1437,22 +1435,19 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
                     radix_sort_pairs(k0, v0, k1, v1, nt, 24, st);
                     Q.task_order = v0;
                 }
-                if (nway == 2) wave_tasks<32, false, 2, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
-                else if (nway == 3) wave_tasks<32, false, 3, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
-                else if (nway == 5) wave_tasks<32, false, 5, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
-                else if (nway == 6) wave_tasks<32, false, 6, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
-                else if (wwarps == 8) wave_tasks<32, false, 4, 8><<<wb, per, WaveCfg<32, 8>::SMEM, st>>>(Q);
-                else if (wwarps == 10) wave_tasks<32, false, 4, 10><<<wb, per, WaveCfg<32, 10>::SMEM, st>>>(Q);
-                else wave_tasks<32, false, 4, 11><<<wb, 11 * 32, WaveCfg<32, 11>::SMEM, st>>>(Q);
+                if (nway == 3) wave_tasks<32, false, 3, 14><<<wb, 14 * 32, WaveCfg<32, 14>::SMEM, st>>>(Q);
+                else if (wwarps == 11) wave_tasks<32, false, 4, 11><<<wb, per, WaveCfg<32, 11>::SMEM, st>>>(Q);
+                else if (wwarps == 12) wave_tasks<32, false, 4, 12><<<wb, per, WaveCfg<32, 12>::SMEM, st>>>(Q);
+                else wave_tasks<32, false, 4, 14><<<wb, 14 * 32, WaveCfg<32, 14>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             unsigned int nwide = 0;
             CUDA_CHECK(cudaMemcpyAsync(&nwide, ctr.p + CTR_NWIDE, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(stream_wait(st));
             if (nwide > 0) {
-                const unsigned per = WaveCfg<64, 5>::WARPS * 32;
+                const unsigned per = WaveCfg<64, 7>::WARPS * 32;
                 const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (nwide + per - 1) / per);
-                wave_tasks<64, true, 4, 5><<<wb, per, WaveCfg<64, 5>::SMEM, st>>>(Q);
+                wave_tasks<64, true, 4, 7><<<wb, per, WaveCfg<64, 7>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;

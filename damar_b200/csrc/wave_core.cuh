@@ -106,13 +106,19 @@ WC_HD uint64_t push_matches(uint64_t b, int n) {             // b << n with n on
 }
 
 // ---- pebble cell (align.c:399-405): {prev, diag, diff, mark}, original coordinates ----------------
+// The reference keeps two chains per path, the A trace points and the B trace points.  Here a path has ONE chain in
+// creation order, each cell tagged with its axis (bit 30 of diff): the front then carries one head per diagonal instead
+// of two (16 bytes per diagonal, 14 warps per SM instead of 11), and the two chains of the reference are the two
+// tag-filtered subsequences of it.
 struct Cell { int32_t prev, diag, diff, mark; };
+constexpr int32_t CELL_B = 1 << 30;                  // tag in Cell::diff: a B-axis trace point
+constexpr int32_t CELL_DIFF = CELL_B - 1;
 
 // ---- per-thread view of its wave-front ring ------------------------------------------------------
-// word arrays: V (furthest anti-diagonal), T lo/hi (match history), HA, HB (chain heads, pool index).
+// word arrays: V (furthest anti-diagonal), T lo/hi (match history), H (head of the path's pebble chain, pool index).
 // The reference also keeps, per diagonal, the next trace point to cross (NA, NB) and relies on the mark of a
-// path's head pebble; both are functions of the previous wave here (see settle): 20 bytes per diagonal.
-enum { F_V = 0, F_TLO = 1, F_THI = 2, F_HA = 3, F_HB = 4, FRONT_WORDS = 5 };
+// path's head pebble; both are functions of the previous wave here (see cellsN): 16 bytes per diagonal.
+enum { F_V = 0, F_TLO = 1, F_THI = 2, F_H = 3, FRONT_WORDS = 4 };
 template <int RING, int STRIDE>
 struct Front {
     uint32_t *base;
@@ -120,11 +126,11 @@ struct Front {
     WC_HD uint32_t *slot(int k) const { return base + (k & (RING - 1)) * STRIDE; }
 };
 
-struct PathState { uint64_t T; uint32_t ha, hb; };
+struct PathState { uint64_t T; uint32_t h; };
 template <class FRONT> WC_HD PathState load_path(const uint32_t *s) {
     PathState p;
     p.T = (uint64_t)s[F_TLO * FRONT::ARR] | ((uint64_t)s[F_THI * FRONT::ARR] << 32);
-    p.ha = s[F_HA * FRONT::ARR]; p.hb = s[F_HB * FRONT::ARR];
+    p.h = s[F_H * FRONT::ARR];
     return p;
 }
 
@@ -180,7 +186,7 @@ struct TaskIn {
 };
 struct TaskOut {                    // original coordinates
     int32_t ex, ey, ediff;
-    int32_t ha, hb;                 // heads of the chosen A / B pebble chains
+    int32_t ha, hb;                 // head of the chosen pebble chain (both: the merged chain)
     int32_t status;
     int32_t waves, cells;           // work counters (wave cells after pruning, as the reference's WAVE_STATS)
 };
@@ -197,7 +203,7 @@ struct Lane {
     int low, hgh, k, dif, more, aclip, bclip;
     int besta, besty, lasta, trima, trimy, trimd;
     int morea, morey, mored, morem;
-    uint32_t trimha, trimhb, moreha, morehb;
+    uint32_t trimh, moreh;
     // sweep registers: previous-wave values of the diagonals above the cursor
     int vp, vc;                     // V[k+1], V[k]
     PathState pp;                   // path state of k+1
@@ -228,7 +234,7 @@ WC_HD uint32_t push_cell(Lane &L, POOL &pool, uint32_t prev, int k, int dif, int
     // back to original coordinates
     const int diag = L.rev ? (L.alen - L.blen) - k : k;
     const int mark = L.rev ? (isA ? L.alen : L.blen) - markA_or_B_pass : markA_or_B_pass;
-    const uint32_t id = push_raw(pool, L.cell_next, L.cell_left, prev, diag, dif, mark);
+    const uint32_t id = push_raw(pool, L.cell_next, L.cell_left, prev, diag, isA ? dif : (dif | CELL_B), mark);
     if (id == NOCELL) { L.status = ST_POOL; return prev; }
     L.cell_left = (L.cell_left ? L.cell_left : (uint32_t)CELL_CHUNK) - 1u;
     L.cell_next = id + 1u;
@@ -286,9 +292,9 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
 
     // root pebbles: forward marks the trace point at or below the seed, reverse the seed itself
     int naI = tp_index1(x, L.goffA, TS), nbI = tp_index1(y, L.goffB, TS);     // index+1 of floor grid point
-    uint32_t ha = push_cell(L, pool, NOCELL, k, 0, t.rev ? x : grid(L.goffA, naI, TS), true);
-    uint32_t hb = push_cell(L, pool, NOCELL, k, 0, t.rev ? y : grid(L.goffB, nbI, TS), false);
-    L.trimha = L.moreha = ha; L.trimhb = L.morehb = hb;
+    uint32_t h = push_cell(L, pool, NOCELL, k, 0, t.rev ? x : grid(L.goffA, naI, TS), true);
+    h = push_cell(L, pool, h, k, 0, t.rev ? y : grid(L.goffB, nbI, TS), false);
+    L.trimh = L.moreh = h;
     naI += 1; nbI += 1;
     {
         const int ra = L.alen - x, rb = L.blen - y;
@@ -297,14 +303,14 @@ WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     }
     if (y == L.blen) { L.more = 0; if (L.bclip < k) L.bclip = k; }
     else if (x == L.alen) { L.more = 0; L.aclip = k; }
-    while (x >= grid(L.goffA, naI, TS)) { ha = push_cell(L, pool, ha, k, 0, grid(L.goffA, naI, TS), true); naI++; }
-    while (y >= grid(L.goffB, nbI, TS)) { hb = push_cell(L, pool, hb, k, 0, grid(L.goffB, nbI, TS), false); nbI++; }
+    while (x >= grid(L.goffA, naI, TS)) { h = push_cell(L, pool, h, k, 0, grid(L.goffA, naI, TS), true); naI++; }
+    while (y >= grid(L.goffB, nbI, TS)) { h = push_cell(L, pool, h, k, 0, grid(L.goffB, nbI, TS), false); nbI++; }
     const int c = (y << 1) + k;
-    if (c > L.besta) { L.besta = L.trima = L.lasta = c; L.besty = L.trimy = y; L.trimha = ha; L.trimhb = hb; }
+    if (c > L.besta) { L.besta = L.trima = L.lasta = c; L.besty = L.trimy = y; L.trimh = h; }
     uint32_t *s = F.slot(k);
     s[F_V * FRONT::ARR] = (uint32_t)c;
     s[F_TLO * FRONT::ARR] = (uint32_t)PATH_INT; s[F_THI * FRONT::ARR] = (uint32_t)(PATH_INT >> 32);
-    s[F_HA * FRONT::ARR] = ha; s[F_HB * FRONT::ARR] = hb;
+    s[F_H * FRONT::ARR] = h;
     L.k = k - 1;                                  // wave 0 is complete: next step is a transition
 }
 
@@ -315,7 +321,7 @@ WC_HD void reach_candidate(Lane &L, const FRONT &F, int kc) {          // align.
     const int mc = popc64(p.T & PATH_MASK61);
     if (L.morem <= mc) {
         L.morem = mc; L.morea = (int32_t)s[F_V * FRONT::ARR]; L.morey = (L.morea - kc) / 2; L.mored = L.dif;
-        L.moreha = p.ha; L.morehb = p.hb;
+        L.moreh = p.h;
     }
 }
 
@@ -368,7 +374,7 @@ WC_HD void transition(Lane &L, const FRONT &F) {
     L.low = low; L.hgh = hgh;
     L.dif += 1;
     L.vp = -1;
-    L.pp.T = PATH_INT; L.pp.ha = L.pp.hb = NOCELL;                    // the (never chosen) state above hgh
+    L.pp.T = PATH_INT; L.pp.h = NOCELL;                    // the (never chosen) state above hgh
     L.k = hgh;
 }
 
@@ -483,13 +489,13 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
         const int js = 63 - clz64((uint64_t)(slow & (0u - slow)));
         slow &= slow - 1u;
         pm &= ~(3u << (2 * js));
-        int ia = 0, ja = 0, ib = 0, jb = 0; uint32_t ha = 0, hb = 0;
+        int ia = 0, ja = 0, ib = 0, jb = 0; uint32_t h = 0;
 #pragma unroll
-        for (int j = 0; j < N; j++) if (j == js) { ia = o[j].ia; ja = o[j].ja; ib = o[j].ib; jb = o[j].jb; ha = q[j].ha; hb = q[j].hb; }
-        for (int i = ia + 1; i <= ja; i++) ha = push_cell(L, pool, ha, k0 - js, L.dif, grid(L.goffA, i, L.TS), true);
-        for (int i = ib + 1; i <= jb; i++) hb = push_cell(L, pool, hb, k0 - js, L.dif, grid(L.goffB, i, L.TS), false);
+        for (int j = 0; j < N; j++) if (j == js) { ia = o[j].ia; ja = o[j].ja; ib = o[j].ib; jb = o[j].jb; h = q[j].h; }
+        for (int i = ia + 1; i <= ja; i++) h = push_cell(L, pool, h, k0 - js, L.dif, grid(L.goffA, i, L.TS), true);
+        for (int i = ib + 1; i <= jb; i++) h = push_cell(L, pool, h, k0 - js, L.dif, grid(L.goffB, i, L.TS), false);
 #pragma unroll
-        for (int j = 0; j < N; j++) if (j == js) { q[j].ha = ha; q[j].hb = hb; }
+        for (int j = 0; j < N; j++) if (j == js) q[j].h = h;
     }
     while (pm) {
         const int bit = 63 - clz64((uint64_t)(pm & (0u - pm)));
@@ -498,19 +504,19 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
         const bool isA = (bit & 1) == 0;
         int idx = 0; uint32_t head = 0;
 #pragma unroll
-        for (int j = 0; j < N; j++) if (j == js) { idx = isA ? o[j].ja : o[j].jb; head = isA ? q[j].ha : q[j].hb; }
+        for (int j = 0; j < N; j++) if (j == js) { idx = isA ? o[j].ja : o[j].jb; head = q[j].h; }
         const uint32_t id = push_cell(L, pool, head, k0 - js, L.dif, grid(isA ? L.goffA : L.goffB, idx, L.TS), isA);
 #pragma unroll
-        for (int j = 0; j < N; j++) if (j == js) { if (isA) q[j].ha = id; else q[j].hb = id; }
+        for (int j = 0; j < N; j++) if (j == js) q[j].h = id;
     }
     // phase 3: the trim point = the newest candidate that passes the test (align.c:918-927); it is nearly always the first tried
     while (cm) {
         const int nj = 63 - clz64((uint64_t)cm);
         cm &= ~(1u << nj);
-        uint64_t nb = 0; int nc = 0, ny = 0; uint32_t ha = 0, hb = 0;
+        uint64_t nb = 0; int nc = 0, ny = 0; uint32_t h = 0;
 #pragma unroll
-        for (int j = 0; j < N; j++) if (j == nj) { nb = o[j].b; nc = o[j].c; ny = o[j].y; ha = q[j].ha; hb = q[j].hb; }
-        if (trim_ok(tabs, nb)) { L.trima = nc; L.trimy = ny; L.trimd = L.dif; L.trimha = ha; L.trimhb = hb; break; }
+        for (int j = 0; j < N; j++) if (j == nj) { nb = o[j].b; nc = o[j].c; ny = o[j].y; h = q[j].h; }
+        if (trim_ok(tabs, nb)) { L.trima = nc; L.trimy = ny; L.trimd = L.dif; L.trimh = h; break; }
     }
     // the new front entries
 #pragma unroll
@@ -519,7 +525,7 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
             uint32_t *t = s[j];
             t[F_V * FRONT::ARR] = (uint32_t)o[j].c;
             t[F_TLO * FRONT::ARR] = (uint32_t)o[j].b; t[F_THI * FRONT::ARR] = (uint32_t)(o[j].b >> 32);
-            t[F_HA * FRONT::ARR] = q[j].ha; t[F_HB * FRONT::ARR] = q[j].hb;
+            t[F_H * FRONT::ARR] = q[j].h;
         }
     // carry the previous-wave values of the diagonal just above the next cursor
     L.vp = v[N]; L.vc = v[N + 1]; L.pp = P[N];
@@ -529,8 +535,8 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
 // end point of the pass in original coordinates (REACH = 1, daligner.c:951; align.c:1001-1012)
 WC_HD void finish(const Lane &L, TaskOut &o) {
     int ex, ey;
-    if (L.morem >= 0) { ex = L.morea - L.morey; ey = L.morey; o.ediff = L.mored; o.ha = (int32_t)L.moreha; o.hb = (int32_t)L.morehb; }
-    else { ex = L.trima - L.trimy; ey = L.trimy; o.ediff = L.trimd; o.ha = (int32_t)L.trimha; o.hb = (int32_t)L.trimhb; }
+    if (L.morem >= 0) { ex = L.morea - L.morey; ey = L.morey; o.ediff = L.mored; o.ha = o.hb = (int32_t)L.moreh; }
+    else { ex = L.trima - L.trimy; ey = L.trimy; o.ediff = L.trimd; o.ha = o.hb = (int32_t)L.trimh; }
     if (L.rev) { ex = L.alen - ex; ey = L.blen - ey; }
     o.ex = ex; o.ey = ey;
     o.status = L.status;
@@ -538,30 +544,42 @@ WC_HD void finish(const Lane &L, TaskOut &o) {
 }
 
 // ---- trace emission from the pebble chains (align.c:1001-1111 forward, 1711-1880 reverse) --------
-// `cells` is the pool; chains end with prev = -1.  Forward: pairs are appended at tr[0..); returns the
-// number of values written.
+// `cells` is the pool; chains end with prev = -1.  MERGED: the chain holds the A and the B trace points of the path in
+// creation order, tagged (CELL_B); the A (B) chain of the reference is its tag-filtered subsequence.  !MERGED: the chain
+// is one axis only (the strided warp kernel keeps two chains).
+template <bool MERGED> WC_HD bool on_axis(const Cell &c, bool isA) { return !MERGED || (((c.diff & CELL_B) == 0) == isA); }
+template <bool MERGED> WC_HD int cell_diff(const Cell &c) { return MERGED ? (c.diff & CELL_DIFF) : c.diff; }
+// first cell of the axis at or behind h (following prev links)
+template <bool MERGED> WC_HD int same_axis(const Cell *cells, int h, bool isA) {
+    while (h >= 0 && !on_axis<MERGED>(cells[h], isA)) h = cells[h].prev;
+    return h;
+}
+
+// Forward: pairs are appended at tr[0..); returns the number of values written.
+template <bool MERGED = false>
 WC_HD int emit_chain_fwd(const Cell *cells, int head, bool isA, int anti, int ex, int ey, int ediff, uint16_t *tr) {
+    head = same_axis<MERGED>(cells, head, isA);
     int n = 0;
-    for (int h = head; h >= 0; h = cells[h].prev) n++;
+    for (int h = head; h >= 0; h = same_axis<MERGED>(cells, cells[h].prev, isA)) n++;
     // cells in forward order are c_0 (root) .. c_{n-1} (head); pair i (i>=1) = (diff_i - diff_{i-1}, p_i - p_{i-1})
     int len = 2 * (n - 1);
     Cell cur = cells[head];
     const int lastk = cur.diag;
     int lastp, laste;
     for (int i = n - 1; i >= 1; i--) {
-        const Cell prv = cells[cur.prev];
+        const Cell prv = cells[same_axis<MERGED>(cells, cur.prev, isA)];
         const int pc = isA ? (cur.mark - cur.diag) : (cur.mark + cur.diag);
         int pp, pe;
         if (i == 1) { pp = isA ? ((anti - prv.diag) / 2) : ((anti + prv.diag) / 2); pe = 0; }
-        else { pp = isA ? (prv.mark - prv.diag) : (prv.mark + prv.diag); pe = prv.diff; }
-        tr[2 * (i - 1)] = (uint16_t)(cur.diff - pe);
+        else { pp = isA ? (prv.mark - prv.diag) : (prv.mark + prv.diag); pe = cell_diff<MERGED>(prv); }
+        tr[2 * (i - 1)] = (uint16_t)(cell_diff<MERGED>(cur) - pe);
         tr[2 * (i - 1) + 1] = (uint16_t)(pc - pp);
         cur = prv;
     }
     {
         const Cell hc = cells[head];
         if (n == 1) { lastp = isA ? ((anti - hc.diag) / 2) : ((anti + hc.diag) / 2); laste = 0; }
-        else { lastp = isA ? (hc.mark - hc.diag) : (hc.mark + hc.diag); laste = hc.diff; }
+        else { lastp = isA ? (hc.mark - hc.diag) : (hc.mark + hc.diag); laste = cell_diff<MERGED>(hc); }
     }
     if (isA) {
         if (lastp + lastk != ex) { tr[len++] = (uint16_t)(ediff - laste); tr[len++] = (uint16_t)(ey - lastp); }
@@ -573,22 +591,29 @@ WC_HD int emit_chain_fwd(const Cell *cells, int head, bool isA, int anti, int ex
     return len;
 }
 
-// Reverse pass: `flen` = number of values the forward pass left at tr[0..); pairs are prepended before
-// tr[0] and the first partial segment is merged into tr[0], tr[1].  Returns the number of values prepended.
-WC_HD int emit_chain_rev(Cell *cells, int head, bool isA, int ex, int ey, int ediff, int TS, int off, int flen, uint16_t *tr) {
+// Reverses the prev links of a chain in place (the reverse pass emits from its root onward); returns the root.
+WC_HD int reverse_chain(Cell *cells, int head) {
     int a = -1, b;
-    for (int h = head; h >= 0; h = b) { b = cells[h].prev; cells[h].prev = a; a = h; }   // reverse the links in place
-    int h = a;                                       // root
+    for (int h = head; h >= 0; h = b) { b = cells[h].prev; cells[h].prev = a; a = h; }
+    return a;
+}
+
+// Reverse pass, on a chain already reversed by reverse_chain (`root`): `flen` = number of values the forward pass
+// left at tr[0..); pairs are prepended before tr[0] and the first partial segment is merged into tr[0], tr[1].
+// Returns the number of values prepended.
+template <bool MERGED = false>
+WC_HD int emit_chain_rev(const Cell *cells, int root, bool isA, int ex, int ey, int ediff, int TS, int off, int flen, uint16_t *tr) {
+    int h = same_axis<MERGED>(cells, root, isA);             // root of this axis (links now lead toward the head)
     Cell c = cells[h];
     int k = c.diag;
     int pb = isA ? (c.mark - k) : (c.mark + k);      // "other" coordinate of the running point
     int e = 0, at = 0;
     const int own = isA ? (pb + k) : (pb - k);       // coordinate on this chain's own axis
     if (own % TS != off) {                           // seed not on a trace boundary: merge first segment
-        h = c.prev;
+        h = same_axis<MERGED>(cells, c.prev, isA);
         int pa, d;
         if (h < 0) { pa = isA ? ey : ex; d = ediff; }
-        else { c = cells[h]; k = c.diag; pa = isA ? (c.mark - k) : (c.mark + k); d = c.diff; }
+        else { c = cells[h]; k = c.diag; pa = isA ? (c.mark - k) : (c.mark + k); d = cell_diff<MERGED>(c); }
         if (flen == 0) {
             tr[--at] = (uint16_t)(pb - pa);
             tr[--at] = isA ? (uint16_t)(d - e) : (uint16_t)(pb - pa);   // sic (align.c:1843-1844)
@@ -596,12 +621,12 @@ WC_HD int emit_chain_rev(Cell *cells, int head, bool isA, int ex, int ey, int ed
         pb = pa; e = d;
     }
     if (h >= 0) {
-        for (h = c.prev; h >= 0; h = c.prev) {
+        for (h = same_axis<MERGED>(cells, c.prev, isA); h >= 0; h = same_axis<MERGED>(cells, c.prev, isA)) {
             c = cells[h]; k = c.diag;
             const int pa = isA ? (c.mark - k) : (c.mark + k);
             tr[--at] = (uint16_t)(pb - pa);
-            tr[--at] = (uint16_t)(c.diff - e);
-            pb = pa; e = c.diff;
+            tr[--at] = (uint16_t)(cell_diff<MERGED>(c) - e);
+            pb = pa; e = cell_diff<MERGED>(c);
         }
         const int endo = isA ? ey : ex;              // end point on the "other" axis
         const int endown = isA ? ex : ey;

@@ -117,10 +117,11 @@ int wc_local_alignment(const uint8_t *aseq, int alen, const uint8_t *bseq, int b
     const int maxtp = 2 * ((alen > blen ? alen : blen) / TS + 2) + 2;
     std::vector<uint16_t> tbuf(8 * maxtp, 0);
     uint16_t *atr = tbuf.data() + 2 * maxtp, *btr = tbuf.data() + 6 * maxtp;
-    const int flenA = emit_chain_fwd(cellvec.data(), fo.ha, true, anti, fo.ex, fo.ey, fo.ediff, atr);
-    const int flenB = emit_chain_fwd(cellvec.data(), fo.hb, false, anti, fo.ex, fo.ey, fo.ediff, btr);
-    const int preA = emit_chain_rev(cellvec.data(), ro.ha, true, ro.ex, ro.ey, ro.ediff, TS, t.aoff, flenA, atr);
-    const int preB = emit_chain_rev(cellvec.data(), ro.hb, false, ro.ex, ro.ey, ro.ediff, TS, t.boff, flenB, btr);
+    const int flenA = emit_chain_fwd<true>(cellvec.data(), fo.ha, true, anti, fo.ex, fo.ey, fo.ediff, atr);
+    const int flenB = emit_chain_fwd<true>(cellvec.data(), fo.hb, false, anti, fo.ex, fo.ey, fo.ediff, btr);
+    const int rroot = reverse_chain(cellvec.data(), ro.ha);
+    const int preA = emit_chain_rev<true>(cellvec.data(), rroot, true, ro.ex, ro.ey, ro.ediff, TS, t.aoff, flenA, atr);
+    const int preB = emit_chain_rev<true>(cellvec.data(), rroot, false, ro.ex, ro.ey, ro.ediff, TS, t.boff, flenB, btr);
     const int atlen = flenA + preA, btlen = flenB + preB;
     uint16_t *at = atr - preA, *bt = btr - preB;
     const int abpos = ro.ex, bbpos = ro.ey, aepos = fo.ex, bepos = fo.ey, diffs = fo.ediff + ro.ediff;
