@@ -1383,6 +1383,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     static const int wave_ctas = getenv("DAMAR_WAVE_CTAS") ? std::max(1, std::min(NUM_SMS_B200, atoi(getenv("DAMAR_WAVE_CTAS")))) : NUM_SMS_B200;
     static std::once_flag attr;
     std::call_once(attr, [] {
+        set_smem(wave_tasks<32, false, 4, 8>, WaveCfg<32, 8>::SMEM);
+        set_smem(wave_tasks<32, false, 4, 10>, WaveCfg<32, 10>::SMEM);
         set_smem(wave_tasks<32, false, 4, 11>, WaveCfg<32, 11>::SMEM);
         set_smem(wave_tasks<32, false, 4, 12>, WaveCfg<32, 12>::SMEM);
         set_smem(wave_tasks<32, false, 4, 14>, WaveCfg<32, 14>::SMEM);
@@ -1436,6 +1438,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
                     Q.task_order = v0;
                 }
                 if (nway == 3) wave_tasks<32, false, 3, 14><<<wb, 14 * 32, WaveCfg<32, 14>::SMEM, st>>>(Q);
+                else if (wwarps == 8) wave_tasks<32, false, 4, 8><<<wb, per, WaveCfg<32, 8>::SMEM, st>>>(Q);
+                else if (wwarps == 10) wave_tasks<32, false, 4, 10><<<wb, per, WaveCfg<32, 10>::SMEM, st>>>(Q);
                 else if (wwarps == 11) wave_tasks<32, false, 4, 11><<<wb, per, WaveCfg<32, 11>::SMEM, st>>>(Q);
                 else if (wwarps == 12) wave_tasks<32, false, 4, 12><<<wb, per, WaveCfg<32, 12>::SMEM, st>>>(Q);
                 else wave_tasks<32, false, 4, 14><<<wb, 14 * 32, WaveCfg<32, 14>::SMEM, st>>>(Q);
