@@ -372,6 +372,9 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
     init()
     if set_filter_params(s.kmer, s.binshift, s.suppress, s.hitmin, s.nthreads):
         raise ValueError("Illegal combination of filter parameters")       # daligner.c:862-866
+    for blk in [ablk] + list(bblks):                                        # daligner.c:499-504 (read_DB)
+        if blk.nreads and int(blk.rlen.min()) < s.kmer:
+            raise ValueError(f"Block {blk.name} contains reads < {s.kmer}bp long !  Run DBsplit.")
     s, freq = _job_options(ablk, bblks, s)
     set_options(s, freq)
     J = _Job()

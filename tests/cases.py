@@ -20,6 +20,11 @@ with open(os.path.join(BIAS, "cases.json")) as f:
     BIAS_CASES = json.load(f)
 
 
+EDGE = os.path.join(GOLDEN, "edge")        # corner cases (tests/golden/make_edge.py)
+with open(os.path.join(EDGE, "cases.json")) as f:
+    EDGE_CASES = json.load(f)
+
+
 def parse_flags(flags):
     """daligner flags -> dict(k,w,h,t,e,l,s,j,M,masks,I,O,A,T) (daligner.c:721-808)."""
     o = dict(k=14, w=6, h=35, t=0, e=0.70, l=1000, s=100, j=4, M=None, masks=[], I=False, O=False, A=False, T=False, b=False)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, GOLDEN, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
 from damar_b200 import api, dbio
 
 pytestmark = pytest.mark.gpu
@@ -67,6 +67,27 @@ def test_las_matches_reference_biased(case):
     for fn, ref in gold.items():
         ok, why = dbio.las_equal(ref, out[fn])
         assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+@pytest.mark.parametrize("case", sorted(EDGE_CASES))
+def test_las_matches_reference_edge_cases(case):
+    """Corner cases against the reference binary's files: reads of exactly k bases, no k-mer match (header-only .las),
+    nothing passing -h, comparison across two DBs (asymmetric)."""
+    o = parse_flags(EDGE_CASES[case]["flags"])
+    blks = [load_block(EDGE, n, ()) for n in EDGE_CASES[case]["blocks"]]
+    out = api.daligner(blks[0], blks[1:], settings(o))
+    gold = golden_files(case, EDGE)
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+def test_reads_shorter_than_k_are_refused():
+    """daligner.c:499-504: a block with a read shorter than k stops the run before any work is done."""
+    blk = load_block(EDGE, "E.1", ())
+    with pytest.raises(ValueError, match="contains reads < 16bp long"):
+        api.daligner(blk, [blk], api.Settings(kmer=16))
 
 
 KMER_CASES = [(TINY, CASES, c, comp) for c, comp in [("default", 0), ("default", 1), ("rndmask", 0), ("rndmask", 1),

@@ -4,7 +4,7 @@ The golden files were written by the UNMODIFIED reference binary (tests/golden/m
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
 from damar_b200 import dbio
 
 
@@ -31,6 +31,22 @@ def test_oracle_matches_reference_biased(case):
     blks = [load_block(BIAS, n, tuple(o["masks"])) for n in BIAS_CASES[case]["blocks"]]
     out = O.daligner(blks[0], blks[1:], oracle_kwargs(o), only_identity=int(o["O"]))
     gold = golden_files(case, BIAS)
+    assert sorted(k for k in out if k != "_stats") == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why}"
+
+
+@pytest.mark.parametrize("case", sorted(EDGE_CASES))
+def test_oracle_matches_reference_edge_cases(case):
+    """Reads of exactly k and k + 1 bases, no k-mer match at all (header-only .las), nothing passing -h, and a comparison
+    across two DBs (only the A side is reported, daligner.c:911-946)."""
+    o = parse_flags(EDGE_CASES[case]["flags"])
+    blks = [load_block(EDGE, n, ()) for n in EDGE_CASES[case]["blocks"]]
+    kw = oracle_kwargs(o)
+    kw["symmetric"] = int(kw["symmetric"] and all(b.root == blks[0].root for b in blks[1:]))
+    out = O.daligner(blks[0], blks[1:], kw, only_identity=int(o["O"]))
+    gold = golden_files(case, EDGE)
     assert sorted(k for k in out if k != "_stats") == sorted(gold)
     for fn, ref in gold.items():
         ok, why = dbio.las_equal(ref, out[fn])
