@@ -404,10 +404,23 @@ WC_HD int choose(int vp, int vc, int vm, int &c) {               // returns +1 /
 // (align.c:918-927); the candidates of a call are therefore tested newest first until one passes.
 struct CellOut { uint64_t b; int c, y, ia, ja, ib, jb; };
 
-// first probe of a slide: equal bases in the first 32-base window (32 = all equal)
-WC_HD int probe32(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by) {
-    const uint64_t d = window_at(aw, ax) ^ window_at(bw, by);
-    return d ? (clz64(d) >> 1) : 32;
+// first probe of a slide: equal bases in the first 16-base window (16 = all equal).  At 12-15 % error a slide passes 16
+// bases in a few percent of the cells only, and 16 bases need two words per read instead of three.
+constexpr int PROBE = 16;
+WC_HD int clz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+WC_HD uint32_t window16_at(const uint32_t *__restrict__ words, uint32_t s) {
+    const uint32_t *w = words + (s >> 4);
+    return funnel_l(ldg32(w + 1), ldg32(w), (int)(s & 15u) * 2);
+}
+WC_HD int probe16(const uint32_t *__restrict__ aw, uint32_t ax, const uint32_t *__restrict__ bw, uint32_t by) {
+    const uint32_t d = window16_at(aw, ax) ^ window16_at(bw, by);
+    return d ? (clz32(d) >> 1) : PROBE;
 }
 
 // N furthest-reaching-point updates per call, on diagonals L.k, L.k - 1, ... (align.c:789-938).  All cells of a
@@ -446,7 +459,7 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
         const int jj = (j < cnt) ? j : 0;
         const int kk = k0 - jj, y = ((j < cnt ? c[j] : c[0]) - kk) >> 1, x = y + kk;
         mx[j] = (L.alen - x < L.blen - y) ? L.alen - x : L.blen - y;
-        n[j] = probe32(L.aw, L.abase + (uint32_t)x, L.bw, L.bbase + (uint32_t)y);
+        n[j] = probe16(L.aw, L.abase + (uint32_t)x, L.bw, L.bbase + (uint32_t)y);
     }
     // phase 1: end of the slide, clips, best / lasta, trace points crossed (visiting order)
     CellOut o[N];
@@ -457,7 +470,7 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
         o[j].ia = o[j].ja = o[j].ib = o[j].jb = 0; o[j].b = 0; o[j].c = 0; o[j].y = 0;
         if (j < cnt) {
             const int kk = k0 - j, y0 = (c[j] - kk) >> 1, x0 = y0 + kk;
-            if (n[j] == 32 && mx[j] > 32) n[j] = 32 + slide(L.aw, L.abase + (uint32_t)(x0 + 32), L.bw, L.bbase + (uint32_t)(y0 + 32), mx[j] - 32);
+            if (n[j] == PROBE && mx[j] > PROBE) n[j] = PROBE + slide(L.aw, L.abase + (uint32_t)(x0 + PROBE), L.bw, L.bbase + (uint32_t)(y0 + PROBE), mx[j] - PROBE);
             if (n[j] > mx[j]) n[j] = mx[j];
             const int d = dd[j];
             const uint64_t b = push_matches(q[j].T << 1, n[j]);
