@@ -52,7 +52,7 @@ def main():
             if d.startswith("d001_"):
                 shutil.rmtree(os.path.join(dbdir, d))
         t0 = time.time()
-        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "daligner")] + bench.ref_flags(4) + [f"{root}.{a}"] + [f"{root}.{b}" for b in bs],
+        subprocess.run([os.path.join(ROOT, "oracle", "_ref", "daligner")] + bench.ref_flags(P) + [f"{root}.{a}"] + [f"{root}.{b}" for b in bs],
                        cwd=dbdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
                        env=dict(os.environ, OMP_NUM_THREADS=str(P)))
         t_ref = time.time() - t0
@@ -64,7 +64,7 @@ def main():
             allok &= ok
             novl += int.from_bytes(v[:8], "little")
             print(f"  {fn}: {len(v)} bytes {'OK' if ok else 'DIFF ' + why}", flush=True)
-        print(f"job {a} vs {bs}: ours {t_gpu:.2f}s  reference(-j4) {t_ref:.2f}s  overlaps {novl}", flush=True)
+        print(f"job {a} vs {bs}: ours {t_gpu:.2f}s  reference(-j{P}) {t_ref:.2f}s  overlaps {novl}", flush=True)
     print("PARITY", "PASS" if allok else "FAIL")
     sys.exit(0 if allok else 1)
 
