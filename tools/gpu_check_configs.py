@@ -14,6 +14,10 @@ import bench  # noqa: E402
 from damar_b200 import api, dbio  # noqa: E402
 
 CONFIGS = {
+    # configs[2]-like block size: two DBsplit -s200 blocks (2 x 200 Mbp, the production block size) of a 20 Mbp genome at 20x,
+    # the non-self pair only: 200 M k-mers per list, chance 14-mer hits dominate
+    "c3s": dict(sim=["20.0", "-c20", "-r3", "-e.12", "-m10000", "-s2000", "-x4000"], split=200, root="D",
+                flags=["-k14", "-w6", "-h35", "-e.70", "-l1000", "-s100", "-M32"], masks=[], jobs=[(2, [1])]),
     # Nanopore-like: N50 ~ 30 kbp, 15 % error; long reads -> long passes, wide fronts (64-ring and strided fallbacks)
     "c4s": dict(sim=["6.0", "-c25", "-r4", "-e.15", "-m22000", "-s18000", "-x4000"], split=200, root="N",
                 flags=["-k14", "-w6", "-h35", "-e.65", "-l1000", "-s100", "-M32"], masks=[]),
@@ -87,7 +91,7 @@ def main():
         s = settings(cfg["flags"])
         P = bench.pow2_floor(os.cpu_count())
         print(f"{name}: {nblocks} block(s), {sum(b.totlen for b in blocks.values()) / 1e6:.0f} Mbp, flags {' '.join(cfg['flags'])}", flush=True)
-        for a, bs in bench.plan(nblocks):
+        for a, bs in cfg.get("jobs") or bench.plan(nblocks):
             api.daligner(blocks[a], [blocks[b] for b in bs], s, as_bytes=False)          # warm-up
             stats = []
             t0 = time.time()
