@@ -72,7 +72,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
-           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs"]
+           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge"]
 
 _lib = None
 
@@ -94,6 +94,8 @@ def load_library():
     L.damar_trace_point_diffs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                           C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     L.damar_trace_point_diffs.restype = C.c_int
+    L.damar_las_merge.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.damar_las_merge.restype = C.c_int
     L.damar_set_biased.argtypes = [C.c_int]
     L.damar_set_biased.restype = None
     L.damar_block_upload.restype = C.c_void_p
@@ -509,6 +511,22 @@ def trace_point_diffs(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las:
         raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
     rec = rec[:novl]
     return (rec, seg[: ntrace // 2], (toff[:novl] // 2).astype(np.int64)) if segments else rec
+
+
+def las_merge(images: Sequence[bytes]) -> bytes:
+    """LAmerge (utils/LAmerge.c): the sorted .las images of one block's pair files -> the block's single .las image."""
+    L = load_library()
+    n = len(images)
+    bufs = (C.c_char_p * n)(*[bytes(b) for b in images])
+    lens = (C.c_int64 * n)(*[len(b) for b in images])
+    out, outlen = C.c_void_p(), C.c_int64()
+    rc = L.damar_las_merge(n, bufs, lens, C.byref(out), C.byref(outlen))
+    if rc != 0:
+        raise ValueError({1: "malformed .las image", 2: "the files have different trace spacings"}.get(rc, f"damar_las_merge: {rc}"))
+    try:
+        return C.string_at(out.value, outlen.value)
+    finally:
+        L.damar_free(out)
 
 
 def las_dir(run_id: int, part: int) -> str:

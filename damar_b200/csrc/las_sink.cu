@@ -199,6 +199,65 @@ int damar_sink_serialise(damar_las_sink *s_, int trace_spacing, int no_trace, in
     return put_range(*s, keys, lo, keys.size(), trace_spacing, no_trace, buf2, len2);
 }
 
+// LAmerge (utils/LAmerge.c, utils/LAmergeUtils.c:31-145): the k-way merge of sorted .las files into one -- what the pipeline
+// runs right after daligner to turn a block's pair files R.i.R.1.las ... R.i.R.n.las into R.i.las.  The files of one block
+// hold disjoint (aread, bread) pairs, so the merge is decided by the leading fields of SORT_OVL (aread, bread, comp, abpos);
+// records are copied verbatim (header: summed novl, common trace spacing).  Host only, like Write_Overlap_Buffer.
+int damar_las_merge(int n, const uint8_t *const *bufs, const int64_t *lens, uint8_t **out, int64_t *outlen) {
+    struct Cur { const uint8_t *p, *end; int64_t left; };
+    std::vector<Cur> cur((size_t)n);
+    int64_t novl = 0, total = 12;
+    int32_t tspace = 0;
+    bool have = false;
+    for (int i = 0; i < n; i++) {
+        if (lens[i] < 12) return 1;
+        int64_t k; int32_t ts;
+        memcpy(&k, bufs[i], 8); memcpy(&ts, bufs[i] + 8, 4);
+        if (k < 0) return 1;
+        if (!have) { tspace = ts; have = true; }
+        else if (ts != tspace) return 2;                    // "PT-point spacing conflict" (LAmerge.c:380-385)
+        cur[(size_t)i] = Cur{bufs[i] + 12, bufs[i] + lens[i], k};
+        novl += k; total += lens[i] - 12;
+    }
+    const int tbytes = (tspace <= 125) ? 1 : 2;
+    uint8_t *img = (uint8_t *)img_alloc((size_t)total);
+    if (img == nullptr) return 3;
+    memcpy(img, &novl, 8); memcpy(img + 8, &tspace, 4);
+    uint8_t *w = img + 12;
+    auto key = [](const uint8_t *r, uint64_t &k0, uint64_t &k1) {
+        int32_t f[9];
+        memcpy(f, r, 36);                                   // tlen, diffs, abpos, bbpos, aepos, bepos, flags, aread, bread
+        k0 = ((uint64_t)(uint32_t)f[7] << 32) | (uint32_t)f[8];
+        k1 = ((uint64_t)((uint32_t)f[6] & 1u) << 32) | (uint32_t)f[2];
+    };
+    struct Item { uint64_t k0, k1; int src; };
+    auto later = [](const Item &a, const Item &b) { return a.k0 != b.k0 ? a.k0 > b.k0 : a.k1 != b.k1 ? a.k1 > b.k1 : a.src > b.src; };
+    std::vector<Item> heap;
+    for (int i = 0; i < n; i++)
+        if (cur[(size_t)i].left > 0) {
+            if (cur[(size_t)i].p + 40 > cur[(size_t)i].end) { img_free(img); return 1; }
+            Item it; it.src = i; key(cur[(size_t)i].p, it.k0, it.k1); heap.push_back(it);
+        }
+    std::make_heap(heap.begin(), heap.end(), later);
+    while (!heap.empty()) {
+        std::pop_heap(heap.begin(), heap.end(), later);
+        const int i = heap.back().src;
+        heap.pop_back();
+        Cur &c = cur[(size_t)i];
+        int32_t tlen; memcpy(&tlen, c.p, 4);
+        const int64_t sz = 40 + (int64_t)tlen * tbytes;
+        if (tlen < 0 || c.p + sz > c.end) { img_free(img); return 1; }
+        memcpy(w, c.p, (size_t)sz); w += sz; c.p += sz; c.left--;
+        if (c.left > 0) {
+            if (c.p + 40 > c.end) { img_free(img); return 1; }
+            Item it; it.src = i; key(c.p, it.k0, it.k1); heap.push_back(it);
+            std::push_heap(heap.begin(), heap.end(), later);
+        }
+    }
+    *out = img; *outlen = (int64_t)(w - img);
+    return 0;
+}
+
 void damar_free(void *p) { img_free(p); }
 
 }  // extern "C"

@@ -186,6 +186,10 @@ int64_t         damar_sink_count(const damar_las_sink *s);
 int  damar_sink_serialise(damar_las_sink *s, int trace_spacing, int no_trace, int only_identity, int split_read,
                           uint8_t **buf1, int64_t *len1, uint8_t **buf2, int64_t *len2);
 void damar_free(void *p);
+/* LAmerge (utils/LAmerge.c; heap merge utils/LAmergeUtils.c:31-145): merges n sorted .las images (e.g. a block's pair files
+ * R.i.R.1.las ... R.i.R.n.las) into one image ordered like SORT_OVL; records are copied verbatim.  Returns 0, 1 for a
+ * malformed image, 2 for mixed trace spacings.  Free *out with damar_free.  Host only.                                   */
+int  damar_las_merge(int n, const uint8_t *const *bufs, const int64_t *lens, uint8_t **out, int64_t *outlen);
 
 #ifdef __cplusplus
 }

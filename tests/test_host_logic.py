@@ -188,3 +188,24 @@ def test_block_exchange_two_ranks_gloo(world):
         for b, (n, s, ms, sz) in blocks.items():
             t = truth[b]
             assert (n, s, ms, sz) == (t.nreads, int(t.bases.astype(np.int64).sum()), int(t.mask_data.astype(np.int64).sum()), t.sizeof_db())
+
+
+def test_las_merge_matches_reference_lamerge():
+    """damar_las_merge (host) against the UNMODIFIED reference LAmerge on committed reference .las files: same bytes
+    (tests/golden/lamerge.json holds size + sha256 of LAmerge's outputs, tests/golden/make_lamerge.py)."""
+    import hashlib
+    import json
+    with open(os.path.join(GOLDEN, "lamerge.json")) as f:
+        gold = json.load(f)
+    for name, g in gold.items():
+        ins = [open(os.path.join(GOLDEN, g["db"], "ref", fn), "rb").read() for fn in g["inputs"]]
+        out = api.las_merge(ins)
+        assert len(out) == g["size"], name
+        assert hashlib.sha256(out).hexdigest() == g["sha256"], name
+    assert gold["T.2"]["sha256"] == gold["T.2.rev"]["sha256"]
+    a = open(os.path.join(GOLDEN, "tiny", "ref", "default", "T.1.T.1.las"), "rb").read()
+    b = open(os.path.join(GOLDEN, "tiny", "ref", "k16s200", "T.1.T.1.las"), "rb").read()
+    with pytest.raises(ValueError, match="trace spacings"):
+        api.las_merge([a, b])
+    with pytest.raises(ValueError, match="malformed"):
+        api.las_merge([a[:-3]])
