@@ -62,8 +62,11 @@ static int pick_device() {
 static int do_init(int device) {
     Context &c = ctx();
     if (c.ready) return 0;
+    const double t_init = now_s();
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_device < 0) {
+        static bool hooked = false;
+        if (!hooked && getenv("DAMAR_PROFILE")) { hooked = true; atexit([] { dump_profile(); }); }   // hosts that never call damar_shutdown
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n <= 0) {
@@ -91,6 +94,7 @@ static int do_init(int device) {
     if (!c.ws) c.ws = new WorkerScratch();
     c.fp = g_fp; c.opt = g_opt;
     c.ready = true;
+    { auto &e = g_prof["init (CUDA context, stream)"]; e.first += now_s() - t_init; e.second++; }
     return 0;
 }
 
