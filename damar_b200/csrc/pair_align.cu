@@ -692,6 +692,7 @@ struct PipeArgs {
     PairTable pt; CandTable ct;
     const uint32_t *list_in; uint32_t n_in;
     uint32_t *flag;                       // filter_pairs: per work pair
+    uint32_t *cand0;                      // filter_pairs: the pair's first seed candidate, as an offset from the pair's first hit
     unsigned int *ctr;                    // device counters, see CTR_*
     uint32_t *wide_list;
     wc::Lane *wide_lane; uint32_t *wide_ring;   // state of the passes that outgrew the 32-diagonal ring: [task][32][FRONT_WORDS]
@@ -832,7 +833,7 @@ __global__ void __launch_bounds__(256) filter_pairs(PipeArgs Q) {
         ScanState S;
         S.pend = pair_extent(P, sidx, pair); S.nidx = sidx; S.j = -1; S.amark2 = 0; S.lidx = S.pe = sidx;
         const int64_t c = find_candidate(P, S, score, lastp, 0, nullptr, nullptr, nullptr);
-        if (lane == 0) Q.flag[w] = (c >= 0) ? 1u : 0u;
+        if (lane == 0) { Q.flag[w] = (c >= 0) ? 1u : 0u; Q.cand0[w] = (c >= 0) ? (uint32_t)(c - sidx) : 0u; }
     }
 }
 __global__ void init_pairs(PipeArgs Q, const uint32_t *__restrict__ flag, const uint64_t *__restrict__ off) {
@@ -843,6 +844,15 @@ __global__ void init_pairs(PipeArgs Q, const uint32_t *__restrict__ flag, const 
     const int64_t sidx = Q.A.work[w];
     Q.pt.sidx[p] = sidx; Q.pt.pend[p] = -1; Q.pt.nidx[p] = sidx; Q.pt.lidx[p] = sidx; Q.pt.pe[p] = sidx; Q.pt.j[p] = -1;
     Q.pt.amark2[p] = 0; Q.pt.nla[p] = 0; Q.pt.novl[p] = 0; Q.pt.flags[p] = 0;
+    // Round 1 needs no scan: filter_pairs already found the pair's first candidate.  The saved walk restarts at the pair's first
+    // panel in round 2 -- seeds before this one were no candidates and this one is then covered by its own alignment's lasta
+    // interval (filter.c:2289, 2318-2333), so the restart finds what a continued walk would.
+    const int64_t c = sidx + (int64_t)Q.cand0[w];
+    const uint64_t key = Q.A.keys[c];
+    const uint64_t pair = key >> Q.A.pbits;
+    Q.ct.pair[p] = (uint32_t)p; Q.ct.hidx[p] = c;
+    Q.ct.ar[p] = (int)(pair & ((1ull << Q.A.abits) - 1ull)); Q.ct.br[p] = (int)(pair >> Q.A.abits);
+    Q.ct.apos[p] = (int)(key & ((1ull << Q.A.pbits) - 1ull)); Q.ct.bpos[p] = (int)Q.A.bpos[c];
 }
 
 // One round of the lasta-ordered candidate walk: every listed pair that is still alive proposes its next seed.
@@ -1313,6 +1323,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     DevBuf<uint32_t> redo_sidx, redo_wi; DevBuf<uint8_t> pair_redo;
     redo_sidx.reserve((size_t)nwork + 1); redo_wi.reserve((size_t)nwork + 1); pair_redo.reserve((size_t)nwork + 1);
     DevBuf<uint32_t> pflag; pflag.reserve((size_t)nwork + 1);
+    DevBuf<uint32_t> pcand; pcand.reserve((size_t)nwork + 1);
     DevBuf<uint64_t> poff; poff.reserve((size_t)nwork + 1);
 
     PipeArgs Q{};
@@ -1332,7 +1343,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     P.tbuf = tbuf.p; P.maxtp = maxtp;
     P.bscore = bscore.p; P.nbuck = nbuck; P.dmin = dmin;
     P.tbytes = tbytes; P.stats = counters.p;
-    Q.flag = pflag.p; Q.ctr = ctr.p;
+    Q.flag = pflag.p; Q.cand0 = pcand.p; Q.ctr = ctr.p;
 
     // ---- stage 3: pairs with at least one seed that passes the -h test ----
     filter_pairs<<<sblocks, 256, 0, st>>>(Q);
@@ -1417,12 +1428,18 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         while (Q.n_in > 0) {
             rounds++;
             CUDA_CHECK(cudaMemsetAsync(ctr.p, 0, sizeof(unsigned int) * CTR_N, st));
-            const unsigned sb = (unsigned)std::min<uint64_t>((uint64_t)sblocks, ((uint64_t)Q.n_in + 7) / 8);
-            scan_round<<<sb, 256, 0, st>>>(Q);
-            KERNEL_CHECK(); count_launch();
             unsigned int ncand = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&ncand, ctr.p + CTR_NCAND, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(stream_wait(st));
+            if (Q.list_in == nullptr) {                          // round 1: init_pairs filled the candidate table
+                ncand = (unsigned int)nactive;
+                CUDA_CHECK(cudaMemcpyAsync(ctr.p + CTR_NCAND, &ncand, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+                CUDA_CHECK(stream_wait(st));
+            } else {
+                const unsigned sb = (unsigned)std::min<uint64_t>((uint64_t)sblocks, ((uint64_t)Q.n_in + 7) / 8);
+                scan_round<<<sb, 256, 0, st>>>(Q);
+                KERNEL_CHECK(); count_launch();
+                CUDA_CHECK(cudaMemcpyAsync(&ncand, ctr.p + CTR_NCAND, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(stream_wait(st));
+            }
             if (ncand == 0) break;
             Timer t_k(st);
             {
