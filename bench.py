@@ -305,6 +305,9 @@ def main():
     barrier()
     dt_e = time.perf_counter() - t1
     clocks = sampler.stop()
+    if os.environ.get("DAMAR_PROFILE"):
+        print(f"[bench] host profile of {args.steps} end-to-end steps (after the sort-only region):", file=sys.stderr)
+        api.load_library().damar_dump_profile()
 
     # ---- N > 1: one all-vs-all of ONE DB (rank 0's) with its block pairs sharded over the ranks (plan.shard_pairs) and the
     # blocks that several ranks need broadcast over NCCL (multi.exchange_blocks): the wall time BASELINE.json's metric asks for.
