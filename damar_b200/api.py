@@ -58,7 +58,7 @@ class Timings(C.Structure):
                 ("wave_cells", C.c_int64), ("kernel_launches", C.c_int64),
                 ("scatter_ms", C.c_double), ("scatter_elems", C.c_int64), ("scatter_launches", C.c_int64),
                 ("align_kernel_ms", C.c_double), ("align_launches", C.c_int64), ("redo_pairs", C.c_int64),
-                ("redo_kernel_ms", C.c_double)]
+                ("redo_kernel_ms", C.c_double), ("scatter_bytes", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -72,7 +72,8 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_match_filter", "damar_index_download", "damar_last_hits_download", "damar_get_timings",
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
-           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge"]
+           "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge",
+           "damar_las_compare", "damar_sort_selftest"]
 
 _lib = None
 
@@ -121,6 +122,10 @@ def load_library():
     L.damar_sink_serialise.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.damar_free.argtypes = [C.c_void_p]
+    L.damar_las_compare.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    L.damar_las_compare.restype = C.c_int64
+    L.damar_sort_selftest.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    L.damar_sort_selftest.restype = C.c_int
     _lib = L
     return L
 
@@ -143,7 +148,8 @@ class Settings:
     minlen: int = 1000        # -l  (MINOVER = 2*minlen)
     trace_spacing: int = 100  # -s
     nthreads: int = 4         # -j
-    mem_limit_gb: int = 0     # -M  (0 == no cap; the reference defaults to physical RAM)
+    mem_limit_gb: Optional[int] = None   # -M in GB; None = physical RAM like daligner.c:702-703 (the -M rule then caps k-mer
+                                         # groups at MAXGRAM = 10000 mutual matches, filter.c:2634-2663); 0 = -M0: no cap
     symmetric: bool = True    # not -A
     identity: bool = False    # -I
     only_identity: bool = False  # -O
@@ -206,6 +212,14 @@ def set_filter_params(kmer: int, binshift: int, suppress: int, hitmin: int, nthr
     return load_library().damar_set_filter_params(kmer, binshift, suppress, hitmin, nthreads)
 
 
+def physical_memory() -> int:
+    """getMemorySize (daligner.c:149-215, the sysconf branch): MEM_LIMIT's default."""
+    try:
+        return int(os.sysconf("SC_PHYS_PAGES")) * int(os.sysconf("SC_PAGESIZE"))
+    except (ValueError, OSError):
+        return 0
+
+
 def set_options(s: Settings, freq: Sequence[float]) -> None:
     o = Options()
     o.verbose = int(s.verbose)
@@ -218,7 +232,7 @@ def set_options(s: Settings, freq: Sequence[float]) -> None:
     o.ave_corr = s.ave_corr
     for i in range(4):
         o.freq[i] = float(freq[i])
-    o.mem_limit = int(s.mem_limit_gb) * (1 << 30)
+    o.mem_limit = physical_memory() if s.mem_limit_gb is None else int(s.mem_limit_gb) * (1 << 30)
     load_library().damar_set_options(C.byref(o))
     load_library().damar_set_biased(int(s.biased))
 
@@ -527,6 +541,29 @@ def las_merge(images: Sequence[bytes]) -> bytes:
         return C.string_at(out.value, outlen.value)
     finally:
         L.damar_free(out)
+
+
+def sort_selftest(n: int, lo_bit: int, hi_bit: int, has_vals: bool, reps: int = 1, seed: int = 1, skew: bool = False) -> float:
+    """Runs the device radix sort on n pseudo-random keys and checks order, stability and permutation on the device;
+    returns the mean device time of one sort in ms."""
+    init()
+    ms = C.c_double(0)
+    if load_library().damar_sort_selftest(n, lo_bit, hi_bit, int(has_vals), reps, seed, int(skew), C.byref(ms)) != 0:
+        raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
+    return ms.value
+
+
+def las_compare(x, y) -> int:
+    """-1 when the two .las images (bytes or LasImage) are equal up to the padding bytes 36..39 of every record, -2 when
+    their lengths differ, else the offset of the first differing byte."""
+    def raw(v):
+        if isinstance(v, LasImage):
+            return v.ptr, v.nbytes, v
+        b = bytes(v)
+        return C.cast(C.c_char_p(b), C.c_void_p).value, len(b), b
+    px, nx, kx = raw(x)
+    py, ny, ky = raw(y)
+    return int(load_library().damar_las_compare(px, nx, py, ny))
 
 
 def las_dir(run_id: int, part: int) -> str:

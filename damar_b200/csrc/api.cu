@@ -12,7 +12,8 @@
 
 namespace damar {
 
-static std::string g_last_error;
+// one message per host thread: workers fail independently, and damar_last_error() hands out a pointer
+static thread_local std::string g_last_error;
 
 void set_error(const char *fmt, ...) {
     char buf[1024];
@@ -160,7 +161,12 @@ void *dev_alloc_bytes(size_t bytes) {
 // uses it (blocks and indices shared between workers are freed only after the workers have been joined).
 void dev_free(void *p) {
     Context &c = ctx();
-    if (!p || !c.ready) return;
+    if (!p) return;
+    if (!c.ready) {                                // after damar_shutdown: no cache to return it to
+        { std::lock_guard<std::mutex> lock(g_mu); g_block_size.erase(p); }
+        cudaFree(p);
+        return;
+    }
     size_t sz = 0;
     {
         std::lock_guard<std::mutex> lock(g_mu);
@@ -236,8 +242,11 @@ void damar_shutdown(void) {
         tl_ctx = &c;
         c.ws->hits.release();
         cudaStreamSynchronize(c.stream);
+        delete c.ws; c.ws = nullptr;                 // scratch buffers go back to the cache, pinned staging and events are released
         release_cached_blocks(c);
+        if (c.wait_ev) { cudaEventDestroy(c.wait_ev); c.wait_ev = nullptr; }
         cudaStreamDestroy(c.stream);
+        c.stream = nullptr;
         c.ready = false;
     }
     tl_ctx = saved;
@@ -397,22 +406,28 @@ int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
     return g_hits.n;
 }
 
+int damar_sort_selftest(int64_t n, int lo_bit, int hi_bit, int has_vals, int reps, uint64_t seed, int skew, double *ms_out) {
+    ensure_init();
+    if (n < 0 || lo_bit < 0 || hi_bit > 64 || hi_bit < lo_bit) { set_error("damar_sort_selftest: bad arguments"); return 1; }
+    return sort_selftest(n, lo_bit, hi_bit, has_vals, reps, seed, skew, ms_out);
+}
+
 void damar_dump_profile(void) { dump_profile(); }
 void damar_get_timings(damar_timings *t) {
     *t = ctx().tm;                                            // per-call fields of the calling worker ...
-    t->kernel_launches = 0; t->scatter_ms = 0; t->scatter_elems = 0; t->scatter_launches = 0;
+    t->kernel_launches = 0; t->scatter_ms = 0; t->scatter_elems = 0; t->scatter_launches = 0; t->scatter_bytes = 0;
     t->align_kernel_ms = 0; t->align_launches = 0; t->redo_kernel_ms = 0;
     for (int i = 0; i < MAX_WORKERS; i++) {                   // ... accumulators summed over all workers
         const Context &c = g_ctx[i];
         t->kernel_launches += c.launches;
-        t->scatter_ms += c.tm.scatter_ms; t->scatter_elems += c.tm.scatter_elems; t->scatter_launches += c.tm.scatter_launches;
+        t->scatter_ms += c.tm.scatter_ms; t->scatter_elems += c.tm.scatter_elems; t->scatter_launches += c.tm.scatter_launches; t->scatter_bytes += c.tm.scatter_bytes;
         t->align_kernel_ms += c.tm.align_kernel_ms; t->align_launches += c.tm.align_launches; t->redo_kernel_ms += c.tm.redo_kernel_ms;
     }
 }
 void damar_reset_kernel_timers(void) {
     for (int i = 0; i < MAX_WORKERS; i++) {
         damar_timings &t = g_ctx[i].tm;
-        t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
+        t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.scatter_bytes = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
     }
 }
 

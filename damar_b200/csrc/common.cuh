@@ -182,6 +182,10 @@ struct DeviceIndex {
 struct SortScratch;
 void radix_sort_pairs(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uint32_t *&vals_alt,
                       int64_t n, int nbits, cudaStream_t st);
+// general form: key bits [lo_bit, hi_bit), vals / vals_alt may be null (keys-only); returns non-zero with the error set
+int radix_sort(uint64_t *&keys, uint32_t *&vals, uint64_t *&keys_alt, uint32_t *&vals_alt, int64_t n, int lo_bit, int hi_bit,
+               cudaStream_t st);
+int sort_selftest(int64_t n, int lo_bit, int hi_bit, int has_vals, int reps, uint64_t seed, int skew, double *ms_out);
 // scan.cu
 void exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int64_t n, uint64_t *total_dev, cudaStream_t st);
 void exclusive_scan_u32_inplace(uint32_t *data, int64_t n, uint32_t *total_dev, cudaStream_t st);
@@ -215,6 +219,10 @@ struct HostOverlaps {                 // views of pinned staging buffers, valid 
 struct WorkerScratch {
     DevBuf<uint32_t> tile_hist;                  // radix_sort.cu
     cudaEvent_t rs_ev[16][2]; bool rs_ev_init = false;
+    ~WorkerScratch() {
+        if (rs_ev_init) for (auto &e : rs_ev) { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); }
+        for (auto &e : up_ev) if (e) cudaEventDestroy(e);
+    }
     DevBuf<uint64_t> scan_tot, scan_sums;        // scan.cu
     DevBuf<uint32_t> tot32_index, tot32_merge;   // kmer_index.cu, seed_merge.cu
     PinnedBuf<uint8_t> h_up[2]; cudaEvent_t up_ev[2] = {nullptr, nullptr};   // upload_block: pinned double buffer

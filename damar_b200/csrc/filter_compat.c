@@ -20,10 +20,12 @@ typedef struct {                 /* what Sort_Kmers hands back as the opaque `ta
 } shim_table;
 
 static int g_nthreads = 4;
+static int g_kmer = 14;
 
 int Set_Filter_Params(int kmer, int binshift, int suppress, int hitmin, int nthreads)
 {
     g_nthreads = nthreads;
+    g_kmer = kmer;
     damar_set_biased(BIASED);                        /* daligner.c parses -b before this call (:729, :862) */
     return damar_set_filter_params(kmer, binshift, suppress, hitmin, nthreads);
 }
@@ -74,7 +76,7 @@ void Match_Filter(char *aname, DAMAR_HITS_DB *ablock, char *bname, DAMAR_HITS_DB
     DAMAR_Overlap_IO_Buffer *buf = OVL_IO_Buffer(spec);
     float *freq = Base_Frequencies(spec);
     int64_t i, *order;
-    (void)ablock; (void)bblock; (void)alen; (void)blen;
+    (void)alen; (void)blen;
 
     memset(&o, 0, sizeof(o));
     o.verbose = VERBOSE; o.minover = MINOVER; o.hgap_min = HGAP_MIN; o.symmetric = SYMMETRIC; o.identity = IDENTITY;
@@ -105,8 +107,12 @@ void Match_Filter(char *aname, DAMAR_HITS_DB *ablock, char *bname, DAMAR_HITS_DB
     }
     free(order);
     if (VERBOSE) {
-        printf("\n     %lld %d-mers\n     %lld seed hits\n     %lld confirmed hits\n", (long long)ov.nhits, 0,
-               (long long)ov.nfilt, (long long)ov.ncheck);
+        /* filter.c:2910-2928 prints these three counts with their fraction of the alen x blen matrix */
+        double mat = (double)ablock->totlen * (double)bblock->totlen;
+        if (mat <= 0.) mat = 1.;
+        printf("\n     %9lld %d-mers (%e of matrix)\n     %9lld seed hits (%e of matrix)\n     %9lld confirmed hits (%e of matrix)\n",
+               (long long)ov.nhits, g_kmer, (double)ov.nhits / mat, (long long)ov.nfilt, (double)ov.nfilt / mat,
+               (long long)ov.ncheck, (double)ov.ncheck / mat);
         fflush(stdout);
     }
     if (tb != NULL && tb != ta) {                    /* the reference consumes btable (filter.c:2880-2881) */

@@ -370,6 +370,7 @@ void ensure_revcomp(DeviceBlock *b) {
     std::lock_guard<std::mutex> lock(mu);
     if (b->packed[1]) return;
     Context &c = ctx();
+    if (b->nreads == 0) { b->packed[1] = alloc_packed(b->npacked_words, c.stream); CUDA_CHECK(cudaMemsetAsync(b->packed[1], 0, sizeof(uint32_t) * b->npacked_words, c.stream)); CUDA_CHECK(stream_wait(c.stream)); return; }
     b->packed[1] = alloc_packed(b->npacked_words, c.stream);
     int64_t nw = b->npacked_words;
     revcomp_packed<<<(unsigned)((nw + 255) / 256), 256, 0, c.stream>>>(b->packed[0], b->packed[1], nw, b->boff, b->rlen,
@@ -391,6 +392,12 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     const int K = fp.kmer;
     cudaStream_t st = c.stream;
     comp = comp ? 1 : 0;
+    if (b->nreads == 0) {                                 // an empty block has no k-mers (Sort_Kmers returns NULL, filter.c:990-993)
+        DeviceIndex *e = new DeviceIndex();
+        e->blk = b; e->comp = comp; e->len = 0;
+        c.tm.extract_ms = c.tm.ksort_ms = 0; c.tm.kmers = 0;
+        return e;
+    }
     if (comp) ensure_revcomp(b);
 
     Timer t_ex(st);

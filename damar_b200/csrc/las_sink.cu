@@ -258,6 +258,28 @@ int damar_las_merge(int n, const uint8_t *const *bufs, const int64_t *lens, uint
     return 0;
 }
 
+/* Byte comparison of two .las images that ignores bytes 36..39 of every record (struct padding the reference leaves
+ * uninitialised, align.c:3345-3346).  Returns -1 when equal, -2 when the lengths differ or an image is malformed,
+ * else the offset of the first differing byte.  Host only (test / bench helper). */
+int64_t damar_las_compare(const uint8_t *x, int64_t xlen, const uint8_t *y, int64_t ylen) {
+    if (xlen != ylen || xlen < 12) return -2;
+    for (int i = 0; i < 12; i++) if (x[i] != y[i]) return i;
+    int64_t novl; int32_t tspace;
+    memcpy(&novl, x, 8); memcpy(&tspace, x + 8, 4);
+    const int tbytes = (tspace <= 125) ? 1 : 2;
+    int64_t o = 12;
+    for (int64_t r = 0; r < novl; r++) {
+        if (o + 40 > xlen) return -2;
+        int32_t tl; memcpy(&tl, x + o, 4);
+        if (memcmp(x + o, y + o, 36) != 0) { for (int i = 0; i < 36; i++) if (x[o + i] != y[o + i]) return o + i; }
+        const int64_t nb = (int64_t)tl * tbytes;
+        if (tl < 0 || o + 40 + nb > xlen) return -2;
+        if (memcmp(x + o + 40, y + o + 40, (size_t)nb) != 0) { for (int64_t i = 0; i < nb; i++) if (x[o + 40 + i] != y[o + 40 + i]) return o + 40 + i; }
+        o += 40 + nb;
+    }
+    return o == xlen ? -1 : -2;
+}
+
 void damar_free(void *p) { img_free(p); }
 
 }  // extern "C"

@@ -165,7 +165,13 @@ typedef struct damar_timings {
     double  align_kernel_ms; int64_t align_launches;
     int64_t redo_pairs;          /* pairs whose wave front outgrew one warp (strided second pass) */
     double  redo_kernel_ms;      /* accumulated like align_kernel_ms */
+    int64_t scatter_bytes;       /* bytes the sort passes moved (read + write), accumulated like scatter_ms */
 } damar_timings;
+/* The device radix sort on its own (stage 1 / stage 2 sorts, filter.c:230-435): n pseudo-random keys are sorted stably on
+ * bits [lo_bit, hi_bit) (with a u32 payload when has_vals), `reps` times, and the result is checked ON THE DEVICE for order,
+ * stability and being a permutation of the input.  *ms_out = mean device time of one sort.  Returns 0 when every check
+ * passed.  Used by the GPU tests and tools/sort_bench.py; not needed by a host.                                           */
+int  damar_sort_selftest(int64_t n, int lo_bit, int hi_bit, int has_vals, int reps, uint64_t seed, int skew, double *ms_out);
 void damar_reset_kernel_timers(void);
 void damar_dump_profile(void);   /* host wall-clock breakdown to stderr */
 void damar_get_timings(damar_timings *t);
@@ -190,6 +196,10 @@ void damar_free(void *p);
  * R.i.R.1.las ... R.i.R.n.las) into one image ordered like SORT_OVL; records are copied verbatim.  Returns 0, 1 for a
  * malformed image, 2 for mixed trace spacings.  Free *out with damar_free.  Host only.                                   */
 int  damar_las_merge(int n, const uint8_t *const *bufs, const int64_t *lens, uint8_t **out, int64_t *outlen);
+/* The comparator of SURVEY section 8c: two .las images are equal when header, bytes 0..35 of every record and every trace
+ * byte agree (bytes 36..39 are struct padding the reference leaves uninitialised, align.c:3345-3346).  Returns -1 when
+ * equal, -2 for different lengths / a malformed image, else the offset of the first differing byte.  Host only.          */
+int64_t damar_las_compare(const uint8_t *x, int64_t xlen, const uint8_t *y, int64_t ylen);
 
 #ifdef __cplusplus
 }

@@ -45,16 +45,21 @@ def parse_flags(flags):
     return o
 
 
+def _phys():
+    from damar_b200.api import physical_memory
+    return physical_memory()
+
+
 def oracle_kwargs(o):
     return dict(k=o["k"], w=o["w"], h=o["h"], t=o["t"], nthreads=o["j"], identity=int(o["I"] or o["O"]),
                 symmetric=int(not o["A"]), minlen=o["l"], tspace=o["s"], no_trace=int(o["T"]), ave_corr=o["e"],
-                mem_limit=(o["M"] or 0) << 30, biased=int(o.get("b", False)))
+                mem_limit=_phys() if o["M"] is None else o["M"] << 30, biased=int(o.get("b", False)))
 
 
 def settings(o):
     from damar_b200.api import Settings
     return Settings(kmer=o["k"], binshift=o["w"], hitmin=o["h"], suppress=o["t"], ave_corr=o["e"], minlen=o["l"],
-                    trace_spacing=o["s"], nthreads=o["j"], mem_limit_gb=o["M"] or 0, symmetric=not o["A"],
+                    trace_spacing=o["s"], nthreads=o["j"], mem_limit_gb=o["M"], symmetric=not o["A"],
                     identity=o["I"], only_identity=o["O"], no_trace=o["T"], biased=o.get("b", False))
 
 

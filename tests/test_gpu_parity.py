@@ -284,3 +284,22 @@ def test_properties_at_scale():
             ref = open(os.path.join(dbdir, f"d001_{part:05d}", fn), "rb").read()
             ok, why = dbio.las_equal(ref, buf)
             assert ok, f"{fn}: {why}"
+
+
+SORT_CASES = [
+    # n, lo_bit, hi_bit, payload, skew
+    (1, 0, 28, False, False), (2, 0, 28, True, False), (777, 0, 28, True, False),            # one partial tile
+    (8192, 0, 28, False, False), (8193, 30, 58, False, False),                              # exactly one tile / one key more
+    (6144 * 3 + 5, 0, 44, True, False),                                                     # pairs: 5 passes of 9 bits
+    (1 << 20, 28, 56, False, False), (1 << 20, 28, 56, False, True),                        # packed k-mer records (k = 14)
+    (3_000_001, 0, 43, True, True), (5_000_000, 16, 60, False, False),                      # seed-hit keys
+    (1_000_000, 0, 64, True, False), (1_000_000, 3, 11, False, True),                       # all 64 bits / one narrow digit
+]
+
+
+@pytest.mark.parametrize("n,lo,hi,vals,skew", SORT_CASES)
+def test_radix_sort_is_stable_and_sorted(n, lo, hi, vals, skew):
+    """The one-sweep LSD radix sort (lex_sort's contract, filter.c:230-435: ascending on the selected bits, stable),
+    checked on the device against order, stability (payload = input index / low key bits = input index) and a
+    permutation checksum."""
+    api.sort_selftest(n, lo, hi, vals, reps=2, seed=n, skew=skew)
