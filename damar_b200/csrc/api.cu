@@ -320,8 +320,8 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0;
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
         ensure_revcomp(ab); ensure_revcomp(bb);               // the reverse wave pass runs on the reverse-complemented reads
-        { HostProf hp("mf.seed_hits"); seed_hits(ai, bi, self, comp, g_hits); }
-        if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); report_and_align(ab, bb, comp, self, g_hits, g_out); }
+        { HostProf hp("mf.seed_hits"); if (seed_hits(ai, bi, self, comp, g_hits) != 0) return 1; }
+        if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); if (report_and_align(ab, bb, comp, self, g_hits, g_out) != 0) return 1; }
     }
     out->novl = g_out.novl;
     out->ovl = g_out.ovl;
@@ -358,25 +358,26 @@ void damar_emission_order(const damar_overlaps *o, int64_t *order) {
 
 // ---- stage read-backs for the parity tests ----
 namespace {
-__global__ void to_kmerpos(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ gpos, int64_t n,
+__global__ void to_kmerpos(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ gpos, int gbits, int64_t n,
                            const uint32_t *__restrict__ boff, int nreads, uint4 *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t p = gpos[i];
+    uint32_t p = gpos ? gpos[i] : (uint32_t)(codes[i] & ((1ull << gbits) - 1ull));
     int lo = 0, hi = nreads;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (boff[mid] <= p) lo = mid; else hi = mid; }
-    uint64_t c = codes[i];
+    uint64_t c = gpos ? codes[i] : (codes[i] >> gbits);
     out[i] = make_uint4((uint32_t)c, (uint32_t)(c >> 32), p - boff[lo], (uint32_t)lo);
 }
-__global__ void to_seedpair(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ bpos, int64_t n, int pbits, int abits,
+__global__ void to_seedpair(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ bpos, int64_t n, int pbits, int abits, int qbits,
                             int4 *__restrict__ out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint64_t k = keys[i];
+    uint64_t k = bpos ? keys[i] : (keys[i] >> qbits);
+    const int bp = bpos ? (int)bpos[i] : (int)(keys[i] & ((1ull << qbits) - 1ull));
     int apos = (int)(k & ((1ull << pbits) - 1));
     int aread = (int)((k >> pbits) & ((1ull << abits) - 1));
     int bread = (int)(k >> (pbits + abits));
-    out[i] = make_int4(apos - (int)bpos[i], apos, aread, bread);
+    out[i] = make_int4(apos - bp, apos, aread, bread);
 }
 }  // namespace
 
@@ -385,7 +386,7 @@ int damar_index_download(const damar_index *idx_, void *kmerpos_out, int64_t cap
     if (idx == nullptr || idx->len > capacity) return 1;
     Context &c = ctx();
     DevBuf<uint4> tmp; tmp.reserve((size_t)idx->len);
-    to_kmerpos<<<(unsigned)((idx->len + 255) / 256), 256, 0, c.stream>>>(idx->codes, idx->gpos, idx->len, idx->blk->boff,
+    to_kmerpos<<<(unsigned)((idx->len + 255) / 256), 256, 0, c.stream>>>(idx->codes, idx->gpos, idx->gbits, idx->len, idx->blk->boff,
                                                                          idx->blk->nreads, tmp.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(kmerpos_out, tmp.p, sizeof(uint4) * idx->len, cudaMemcpyDeviceToHost, c.stream));
@@ -399,7 +400,7 @@ int64_t damar_last_hits_download(void *seedpair_out, int64_t capacity) {
     Context &c = ctx();
     DevBuf<int4> tmp; tmp.reserve((size_t)g_hits.n);
     to_seedpair<<<(unsigned)((g_hits.n + 255) / 256), 256, 0, c.stream>>>(g_hits.keys, g_hits.bpos, g_hits.n, g_hits.pbits,
-                                                                         g_hits.abits, tmp.p);
+                                                                         g_hits.abits, g_hits.qbits, tmp.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(seedpair_out, tmp.p, sizeof(int4) * g_hits.n, cudaMemcpyDeviceToHost, c.stream));
     CUDA_CHECK(stream_wait(c.stream));

@@ -172,8 +172,11 @@ struct DeviceIndex {
     DeviceBlock *blk = nullptr;
     int comp = 0;
     int64_t len = 0;
-    uint64_t *codes = nullptr;   // ascending, stable: ties in gpos order
+    // One 64-bit word per k-mer, code << gbits | gpos, whenever 2k + gbits <= 64 (gpos == nullptr then); else the
+    // code in `codes` and the position in `gpos`.  Ascending by code, stable: ties in gpos order.
+    uint64_t *codes = nullptr;
     uint32_t *gpos = nullptr;    // position of the k-mer's LAST base (rpos = gpos - boff[read])
+    int gbits = 0;               // width of the gpos field of a packed entry
     ~DeviceIndex();
 };
 
@@ -197,14 +200,16 @@ DeviceIndex *build_index(DeviceBlock *b, int comp);
 
 // seed_merge.cu
 struct SeedHits {
-    uint64_t *keys = nullptr;   // (bread << (abits+pbits)) | (aread << pbits) | apos
+    // key = (bread << (abits+pbits)) | (aread << pbits) | apos with bpos beside it, or -- bpos == nullptr -- ONE word
+    // per hit: key << qbits | bpos
+    uint64_t *keys = nullptr;
     uint32_t *bpos = nullptr;
     int64_t n = 0;
-    int pbits = 0, abits = 0, bbits = 0;
+    int pbits = 0, abits = 0, bbits = 0, qbits = 0;
     int32_t limit = 0;
     void release();
 };
-void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out);
+int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out);   // non-zero: error set
 
 // pair_align.cu
 struct HostOverlaps {                 // views of pinned staging buffers, valid until the next call
@@ -237,7 +242,7 @@ inline WorkerScratch &scratch() { return *ctx().ws; }
 int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap *ovl, const uint64_t *toff, const void *trace,
                            int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs);
 
-void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
-                      HostOverlaps &out);
+int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
+                     HostOverlaps &out);   // non-zero: error set (capacity limits are errors, not exits)
 
 }  // namespace damar

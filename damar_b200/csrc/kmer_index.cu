@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(256) extract_tuples(const uint32_t *__restrict
                                                      const int32_t *__restrict__ rlen, int nreads, int64_t nbases, int K,
                                                      const int64_t *__restrict__ anno, const int32_t *__restrict__ data,
                                                      const uint32_t *__restrict__ kbase, const uint32_t *__restrict__ gap_pref,
-                                                     uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos) {
+                                                     uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos, int gbits) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t warp_p0 = p - (threadIdx.x & 31);
     if (warp_p0 >= nbases) return;
@@ -184,8 +184,9 @@ __global__ void __launch_bounds__(256) extract_tuples(const uint32_t *__restrict
     const uint32_t hi32 = __funnelshift_l(x1, x0, o);
     const uint32_t lo32 = __funnelshift_l(x2, x1, o);
     const uint64_t win = ((uint64_t)hi32 << 32) | lo32;
-    codes[idx] = win >> (64 - 2 * K);
-    gpos[idx] = (uint32_t)p;
+    const uint64_t code = win >> (64 - 2 * K);
+    if (gpos) { codes[idx] = code; gpos[idx] = (uint32_t)p; }
+    else codes[idx] = (code << gbits) | (uint64_t)p;           // one word per k-mer
 }
 
 // -b: variable-length k-mers whose summed -log4 base frequency reaches K "bases" of information
@@ -198,7 +199,7 @@ __device__ __forceinline__ int bias_of(const BiasTable &t, uint32_t x) { return 
 
 template <bool EMIT>
 __device__ uint32_t biased_stretch(const uint32_t *__restrict__ words, int64_t g0, int p0, int q, bool masked, int K, uint64_t kmask,
-                                   const BiasTable &bt, uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos, uint32_t n) {
+                                   const BiasTable &bt, uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos, int gbits, uint32_t n) {
     uint64_t c = 0;
     int a = 0, k = 1, p = p0;
     uint32_t cnt = 0;
@@ -219,7 +220,11 @@ __device__ uint32_t biased_stretch(const uint32_t *__restrict__ words, int64_t g
             a = u; k--;
         }
         if (a > bt.logthresh) {
-            if (EMIT) { codes[n + cnt] = (c << (2 * (K - k))) & kmask; gpos[n + cnt] = (uint32_t)(g0 + p); }
+            if (EMIT) {
+                const uint64_t code = (c << (2 * (K - k))) & kmask;
+                if (gpos) { codes[n + cnt] = code; gpos[n + cnt] = (uint32_t)(g0 + p); }
+                else codes[n + cnt] = (code << gbits) | (uint64_t)(g0 + p);
+            }
             cnt++;
         }
         p++;
@@ -233,20 +238,20 @@ template <bool EMIT>
 __global__ void biased_tuples(const uint32_t *__restrict__ words, const uint32_t *__restrict__ boff, const int32_t *__restrict__ rlen,
                               int nreads, int K, uint64_t kmask, const int64_t *__restrict__ anno, const int32_t *__restrict__ data,
                               BiasTable bt, uint32_t *__restrict__ per_read, const uint32_t *__restrict__ kbase,
-                              uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos) {
+                              uint64_t *__restrict__ codes, uint32_t *__restrict__ gpos, int gbits) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nreads) return;
     const int len = rlen[r];
     const int64_t g0 = boff[r];
     uint32_t n = EMIT ? kbase[r] : 0u, n0 = n;
     if (anno == nullptr) {
-        n += biased_stretch<EMIT>(words, g0, 0, len, false, K, kmask, bt, codes, gpos, n);
+        n += biased_stretch<EMIT>(words, g0, 0, len, false, K, kmask, bt, codes, gpos, gbits, n);
     } else {
         const int64_t b = anno[r], f = anno[r + 1];
         for (int64_t j = b; j <= f; j += 2) {
             const int p = (j == b) ? 0 : data[j - 1];
             const int q = (j == f) ? len : data[j];
-            if (p + K <= q) n += biased_stretch<EMIT>(words, g0, p, q, true, K, kmask, bt, codes, gpos, n);
+            if (p + K <= q) n += biased_stretch<EMIT>(words, g0, p, q, true, K, kmask, bt, codes, gpos, gbits, n);
         }
     }
     if (!EMIT) per_read[r] = n - n0;
@@ -255,13 +260,14 @@ __global__ void biased_tuples(const uint32_t *__restrict__ words, const uint32_t
 // -t suppression (compsize_thread / compress_thread, filter.c:700-751): keep[i] = 1 iff the
 // run of equal codes containing i is shorter than `too_frequent`.  A thread only needs to look
 // `too_frequent` entries to either side.
-__global__ void mark_suppressed(const uint64_t *__restrict__ codes, int64_t n, int too_frequent, uint32_t *__restrict__ keep) {
+// cshift = gbits for packed entries (the code is what is left above), 0 for (code, gpos) pairs
+__global__ void mark_suppressed(const uint64_t *__restrict__ codes, int cshift, int64_t n, int too_frequent, uint32_t *__restrict__ keep) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t c = codes[i];
+    const uint64_t c = codes[i] >> cshift;
     int run = 1;
-    for (int64_t j = i - 1; j >= 0 && run < too_frequent && codes[j] == c; j--) run++;
-    for (int64_t j = i + 1; j < n && run < too_frequent && codes[j] == c; j++) run++;
+    for (int64_t j = i - 1; j >= 0 && run < too_frequent && (codes[j] >> cshift) == c; j--) run++;
+    for (int64_t j = i + 1; j < n && run < too_frequent && (codes[j] >> cshift) == c; j++) run++;
     keep[i] = (run < too_frequent) ? 1u : 0u;
 }
 __global__ void compact_kept(const uint64_t *__restrict__ codes, const uint32_t *__restrict__ gpos, const uint32_t *__restrict__ keep,
@@ -269,7 +275,7 @@ __global__ void compact_kept(const uint64_t *__restrict__ codes, const uint32_t 
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !keep[i]) return;
     ocodes[off[i]] = codes[i];
-    ogpos[off[i]] = gpos[i];
+    if (gpos) ogpos[off[i]] = gpos[i];
 }
 
 }  // namespace
@@ -415,7 +421,7 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
         bias_log_base(b->freq, lb);              // latched at the first Sort_Kmers after Set_Filter_Params (filter.c:774)
         bt = BiasTable{lb[0], lb[1], lb[2], lb[3], 10000 * K, 10000 * (K - 2)};   // MAX_BIAS = 2 (filter.c:69)
         biased_tuples<false><<<(b->nreads + 63) / 64, 64, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, K, fp.kmask, anno, data,
-                                                                    bt, per_read.p, nullptr, nullptr, nullptr);
+                                                                    bt, per_read.p, nullptr, nullptr, nullptr, 0);
     } else {
         count_tuples<<<(b->nreads + 255) / 256, 256, 0, st>>>(b->rlen, b->nreads, K, anno, data, per_read.p, gap_pref.p);
     }
@@ -433,27 +439,35 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     idx->blk = b; idx->comp = comp; idx->len = 0;
     if (kmers <= 0) { c.tm.extract_ms = t_ex.stop(); c.tm.ksort_ms = 0; c.tm.kmers = 0; return idx; }
 
-    uint64_t *k0, *k1; uint32_t *g0, *g1;
+    // one 64-bit word per k-mer (code << gbits | gpos) whenever that fits: 8-byte records through the sort and the merge
+    int gbits = 1;
+    while ((1ll << gbits) < b->nbases + 1) gbits++;
+    static const bool pack_ok = !(getenv("DAMAR_PACK") && atoi(getenv("DAMAR_PACK")) == 0);
+    const bool packed = pack_ok && 2 * K + gbits <= 64;
+    uint64_t *k0, *k1; uint32_t *g0 = nullptr, *g1 = nullptr;
     k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
     k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
-    g0 = (std::remove_reference<decltype(g0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 2));
-    g1 = (std::remove_reference<decltype(g1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 2));
+    if (!packed) {
+        g0 = (std::remove_reference<decltype(g0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 4));
+        g1 = (std::remove_reference<decltype(g1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 4));
+    }
     if (fp.biased)
         biased_tuples<true><<<(b->nreads + 63) / 64, 64, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, K, fp.kmask, anno, data,
-                                                                   bt, nullptr, per_read.p, k0, g0);
+                                                                   bt, nullptr, per_read.p, k0, g0, gbits);
     else
         extract_tuples<<<(unsigned)((b->nbases + 255) / 256), 256, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, b->nbases, K,
-                                                                            anno, data, per_read.p, gap_pref.p, k0, g0);
+                                                                            anno, data, per_read.p, gap_pref.p, k0, g0, gbits);
     KERNEL_CHECK(); count_launch();
     c.tm.extract_ms = t_ex.stop();
 
     Timer t_sort(st);
-    radix_sort_pairs(k0, g0, k1, g1, kmers, 2 * K, st);
+    if ((packed ? radix_sort(k0, g0, k1, g1, kmers, gbits, gbits + 2 * K, st) : radix_sort(k0, g0, k1, g1, kmers, 0, 2 * K, st)) != 0)
+        fatal("Sort_Kmers: %s", damar_last_error());
 
     if (fp.suppress > 0) {                                // -t
         DevBuf<uint32_t> keep; DevBuf<uint64_t> off;
         keep.reserve((size_t)kmers); off.reserve((size_t)kmers);
-        mark_suppressed<<<(unsigned)((kmers + 255) / 256), 256, 0, st>>>(k0, kmers, fp.suppress, keep.p);
+        mark_suppressed<<<(unsigned)((kmers + 255) / 256), 256, 0, st>>>(k0, packed ? gbits : 0, kmers, fp.suppress, keep.p);
         KERNEL_CHECK();
         exclusive_scan_u32_to_u64(keep.p, off.p, kmers, total.p, st);
         compact_kept<<<(unsigned)((kmers + 255) / 256), 256, 0, st>>>(k0, g0, keep.p, off.p, kmers, k1, g1);
@@ -465,8 +479,8 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
         std::swap(k0, k1); std::swap(g0, g1);
     }
     c.tm.ksort_ms = t_sort.stop();
-    dev_free(k1); dev_free(g1);
-    idx->codes = k0; idx->gpos = g0; idx->len = kmers;
+    dev_free(k1); if (g1) dev_free(g1);
+    idx->codes = k0; idx->gpos = g0; idx->gbits = packed ? gbits : 0; idx->len = kmers;
     c.tm.kmers = kmers;
     return idx;
 }

@@ -35,7 +35,14 @@ constexpr int TRIM_MASK = 0x7fff;
 constexpr int TRIM_MLAG = 200;
 constexpr int WAVE_LAG = 30;
 constexpr int FRACTION = 1000;
-constexpr int MAX_LA_PER_PAIR = 127;   // the emission rank keeps the alignment number of a pair in 7 bits
+// Emission rank of a record = pair << (SEQ_LA_BITS + 1) | B side << SEQ_LA_BITS | alignment number of the pair.  The
+// reference keeps a pair's alignments in realloc'ed arrays (filter.c:2318-2380); here the per-pair interval list grows
+// in a device arena and only the rank field bounds the count (an error return, never a truncation).
+constexpr int SEQ_LA_BITS = 12;
+constexpr int MAX_LA_PER_PAIR = (1 << SEQ_LA_BITS) - 1;
+constexpr uint64_t SEQ_B = 1ull << SEQ_LA_BITS;
+constexpr int SEQ_PAIR_SHIFT = SEQ_LA_BITS + 1;
+constexpr int LA_CAP0 = 4;             // interval slots a pair starts with
 constexpr int IMAX = 0x7fffffff;
 
 constexpr int AL_WARPS = 4;            // warps per CTA of the alignment kernel
@@ -90,7 +97,9 @@ __global__ void collect_work_pairs(const uint32_t *__restrict__ flag, const uint
 
 struct AlignArgs {
     // hits
-    const uint64_t *keys; const uint32_t *bpos; int64_t nhits; int pbits, abits;
+    // one hit = key (bread | aread | apos) + bpos, or -- bpos == nullptr -- one word (bread | aread | apos | bpos) with
+    // kshift = number of bpos bits (seed_merge.cu)
+    const uint64_t *keys; const uint32_t *bpos; int64_t nhits; int pbits, abits, kshift; uint32_t qmask;
     const uint32_t *work; uint32_t nwork; unsigned int *next_work;
     const uint32_t *work_wi;           // optional: original work index of work[i] (second, strided pass)
     uint32_t *redo_sidx, *redo_wi; unsigned int *redo_count; uint8_t *pair_redo;   // fast pass: pairs handed to the strided pass
@@ -110,7 +119,12 @@ struct AlignArgs {
     damar_overlap *recs; uint64_t *rec_toff, *rec_seq; unsigned long long rec_cap; unsigned long long *rec_count;
     void *trace; int tbytes; unsigned long long trace_cap; unsigned long long *trace_count;
     unsigned long long *stats;         // [0]=LA calls [1]=multi-LA pairs [2]=wave cells [3]=overflow flags [4]=pairs
+    int32_t *la_scratch;               // strided kernel: [nwarps][3][MAX_LA_PER_PAIR + 1] interval lists
 };
+
+__device__ __forceinline__ uint64_t hit_pair(const AlignArgs &P, int64_t j) { return P.keys[j] >> (P.pbits + P.kshift); }
+__device__ __forceinline__ int hit_apos(const AlignArgs &P, int64_t j) { return (int)((P.keys[j] >> P.kshift) & ((1ull << P.pbits) - 1ull)); }
+__device__ __forceinline__ int hit_bpos(const AlignArgs &P, int64_t j) { return P.bpos ? (int)P.bpos[j] : (int)((uint32_t)P.keys[j] & P.qmask); }
 
 struct Path {
     int abpos, bbpos, aepos, bepos, diffs, tlen;
@@ -478,10 +492,9 @@ __device__ void emit_record(const AlignArgs &P, const Path &p, int aread, int br
 }
 
 __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArgs P) {
-    __shared__ int la_low[AL_WARPS][MAX_LA_PER_PAIR], la_hgh[AL_WARPS][MAX_LA_PER_PAIR], la_ae[AL_WARPS][MAX_LA_PER_PAIR];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * AL_WARPS + wib;
-    const uint64_t pmask = (1ull << P.pbits) - 1ull;
+    int32_t *la_low = P.la_scratch + (size_t)gw * 3 * (MAX_LA_PER_PAIR + 1), *la_hgh = la_low + (MAX_LA_PER_PAIR + 1), *la_ae = la_hgh + (MAX_LA_PER_PAIR + 1);
 
     WarpLA S;
     {
@@ -508,7 +521,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
         if (wslot >= P.nwork) break;
         const int64_t sidx = P.work[wslot];
         const unsigned wi = P.work_wi ? P.work_wi[wslot] : wslot;
-        const uint64_t pair = P.keys[sidx] >> P.pbits;
+        const uint64_t pair = hit_pair(P, sidx);
         const int ar = (int)(pair & ((1ull << P.abits) - 1ull)), br = (int)(pair >> P.abits);
         const int alen = P.arlen[ar], blen = P.brlen[br];
         const bool selfie = P.self && !P.comp && ar == br;    // aseq == bseq pointer test, align.c:1949
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
         int64_t pend = sidx;
         for (;;) {
             const int64_t j = pend + lane;
-            const bool same = (j < P.nhits) && ((P.keys[j] >> P.pbits) == pair);
+            const bool same = (j < P.nhits) && (hit_pair(P, j) == pair);
             const unsigned m = __ballot_sync(FULL, same);
             if (m == FULL) { pend += 32; continue; }
             pend += __ffs(~m) - 1;
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
                 bool gotpe = false, goth2 = false;
                 for (int64_t j0 = lidx; j0 < pend && !(gotpe && goth2); j0 += 32) {
                     const int64_t j = j0 + lane;
-                    const int apos = (j < pend) ? (int)(P.keys[j] & pmask) : IMAX;
+                    const int apos = (j < pend) ? hit_apos(P, j) : IMAX;
                     const unsigned over = __ballot_sync(FULL, (j < pend) && apos > amark);
                     const unsigned over2 = __ballot_sync(FULL, (j < pend) && apos > amark2);
                     if (!goth2 && over2) { h2 = j0 + __ffs(over2) - 1; goth2 = true; }
@@ -553,7 +566,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
                 const int64_t j = j0 + lane;
                 const bool v = j < pe;
                 int apos = 0, d = IMAX - lane;                 // distinct dummies so inactive lanes never match
-                if (v) { apos = (int)(P.keys[j] & pmask); d = (apos - (int)P.bpos[j]) >> P.W; }
+                if (v) { apos = hit_apos(P, j); d = (apos - hit_bpos(P, j)) >> P.W; }
                 const unsigned peers = __match_any_sync(FULL, d);
                 const unsigned lower = peers & ((1u << lane) - 1u);
                 int prev = 0;
@@ -575,7 +588,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
                 int apos = 0, bpos = 0, d = 0;
                 bool cand = false;
                 if (v) {
-                    apos = (int)(P.keys[j] & pmask); bpos = (int)P.bpos[j]; d = (apos - bpos) >> P.W;
+                    apos = hit_apos(P, j); bpos = hit_bpos(P, j); d = (apos - bpos) >> P.W;
                     const int s = score[d];
                     cand = (s + score[d + 1] >= P.H) || (s + score[d - 1] >= P.H);
                 }
@@ -586,7 +599,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
                     // apos > lasta[d] (filter.c:2289) against the pair's alignment list
                     bool blocked = false;
                     for (int q = lane; q < nla; q += 32)
-                        if (la_low[wib][q] <= cd && cd <= la_hgh[wib][q] && capos <= la_ae[wib][q]) blocked = true;
+                        if (la_low[q] <= cd && cd <= la_hgh[q] && capos <= la_ae[q]) blocked = true;
                     if (__any_sync(FULL, blocked)) continue;
                     Path ap, bp;
                     n_la++;
@@ -617,14 +630,14 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
                         if (cd < lo) lo = cd; else if (cd > hi) hi = cd;
                     }
                     if (nla < MAX_LA_PER_PAIR) {
-                        if (lane == 0) { la_low[wib][nla] = lo; la_hgh[wib][nla] = hi; la_ae[wib][nla] = ap.aepos; }
+                        if (lane == 0) { la_low[nla] = lo; la_hgh[nla] = hi; la_ae[nla] = ap.aepos; }
                         nla++;
                     } else if (lane == 0) atomicOr(&P.stats[3], 2ull);
                     __syncwarp();
                     if ((ap.aepos - ap.abpos) + (ap.bepos - ap.bbpos) >= P.minover) {   // filter.c:2335
-                        const uint64_t seq = ((uint64_t)wi << 8) | (uint64_t)(novl & 127);
+                        const uint64_t seq = ((uint64_t)wi << SEQ_PAIR_SHIFT) | (uint64_t)(novl & MAX_LA_PER_PAIR);
                         emit_record(P, ap, ar + P.afirst, br + P.bfirst, seq);
-                        if (doB) emit_record(P, bp, br + P.bfirst, ar + P.afirst, seq | 128ull);
+                        if (doB) emit_record(P, bp, br + P.bfirst, ar + P.afirst, seq | SEQ_B);
                         novl++;
                     }
                     __syncwarp();
@@ -635,8 +648,8 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
             for (int64_t j0 = lidx; j0 < pe; j0 += 32) {
                 const int64_t j = j0 + lane;
                 if (j < pe) {
-                    const int apos = (int)(P.keys[j] & pmask);
-                    const int d = (apos - (int)P.bpos[j]) >> P.W;
+                    const int apos = hit_apos(P, j);
+                    const int d = (apos - hit_bpos(P, j)) >> P.W;
                     score[d] = 0; lastp[d] = 0;
                 }
             }
@@ -678,7 +691,10 @@ struct PairTable {          // one slot per active pair
     int64_t *sidx, *pend, *nidx, *lidx, *pe, *j;
     int32_t *amark2, *nla, *novl;
     uint32_t *flags;
-    int32_t *la_low, *la_hgh, *la_ae;     // [slots][MAX_LA_PER_PAIR]
+    // lasta as an interval list per pair: la_off[p] / la_cap[p] name the pair's slots in the arena (la_low, la_hgh, la_ae);
+    // a full list moves to a region twice as large taken from la_top
+    uint32_t *la_off, *la_cap; unsigned int *la_top; uint32_t la_arena;
+    int32_t *la_low, *la_hgh, *la_ae;
 };
 struct CandTable {          // one slot per local alignment of the current round
     uint32_t *pair;         // active pair slot
@@ -709,7 +725,7 @@ __device__ int64_t pair_extent(const AlignArgs &P, int64_t from, uint64_t pair) 
     int64_t pend = from;
     for (;;) {
         const int64_t j = pend + lane;
-        const bool same = (j < P.nhits) && ((P.keys[j] >> P.pbits) == pair);
+        const bool same = (j < P.nhits) && (hit_pair(P, j) == pair);
         const unsigned m = __ballot_sync(FULL, same);
         if (m == FULL) { pend += 32; continue; }
         pend += __ffs(~m) - 1;
@@ -721,12 +737,11 @@ __device__ int64_t pair_extent(const AlignArgs &P, int64_t from, uint64_t pair) 
 // pass 1 of a panel: covered bases per diagonal bucket (filter.c:2268-2277)
 __device__ void panel_score(const AlignArgs &P, int64_t lidx, int64_t pe, int32_t *score, int32_t *lastp) {
     const int lane = threadIdx.x & 31;
-    const uint64_t pmask = (1ull << P.pbits) - 1ull;
     for (int64_t j0 = lidx; j0 < pe; j0 += 32) {
         const int64_t j = j0 + lane;
         const bool v = j < pe;
         int apos = 0, d = IMAX - lane;                 // distinct dummies so inactive lanes never match
-        if (v) { apos = (int)(P.keys[j] & pmask); d = (apos - (int)P.bpos[j]) >> P.W; }
+        if (v) { apos = hit_apos(P, j); d = (apos - hit_bpos(P, j)) >> P.W; }
         const unsigned peers = __match_any_sync(FULL, d);
         const unsigned lower = peers & ((1u << lane) - 1u);
         int prev = 0;
@@ -745,12 +760,11 @@ __device__ void panel_score(const AlignArgs &P, int64_t lidx, int64_t pe, int32_
 // pass 3: clear the touched buckets (filter.c:2407-2411)
 __device__ void panel_clear(const AlignArgs &P, int64_t lidx, int64_t pe, int32_t *score, int32_t *lastp) {
     const int lane = threadIdx.x & 31;
-    const uint64_t pmask = (1ull << P.pbits) - 1ull;
     for (int64_t j0 = lidx; j0 < pe; j0 += 32) {
         const int64_t j = j0 + lane;
         if (j < pe) {
-            const int apos = (int)(P.keys[j] & pmask);
-            const int d = (apos - (int)P.bpos[j]) >> P.W;
+            const int apos = hit_apos(P, j);
+            const int d = (apos - hit_bpos(P, j)) >> P.W;
             score[d] = 0; lastp[d] = 0;
         }
     }
@@ -763,7 +777,6 @@ __device__ void panel_clear(const AlignArgs &P, int64_t lidx, int64_t pe, int32_
 __device__ int64_t find_candidate(const AlignArgs &P, ScanState &S, int32_t *score, int32_t *lastp,
                                   int nla, const int32_t *la_low, const int32_t *la_hgh, const int32_t *la_ae) {
     const int lane = threadIdx.x & 31;
-    const uint64_t pmask = (1ull << P.pbits) - 1ull;
     bool scored = false;
     for (;;) {
         if (S.j < 0) {                                         // open the next panel
@@ -775,7 +788,7 @@ __device__ int64_t find_candidate(const AlignArgs &P, ScanState &S, int32_t *sco
             bool gotpe = false, goth2 = false;
             for (int64_t j0 = lidx; j0 < S.pend && !(gotpe && goth2); j0 += 32) {
                 const int64_t j = j0 + lane;
-                const int apos = (j < S.pend) ? (int)(P.keys[j] & pmask) : IMAX;
+                const int apos = (j < S.pend) ? hit_apos(P, j) : IMAX;
                 const unsigned over = __ballot_sync(FULL, (j < S.pend) && apos > amark);
                 const unsigned over2 = __ballot_sync(FULL, (j < S.pend) && apos > S.amark2);
                 if (!goth2 && over2) { h2 = j0 + __ffs(over2) - 1; goth2 = true; }
@@ -794,7 +807,7 @@ __device__ int64_t find_candidate(const AlignArgs &P, ScanState &S, int32_t *sco
             int apos = 0, d = 0;
             bool cand = false;
             if (v) {
-                apos = (int)(P.keys[j] & pmask); d = (apos - (int)P.bpos[j]) >> P.W;
+                apos = hit_apos(P, j); d = (apos - hit_bpos(P, j)) >> P.W;
                 const int s = score[d];
                 cand = (s + score[d + 1] >= P.H) || (s + score[d - 1] >= P.H);
             }
@@ -829,7 +842,7 @@ __global__ void __launch_bounds__(256) filter_pairs(PipeArgs Q) {
     int32_t *score = warp_buckets(P, gw), *lastp = score + P.nbuck;
     for (uint32_t w = gw; w < P.nwork; w += nw) {
         const int64_t sidx = P.work[w];
-        const uint64_t pair = P.keys[sidx] >> P.pbits;
+        const uint64_t pair = hit_pair(P, sidx);
         ScanState S;
         S.pend = pair_extent(P, sidx, pair); S.nidx = sidx; S.j = -1; S.amark2 = 0; S.lidx = S.pe = sidx;
         const int64_t c = find_candidate(P, S, score, lastp, 0, nullptr, nullptr, nullptr);
@@ -844,15 +857,15 @@ __global__ void init_pairs(PipeArgs Q, const uint32_t *__restrict__ flag, const 
     const int64_t sidx = Q.A.work[w];
     Q.pt.sidx[p] = sidx; Q.pt.pend[p] = -1; Q.pt.nidx[p] = sidx; Q.pt.lidx[p] = sidx; Q.pt.pe[p] = sidx; Q.pt.j[p] = -1;
     Q.pt.amark2[p] = 0; Q.pt.nla[p] = 0; Q.pt.novl[p] = 0; Q.pt.flags[p] = 0;
+    Q.pt.la_off[p] = (uint32_t)p * LA_CAP0; Q.pt.la_cap[p] = LA_CAP0;
     // Round 1 needs no scan: filter_pairs already found the pair's first candidate.  The saved walk restarts at the pair's first
     // panel in round 2 -- seeds before this one were no candidates and this one is then covered by its own alignment's lasta
     // interval (filter.c:2289, 2318-2333), so the restart finds what a continued walk would.
     const int64_t c = sidx + (int64_t)Q.cand0[w];
-    const uint64_t key = Q.A.keys[c];
-    const uint64_t pair = key >> Q.A.pbits;
+    const uint64_t pair = hit_pair(Q.A, c);
     Q.ct.pair[p] = (uint32_t)p; Q.ct.hidx[p] = c;
     Q.ct.ar[p] = (int)(pair & ((1ull << Q.A.abits) - 1ull)); Q.ct.br[p] = (int)(pair >> Q.A.abits);
-    Q.ct.apos[p] = (int)(key & ((1ull << Q.A.pbits) - 1ull)); Q.ct.bpos[p] = (int)Q.A.bpos[c];
+    Q.ct.apos[p] = hit_apos(Q.A, c); Q.ct.bpos[p] = hit_bpos(Q.A, c);
 }
 
 // One round of the lasta-ordered candidate walk: every listed pair that is still alive proposes its next seed.
@@ -866,13 +879,13 @@ __global__ void __launch_bounds__(256) scan_round(PipeArgs Q) {
         const uint32_t p = Q.list_in ? Q.list_in[i] : i;
         if (Q.pt.flags[p] & (PF_DONE | PF_REDO)) continue;
         const int64_t sidx = Q.pt.sidx[p];
-        const uint64_t pair = P.keys[sidx] >> P.pbits;
+        const uint64_t pair = hit_pair(P, sidx);
         ScanState S;
         S.pend = Q.pt.pend[p];
         if (S.pend < 0) S.pend = pair_extent(P, sidx, pair);
         S.nidx = Q.pt.nidx[p]; S.lidx = Q.pt.lidx[p]; S.pe = Q.pt.pe[p]; S.j = Q.pt.j[p]; S.amark2 = Q.pt.amark2[p];
         const int nla = Q.pt.nla[p];
-        const size_t lo = (size_t)p * MAX_LA_PER_PAIR;
+        const size_t lo = Q.pt.la_off[p];
         const int64_t c = find_candidate(P, S, score, lastp, nla, Q.pt.la_low + lo, Q.pt.la_hgh + lo, Q.pt.la_ae + lo);
         if (lane == 0) {
             Q.pt.pend[p] = S.pend; Q.pt.nidx[p] = S.nidx; Q.pt.lidx[p] = S.lidx; Q.pt.pe[p] = S.pe; Q.pt.j[p] = S.j; Q.pt.amark2[p] = S.amark2;
@@ -881,10 +894,10 @@ __global__ void __launch_bounds__(256) scan_round(PipeArgs Q) {
                 if (Q.pt.novl[p] > 1) n_multi++;
             } else {
                 const unsigned slot = atomicAdd(&Q.ctr[CTR_NCAND], 1u);
-                const int apos = (int)(P.keys[c] & ((1ull << P.pbits) - 1ull));
+                const int apos = hit_apos(P, c);
                 Q.ct.pair[slot] = p; Q.ct.hidx[slot] = c;
                 Q.ct.ar[slot] = (int)(pair & ((1ull << P.abits) - 1ull)); Q.ct.br[slot] = (int)(pair >> P.abits);
-                Q.ct.apos[slot] = apos; Q.ct.bpos[slot] = (int)P.bpos[c];
+                Q.ct.apos[slot] = apos; Q.ct.bpos[slot] = hit_bpos(P, c);
             }
         }
         __syncwarp();
@@ -1099,16 +1112,33 @@ __global__ void __launch_bounds__(256) finish_las(PipeArgs Q) {
         }
         const int nla = Q.pt.nla[p], novl = Q.pt.novl[p];
         if (nla < MAX_LA_PER_PAIR) {
-            if (lane == 0) {
-                const size_t o = (size_t)p * MAX_LA_PER_PAIR + nla;
+            uint32_t off = Q.pt.la_off[p];
+            const uint32_t cap = Q.pt.la_cap[p];
+            bool room = true;
+            if ((uint32_t)nla == cap) {                            // the pair's list is full: move it to a region twice as large
+                uint32_t noff = 0;
+                if (lane == 0) noff = atomicAdd(Q.pt.la_top, 2u * cap);
+                noff = __shfl_sync(FULL, noff, 0);
+                if ((uint64_t)noff + 2ull * cap > (uint64_t)Q.pt.la_arena) { room = false; if (lane == 0) atomicOr(&P.stats[3], 32ull); }
+                else {
+                    for (int q = lane; q < nla; q += 32) {
+                        Q.pt.la_low[noff + q] = Q.pt.la_low[off + q]; Q.pt.la_hgh[noff + q] = Q.pt.la_hgh[off + q]; Q.pt.la_ae[noff + q] = Q.pt.la_ae[off + q];
+                    }
+                    __syncwarp();
+                    if (lane == 0) { Q.pt.la_off[p] = noff; Q.pt.la_cap[p] = 2u * cap; }
+                    off = noff;
+                }
+            }
+            if (room && lane == 0) {
+                const size_t o = (size_t)off + nla;
                 Q.pt.la_low[o] = lo; Q.pt.la_hgh[o] = hi; Q.pt.la_ae[o] = ap.aepos; Q.pt.nla[p] = nla + 1;
             }
         } else if (lane == 0) atomicOr(&P.stats[3], 2ull);
         if ((ap.aepos - ap.abpos) + (ap.bepos - ap.bbpos) >= P.minover) {   // filter.c:2335
             const bool doB = P.symmetric && (ar != br || !P.self || !P.comp);   // filter.c:2301
-            const uint64_t seq = ((uint64_t)wi << 8) | (uint64_t)(novl & 127);
+            const uint64_t seq = ((uint64_t)wi << SEQ_PAIR_SHIFT) | (uint64_t)(novl & MAX_LA_PER_PAIR);
             emit_record(P, ap, ar + P.afirst, br + P.bfirst, seq);
-            if (doB) emit_record(P, bp, br + P.bfirst, ar + P.afirst, seq | 128ull);
+            if (doB) emit_record(P, bp, br + P.bfirst, ar + P.afirst, seq | SEQ_B);
             if (lane == 0) Q.pt.novl[p] = novl + 1;
         }
         __syncwarp();
@@ -1184,7 +1214,7 @@ __global__ void hr_sort_keys(HrArgs H, uint64_t *__restrict__ keys, uint32_t *__
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H.nrec) return;
     const uint64_t sq = H.seq[i];
-    const bool dead = (i < H.nrec_fast) && H.pair_redo != nullptr && H.pair_redo[sq >> 8];
+    const bool dead = (i < H.nrec_fast) && H.pair_redo != nullptr && H.pair_redo[sq >> SEQ_PAIR_SHIFT];
     H.dead[i] = dead ? 1 : 0;
     keys[i] = dead ? ~0ull : sq;
     vals[i] = (uint32_t)i;
@@ -1195,16 +1225,16 @@ __global__ void __launch_bounds__(64) handle_redundancies_pairs(HrArgs H) {
     if (j >= H.nrec) return;
     const uint32_t i0 = H.order[j];
     if (H.dead[i0]) return;
-    const uint64_t wi = H.seq[i0] >> 8;
-    if (j > 0) { const uint32_t ip = H.order[j - 1]; if (!H.dead[ip] && (H.seq[ip] >> 8) == wi) return; }   // not the pair's first record
-    uint32_t ia[MAX_LA_PER_PAIR], ib[MAX_LA_PER_PAIR];
+    const uint64_t wi = H.seq[i0] >> SEQ_PAIR_SHIFT;
+    if (j > 0) { const uint32_t ip = H.order[j - 1]; if (!H.dead[ip] && (H.seq[ip] >> SEQ_PAIR_SHIFT) == wi) return; }   // not the pair's first record
+    // the pair's records are contiguous in rank order: its A records (alignment order), then its B records
     int na = 0, nb = 0;
     for (unsigned long long q = j; q < H.nrec; q++) {
         const uint32_t i = H.order[q];
-        if (H.dead[i] || (H.seq[i] >> 8) != wi) break;
-        if (H.seq[i] & 128ull) { if (nb < MAX_LA_PER_PAIR) ib[nb++] = i; }
-        else if (na < MAX_LA_PER_PAIR) ia[na++] = i;
+        if (H.dead[i] || (H.seq[i] >> SEQ_PAIR_SHIFT) != wi) break;
+        if (H.seq[i] & SEQ_B) nb++; else na++;
     }
+    const uint32_t *ia = H.order + j, *ib = H.order + j + na;
     if (na < 2 && nb < 2) return;
 
     PoolArena al{H.pool, H.pool_cap, H.pool_top, false};
@@ -1258,19 +1288,19 @@ __global__ void __launch_bounds__(64) handle_redundancies_pairs(HrArgs H) {
             for (int k = 0; k < p.tlen; k++) t[k] = p.trace[k];
         }
     };
-    for (int k = 0; k < na; k++) { if (k < sa_n) store(ia[k], am[k], (wi << 8) | (uint64_t)k); else H.dead[ia[k]] = 1; }
-    for (int k = 0; k < nb; k++) { if (k < sb_n) store(ib[k], bm[k], (wi << 8) | 128ull | (uint64_t)k); else H.dead[ib[k]] = 1; }
+    for (int k = 0; k < na; k++) { if (k < sa_n) store(ia[k], am[k], (wi << SEQ_PAIR_SHIFT) | (uint64_t)k); else H.dead[ia[k]] = 1; }
+    for (int k = 0; k < nb; k++) { if (k < sb_n) store(ib[k], bm[k], (wi << SEQ_PAIR_SHIFT) | SEQ_B | (uint64_t)k); else H.dead[ib[k]] = 1; }
 }
 
 }  // namespace
 
-void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out) {
+int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const FilterParams &fp = c.fp;
     const int64_t n = hits.n;
     const int minhit = (fp.hitmin - 1) / fp.kmer + 1;
-    if (n >= (int64_t)0xffffffffll) fatal("more than 2^32 seed hits in one comparison (%lld): lower -M", (long long)n);
+    if (n >= (int64_t)0xffffffffll) { set_error("more than 2^32 seed hits in one comparison (%lld): lower -M or -t", (long long)n); return 1; }
 
     // ---- work list: first hit of every pair with at least minhit hits (filter.c:2210-2221) ----
     HostProf *hp1 = new HostProf("ra.worklist");
@@ -1280,10 +1310,11 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     DevBuf<uint32_t> flag; flag.reserve((size_t)n);
     DevBuf<uint64_t> off; off.reserve((size_t)n);
     DevBuf<uint64_t> total; total.reserve(1);
-    slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits, ends.p);
+    const int kshift = hits.bpos ? 0 : hits.qbits;
+    slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits + kshift, ends.p);
     KERNEL_CHECK();
     const unsigned hb = (unsigned)((n + 255) / 256);
-    flag_work_pairs<<<hb, 256, 0, st>>>(hits.keys, n, hits.pbits, minhit, ends.p, nslices, flag.p);
+    flag_work_pairs<<<hb, 256, 0, st>>>(hits.keys, n, hits.pbits + kshift, minhit, ends.p, nslices, flag.p);
     KERNEL_CHECK();
     exclusive_scan_u32_to_u64(flag.p, off.p, n, total.p, st);
     uint64_t nwork = 0;
@@ -1294,7 +1325,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     KERNEL_CHECK();
     count_launch(3);
     flag.release(); off.release();
-    if (nwork == 0) { c.tm.pairs_ms = t_pairs.stop(); delete hp1; return; }
+    if (nwork == 0) { c.tm.pairs_ms = t_pairs.stop(); delete hp1; return 0; }
 
     // ---- common arguments ----
     int ave_path, dscore; std::vector<int16_t> hs, ht;
@@ -1329,12 +1360,13 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     PipeArgs Q{};
     AlignArgs &P = Q.A;
     P.keys = hits.keys; P.bpos = hits.bpos; P.nhits = n; P.pbits = hits.pbits; P.abits = hits.abits;
+    P.kshift = kshift; P.qmask = kshift ? ((1u << kshift) - 1u) : 0u;
     P.work = work.p; P.nwork = (uint32_t)nwork; P.next_work = next.p; P.work_wi = nullptr;
     P.redo_sidx = redo_sidx.p; P.redo_wi = redo_wi.p; P.redo_count = next.p + 1; P.pair_redo = pair_redo.p;
     const int bsel = (comp && !bb->as_is) ? 1 : 0;
     P.awords = ab->packed[0]; P.bwords = bb->packed[bsel];
     Q.aw[0] = ab->packed[0]; Q.aw[1] = ab->packed[1]; Q.bw[0] = bb->packed[bsel]; Q.bw[1] = bb->packed[1 - bsel];
-    if (!Q.aw[1] || !Q.bw[1]) fatal("report_and_align: reverse-complemented reads are not resident");
+    if (!Q.aw[1] || !Q.bw[1]) { set_error("report_and_align: reverse-complemented reads are not resident"); delete hp1; return 1; }
     P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
     P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
     P.K = fp.kmer; P.W = fp.binshift; P.H = fp.hitmin; P.minhit = minhit; P.TS = TS; P.minover = c.opt.minover;
@@ -1362,15 +1394,17 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     const size_t na = (size_t)nactive + 1;
     DevBuf<uint32_t> pt_wslot, pt_flags, ct_pair, list_buf, wide_list;
     DevBuf<int64_t> pt_i64, ct_hidx;
-    DevBuf<int32_t> pt_i32, pt_la, ct_i32;
+    DevBuf<int32_t> pt_i32, pt_la, ct_i32, la_scratch;
+    DevBuf<uint32_t> pt_laoff; DevBuf<unsigned int> la_top;
+    size_t la_arena = na * LA_CAP0 + 2 * na + (1u << 16);      // grows (x4) when a round runs out of interval slots
     DevBuf<wc::TaskOut> ct_res;
-    pt_wslot.reserve(na); pt_flags.reserve(na); pt_i64.reserve(6 * na); pt_i32.reserve(3 * na); pt_la.reserve(3 * na * MAX_LA_PER_PAIR);
+    pt_wslot.reserve(na); pt_flags.reserve(na); pt_i64.reserve(6 * na); pt_i32.reserve(3 * na); pt_laoff.reserve(2 * na); la_top.reserve(1);
     ct_pair.reserve(na); list_buf.reserve(na); wide_list.reserve(2 * na); ct_hidx.reserve(na); ct_i32.reserve(4 * na); ct_res.reserve(2 * na);
     Q.pt.wslot = pt_wslot.p; Q.pt.flags = pt_flags.p;
     Q.pt.sidx = pt_i64.p; Q.pt.pend = pt_i64.p + na; Q.pt.nidx = pt_i64.p + 2 * na; Q.pt.lidx = pt_i64.p + 3 * na;
     Q.pt.pe = pt_i64.p + 4 * na; Q.pt.j = pt_i64.p + 5 * na;
     Q.pt.amark2 = pt_i32.p; Q.pt.nla = pt_i32.p + na; Q.pt.novl = pt_i32.p + 2 * na;
-    Q.pt.la_low = pt_la.p; Q.pt.la_hgh = pt_la.p + na * MAX_LA_PER_PAIR; Q.pt.la_ae = pt_la.p + 2 * na * MAX_LA_PER_PAIR;
+    Q.pt.la_off = pt_laoff.p; Q.pt.la_cap = pt_laoff.p + na; Q.pt.la_top = la_top.p;
     Q.ct.pair = ct_pair.p; Q.ct.hidx = ct_hidx.p; Q.ct.res = ct_res.p;
     Q.ct.ar = ct_i32.p; Q.ct.br = ct_i32.p + na; Q.ct.apos = ct_i32.p + 2 * na; Q.ct.bpos = ct_i32.p + 3 * na;
     Q.wide_list = wide_list.p;
@@ -1417,6 +1451,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
         CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 8, st));
         CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int) * 4, st));
         CUDA_CHECK(cudaMemsetAsync(pair_redo.p, 0, (size_t)nwork + 1, st));
+        if (la_arena > 0xfffffff0ull) la_arena = 0xfffffff0ull;
+        pt_la.reserve(3 * la_arena);
+        Q.pt.la_low = pt_la.p; Q.pt.la_hgh = pt_la.p + la_arena; Q.pt.la_ae = pt_la.p + 2 * la_arena; Q.pt.la_arena = (uint32_t)la_arena;
+        { const unsigned int top0 = (unsigned int)(na * LA_CAP0); CUDA_CHECK(cudaMemcpyAsync(la_top.p, &top0, sizeof(top0), cudaMemcpyHostToDevice, st)); }
         P.recs = recs.p; P.rec_toff = rtoff.p; P.rec_seq = rseq.p; P.rec_cap = rec_cap; P.rec_count = counters.p + 5;
         P.trace = trace.p; P.trace_cap = trace_cap; P.trace_count = counters.p + 6;
 
@@ -1490,6 +1528,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             NA.reserve((size_t)lw * ring); NB.reserve((size_t)lw * ring); cells.reserve((size_t)lw * cells_cap);
             P.ring = ring; P.V = V.p; P.HA = HA.p; P.HB = HB.p; P.HM = HM.p; P.HN = HN.p; P.NA = NA.p; P.NB = NB.p; P.T = T.p;
             P.cells = cells.p; P.cells_cap = cells_cap;
+            la_scratch.reserve((size_t)lw * 3 * (MAX_LA_PER_PAIR + 1));
+            P.la_scratch = la_scratch.p;
             CUDA_CHECK(cudaMemsetAsync(next.p, 0, sizeof(unsigned int), st));
             AlignArgs R = P;
             R.work = redo_sidx.p; R.work_wi = redo_wi.p; R.nwork = nredo;
@@ -1524,8 +1564,8 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
                 size_t pool_words = pool_mb ? (pool_mb << 18) : std::min<size_t>((size_t)2 << 30, ((size_t)hc[1] << 16) + ((size_t)16 << 20));
                 hr_pool.reserve(pool_words); hr_top.reserve(1);
                 CUDA_CHECK(cudaMemsetAsync(hr_top.p, 0, sizeof(unsigned long long), st));
-                int kb = 9;                                                      // rank = pair << 8 | B flag | alignment number
-                while ((1ull << (kb - 8)) < (unsigned long long)nwork + 2) kb++;
+                int kb = SEQ_PAIR_SHIFT + 1;                                     // rank = pair | B flag | alignment number
+                while ((1ull << (kb - SEQ_PAIR_SHIFT)) < (unsigned long long)nwork + 2) kb++;
                 radix_sort_pairs(k0, v0, k1, v1, (int64_t)nrec, kb, st);
                 H.order = v0; H.pool = hr_pool.p; H.pool_cap = pool_words; H.pool_top = hr_top.p;
                 handle_redundancies_pairs<<<(unsigned)((nrec + 63) / 64), 64, 0, st>>>(H);
@@ -1534,9 +1574,10 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
             CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
             CUDA_CHECK(stream_wait(st));
         }
-        if ((hc[3] & 1ull) && attempt < 4) {            // output buffers too small: grow and rerun
+        if ((hc[3] & (1ull | 32ull)) && attempt < 6) {  // output buffers or the interval arena too small: grow and rerun
             if (hc[5] > rec_cap) rec_cap = hc[5] + 1024;
             if (hc[6] > trace_cap) trace_cap = hc[6] + 1024;
+            if (hc[3] & 32ull) la_arena *= 4;
             CUDA_CHECK(cudaMemsetAsync(bscore.p, 0, sizeof(int32_t) * (size_t)nwarps * 2 * nbuck, st));
             continue;
         }
@@ -1544,12 +1585,12 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     }
     c.tm.align_ms = t_align.stop();
     delete hp3;
-    if (hc[3] & 6ull)
-        fatal("alignment scratch overflow (flags %llu): wave wider than %d diagonals, pebble arena or per-pair alignment list exhausted",
-              hc[3], ring);
-    if (hc[3] & 1ull) fatal("alignment output buffers overflowed repeatedly");
-    if (hc[3] & 16ull) fatal("Handle_Redundancies scratch pool exhausted; raise DAMAR_HR_POOL_MB");
-    if (hc[3] & 8ull) fatal("Compression of trace to bytes fails, value too big");   // align.c:3385-3388
+    // capacity errors are reported to the caller (damar_match_filter returns non-zero), never a silent truncation
+    if (hc[3] & 4ull) { set_error("alignment scratch overflow: wave wider than %d diagonals or pebble arena exhausted", ring); return 1; }
+    if (hc[3] & 2ull) { set_error("a read pair has more than %d local alignments in one orientation", MAX_LA_PER_PAIR); return 1; }
+    if (hc[3] & (1ull | 32ull)) { set_error("alignment output buffers overflowed repeatedly"); return 1; }
+    if (hc[3] & 16ull) { set_error("Handle_Redundancies scratch pool exhausted; raise DAMAR_HR_POOL_MB"); return 1; }
+    if (hc[3] & 8ull) { set_error("Compression of trace to bytes fails, value too big"); return 1; }   // align.c:3385-3388
 
     // ---- download into pinned staging; records stay in device emission order, `seq` carries the
     //      order the reference's thread buffers would have had ----
@@ -1584,6 +1625,7 @@ void report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, in
     out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)nwork;
     c.tm.download_ms = t_dl.stop();
     (void)rounds;
+    return 0;
 }
 
 }  // namespace damar

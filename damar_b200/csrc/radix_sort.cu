@@ -118,9 +118,9 @@ struct OsCfg {
     static constexpr int WTILE = 32 * ITEMS;
     static constexpr int KEY_BYTES = TILE * 8;
     static constexpr int VAL_BYTES = HAS_VALS ? TILE * 4 : 0;
-    static constexpr int HIST_BYTES = OS_WARPS * RADIX * 2;      // warp-private u16 counters, laid over the key buffer
-    static constexpr int SMEM = KEY_BYTES + VAL_BYTES + 2 * RADIX * 4;
-    static_assert(HIST_BYTES <= KEY_BYTES, "the counters must fit the key buffer they alias");
+    static constexpr int HIST_BYTES = OS_WARPS * RADIX * 2;      // warp-private u16 counters
+    static constexpr int SMEM = KEY_BYTES + VAL_BYTES + HIST_BYTES + 2 * RADIX * 4;
+    static_assert(2 * (SMEM + 1024) <= 227 * 1024, "two CTAs per SM");
     static_assert(RADIX / 2 <= OS_THREADS, "one thread per pair of digits");
     static_assert(TILE < 65536, "16-bit ranks");
 };
@@ -132,8 +132,8 @@ __global__ void __launch_bounds__(OS_THREADS, 2) os_pass(PassArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *skeys = reinterpret_cast<uint64_t *>(smem);
     uint32_t *svals = reinterpret_cast<uint32_t *>(smem + C::KEY_BYTES);
-    uint32_t *whist = reinterpret_cast<uint32_t *>(smem);                        // [OS_WARPS][HW], digits 2j / 2j+1 in the halves of word j
-    uint32_t *dstart = reinterpret_cast<uint32_t *>(smem + C::KEY_BYTES + C::VAL_BYTES);
+    uint32_t *whist = reinterpret_cast<uint32_t *>(smem + C::KEY_BYTES + C::VAL_BYTES);   // [OS_WARPS][HW], digits 2j / 2j+1 in the halves of word j
+    uint32_t *dstart = reinterpret_cast<uint32_t *>(smem + C::KEY_BYTES + C::VAL_BYTES + C::HIST_BYTES);
     uint32_t *gbase = dstart + RADIX;
     __shared__ __align__(8) uint64_t mbar;
     __shared__ unsigned s_tile;
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(OS_THREADS, 2) os_pass(PassArgs a) {
         const bool by_bulk = full && a.bulk;
 
         // ---- the tile's keys (and payloads) into shared memory: one bulk copy each ----
-        uint64_t key[ITEMS];
+        for (int j = lane; j < HW; j += 32) whist[w * HW + j] = 0;
         if (by_bulk) {
             if (tid == 0) {
                 mbar_expect_tx(&mbar, (uint32_t)(C::KEY_BYTES + C::VAL_BYTES));
@@ -164,34 +164,30 @@ __global__ void __launch_bounds__(OS_THREADS, 2) os_pass(PassArgs a) {
             }
             mbar_wait(&mbar, phase);
             phase ^= 1u;
-#pragma unroll
-            for (int i = 0; i < ITEMS; i++) key[i] = skeys[w * WTILE + i * 32 + lane];
         } else {                                       // last, partial tile (or unaligned source): plain loads, a bulk copy needs 16-byte multiples
 #pragma unroll
             for (int i = 0; i < ITEMS; i++) {
                 const int t = w * WTILE + i * 32 + lane;
-                key[i] = (t < nvalid) ? a.kin[base + t] : ~0ull;
+                skeys[t] = (t < nvalid) ? a.kin[base + t] : ~0ull;
                 if (HAS_VALS && t < nvalid) svals[t] = a.vin[base + t];
             }
         }
-        __syncthreads();                               // every key is in registers: the key buffer becomes the counters
-        for (int j = lane; j < HW; j += 32) whist[w * HW + j] = 0;
-        __syncwarp();
+        __syncwarp();                                  // a warp ranks the keys it loaded (or that the bulk copy delivered)
 
-        // ---- stable rank inside the warp's 32 x ITEMS keys ----
+        // ---- stable rank inside the warp's 32 x ITEMS keys; the keys stay in shared memory ----
         uint32_t rank2[(ITEMS + 1) / 2];               // 16-bit ranks, two per register
 #pragma unroll
         for (int i = 0; i < (ITEMS + 1) / 2; i++) rank2[i] = 0;
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
-            const uint32_t d = (uint32_t)(key[i] >> a.shift) & a.mask;
+            const uint32_t d = (uint32_t)(skeys[w * WTILE + i * 32 + lane] >> a.shift) & a.mask;
             uint32_t peers = 0xffffffffu;
 #pragma unroll
-            for (int b = 0; b < BITS; b++) {
-                const bool bit = (d >> b) & 1u;
-                const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                peers &= bit ? bal : ~bal;
-            }
+            for (int b = 0; b < BITS; b++)             // lanes whose digit agrees with mine in bit b: 4 instructions per bit
+                asm("{ .reg .pred p; .reg .b32 t, bal;\n"
+                    "  and.b32 t, %1, %2; setp.ne.u32 p, t, 0; vote.sync.ballot.b32 bal, p, 0xffffffff;\n"
+                    "  @p and.b32 %0, %0, bal; @!p lop3.b32 %0, %0, bal, 0, 0x30; }"
+                    : "+r"(peers) : "r"(d), "r"(1u << b));
             const uint32_t lower = peers & lt;
             const int sh16 = (int)(d & 1u) * 16;
             uint32_t prev = 0;
@@ -232,16 +228,19 @@ __global__ void __launch_bounds__(OS_THREADS, 2) os_pass(PassArgs a) {
         }
         __syncthreads();
 
-        // ---- slot of every key inside the reordered tile ----
+        // ---- slot of every key inside the reordered tile; the keys pass through registers on their way ----
+        uint64_t key[ITEMS];
         uint32_t val[HAS_VALS ? ITEMS : 1];
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
+            const int t = w * WTILE + i * 32 + lane;
+            key[i] = skeys[t];
             const uint32_t d = (uint32_t)(key[i] >> a.shift) & a.mask;
             const uint32_t wp = (whist[w * HW + (d >> 1)] >> ((d & 1u) * 16)) & 0xffffu;
             rank2[i >> 1] += (dstart[d] + wp) << ((i & 1) * 16);   // slot < TILE < 2^16: no carry into the neighbour
-            if (HAS_VALS) { const int t = w * WTILE + i * 32 + lane; val[i] = (t < nvalid) ? svals[t] : 0u; }
+            if (HAS_VALS) val[i] = (t < nvalid) ? svals[t] : 0u;
         }
-        __syncthreads();                               // the counters are dead: the buffer becomes the reordered tile
+        __syncthreads();                               // every key is in registers: the buffer becomes the reordered tile
 #pragma unroll
         for (int i = 0; i < ITEMS; i++) {
             const uint32_t p = (rank2[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
@@ -297,10 +296,12 @@ int keys_items() {                                     // DAMAR_SORT_ITEMS=12|14
 }
 template <int BITS, bool HAS_VALS>
 void launch_items(const PassArgs &a, int items, cudaStream_t st) {
-    if (HAS_VALS) launch_pass<BITS, ITEMS_PAIRS, HAS_VALS>(a, st);
-    else if (items == 12) launch_pass<BITS, 12, HAS_VALS>(a, st);
-    else if (items == 14) launch_pass<BITS, 14, HAS_VALS>(a, st);
-    else launch_pass<BITS, ITEMS_KEYS, HAS_VALS>(a, st);
+    if constexpr (HAS_VALS) launch_pass<BITS, ITEMS_PAIRS, true>(a, st);
+    else {
+        if (items == 12) launch_pass<BITS, 12, false>(a, st);
+        else if (items == 14) launch_pass<BITS, 14, false>(a, st);
+        else launch_pass<BITS, ITEMS_KEYS, false>(a, st);
+    }
 }
 
 int max_digit_bits() {
@@ -401,18 +402,24 @@ __global__ void st_fill(uint64_t *keys, uint32_t *vals, int64_t n, int lo_bit, i
 __global__ void st_check(const uint64_t *keys, const uint32_t *vals, int64_t n, int lo_bit, int hi_bit, int low_is_index,
                          unsigned long long *bad, unsigned long long *sum) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t m = (hi_bit - lo_bit >= 64) ? ~0ull : ((1ull << (hi_bit - lo_bit)) - 1ull);
-    const uint64_t k = keys[i];
-    atomicAdd(sum, (unsigned long long)mix64(k ^ (vals ? ((uint64_t)vals[i] << 1) : 0ull)));
-    if (i == 0) return;
-    const uint64_t a = (keys[i - 1] >> lo_bit) & m, b = (k >> lo_bit) & m;
-    bool v = a > b;
-    if (a == b) {
-        if (vals && vals[i - 1] >= vals[i]) v = true;
-        if (!vals && low_is_index && (keys[i - 1] & ((1ull << lo_bit) - 1ull)) >= (k & ((1ull << lo_bit) - 1ull))) v = true;
+    unsigned long long h = 0; bool v = false;
+    if (i < n) {
+        const uint64_t m = (hi_bit - lo_bit >= 64) ? ~0ull : ((1ull << (hi_bit - lo_bit)) - 1ull);
+        const uint64_t k = keys[i];
+        h = mix64(k ^ (vals ? ((uint64_t)vals[i] << 1) : 0ull));
+        if (i > 0 && hi_bit > lo_bit) {
+            const uint64_t a = (keys[i - 1] >> lo_bit) & m, b = (k >> lo_bit) & m;
+            v = a > b;
+            if (a == b) {
+                if (vals && vals[i - 1] >= vals[i]) v = true;
+                if (!vals && low_is_index && (keys[i - 1] & ((1ull << lo_bit) - 1ull)) >= (k & ((1ull << lo_bit) - 1ull))) v = true;
+            }
+        }
     }
-    if (v) atomicAdd(bad, 1ull);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    const unsigned nv = __popc(__ballot_sync(0xffffffffu, v));
+    if ((threadIdx.x & 31) == 0) { if (h) atomicAdd(sum, h); if (nv) atomicAdd(bad, (unsigned long long)nv); }
 }
 }  // namespace
 

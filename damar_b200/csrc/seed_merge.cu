@@ -5,17 +5,25 @@
 // (filter.c:2634-2702), merge_thread (filter.c:1170-1358) and the seed-hit lex_sort
 // (filter.c:2561-2580, 2776-2781).
 //
-// Shape of the computation on the device:
-//   1. run-length encode the A list by code  -> group id per entry, start per group
-//   2. one thread per A group: locate the equal-code run in B (two binary searches; the
-//      searches of neighbouring threads walk neighbouring cache lines because both lists are
-//      sorted), compute the group's match count ct, optionally histogram it (-M rule)
-//   3. host: pick `limit` from the 10000-bin histogram exactly as filter.c:2645-2663 does
-//   4. one thread per A entry: number of B partners it emits (0 when ct >= limit); scan
-//   5. one thread per A entry: write its hits; hit = (key, bpos) with
-//         key = bread << (abits+pbits) | aread << pbits | apos
-//   6. stable radix sort on the key: ties keep merge order (= bpos ascending), which is the
-//      order report_thread depends on.
+// Two sweeps over the lists (round 1 made six):
+//   merge_bounds   one thread per tile of MT_TA A entries: the tile's first entry moved back to the start of its
+//                  equal-code run, and the first B entry whose code is not smaller -- tiles hold whole runs and
+//                  the B entries that can match a tile form one window
+//   merge_tiles<false>  COUNT: a CTA stages a tile and its B window in shared memory; one thread per A ENTRY finds
+//                  the entry's run and the matching B run by bisection in shared memory, its number of partners
+//                  (all of the B run, or -- self comparison -- those of earlier reads) and adds it to the run's
+//                  match count ct; runs with ct < limit contribute to the tile's hit count, every run to the
+//                  10000-bin histogram of the -M rule.  The limit is not known before the histogram is: the sweep
+//                  runs with the limit the rule yields whenever memory is plentiful (MAXGRAM) and is repeated
+//                  only if the host then picks a smaller one.
+//   (scan of the tile counts)
+//   merge_tiles<true>   EMIT: the same staging and per-entry work, an exclusive scan of the entries' hit counts,
+//                  then one thread per HIT: which entry it belongs to (bisection of the scan), which B partner,
+//                  (bread, bpos) of that partner -- all lanes busy and the stores coalesced, whatever the run lengths
+// A run (or a window) too large for shared memory is handled by its CTA straight from global memory.
+// A hit is ONE 64-bit word  bread | aread | apos | bpos  whenever those fit (they do for every configuration of
+// BASELINE.json), sorted keys-only on its upper fields; the stable sort keeps ties in merge order (= bpos ascending),
+// which report_thread depends on.  Otherwise key + bpos pairs as in round 1.
 #include <type_traits>
 
 #include <mutex>
@@ -25,32 +33,20 @@
 namespace damar {
 namespace {
 
-constexpr int MAXGRAM = 10000;   // filter.c:71
+constexpr int MAXGRAM = 10000;     // filter.c:71
+constexpr int MT_THREADS = 512;
+constexpr int MT_TA = 1024;        // nominal A entries per tile
+constexpr int MT_CAPA = 2048;      // A entries / B entries one shared-memory segment can hold
+constexpr int MT_CAPB = 3072;
+constexpr uint32_t HAS_RUN = 0x8000u;
 
-__global__ void mark_heads(const uint64_t *__restrict__ codes, int64_t n, uint32_t *__restrict__ head) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    head[i] = (i == 0 || codes[i] != codes[i - 1]) ? 1u : 0u;
-}
-// gid[] holds the exclusive scan of the head flags on entry, the group id on exit
-__global__ void finish_groups(const uint64_t *__restrict__ codes, int64_t n, uint32_t *__restrict__ gid, uint32_t *__restrict__ gstart) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    bool h = (i == 0 || codes[i] != codes[i - 1]);
-    uint32_t g = gid[i] + (h ? 1u : 0u) - 1u;
-    gid[i] = g;
-    if (h) gstart[g] = (uint32_t)i;
-}
-
-__device__ __forceinline__ int64_t lower_bound_u64(const uint64_t *__restrict__ a, int64_t n, uint64_t x) {
-    int64_t l = 0, r = n;
-    while (l < r) { int64_t m = (l + r) >> 1; if (a[m] < x) l = m + 1; else r = m; }
-    return l;
-}
-__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__ a, uint32_t l, uint32_t r, uint32_t x) {
-    while (l < r) { uint32_t m = (l + r) >> 1; if (a[m] < x) l = m + 1; else r = m; }
-    return l;
-}
+// A sorted k-mer list: packed (gpos == nullptr, entry = code << gbits | gpos) or (code, gpos) pairs
+struct KList {
+    const uint64_t *ent; const uint32_t *gpos; int64_t len; int gbits;
+    __device__ __forceinline__ uint64_t ecode(uint64_t e) const { return gpos ? e : (e >> gbits); }
+    __device__ __forceinline__ uint64_t code(int64_t i) const { return ecode(ent[i]); }
+    __device__ __forceinline__ uint32_t epos(uint64_t e, int64_t i) const { return gpos ? gpos[i] : (uint32_t)(e & ((1ull << gbits) - 1ull)); }
+};
 // the read whose slot range [boff[r], boff[r+1]) holds gpos p, from the block's lookup table (kmer_index.cu::build_rtab)
 struct ReadMap { const uint32_t *boff, *rtab; };
 __device__ __forceinline__ int read_of(const ReadMap m, uint32_t p) {
@@ -59,165 +55,352 @@ __device__ __forceinline__ int read_of(const ReadMap m, uint32_t p) {
     return r;
 }
 
-// Number of B-group entries admitted for A entry (gpos ga) in a self comparison:
+// first index in [lo, hi) whose code is >= c (GT: > c)
+template <bool GT>
+__device__ __forceinline__ int64_t bound_code(const KList &L, int64_t lo, int64_t hi, uint64_t c) {
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; const uint64_t x = L.code(m); if (GT ? (x <= c) : (x < c)) lo = m + 1; else hi = m; }
+    return lo;
+}
+// start / end of the equal-code run that holds entry p (gallop, then bisect: runs are short)
+__device__ int64_t run_start(const KList &L, int64_t p) {
+    const uint64_t c = L.code(p);
+    int64_t lo = p, w = 1;
+    while (lo > 0) {
+        int64_t q = lo - w; if (q < 0) q = 0;
+        if (L.code(q) == c) { lo = q; w <<= 1; }
+        else return bound_code<false>(L, q + 1, lo, c);
+    }
+    return 0;
+}
+__device__ int64_t run_end(const KList &L, int64_t p) {
+    const uint64_t c = L.code(p);
+    int64_t hi = p + 1, w = 1;
+    while (hi < L.len) {
+        int64_t q = hi + w - 1; if (q >= L.len) q = L.len - 1;
+        if (L.code(q) == c) { hi = q + 1; w <<= 1; }
+        else return bound_code<true>(L, hi, q, c);
+    }
+    return L.len;
+}
+// the same inside a staged segment s[0, n)
+struct Staged {
+    const uint64_t *s; int n; int gbits; bool pairs;
+    __device__ __forceinline__ uint64_t code(int i) const { return pairs ? s[i] : (s[i] >> gbits); }
+};
+template <bool GT>
+__device__ __forceinline__ int sbound(const Staged &S, int lo, int hi, uint64_t c) {
+    while (lo < hi) { const int m = (lo + hi) >> 1; const uint64_t x = S.code(m); if (GT ? (x <= c) : (x < c)) lo = m + 1; else hi = m; }
+    return lo;
+}
+__device__ __forceinline__ int srun_start(const Staged &S, int p, uint64_t c) {
+    int lo = p, w = 1;
+    while (lo > 0) {
+        int q = lo - w; if (q < 0) q = 0;
+        if (S.code(q) == c) { lo = q; w <<= 1; }
+        else return sbound<false>(S, q + 1, lo, c);
+    }
+    return 0;
+}
+__device__ __forceinline__ int srun_end(const Staged &S, int p, uint64_t c) {
+    int hi = p + 1, w = 1;
+    while (hi < S.n) {
+        int q = hi + w - 1; if (q >= S.n) q = S.n - 1;
+        if (S.code(q) == c) { hi = q + 1; w <<= 1; }
+        else return sbound<true>(S, hi, q, c);
+    }
+    return S.n;
+}
+
+struct MergeArgs {
+    KList A, B;
+    ReadMap amap, bmap;                           // amap: the A block (== B block when self)
+    int self, comp, identity, same_list;
+    uint32_t limit;
+    uint32_t ntiles;
+    int64_t *tstart, *twin;                       // [ntiles + 1]
+    unsigned long long *tcount;                   // [ntiles] hits of the tile (COUNT), their exclusive scan (EMIT)
+    unsigned long long *gram;                     // MAXGRAM bins or nullptr
+    uint64_t *keys; uint32_t *bpos;               // EMIT: bpos == nullptr -> one packed word per hit
+    int pbits, abits, qbits;
+};
+
+__global__ void merge_bounds(MergeArgs a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > a.ntiles) return;
+    if (t == a.ntiles) { a.tstart[t] = a.A.len; a.twin[t] = a.B.len; return; }
+    const int64_t s = (t == 0) ? 0 : run_start(a.A, (int64_t)t * MT_TA);
+    a.tstart[t] = s;
+    a.twin[t] = a.same_list ? s : bound_code<false>(a.B, 0, a.B.len, a.A.code(s));
+}
+
+// Threshold below which a B entry's gpos makes it a partner of the A entry at gpos ga in a self comparison:
 //   default      : b.read <  a.read                          (filter.c:1108-1112)
 //   -I, N        : (b.read,b.rpos) < (a.read,a.rpos)         (filter.c:1097-1104)
 //   -I, C        : b.read <= a.read                          (filter.c:1092-1096)
-// All three are "gposB < threshold" because the group is in gpos order and both blocks share boff.
-__device__ __forceinline__ uint32_t self_partners(const uint32_t *__restrict__ bgpos, uint32_t jb, uint32_t ib, uint32_t ga,
-                                                  const ReadMap m, int identity, int comp) {
-    uint32_t thr;
-    if (identity && !comp) thr = ga;
-    else {
-        int r = read_of(m, ga);
-        thr = (identity && comp) ? m.boff[r + 1] : m.boff[r];
-    }
-    return lower_bound_u32(bgpos, jb, ib, thr) - jb;
+// All three are "gposB < threshold" because a run is in gpos order and both blocks share boff.
+__device__ __forceinline__ uint32_t self_threshold(const MergeArgs &a, uint32_t ga) {
+    if (a.identity && !a.comp) return ga;
+    const int r = read_of(a.amap, ga);
+    return (a.identity && a.comp) ? a.amap.boff[r + 1] : a.amap.boff[r];
 }
 
-struct GroupArgs {
-    const uint64_t *acodes; const uint32_t *agpos; int64_t alen;
-    const uint64_t *bcodes; const uint32_t *bgpos; int64_t blen;
-    const uint32_t *gstart; uint32_t ngroups;
-    ReadMap amap;                                // of the A block (== B block when self)
-    int self, comp, identity, same_list;
-    uint32_t *gjb, *gnb, *gct;                   // per group: B run start, B run length, min(ct, 2^32-1)
-    unsigned long long *gram;                    // MAXGRAM bins or nullptr
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long *sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+    for (int x = 0; x < MT_THREADS / 32; x++) t += sh[x];
+    return t;
+}
+
+struct MtSmem {
+    uint64_t sA[MT_CAPA];
+    uint64_t sB[MT_CAPB];
+    uint32_t cnt[MT_CAPA + 4];                    // partners per entry, then their exclusive scan
+    uint32_t gct[MT_CAPA];                        // match count of the run that starts at this entry
+    uint16_t jbw[MT_CAPA];                        // start of the entry's B run inside the window | HAS_RUN
+    uint16_t rsw[MT_CAPA];                        // start of the entry's A run inside the segment
+    union { uint32_t gram[MAXGRAM]; uint64_t klow[MT_CAPA]; } u;   // COUNT: histogram; EMIT: aread << pbits | apos per entry
+    unsigned long long red[MT_THREADS / 32];
+    uint32_t wsum[MT_THREADS / 32];
+    int64_t seg[4];                               // q, we, giant, -
 };
 
-// [jb, ib) = the run of `code` inside the sorted window w[0, n)
-__device__ __forceinline__ void equal_run(const uint64_t *w, int64_t n, uint64_t code, int64_t &jb, int64_t &ib) {
-    jb = lower_bound_u64(w, n, code);
-    ib = jb;
-    if (jb < n && w[jb] == code) {                               // equal-code runs are short: gallop, then bisect
-        int64_t step = 1, e = jb + 1;
-        while (e < n && w[e] == code) { e += step; step <<= 1; }
-        const int64_t from = e - (step >> 1), to = (e < n) ? e : n;
-        ib = (code == ~0ull) ? n : from + lower_bound_u64(w + from, to - from, code + 1);
-    }
-}
+template <bool EMIT>
+__global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MtSmem &S = *reinterpret_cast<MtSmem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool histo = !EMIT && a.gram != nullptr;
+    const bool packed_out = a.bpos == nullptr;
+    if (histo) { for (int i = tid; i < MAXGRAM; i += MT_THREADS) S.u.gram[i] = 0; }
+    __syncthreads();
 
-// Each CTA owns a contiguous chunk of A groups and walks it in tiles of MG_TILE groups.  Because both
-// lists are sorted, the B entries that can match a tile lie in one window [lo, hi): two threads
-// locate it with a full binary search; the window's codes are then staged in shared memory (coalesced
-// stream of the B list, read once) and every thread bisects there.  Windows larger than MG_WIN entries
-// (a tile that spans a very frequent code) are searched in place.
-// Self comparison of a list with itself (N orientation): the B run IS the A run and the partners of an entry
-// are the entries of the run that belong to earlier reads -- a run of one k-mer (most of them: any k-mer with
-// a sequencing error in it) has none and needs no search at all.
-constexpr int MG_TILE = 2048;
-constexpr int MG_WIN = 4096;
-// window of B entries that can match tile t of A groups: one thread per tile, so the two 27-step bisections of the whole
-// B list (DRAM latency each step) of all tiles run side by side instead of one tile after the other inside a CTA
-__global__ void tile_windows(GroupArgs a, int64_t *__restrict__ wlo, int64_t *__restrict__ whi, uint32_t ntiles) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    const uint64_t t0 = (uint64_t)t * MG_TILE, t1 = (t0 + MG_TILE < a.ngroups) ? t0 + MG_TILE : a.ngroups;
-    const uint64_t first = a.acodes[a.gstart[t0]], last = a.acodes[a.gstart[t1 - 1]];
-    wlo[t] = lower_bound_u64(a.bcodes, a.blen, first);
-    whi[t] = (last == ~0ull) ? a.blen : lower_bound_u64(a.bcodes, a.blen, last + 1);
-}
+    for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int64_t a0 = a.tstart[tile], a1 = a.tstart[tile + 1];
+        if (a1 <= a0) { if (!EMIT && tid == 0) a.tcount[tile] = 0; continue; }
+        const int64_t b0 = a.twin[tile], b1 = a.twin[tile + 1];
+        unsigned long long tile_hits = 0;                       // COUNT: hits so far; EMIT: output cursor
+        if (EMIT) tile_hits = a.tcount[tile];
+        int64_t p = a0, wb = b0;
+        while (p < a1) {
+            // ---- next segment [p, q) x [wb, we): whole runs that fit shared memory, or one oversized run ----
+            int64_t q, we; bool giant = false;
+            if (a1 - p <= MT_CAPA && (a.same_list || b1 - wb <= MT_CAPB)) { q = a1; we = b1; }
+            else {
+                __syncthreads();
+                if (tid == 0) {
+                    int64_t span = MT_CAPA, qq, ww; bool g = false;
+                    for (;;) {
+                        bool single = (span == 0);
+                        if (!single) {
+                            const int64_t cand = p + span;
+                            qq = (cand >= a1) ? a1 : run_start(a.A, cand);              // whole runs in [p, qq)
+                            single = qq <= p;                                            // the run at p alone is longer than `span`
+                        }
+                        if (single) qq = run_end(a.A, p);                                // <= a1: tiles end on run boundaries
+                        ww = a.same_list ? qq : ((qq >= a.A.len) ? b1 : bound_code<false>(a.B, wb, b1, a.A.code(qq)));
+                        const bool fits = (qq - p <= MT_CAPA) && (a.same_list || ww - wb <= MT_CAPB);
+                        if (fits) break;
+                        if (single) { g = true; break; }
+                        span >>= 1;                                                      // window too large: fewer A entries
+                    }
+                    S.seg[0] = qq; S.seg[1] = ww; S.seg[2] = g ? 1 : 0;
+                }
+                __syncthreads();
+                q = S.seg[0]; we = S.seg[1]; giant = S.seg[2] != 0;
+            }
 
-__global__ void __launch_bounds__(256) match_groups(GroupArgs a, const int64_t *__restrict__ wlo, const int64_t *__restrict__ whi, uint32_t ntiles) {
-    extern __shared__ uint32_t sgram[];
-    __shared__ uint64_t swin[MG_WIN];
-    const bool histo = (a.gram != nullptr);
-    if (histo) { for (int i = threadIdx.x; i < MAXGRAM; i += blockDim.x) sgram[i] = 0; }
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t t0 = (uint64_t)tile * MG_TILE, t1 = (t0 + MG_TILE < a.ngroups) ? t0 + MG_TILE : a.ngroups;
-        __syncthreads();
-        const int64_t lo = a.same_list ? 0 : wlo[tile], hi = a.same_list ? 0 : whi[tile];
-        const bool staged = !a.same_list && (hi - lo <= MG_WIN);
-        if (staged) {
-            for (int i = threadIdx.x; i < (int)(hi - lo); i += blockDim.x) swin[i] = a.bcodes[lo + i];
-            __syncthreads();
-        }
-        for (uint64_t gg = t0 + threadIdx.x; gg < t1; gg += blockDim.x) {
-            const uint32_t g = (uint32_t)gg;
-            const uint32_t ja = a.gstart[g];
-            const uint32_t ia = (g + 1 < a.ngroups) ? a.gstart[g + 1] : (uint32_t)a.alen;
-            uint32_t jb, ib;
-            unsigned long long ct = 0;
-            if (a.same_list) {
-                jb = ja; ib = ia;
-                const unsigned long long n = ia - ja;
-                if (!a.self) ct = n * n;
-                else if (a.identity) ct = n * (n - 1) / 2;          // partners of the x-th entry: the x before it (filter.c:1097-1104)
-                else if (n > 1) {                                    // entries of earlier reads (filter.c:1108-1112)
-                    uint32_t rs = ja, bhi = 0;
-                    for (uint32_t x = ja; x < ia; x++) {
-                        const uint32_t gp = a.agpos[x];
-                        if (gp >= bhi) { rs = x; bhi = a.amap.boff[read_of(a.amap, gp) + 1]; }
-                        ct += rs - ja;
+            if (!giant) {
+                // ================= fast path: the segment and its window in shared memory =================
+                const int na = (int)(q - p), nb = a.same_list ? na : (int)(we - wb);
+                __syncthreads();
+                for (int i = tid; i < na; i += MT_THREADS) { S.sA[i] = a.A.ent[p + i]; S.gct[i] = 0; }
+                if (!a.same_list) for (int i = tid; i < nb; i += MT_THREADS) S.sB[i] = a.B.ent[wb + i];
+                __syncthreads();
+                const Staged SA{S.sA, na, a.A.gbits, a.A.gpos != nullptr};
+                const Staged SB{a.same_list ? S.sA : S.sB, nb, a.B.gbits, a.B.gpos != nullptr};
+                for (int i = tid; i < na; i += MT_THREADS) {
+                    const uint64_t c = SA.code(i);
+                    const int rs = srun_start(SA, i, c);
+                    int jb, ib;
+                    if (a.same_list) { jb = rs; ib = srun_end(SA, i, c); }
+                    else { jb = sbound<false>(SB, 0, nb, c); ib = (jb < nb && SB.code(jb) == c) ? srun_end(SB, jb, c) : jb; }
+                    const int nbr = ib - jb;
+                    uint32_t cn = 0;
+                    if (nbr > 0 && !(a.same_list && a.self && nbr == 1)) {     // a run of one k-mer of the list itself has no partner
+                        if (a.self) {
+                            const uint32_t thr = self_threshold(a, a.A.epos(S.sA[i], p + i));
+                            int lo = jb, hi = ib;                               // partners = B run entries with gpos < thr
+                            while (lo < hi) { const int m = (lo + hi) >> 1; if (a.B.epos(SB.s[m], (a.same_list ? p : wb) + m) < thr) lo = m + 1; else hi = m; }
+                            cn = (uint32_t)(lo - jb);
+                        } else cn = (uint32_t)nbr;
+                    }
+                    S.cnt[i] = cn;
+                    S.jbw[i] = (uint16_t)((uint32_t)jb | (nbr > 0 ? HAS_RUN : 0u));
+                    S.rsw[i] = (uint16_t)rs;
+                    if (a.self) { if (cn) atomicAdd(&S.gct[rs], cn); }
+                    else if (i == rs) {                                          // ct = |A run| x |B run| (filter.c:1148-1149)
+                        const unsigned long long ct = (unsigned long long)(srun_end(SA, i, c) - rs) * (unsigned long long)nbr;
+                        S.gct[rs] = ct > 0xffffffffull ? 0xffffffffu : (uint32_t)ct;
                     }
                 }
+                __syncthreads();
+                for (int i = tid; i < na; i += MT_THREADS) {
+                    const int rs = S.rsw[i];
+                    const uint32_t ct = S.gct[rs];
+                    const bool has = (S.jbw[i] & HAS_RUN) != 0;
+                    if (!(has && ct < a.limit)) S.cnt[i] = 0;
+                    if (histo && i == rs && has && ct < MAXGRAM) atomicAdd(&S.u.gram[ct], 1u);
+                }
+                __syncthreads();
+                // exclusive scan of cnt[0, na) in place; cnt[na] = total
+                uint32_t total;
+                {
+                    constexpr int PER = MT_CAPA / MT_THREADS;
+                    uint32_t v[PER], s = 0;
+#pragma unroll
+                    for (int x = 0; x < PER; x++) { const int i = tid * PER + x; v[x] = (i < na) ? S.cnt[i] : 0u; s += v[x]; }
+                    uint32_t inc = s;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                    if (lane == 31) S.wsum[w] = inc;
+                    __syncthreads();
+                    uint32_t off = 0, tot = 0;
+#pragma unroll
+                    for (int x = 0; x < MT_THREADS / 32; x++) { const uint32_t t = S.wsum[x]; if (x < w) off += t; tot += t; }
+                    total = tot;
+                    uint32_t run = off + inc - s;
+#pragma unroll
+                    for (int x = 0; x < PER; x++) { const int i = tid * PER + x; if (i < na) S.cnt[i] = run; run += v[x]; }
+                    if (tid == 0) S.cnt[na] = tot;
+                }
+                if (EMIT && total > 0) {
+                    __syncthreads();
+                    for (int i = tid; i < na; i += MT_THREADS)
+                        if (S.cnt[i + 1] > S.cnt[i]) {
+                            const uint32_t ga = a.A.epos(S.sA[i], p + i);
+                            const int ar = read_of(a.amap, ga);
+                            S.u.klow[i] = ((uint64_t)ar << a.pbits) | (uint64_t)(ga - a.amap.boff[ar]);
+                        }
+                    __syncthreads();
+                    const int64_t bgl = a.same_list ? p : wb;               // global index of window entry 0
+                    for (uint32_t h = tid; h < total; h += MT_THREADS) {
+                        int lo = 0, hi = na;                                 // last entry whose scan value is <= h
+                        while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (S.cnt[m] <= h) lo = m; else hi = m; }
+                        const int i = lo;
+                        const int j = (int)(S.jbw[i] & (HAS_RUN - 1u)) + (int)(h - S.cnt[i]);
+                        const uint32_t gb = a.B.epos(SB.s[j], bgl + j);
+                        const int br = read_of(a.bmap, gb);
+                        const uint32_t bp = gb - a.bmap.boff[br];
+                        const unsigned long long o = tile_hits + h;
+                        if (packed_out) a.keys[o] = ((((uint64_t)br << (a.pbits + a.abits)) | S.u.klow[i]) << a.qbits) | bp;
+                        else { a.keys[o] = ((uint64_t)br << (a.pbits + a.abits)) | S.u.klow[i]; a.bpos[o] = bp; }
+                    }
+                }
+                tile_hits += total;
             } else {
-                const uint64_t code = a.acodes[ja];
-                int64_t rj, ri;
-                if (staged) equal_run(swin, hi - lo, code, rj, ri);
-                else equal_run(a.bcodes + lo, hi - lo, code, rj, ri);
-                jb = (uint32_t)(lo + rj); ib = (uint32_t)(lo + ri);
-                if (ib > jb) {
-                    if (a.self) {
-                        for (uint32_t x = ja; x < ia; x++)
-                            ct += self_partners(a.bgpos, jb, ib, a.agpos[x], a.amap, a.identity, a.comp);
-                    } else
-                        ct = (unsigned long long)(ia - ja) * (unsigned long long)(ib - jb);
+                // ================= one oversized run (or window), straight from global memory =================
+                const uint64_t c = a.A.code(p);
+                __syncthreads();
+                if (tid == 0) {
+                    int64_t jb, ib;
+                    if (a.same_list) { jb = p; ib = q; }
+                    else { jb = bound_code<false>(a.B, wb, we, c); ib = bound_code<true>(a.B, jb, we, c); }
+                    S.seg[0] = jb; S.seg[1] = ib;
+                }
+                __syncthreads();
+                const int64_t jb = S.seg[0], ib = S.seg[1], nbr = ib - jb, nA = q - p;
+                if (nbr > 0) {
+                    const bool lonely = a.same_list && a.self && nbr == 1;
+                    auto partners = [&](int64_t i) -> unsigned long long {
+                        if (lonely) return 0ull;
+                        if (!a.self) return (unsigned long long)nbr;
+                        const uint32_t thr = self_threshold(a, a.A.epos(a.A.ent[i], i));
+                        int64_t lo = jb, hi = ib;
+                        while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (a.B.epos(a.B.ent[m], m) < thr) lo = m + 1; else hi = m; }
+                        return (unsigned long long)(lo - jb);
+                    };
+                    unsigned long long ct;
+                    if (!a.self) ct = (unsigned long long)nA * (unsigned long long)nbr;
+                    else {
+                        unsigned long long mine = 0;
+                        for (int64_t i = p + tid; i < q; i += MT_THREADS) mine += partners(i);
+                        ct = block_sum(mine, S.red);
+                    }
+                    const unsigned long long hits_of_run = a.self ? ct : (lonely ? 0ull : ct);
+                    const uint32_t ct32 = ct > 0xffffffffull ? 0xffffffffu : (uint32_t)ct;
+                    if (histo && tid == 0 && ct32 < MAXGRAM) atomicAdd(&S.u.gram[ct32], 1u);
+                    if (ct32 < a.limit) {
+                        if (EMIT) {
+                            for (int64_t base = p; base < q; base += MT_THREADS) {      // entries of the run, a block at a time
+                                const int64_t i = base + tid;
+                                const unsigned long long cn = (i < q) ? partners(i) : 0ull;
+                                unsigned long long inc = cn;
+#pragma unroll
+                                for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                                __syncthreads();
+                                if (lane == 31) S.red[w] = inc;
+                                __syncthreads();
+                                unsigned long long off = 0, tot = 0;
+                                for (int x = 0; x < MT_THREADS / 32; x++) { if (x < w) off += S.red[x]; tot += S.red[x]; }
+                                if (cn) {
+                                    const uint32_t ga = a.A.epos(a.A.ent[i], i);
+                                    const int ar = read_of(a.amap, ga);
+                                    const uint64_t klow = ((uint64_t)ar << a.pbits) | (uint64_t)(ga - a.amap.boff[ar]);
+                                    unsigned long long o = tile_hits + off + inc - cn;
+                                    for (unsigned long long x = 0; x < cn; x++, o++) {
+                                        const uint32_t gb = a.B.epos(a.B.ent[jb + (int64_t)x], jb + (int64_t)x);
+                                        const int br = read_of(a.bmap, gb);
+                                        const uint32_t bp = gb - a.bmap.boff[br];
+                                        if (packed_out) a.keys[o] = ((((uint64_t)br << (a.pbits + a.abits)) | klow) << a.qbits) | bp;
+                                        else { a.keys[o] = ((uint64_t)br << (a.pbits + a.abits)) | klow; a.bpos[o] = bp; }
+                                    }
+                                }
+                                tile_hits += tot;
+                            }
+                        } else tile_hits += hits_of_run;
+                    }
                 }
             }
-            if (histo && ib > jb && ct < MAXGRAM) atomicAdd(&sgram[(uint32_t)ct], 1u);
-            a.gjb[g] = jb; a.gnb[g] = ib - jb;
-            a.gct[g] = (ct > 0xffffffffull) ? 0xffffffffu : (uint32_t)ct;
+            p = q; wb = we;
         }
+        if (!EMIT && tid == 0) a.tcount[tile] = tile_hits;
     }
     if (histo) {
         __syncthreads();
-        for (int i = threadIdx.x; i < MAXGRAM; i += blockDim.x)
-            if (sgram[i]) atomicAdd(&a.gram[i], (unsigned long long)sgram[i]);
+        for (int i = tid; i < MAXGRAM; i += MT_THREADS)
+            if (S.u.gram[i]) atomicAdd(&a.gram[i], (unsigned long long)S.u.gram[i]);
     }
 }
 
-struct EntryArgs {
-    const uint32_t *agpos; int64_t alen; const uint32_t *bgpos;
-    const uint32_t *gid, *gjb, *gnb, *gct;
-    ReadMap amap, bmap;
-    int self, comp, identity, same_list; uint32_t limit;
-    uint32_t *cnt; const uint64_t *off;
-    uint64_t *keys; uint32_t *bpos; int pbits, abits;
-};
-
-__global__ void __launch_bounds__(256) count_entries(EntryArgs e) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= e.alen) return;
-    const uint32_t g = e.gid[i];
-    uint32_t c = 0;
-    const uint32_t nb = e.gnb[g];
-    if (nb > 0 && e.gct[g] < e.limit && !(e.same_list && e.self && nb == 1)) {   // a run of one k-mer of the list itself has no partner
-        if (e.self) c = self_partners(e.bgpos, e.gjb[g], e.gjb[g] + nb, e.agpos[i], e.amap, e.identity, e.comp);
-        else c = nb;
+// exclusive scan of m 64-bit counts in place, total to *total (one CTA: m is the number of tiles)
+__global__ void __launch_bounds__(1024) scan_counts(unsigned long long *v, uint32_t m, unsigned long long *total) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long x = (i < m) ? v[i] : 0ull;
+        unsigned long long inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        unsigned long long off = 0, tot = 0;
+        for (int x2 = 0; x2 < 32; x2++) { if (x2 < w) off += wsum[x2]; tot += wsum[x2]; }
+        const unsigned long long carry = carry_s;
+        if (i < m) v[i] = carry + off + inc - x;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
     }
-    e.cnt[i] = c;
-}
-
-__global__ void __launch_bounds__(256) emit_hits(EntryArgs e) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= e.alen) return;
-    const uint32_t c = e.cnt[i];
-    if (c == 0) return;
-    const uint32_t g = e.gid[i];
-    const uint32_t jb = e.gjb[g];
-    const uint32_t ga = e.agpos[i];
-    const int ar = read_of(e.amap, ga);
-    const uint32_t apos = ga - e.amap.boff[ar];
-    const uint64_t klow = ((uint64_t)ar << e.pbits) | apos;
-    uint64_t o = e.off[i];
-    int br = -1; uint32_t blo = 0, bhi = 0;
-    for (uint32_t x = 0; x < c; x++, o++) {
-        const uint32_t gb = e.bgpos[jb + x];
-        if (br < 0 || gb < blo || gb >= bhi) { br = read_of(e.bmap, gb); blo = e.bmap.boff[br]; bhi = e.bmap.boff[br + 1]; }
-        e.keys[o] = ((uint64_t)br << (e.pbits + e.abits)) | klow;
-        e.bpos[o] = gb - blo;
-    }
+    if (threadIdx.x == 0) *total = carry_s;
 }
 
 int bits_for(int64_t maxval_exclusive) {   // smallest b with 2^b >= maxval_exclusive (>= 1)
@@ -228,7 +411,7 @@ int bits_for(int64_t maxval_exclusive) {   // smallest b with 2^b >= maxval_excl
 
 }  // namespace
 
-void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out) {
+int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const DeviceBlock *ab = ai->blk, *bb = bi->blk;
@@ -239,56 +422,45 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
 
     HostProf *hp1 = new HostProf("sh.count");
     Timer t_count(st);
-    // 1. groups of A
-    DevBuf<uint32_t> gid, gstart, gjb, gnb, gct, cnt;
-    DevBuf<uint64_t> off, total;
+    const uint32_t ntiles = (uint32_t)((alen + MT_TA - 1) / MT_TA);
+    DevBuf<int64_t> tbounds; tbounds.reserve(2 * ((size_t)ntiles + 1));
+    DevBuf<unsigned long long> tcount; tcount.reserve((size_t)ntiles + 2);
     DevBuf<unsigned long long> gram;
-    gid.reserve((size_t)alen); total.reserve(1);
-    DevBuf<uint32_t> &tot32 = scratch().tot32_merge; tot32.reserve(1);
-    const unsigned eb = (unsigned)((alen + 255) / 256);
-    mark_heads<<<eb, 256, 0, st>>>(ai->codes, alen, gid.p);
-    KERNEL_CHECK();
-    exclusive_scan_u32_inplace(gid.p, alen, tot32.p, st);
-    uint32_t ngroups = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&ngroups, tot32.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(stream_wait(st));
-    gstart.reserve((size_t)ngroups + 1); gjb.reserve(ngroups); gnb.reserve(ngroups); gct.reserve(ngroups);
-    finish_groups<<<eb, 256, 0, st>>>(ai->codes, alen, gid.p, gstart.p);
-    KERNEL_CHECK();
-    count_launch(2);
-
-    // 2. per-group match
     const bool use_limit = (c.opt.mem_limit > 0);
     if (use_limit) { gram.reserve(MAXGRAM); CUDA_CHECK(cudaMemsetAsync(gram.p, 0, sizeof(unsigned long long) * MAXGRAM, st)); }
-    GroupArgs ga{};
-    ga.acodes = ai->codes; ga.agpos = ai->gpos; ga.alen = alen;
-    ga.bcodes = bi->codes; ga.bgpos = bi->gpos; ga.blen = blen;
-    ga.gstart = gstart.p; ga.ngroups = ngroups; ga.amap = ReadMap{ab->boff, ab->rtab};
-    ga.self = self; ga.comp = comp; ga.identity = c.opt.identity; ga.same_list = same_list;
-    ga.gjb = gjb.p; ga.gnb = gnb.p; ga.gct = gct.p; ga.gram = use_limit ? gram.p : nullptr;
-    {
-        static std::once_flag attr;
-        std::call_once(attr, [] { CUDA_CHECK(cudaFuncSetAttribute(match_groups, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXGRAM * 4)); });
-        const unsigned ntiles = (ngroups + MG_TILE - 1) / MG_TILE;
-        unsigned blocks = ntiles;
-        if (blocks > NUM_SMS_B200 * 8) blocks = NUM_SMS_B200 * 8;
-        if (blocks == 0) blocks = 1;
-        DevBuf<int64_t> wlo, whi;
-        if (!same_list && ntiles > 0) {
-            wlo.reserve(ntiles); whi.reserve(ntiles);
-            tile_windows<<<(ntiles + 127) / 128, 128, 0, st>>>(ga, wlo.p, whi.p, ntiles);
-            KERNEL_CHECK(); count_launch();
-        }
-        match_groups<<<blocks, 256, use_limit ? MAXGRAM * 4 : 0, st>>>(ga, wlo.p, whi.p, ntiles);
-        KERNEL_CHECK(); count_launch();
-    }
 
-    // 3. limit (filter.c:2634-2699), evaluated on the host from the histogram like the reference's main thread
+    MergeArgs m{};
+    m.A = KList{ai->codes, ai->gpos, alen, ai->gbits};
+    m.B = KList{bi->codes, bi->gpos, blen, bi->gbits};
+    m.amap = ReadMap{ab->boff, ab->rtab}; m.bmap = ReadMap{bb->boff, bb->rtab};
+    m.self = self; m.comp = comp; m.identity = c.opt.identity; m.same_list = same_list;
+    m.ntiles = ntiles; m.tstart = tbounds.p; m.twin = tbounds.p + ntiles + 1; m.tcount = tcount.p;
+    m.gram = use_limit ? gram.p : nullptr;
+    // the -M rule yields MAXGRAM whenever the hits fit the allowance (filter.c:2650-2656): count with that limit first
+    m.limit = use_limit ? (uint32_t)MAXGRAM : (uint32_t)INT32_MAX;
+
+    static std::once_flag attr;
+    std::call_once(attr, [] {
+        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem)));
+        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem)));
+    });
+    const unsigned grid = ntiles < 2u * NUM_SMS_B200 ? ntiles : 2u * NUM_SMS_B200;
+    merge_bounds<<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(m);
+    KERNEL_CHECK();
+    merge_tiles<false><<<grid, MT_THREADS, sizeof(MtSmem), st>>>(m);
+    KERNEL_CHECK();
+    scan_counts<<<1, 1024, 0, st>>>(tcount.p, ntiles, tcount.p + ntiles);
+    KERNEL_CHECK();
+    count_launch(3);
+
+    // the limit (filter.c:2634-2699), evaluated on the host from the histogram like the reference's main thread
+    unsigned long long nhits = 0;
     int64_t limit = INT32_MAX;
+    std::vector<unsigned long long> histo;
+    if (use_limit) { histo.resize(MAXGRAM); CUDA_CHECK(cudaMemcpyAsync(histo.data(), gram.p, sizeof(unsigned long long) * MAXGRAM, cudaMemcpyDeviceToHost, st)); }
+    CUDA_CHECK(cudaMemcpyAsync(&nhits, tcount.p + ntiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(stream_wait(st));
     if (use_limit) {
-        std::vector<unsigned long long> histo(MAXGRAM);
-        CUDA_CHECK(cudaMemcpyAsync(histo.data(), gram.p, sizeof(unsigned long long) * MAXGRAM, cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(stream_wait(st));
         int64_t avail = (int64_t)(((int64_t)(c.opt.mem_limit - (uint64_t)(ab->sizeof_db + bb->sizeof_db))) / (uint64_t)16);
         if (same_list || avail > alen + 2 * blen) avail = (avail - alen) / 2;
         else avail = avail - (alen + blen);
@@ -296,56 +468,61 @@ void seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp,
         int64_t tom = 0; int j;
         for (j = 0; j < MAXGRAM; j++) { tom += j * (int64_t)histo[j]; if (tom > avail) break; }
         limit = j;
-        if (limit <= 1) fatal("Insufficient memory allocation (%.1fGb), reduce block size or increase allocation", (1. * c.opt.mem_limit) / 0x40000000ll);
+        if (limit <= 1) { set_error("Insufficient memory allocation (%.1fGb), reduce block size or increase allocation", (1. * c.opt.mem_limit) / 0x40000000ll); delete hp1; return 1; }
         if (limit < 10) fprintf(stderr, "\nWarning: Sensitivity hampered by low memory allocation (%.1fGb), reduce block size or increase allocation\n", (1. * c.opt.mem_limit) / 0x40000000ll);
         if (c.opt.verbose) printf("   Capping mutual k-mer matches over %d (effectively -t%d)\n", (int)limit, (int)__builtin_sqrt(1. * limit));
+        if (limit != MAXGRAM) {                         // a tighter cap than assumed: count again with it
+            m.limit = (uint32_t)limit; m.gram = nullptr;
+            merge_tiles<false><<<grid, MT_THREADS, sizeof(MtSmem), st>>>(m);
+            KERNEL_CHECK();
+            scan_counts<<<1, 1024, 0, st>>>(tcount.p, ntiles, tcount.p + ntiles);
+            KERNEL_CHECK();
+            count_launch(2);
+            CUDA_CHECK(cudaMemcpyAsync(&nhits, tcount.p + ntiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(stream_wait(st));
+        }
     }
     out.limit = (int32_t)limit;
     c.tm.count_ms = t_count.stop();
-
     delete hp1;
-    // 4. per-entry partner counts + scan
+
     HostProf *hp2 = new HostProf("sh.merge");
     Timer t_merge(st);
-    cnt.reserve((size_t)alen); off.reserve((size_t)alen);
-    EntryArgs ea{};
-    ea.agpos = ai->gpos; ea.alen = alen; ea.bgpos = bi->gpos;
-    ea.gid = gid.p; ea.gjb = gjb.p; ea.gnb = gnb.p; ea.gct = gct.p;
-    ea.amap = ReadMap{ab->boff, ab->rtab}; ea.bmap = ReadMap{bb->boff, bb->rtab};
-    ea.self = self; ea.comp = comp; ea.identity = c.opt.identity; ea.same_list = same_list; ea.limit = (uint32_t)limit;
-    ea.cnt = cnt.p; ea.off = off.p;
-    count_entries<<<eb, 256, 0, st>>>(ea);
-    KERNEL_CHECK(); count_launch();
-    exclusive_scan_u32_to_u64(cnt.p, off.p, alen, total.p, st);
-    uint64_t nhits = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&nhits, total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(stream_wait(st));
     if (c.opt.verbose) { printf("   Hit count = %lld\n", (long long)nhits); fflush(stdout); }
-    if (nhits == 0) { c.tm.merge_ms = t_merge.stop(); delete hp2; return; }
+    if (nhits == 0) { c.tm.merge_ms = t_merge.stop(); delete hp2; return 0; }
 
     out.pbits = bits_for(ab->maxlen);
     out.abits = bits_for(ab->nreads);
     out.bbits = bits_for(bb->nreads);
-    if (out.pbits + out.abits + out.bbits > 64)
-        fatal("seed-hit key needs %d bits (> 64): block too large for this build", out.pbits + out.abits + out.bbits);
+    out.qbits = bits_for(bb->maxlen);
+    const int kbits = out.pbits + out.abits + out.bbits;
+    if (kbits > 64) { set_error("seed-hit key needs %d bits (> 64): block too large for this build", kbits); delete hp2; return 1; }
+    static const bool pack_ok = !(getenv("DAMAR_PACK") && atoi(getenv("DAMAR_PACK")) == 0);
+    const bool packed = pack_ok && kbits + out.qbits <= 64;
 
-    uint64_t *k0, *k1; uint32_t *v0, *v1;
-    k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 1));
-    k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 1));
-    v0 = (std::remove_reference<decltype(v0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 1));
-    v1 = (std::remove_reference<decltype(v1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 1));
-    ea.keys = k0; ea.bpos = v0; ea.pbits = out.pbits; ea.abits = out.abits;
-    emit_hits<<<eb, 256, 0, st>>>(ea);
+    uint64_t *k0, *k1; uint32_t *v0 = nullptr, *v1 = nullptr;
+    k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2));
+    k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2));
+    if (!packed) {
+        v0 = (std::remove_reference<decltype(v0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4));
+        v1 = (std::remove_reference<decltype(v1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4));
+    }
+    m.keys = k0; m.bpos = v0; m.pbits = out.pbits; m.abits = out.abits; m.qbits = out.qbits;
+    m.limit = (uint32_t)limit; m.gram = nullptr;
+    merge_tiles<true><<<grid, MT_THREADS, sizeof(MtSmem), st>>>(m);
     KERNEL_CHECK(); count_launch();
     c.tm.merge_ms = t_merge.stop();
-
     delete hp2;
+
     HostProf hp3("sh.sort+free");
     Timer t_sort(st);
-    radix_sort_pairs(k0, v0, k1, v1, (int64_t)nhits, out.pbits + out.abits + out.bbits, st);
+    const int rc = packed ? radix_sort(k0, v0, k1, v1, (int64_t)nhits, out.qbits, out.qbits + kbits, st)
+                          : radix_sort(k0, v0, k1, v1, (int64_t)nhits, 0, kbits, st);
     c.tm.hsort_ms = t_sort.stop();
-    dev_free(k1); dev_free(v1);
+    dev_free(k1); if (v1) dev_free(v1);
+    if (rc != 0) { dev_free(k0); if (v0) dev_free(v0); return 1; }
     out.keys = k0; out.bpos = v0; out.n = (int64_t)nhits;
+    return 0;
 }
 
 }  // namespace damar

@@ -25,6 +25,11 @@ with open(os.path.join(EDGE, "cases.json")) as f:
     EDGE_CASES = json.load(f)
 
 
+GRAM = os.path.join(GOLDEN, "gram")        # MAXGRAM cap, oversized runs, > 127 alignments per pair (tests/golden/make_gram.py)
+with open(os.path.join(GRAM, "cases.json")) as f:
+    GRAM_CASES = json.load(f)
+
+
 def parse_flags(flags):
     """daligner flags -> dict(k,w,h,t,e,l,s,j,M,masks,I,O,A,T) (daligner.c:721-808)."""
     o = dict(k=14, w=6, h=35, t=0, e=0.70, l=1000, s=100, j=4, M=None, masks=[], I=False, O=False, A=False, T=False, b=False)

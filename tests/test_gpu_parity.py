@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, GRAM, GRAM_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
 from damar_b200 import api, dbio
 
 pytestmark = pytest.mark.gpu
@@ -81,6 +81,48 @@ def test_las_matches_reference_edge_cases(case):
     for fn, ref in gold.items():
         ok, why = dbio.las_equal(ref, out[fn])
         assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+@pytest.mark.parametrize("case", sorted(GRAM_CASES))
+def test_las_matches_reference_on_repeats(case):
+    """K-mer groups of >= 10000 mutual matches (dropped under the default -M = physical memory, kept with -M0,
+    filter.c:2634-2663), an equal-code run of ~6000 entries (the merge kernel's global-memory path) and ONE read pair
+    with 142 local alignments (the growing per-pair interval list + Handle_Redundancies over 142 paths)."""
+    o = parse_flags(GRAM_CASES[case]["flags"])
+    blks = [load_block(GRAM, n, ()) for n in GRAM_CASES[case]["blocks"]]
+    stats = []
+    out = api.daligner(blks[0], [blks[0] if n == GRAM_CASES[case]["blocks"][0] else b for n, b in zip(GRAM_CASES[case]["blocks"][1:], blks[1:])],
+                       settings(o), stats=stats)
+    gold = golden_files(case, GRAM)
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+    if case == "gram_default":
+        assert stats[0]["t0"]["hits"] < 100000          # the shared element's k-mers were capped ...
+    if case == "gram_M0":
+        assert stats[0]["t0"]["hits"] > 3000000         # ... and are all there without the cap
+
+
+def test_unpacked_records_give_the_same_files():
+    """DAMAR_PACK=0 keeps (code, gpos) and (key, bpos) as pairs instead of one 64-bit word per k-mer / seed hit -- the
+    layout blocks too large for the packed words fall back to.  Run in a fresh process (the switch is read once)."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from cases import *\nfrom damar_b200 import api, dbio\n"
+            "for table, dbdir, names in ((CASES, TINY, ['default', 'identity', 'rndmask', 'k16s200']), (GRAM_CASES, GRAM, ['gram_M0']), (BIAS_CASES, BIAS, ['bias_b'])):\n"
+            "    for case in names:\n"
+            "        o = parse_flags(table[case]['flags'])\n"
+            "        blks = {n: load_block(dbdir, n, tuple(o['masks'])) for n in set(table[case]['blocks'])}\n"
+            "        nm = table[case]['blocks']\n"
+            "        out = api.daligner(blks[nm[0]], [blks[n] for n in nm[1:]], settings(o))\n"
+            "        for fn, ref in golden_files(case, dbdir).items():\n"
+            "            ok, why = dbio.las_equal(ref, out[fn])\n"
+            "            assert ok, (case, fn, why)\n"
+            "print('unpacked ok')\n") % (os.path.dirname(GOLDEN).rsplit('/tests', 1)[0], os.path.dirname(GOLDEN))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "DAMAR_PACK": "0"}, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "unpacked ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_reads_shorter_than_k_are_refused():

@@ -4,7 +4,7 @@ The golden files were written by the UNMODIFIED reference binary (tests/golden/m
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GRAM, GRAM_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
 from damar_b200 import dbio
 
 
@@ -51,6 +51,28 @@ def test_oracle_matches_reference_edge_cases(case):
     for fn, ref in gold.items():
         ok, why = dbio.las_equal(ref, out[fn])
         assert ok, f"{case}/{fn}: {why}"
+
+
+@pytest.mark.parametrize("case", sorted(GRAM_CASES))
+def test_oracle_matches_reference_on_repeats(case):
+    """K-mer groups above the MAXGRAM cap under the default -M (= physical memory; dropped) and -M0 (kept), an equal-code
+    run of ~6000 entries, and one read pair with 142 local alignments (tests/golden/make_gram.py).  The oracle's unfused
+    alignments go through the product's Handle_Redundancies pass compiled for the host, as in test_path_fuse.py."""
+    from test_path_fuse import oracle_daligner_fused
+    o = parse_flags(GRAM_CASES[case]["flags"])
+    blks = [load_block(GRAM, n, ()) for n in GRAM_CASES[case]["blocks"]]
+    out, _ = oracle_daligner_fused(blks[0], [blks[0] if n == GRAM_CASES[case]["blocks"][0] else b for n, b in zip(GRAM_CASES[case]["blocks"][1:], blks[1:])],
+                                   oracle_kwargs(o), fuse=True)
+    gold = golden_files(case, GRAM)
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why}"
+
+
+def test_default_memory_cap_changes_output():
+    a, b = golden_files("gram_default", GRAM), golden_files("gram_M0", GRAM)
+    assert len(b["R.1.R.1.las"]) > 100 * len(a["R.1.R.1.las"])
 
 
 def test_biased_option_changes_output():
