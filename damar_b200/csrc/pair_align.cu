@@ -710,12 +710,12 @@ struct PipeArgs {
     uint32_t *flag;                       // filter_pairs: per work pair
     uint32_t *cand0;                      // filter_pairs: the pair's first seed candidate, as an offset from the pair's first hit
     unsigned int *ctr;                    // device counters, see CTR_*
-    uint32_t *wide_list;
+    uint32_t *wide_list, *wide_ready; unsigned int wide_cap; int wide_warps;
     wc::Lane *wide_lane; uint32_t *wide_ring;   // state of the passes that outgrew the 32-diagonal ring: [task][32][FRONT_WORDS]
     const uint32_t *task_order;           // tasks of the round, longest expected pass first (or null: index order)
     wc::Cell *pool; unsigned int pool_cap;
 };
-enum { CTR_NCAND = 0, CTR_NEXT = 1, CTR_NWIDE = 2, CTR_POOL = 3, CTR_NEXT_WIDE = 4, CTR_RETRY = 5, CTR_N = 8 };
+enum { CTR_NCAND = 0, CTR_NEXT = 1, CTR_NWIDE = 2, CTR_POOL = 3, CTR_NEXT_WIDE = 4, CTR_RETRY = 5, CTR_RETIRED = 6, CTR_N = 8 };
 
 struct ScanState { int64_t pend, nidx, lidx, pe, j; int amark2; };
 
@@ -930,15 +930,23 @@ struct DevPool {
     __device__ void store(uint32_t id, const wc::Cell &c) { *reinterpret_cast<int4 *>(cells + id) = make_int4(c.prev, c.diag, c.diff, c.mark); }
 };
 
-template <int RING, int WARPS_>
+template <int WARPS_>
 struct WaveCfg {
-    static constexpr int WARPS = WARPS_;                      // 16 KB (RING 32) / 32 KB (RING 64) of front per warp
-    static constexpr int SMEM = WARPS * wc::FRONT_WORDS * RING * 32 * 4;
+    static constexpr int WARPS = WARPS_;                      // 16 KB of front per warp: 32 lanes x 32 diagonals or 16 lanes x 64
+    static constexpr int SMEM = WARPS * wc::FRONT_WORDS * wc::FrontRT::ARR * 4;
 };
 
-// Tasks [0, 2 * ncand) when WIDE == false (task t = pass (t & 1) of alignment t >> 1), the ST_WIDE leftovers of
-// that pass listed in wide_list when WIDE == true.
-template <int RING, bool WIDE, int NWAY, int WARPS>
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
+
+// Task t of [0, 2 * ncand) = pass (t & 1) of alignment t >> 1.  A warp works in one of two SHAPES on the same 16 KB of
+// shared memory: NARROW -- 32 lanes, a 32-diagonal ring each, tasks drawn from the round's queue -- or WIDE -- 16 lanes, a
+// 64-diagonal ring each, resuming the passes that narrow lanes had to PARK because their front outgrew 32 diagonals
+// (state + ring copied to global memory, a ready flag raised).  `wide_warps` warps of every CTA are wide from the start,
+// so a parked pass continues within microseconds while the bulk of the round is still running; a narrow warp turns wide
+// when the queue is empty.  (Round 1 ran the parked passes in a second kernel after the first: 2 % of the passes, on 15
+// SMs, for a quarter of the stage's time.)  A wide lane leaves when every task has left the narrow queue's lanes
+// (CTR_RETIRED == number of tasks: no pass can be parked any more) and no parked pass is unclaimed.
+template <int NWAY, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     extern __shared__ uint32_t front_smem[];
     __shared__ int16_t s_t7[128], s_t8[256];                  // the trim test tables (wave_core.cuh)
@@ -950,77 +958,121 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     }
     __syncthreads();
     const wc::TrimTabs tabs{s_t7, s_t8, P.dscore};
-    wc::Front<RING, 32> F{front_smem + (size_t)wib * wc::FRONT_WORDS * RING * 32 + lane};
+    uint32_t *region = front_smem + (size_t)wib * wc::FRONT_WORDS * wc::FrontRT::ARR;
     DevPool pool{Q.pool, &Q.ctr[CTR_POOL], Q.pool_cap};
-    const unsigned ntasks = WIDE ? Q.ctr[CTR_NWIDE] : 2u * Q.ctr[CTR_NCAND];
-    unsigned int *next = &Q.ctr[WIDE ? CTR_NEXT_WIDE : CTR_NEXT];
+    const unsigned ntasks = 2u * Q.ctr[CTR_NCAND];
+    unsigned retired = 0;                                     // tasks this lane took off the narrow queue and finished or parked
 
     wc::Lane L;
     L.status = wc::ST_IDLE; L.k = 0; L.low = 0;
     unsigned task = 0;
     unsigned long long cells_done = 0;
-    for (;;) {
-        if (L.status != wc::ST_RUN && L.status != wc::ST_EXIT) {
-            if (L.status != wc::ST_IDLE) {                    // retire the finished task
-                wc::TaskOut o;
-                wc::finish(L, o);
-                Q.ct.res[task] = o;
-                if (WIDE || L.status != wc::ST_WIDE) cells_done += o.cells;
-                if (!WIDE && L.status == wc::ST_WIDE) {         // park the pass: the 64-diagonal kernel resumes it where it stands
-                    const unsigned w = atomicAdd(&Q.ctr[CTR_NWIDE], 1u);
-                    Q.wide_list[w] = task;
-                    Q.wide_lane[w] = L;
-                    uint32_t *dst = Q.wide_ring + (size_t)w * 32 * wc::FRONT_WORDS;
-                    for (int k = L.low; k <= L.hgh; k++) {
-                        const uint32_t *sl = F.slot(k);
+    bool wide = wib >= WARPS - Q.wide_warps;                  // warp-uniform; a narrow warp turns wide once, never back
+    wc::FrontRT F = wide ? wc::FrontRT{region + (lane & 15), 63, 4} : wc::FrontRT{region + lane, 31, 5};
+    if (wide && lane >= 16) L.status = wc::ST_EXIT;
+    unsigned await = 0;
+    bool waiting = false;
+    for (unsigned iter = 0;; iter++) {
+        bool any_run = true;
+        if (!wide) {
+            // ---------------- NARROW: 32 lanes x 32 diagonals, tasks from the round's queue ----------------
+            if (L.status != wc::ST_RUN && L.status != wc::ST_EXIT) {
+                if (L.status != wc::ST_IDLE) {                    // retire the finished task
+                    wc::TaskOut o;
+                    wc::finish(L, o);
+                    Q.ct.res[task] = o;
+                    retired++;
+                    if (L.status != wc::ST_WIDE) cells_done += o.cells;
+                    else {                                        // park the pass: a wide lane resumes it where it stands
+                        const unsigned w = atomicAdd(&Q.ctr[CTR_NWIDE], 1u);
+                        Q.wide_list[w] = task;
+                        Q.wide_lane[w] = L;
+                        uint32_t *dst = Q.wide_ring + (size_t)w * 32 * wc::FRONT_WORDS;
+                        for (int k = L.low; k <= L.hgh; k++) {
+                            const uint32_t *sl = F.slot(k);
 #pragma unroll
-                        for (int a = 0; a < wc::FRONT_WORDS; a++) dst[(k - L.low) * wc::FRONT_WORDS + a] = sl[a * wc::Front<RING, 32>::ARR];
+                            for (int a = 0; a < wc::FRONT_WORDS; a++) dst[(k - L.low) * wc::FRONT_WORDS + a] = sl[a * wc::FrontRT::ARR];
+                        }
+                        __threadfence();
+                        *reinterpret_cast<volatile uint32_t *>(Q.wide_ready + w) = 1u;
                     }
                 }
-            }
-            // fetch the next task (one atomic per warp-wide batch of idle lanes)
-            const unsigned idle = __activemask();
-            const int leader = __ffs(idle) - 1;
-            unsigned base = 0;
-            if (lane == leader) base = atomicAdd(next, (unsigned)__popc(idle));
-            base = __shfl_sync(idle, base, leader);
-            const unsigned t = base + __popc(idle & ((1u << lane) - 1u));
-            if (t >= ntasks) L.status = wc::ST_EXIT;
-            else if (WIDE) {                                  // resume a parked pass at its wave boundary
-                task = Q.wide_list[t];
-                L = Q.wide_lane[t];
-                const uint32_t *src = Q.wide_ring + (size_t)t * 32 * wc::FRONT_WORDS;
-                for (int k = L.low; k <= L.hgh; k++) {
-                    uint32_t *sl = F.slot(k);
-#pragma unroll
-                    for (int a = 0; a < wc::FRONT_WORDS; a++) sl[a * wc::Front<RING, 32>::ARR] = src[(k - L.low) * wc::FRONT_WORDS + a];
+                // fetch the next task (one atomic per warp-wide batch of idle lanes)
+                const unsigned idle = __activemask();
+                const int leader = __ffs(idle) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(&Q.ctr[CTR_NEXT], (unsigned)__popc(idle));
+                base = __shfl_sync(idle, base, leader);
+                const unsigned t = base + __popc(idle & ((1u << lane) - 1u));
+                if (t >= ntasks) L.status = wc::ST_EXIT;
+                else {
+                    task = Q.task_order ? Q.task_order[t] : t;
+                    const unsigned slot = task >> 1;
+                    const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
+                    wc::TaskIn in;
+                    in.rev = (int)(task & 1u);
+                    in.aw = Q.aw[in.rev]; in.bw = Q.bw[in.rev];
+                    in.abase = P.aboff[ar]; in.bbase = P.bboff[br];
+                    in.alen = P.arlen[ar]; in.blen = P.brlen[br];
+                    in.diag = apos - bpos; in.anti = apos + bpos;
+                    in.aoff = 0; in.boff = P.comp ? (in.blen % P.TS) : 0;                     // align.c:1970-1984
+                    const bool selfie = P.self && !P.comp && ar == br;                       // align.c:1949
+                    in.minp = (selfie && in.diag >= 0) ? 1 : -IMAX;                          // align.c:1951-1968
+                    in.maxp = (selfie && in.diag <= 0) ? -1 : IMAX;
+                    in.TS = P.TS; in.path_ave = P.ave_path;
+                    wc::setup(L, in, F, pool);
                 }
-                // transition() runs again from the top: clipping and pruning are idempotent, only its counters are not
-                L.waves -= 1; L.cells -= (uint32_t)(L.hgh - L.low + 1);
-                L.k = L.low - 1; L.status = wc::ST_RUN;
-            } else {
-                task = Q.task_order ? Q.task_order[t] : t;
-                const unsigned slot = task >> 1;
-                const int ar = Q.ct.ar[slot], br = Q.ct.br[slot], apos = Q.ct.apos[slot], bpos = Q.ct.bpos[slot];
-                wc::TaskIn in;
-                in.rev = (int)(task & 1u);
-                in.aw = Q.aw[in.rev]; in.bw = Q.bw[in.rev];
-                in.abase = P.aboff[ar]; in.bbase = P.bboff[br];
-                in.alen = P.arlen[ar]; in.blen = P.brlen[br];
-                in.diag = apos - bpos; in.anti = apos + bpos;
-                in.aoff = 0; in.boff = P.comp ? (in.blen % P.TS) : 0;                     // align.c:1970-1984
-                const bool selfie = P.self && !P.comp && ar == br;                       // align.c:1949
-                in.minp = (selfie && in.diag >= 0) ? 1 : -IMAX;                          // align.c:1951-1968
-                in.maxp = (selfie && in.diag <= 0) ? -1 : IMAX;
-                in.TS = P.TS; in.path_ave = P.ave_path;
-                wc::setup(L, in, F, pool);
             }
+            if (__all_sync(FULL, L.status == wc::ST_EXIT)) {      // the queue is empty: help with the parked passes
+                __threadfence();                                  // this lane's parked passes are visible before its tasks count as retired
+                if (retired) atomicAdd(&Q.ctr[CTR_RETIRED], retired);
+                __syncwarp();
+                wide = true;
+                F = wc::FrontRT{region + (lane & 15), 63, 4};
+                L.status = (lane < 16) ? wc::ST_IDLE : wc::ST_EXIT;
+                continue;
+            }
+        } else {
+            // ---------------- WIDE: 16 lanes x 64 diagonals, parked passes ----------------
+            const bool mine = lane < 16;
+            if (mine && !waiting && L.status != wc::ST_RUN && L.status != wc::ST_EXIT) {
+                if (L.status != wc::ST_IDLE) {                    // retire; a front beyond 64 diagonals stays ST_WIDE: the pair goes to the strided kernel
+                    wc::TaskOut o;
+                    wc::finish(L, o);
+                    Q.ct.res[task] = o;
+                    cells_done += o.cells;
+                }
+                await = atomicAdd(&Q.ctr[CTR_NEXT_WIDE], 1u);
+                waiting = true;
+                L.status = wc::ST_IDLE;
+            }
+            any_run = __any_sync(FULL, L.status == wc::ST_RUN);
+            if (mine && waiting && (!any_run || (iter & 7u) == 0)) {   // polling costs an L2 round trip: rarely while neighbours run
+                if (await < Q.wide_cap && ld_volatile_u32(Q.wide_ready + await) != 0u) {
+                    __threadfence();
+                    task = Q.wide_list[await];
+                    L = Q.wide_lane[await];
+                    const uint32_t *src = Q.wide_ring + (size_t)await * 32 * wc::FRONT_WORDS;
+                    for (int k = L.low; k <= L.hgh; k++) {
+                        uint32_t *sl = F.slot(k);
+#pragma unroll
+                        for (int a = 0; a < wc::FRONT_WORDS; a++) sl[a * wc::FrontRT::ARR] = src[(k - L.low) * wc::FRONT_WORDS + a];
+                    }
+                    // transition() runs again from the top: clipping and pruning are idempotent, only its counters are not
+                    L.waves -= 1; L.cells -= (uint32_t)(L.hgh - L.low + 1);
+                    L.k = L.low - 1; L.status = wc::ST_RUN;
+                    waiting = false;
+                } else if (ld_volatile_u32(&Q.ctr[CTR_RETIRED]) >= ntasks) {
+                    __threadfence();
+                    if (await >= ld_volatile_u32(&Q.ctr[CTR_NWIDE])) { L.status = wc::ST_EXIT; waiting = false; }
+                }
+            }
+            if (__all_sync(FULL, L.status == wc::ST_EXIT)) break;
         }
-        if (__all_sync(FULL, L.status == wc::ST_EXIT)) break;
         if (L.status == wc::ST_RUN) {
-            if (L.k < L.low) wc::transition<RING>(L, F);
+            if (L.k < L.low) wc::transition(L, F);
             if (L.status == wc::ST_RUN && L.k >= L.low) wc::cellsN<NWAY>(L, F, tabs, pool);
-        }
+        } else if (!any_run) __nanosleep(256);
     }
     if (cells_done) atomicAdd(&P.stats[2], cells_done);
 }
@@ -1408,12 +1460,11 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     Q.ct.pair = ct_pair.p; Q.ct.hidx = ct_hidx.p; Q.ct.res = ct_res.p;
     Q.ct.ar = ct_i32.p; Q.ct.br = ct_i32.p + na; Q.ct.apos = ct_i32.p + 2 * na; Q.ct.bpos = ct_i32.p + 3 * na;
     Q.wide_list = wide_list.p;
-    DevBuf<wc::Lane> wide_lane; DevBuf<uint32_t> wide_ring;
-    wide_lane.reserve(2 * na); wide_ring.reserve(2 * na * 32 * wc::FRONT_WORDS);
-    Q.wide_lane = wide_lane.p; Q.wide_ring = wide_ring.p;
+    DevBuf<wc::Lane> wide_lane; DevBuf<uint32_t> wide_ring, wide_ready;
+    wide_lane.reserve(2 * na); wide_ring.reserve(2 * na * 32 * wc::FRONT_WORDS); wide_ready.reserve(2 * na);
+    Q.wide_lane = wide_lane.p; Q.wide_ring = wide_ring.p; Q.wide_ready = wide_ready.p; Q.wide_cap = (unsigned int)(2 * na);
     DevBuf<uint64_t> okeys; DevBuf<uint32_t> ovals;
     okeys.reserve(4 * na); ovals.reserve(4 * na);
-    static const int nway = getenv("DAMAR_NWAY") ? atoi(getenv("DAMAR_NWAY")) : 4;
     static const bool lpt = !(getenv("DAMAR_LPT") && atoi(getenv("DAMAR_LPT")) == 0);
 
     // pebble pool: measured need is ~300 cells per alignment on 10 kbp reads; a dry pool only delays alignments a round
@@ -1422,19 +1473,20 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
-    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 12;
+    // warps per CTA of the wave kernel (16 KB of shared memory each), `wide_warps` of them in the 64-diagonal shape from the start
+    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 13;
+    static const int wide_warps = getenv("DAMAR_WIDE_WARPS") ? std::max(0, std::min(4, atoi(getenv("DAMAR_WIDE_WARPS")))) : 1;
+    Q.wide_warps = wide_warps;
     // CTAs (= SMs, one CTA fills an SM's shared memory) of one comparison's wave kernel; fewer than 148 lets the kernels of
     // concurrent comparisons run side by side so that the tail of one overlaps the bulk of another
     static const int wave_ctas = getenv("DAMAR_WAVE_CTAS") ? std::max(1, std::min(NUM_SMS_B200, atoi(getenv("DAMAR_WAVE_CTAS")))) : NUM_SMS_B200;
     static std::once_flag attr;
     std::call_once(attr, [] {
-        set_smem(wave_tasks<32, false, 4, 8>, WaveCfg<32, 8>::SMEM);
-        set_smem(wave_tasks<32, false, 4, 10>, WaveCfg<32, 10>::SMEM);
-        set_smem(wave_tasks<32, false, 4, 11>, WaveCfg<32, 11>::SMEM);
-        set_smem(wave_tasks<32, false, 4, 12>, WaveCfg<32, 12>::SMEM);
-        set_smem(wave_tasks<32, false, 4, 14>, WaveCfg<32, 14>::SMEM);
-        set_smem(wave_tasks<32, false, 3, 14>, WaveCfg<32, 14>::SMEM);
-        set_smem(wave_tasks<64, true, 4, 7>, WaveCfg<64, 7>::SMEM);
+        set_smem(wave_tasks<4, 8>, WaveCfg<8>::SMEM);
+        set_smem(wave_tasks<4, 10>, WaveCfg<10>::SMEM);
+        set_smem(wave_tasks<4, 12>, WaveCfg<12>::SMEM);
+        set_smem(wave_tasks<4, 13>, WaveCfg<13>::SMEM);
+        set_smem(wave_tasks<4, 14>, WaveCfg<14>::SMEM);
     });
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0;
@@ -1492,21 +1544,12 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                     radix_sort_pairs(k0, v0, k1, v1, nt, 24, st);
                     Q.task_order = v0;
                 }
-                if (nway == 3) wave_tasks<32, false, 3, 14><<<wb, 14 * 32, WaveCfg<32, 14>::SMEM, st>>>(Q);
-                else if (wwarps == 8) wave_tasks<32, false, 4, 8><<<wb, per, WaveCfg<32, 8>::SMEM, st>>>(Q);
-                else if (wwarps == 10) wave_tasks<32, false, 4, 10><<<wb, per, WaveCfg<32, 10>::SMEM, st>>>(Q);
-                else if (wwarps == 11) wave_tasks<32, false, 4, 11><<<wb, per, WaveCfg<32, 11>::SMEM, st>>>(Q);
-                else if (wwarps == 12) wave_tasks<32, false, 4, 12><<<wb, per, WaveCfg<32, 12>::SMEM, st>>>(Q);
-                else wave_tasks<32, false, 4, 14><<<wb, 14 * 32, WaveCfg<32, 14>::SMEM, st>>>(Q);
-                KERNEL_CHECK(); count_launch();
-            }
-            unsigned int nwide = 0;
-            CUDA_CHECK(cudaMemcpyAsync(&nwide, ctr.p + CTR_NWIDE, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-            CUDA_CHECK(stream_wait(st));
-            if (nwide > 0) {
-                const unsigned per = WaveCfg<64, 7>::WARPS * 32;
-                const unsigned wb = std::min<unsigned>(NUM_SMS_B200, (nwide + per - 1) / per);
-                wave_tasks<64, true, 4, 7><<<wb, per, WaveCfg<64, 7>::SMEM, st>>>(Q);
+                CUDA_CHECK(cudaMemsetAsync(wide_ready.p, 0, sizeof(uint32_t) * 2 * (size_t)ncand, st));
+                if (wwarps == 8) wave_tasks<4, 8><<<wb, per, WaveCfg<8>::SMEM, st>>>(Q);
+                else if (wwarps == 10) wave_tasks<4, 10><<<wb, per, WaveCfg<10>::SMEM, st>>>(Q);
+                else if (wwarps == 12) wave_tasks<4, 12><<<wb, per, WaveCfg<12>::SMEM, st>>>(Q);
+                else if (wwarps == 14) wave_tasks<4, 14><<<wb, per, WaveCfg<14>::SMEM, st>>>(Q);
+                else wave_tasks<4, 13><<<wb, per, WaveCfg<13>::SMEM, st>>>(Q);
                 KERNEL_CHECK(); count_launch();
             }
             c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;

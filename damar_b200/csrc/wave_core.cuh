@@ -124,6 +124,16 @@ struct Front {
     uint32_t *base;
     static constexpr int ARR = RING * STRIDE;                   // words between two arrays of one slot
     WC_HD uint32_t *slot(int k) const { return base + (k & (RING - 1)) * STRIDE; }
+    WC_HD int ring() const { return RING; }
+};
+
+// The same with the ring size chosen at run time: 32 lanes x 32 diagonals or 16 lanes x 64 diagonals occupy the same
+// 4 x 1024 words of a warp, so a warp can change between the two shapes (pair_align.cu::wave_tasks).
+struct FrontRT {
+    uint32_t *base; int rmask, sshift;                           // ring - 1, log2(threads that share the region)
+    static constexpr int ARR = 1024;
+    WC_HD uint32_t *slot(int k) const { return base + ((k & rmask) << sshift); }
+    WC_HD int ring() const { return rmask + 1; }
 };
 
 struct PathState { uint64_t T; uint32_t h; };
@@ -328,7 +338,7 @@ WC_HD void reach_candidate(Lane &L, const FRONT &F, int kc) {          // align.
 // End of a wave: boundary clipping (align.c:628-658, 943-975), pruning (:977-986), the loop test
 // (:667) and the widening of the next wave (:756-772).  Leaves the lane either finished
 // (status != ST_RUN) or positioned on k = hgh of the new wave.
-template <int RING, class FRONT>
+template <class FRONT>
 WC_HD void transition(Lane &L, const FRONT &F) {
     if (L.more == 0) {
         if (L.besty < L.blen && L.besta - L.besty < L.alen) L.more = 1;
@@ -367,7 +377,7 @@ WC_HD void transition(Lane &L, const FRONT &F) {
     if (!(L.more && L.lasta >= L.besta - TRIM_MLAG) || L.hgh < L.low) { L.status = ST_DONE; return; }
 
     int low = L.low - 1, hgh = L.hgh + 1;
-    if (hgh - low + 1 > RING) { L.status = ST_WIDE; return; }
+    if (hgh - low + 1 > F.ring()) { L.status = ST_WIDE; return; }
     if (low >= L.minp) F.slot(low)[F_V * FRONT::ARR] = (uint32_t)-1; else low += 1;
     if (hgh <= L.maxp) { F.slot(hgh)[F_V * FRONT::ARR] = (uint32_t)-1; L.vc = -1; }
     else { hgh -= 1; L.vc = (int32_t)F.slot(hgh)[F_V * FRONT::ARR]; }

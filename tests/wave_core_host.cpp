@@ -44,7 +44,7 @@ int run_pass(const TaskIn &t, const TrimTabs &tabs, HostPool &pool, TaskOut &out
     Lane L;
     setup(L, t, F, pool);
     while (L.status == ST_RUN) {
-        if (L.k < L.low) transition<RING>(L, F);
+        if (L.k < L.low) transition(L, F);
         if (L.status == ST_RUN && L.k >= L.low) {
             if (g_nway == 2) cellsN<2>(L, F, tabs, pool);
             else if (g_nway == 4) cellsN<4>(L, F, tabs, pool);
