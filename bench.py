@@ -48,6 +48,15 @@ WORKLOADS = {
                desc="5 Mbp x30 CLR-like, one block self-compare"),
     "small": dict(sim=["1.0", "-c20", "-r1", "-e.12"], split=10, root="S",
                   desc="1 Mbp x20, 2 blocks (smoke-sized)"),
+    # BASELINE configs[2]: ONE DB, its block pairs sharded over the GPUs of the box (strong scaling), shared blocks broadcast
+    # device to device over NCCL.  c3 = the configuration as named; c3q = the same plan shape (21 blocks, 231 pairs) at a
+    # quarter of the bases, for development runs.
+    "c3": dict(sim=["140", "-c30", "-r3", "-e.12", "-m10000", "-s2000", "-x4000"], split=200, root="D", sharded=True,
+               desc="Drosophila-scale 140 Mbp x30 (simulator.c model, 12% error), DBsplit -s200 -> 21 blocks, all 231 block pairs sharded over the GPUs"),
+    "c3q": dict(sim=["35", "-c30", "-r3", "-e.12", "-m10000", "-s2000", "-x4000"], split=50, root="Q", sharded=True,
+                desc="35 Mbp x30 (quarter-scale configs[2]), DBsplit -s50 -> 21 blocks, all 231 block pairs sharded over the GPUs"),
+    "c2s": dict(sim=["4.6", "-c60", "-r2", "-e.12", "-m10000", "-s2000", "-x4000"], split=70, root="E", sharded=True,
+                desc="configs[1] data (4 blocks, 10 block pairs) run as ONE sharded all-vs-all"),
 }
 DAL_FLAGS = dict(k=14, w=6, h=35, e=0.70, l=1000, s=100, M=32)
 
@@ -138,6 +147,50 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def roofline_lines(tm_alone, tm, dt, world, steps):
+    """roofline = the dominant HBM-bound kernel, os_pass (one digit pass of the one-sweep radix sort), measured alone
+    (tm_alone) and inside the timed steps (tm); stage4 = the kernel with the largest share of a step, wave_tasks, which is
+    bound by integer issue slots, not by HBM or tensor cores."""
+    peak, peak_src = peaks()
+    sc_ms, sc_el, sc_n, sc_b = tm_alone["scatter_ms"], tm_alone["scatter_elems"], tm_alone["scatter_launches"], tm_alone["scatter_bytes"]
+    alg_bytes = 32.0 * sc_el / max(sc_n, 1)                       # SURVEY 8d, per pass: 16 B read + 16 B write per record
+    achieved = (32.0 * sc_el) / (sc_ms / 1000.0) / 1e9 if sc_ms > 0 else 0.0
+    in_step = (32.0 * tm["scatter_elems"]) / (tm["scatter_ms"] / 1000.0) / 1e9 if tm["scatter_ms"] > 0 else 0.0
+    whole = tm_alone["sort_contract_bytes"] / (tm_alone["sort_ms"] / 1000.0) / 1e9 if tm_alone["sort_ms"] > 0 else 0.0
+    roofline = {"kernel": "os_pass (one-sweep radix sort: bulk-copy tile load, stable rank, look-back, scatter)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "measured": "CUDA events around every os_pass launch of the k-mer sorts of all blocks x orientations of the workload, "
+                            "run one at a time after the timed steps (same data, same kernels)",
+                "in_step": {"achieved": in_step, "frac": in_step / peak, "launches": tm["scatter_launches"],
+                            "avg_launch_ms": tm["scatter_ms"] / max(tm["scatter_launches"], 1),
+                            "share_of_step": (tm["scatter_ms"] / 1000.0) / dt if world == 1 else None,
+                            "note": "event intervals inside the timed steps, several comparisons in flight: a launch also waits for "
+                                    "SMs held by other comparisons' wave kernels"},
+                # records are ONE 8-byte word here (16 B read + written per element and pass); dram bytes per element from
+                # ncu --set full (profiles/r02_os_pass_ncu.txt): 8.1 read + 13.1 written (look-back words, partial sectors)
+                "traffic": 21.2 * sc_el / max(sc_n, 1), "traffic_source": "ncu --set full dram__bytes_read+write per element x elements per launch",
+                "moved_bytes_per_launch": sc_b / max(sc_n, 1),
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launches": sc_n, "avg_launch_ms": sc_ms / max(sc_n, 1),
+                "whole_sort": {"what": "histogram + scan + all passes of a k-mer sort against the contract bytes of SURVEY 8d "
+                                       "(16-byte records, 8-bit digits: 16 n (1 + 2 ceil(bits / 8)))",
+                               "achieved": whole, "frac": whole / peak, "elements": tm_alone["sort_elems"], "ms": tm_alone["sort_ms"]},
+                # device time the kernel needs for the elements it sorted inside the timed steps (k-mer AND seed-hit sorts),
+                # at the per-element rate measured alone, over the wall time of those steps: comparable with the kernel's
+                # share of the ncu launch list (profiles/), where every launch also runs alone
+                "share_of_step": ((sc_ms / max(sc_el, 1)) * tm["scatter_elems"] / 1000.0) / dt if world == 1 else None}
+    ak = tm["align_kernel_ms"] / 1000.0
+    stage4 = {"kernel": "wave_tasks (O(ND) wave extension, one thread per pass)", "bound": "integer issue (not HBM, no tensor cores)",
+              "wave_cells_per_step": tm["cells_total"] // max(steps, 1), "local_alignments_per_step": tm["la_total"] // max(steps, 1),
+              "wide_passes_per_step": tm["wide_total"] // max(steps, 1),
+              "kernel_ms_per_step_summed_over_comparisons": 1000 * ak / max(steps, 1),
+              "cells_per_s_per_launch": tm["cells_total"] / ak if ak > 0 else None,
+              "cells_per_s_of_step": tm["cells_total"] / dt if dt > 0 else None,
+              "note": "kernel_ms sums the event intervals of up to 6 concurrent comparisons, so cells_per_s_per_launch understates a launch "
+                      "running alone; issue-slot / lane figures of the kernel alone are in profiles/ (ncu --set full)"}
+    return roofline, stage4
+
+
 def ref_flags(threads: int):
     f = DAL_FLAGS
     return [f"-j{threads}", f"-k{f['k']}", f"-w{f['w']}", f"-h{f['h']}", f"-e{f['e']}", f"-l{f['l']}", f"-s{f['s']}", f"-M{f['M']}"]
@@ -179,6 +232,106 @@ def run_reference_job(dbdir: str, root: str, a: int, bs, threads: int, keep=None
     return novl, dt
 
 
+def main_sharded(args, rank, world, local_rank, cores, config, torch, dist, api, dbio):
+    """ONE DB, its block pairs sharded over the ranks (plan.shard_pairs), every block read by one owner rank and broadcast
+    PACKED, device to device, to the other ranks that need it (multi.exchange_blocks_device).  Strong scaling: the work is
+    fixed, value = overlaps of the whole all-vs-all / max-over-ranks time."""
+    from damar_b200 import multi
+    from damar_b200 import plan as planmod
+    device = f"cuda:{local_rank}"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        make_db(args.workload)
+    barrier()
+    dbdir, root, nblocks = make_db(args.workload)
+    s = api.Settings(kmer=DAL_FLAGS["k"], binshift=DAL_FLAGS["w"], hitmin=DAL_FLAGS["h"], ave_corr=DAL_FLAGS["e"],
+                     minlen=DAL_FLAGS["l"], trace_spacing=DAL_FLAGS["s"], mem_limit_gb=DAL_FLAGS["M"], nthreads=4)
+    shards = planmod.shard_pairs(nblocks, world)
+    owners = planmod.block_owners(shards)
+    host_blocks = {b: dbio.read_block(os.path.join(dbdir, f"{root}.{b}")) for b, (owner, _) in owners.items() if owner == rank}
+    h2d = sum(int(b.bases.nbytes + b.boff.nbytes + b.rlen.nbytes) for b in host_blocks.values())
+    for _ in range(max(1, args.warmup)):                           # whole passes incl. the exchange: NCCL groups, kernels, caches
+        multi.run_sharded(dbdir, root, nblocks, s, rank, world, dist=dist, device=device, host_blocks=host_blocks)
+    st = {}
+    resident = multi.exchange_blocks_device(dbdir, root, shards, rank, world, dist, device, host_blocks=host_blocks, stats=st)
+    sampler = ClockSampler(local_rank)
+    api.reset_kernel_timers()
+    l0 = api.timings()["kernel_launches"]
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    novl = 0
+    for _ in range(args.steps):
+        n, files = multi.run_sharded(dbdir, root, nblocks, s, rank, world, dist=dist, device=device, resident=resident)
+        novl += n
+    barrier()
+    dt = time.perf_counter() - t0
+    tm = api.timings()
+    launches = tm["kernel_launches"] - l0
+    for h in resident[1].values():
+        h.free()
+    barrier()
+    t1 = time.perf_counter()
+    novl_e, d2h = 0, 0
+    for _ in range(args.steps):
+        n, files = multi.run_sharded(dbdir, root, nblocks, s, rank, world, dist=dist, device=device, host_blocks=host_blocks)
+        novl_e += n
+        d2h = sum(files.values())
+    barrier()
+    dt_e = time.perf_counter() - t1
+    clocks = sampler.stop()
+    nvl = st.get("nvlink_bytes", 0)
+    if world > 1:
+        t = torch.tensor([dt, dt_e, float(novl), float(novl_e), float(launches), float(h2d), float(d2h), float(nvl)], dtype=torch.float64, device="cuda")
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dt, dt_e = float(tmax[0]), float(tmax[1])
+        novl, novl_e, launches = int(tsum[2]), int(tsum[3]), int(tsum[4])
+        h2d, d2h, nvl = int(tsum[5]), int(tsum[6]), int(tsum[7])
+    roofline, stage4 = roofline_lines(tm, tm, dt, world, args.steps)
+    roofline["measured"] = "CUDA events around every os_pass launch inside the timed steps of rank 0 (several comparisons in flight)"
+    config = dict(config, block_pairs=nblocks * (nblocks + 1) // 2, blocks=nblocks,
+                  pairs_per_rank=[sum(len(j.bs) for j in sh) for sh in shards],
+                  exchange="owner reads a block, packs it on its GPU and broadcasts the packed words device to device (NCCL) "
+                           "to the ranks that also need it")
+    line = {"metric": "daligner overlaps/s", "value": novl / dt, "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+            "e2e": {"value": novl_e / dt_e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1000 * dt_e / args.steps, "nvlink_bytes_per_step": nvl},
+            "all_vs_all": {"wall_ms": 1000 * dt_e / args.steps, "overlaps": novl_e // max(args.steps, 1), "n_gpus": world,
+                           "what": "whole all-vs-all from host buffers on the owner ranks to sorted .las images in host memory"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stage4": stage4,
+            "overlaps_per_step": novl // max(args.steps, 1)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:                                                     # bounded sample: one non-self block pair, byte-compared
+            P = pow2_floor(cores)
+            a, b = min(2, nblocks), 1
+            ref_files = {}
+            n_ref, t_ref = run_reference_job(dbdir, root, a, [b], P, keep=ref_files)
+            blks = {i: (host_blocks.get(i) or dbio.read_block(os.path.join(dbdir, f"{root}.{i}"))) for i in {a, b}}
+            got = api.daligner(blks[a], [blks[b]], s, as_bytes=False)
+            bad = [fn for fn, ref in ref_files.items() if fn not in got or api.las_compare(ref, got[fn]) != -1]
+            line["cpu_baseline"] = {"value": n_ref / t_ref, "unit": "overlaps/s", "cores": P, "kind": "reference",
+                                    "sample": f"reference `daligner -j{P} {root}.{a} {root}.{b}` (1 of {nblocks * (nblocks + 1) // 2} block pairs, "
+                                              f"{n_ref} overlaps in {t_ref:.1f} s) on {cores} host cores"}
+            line["parity"] = {"checked": True, "files": len(ref_files), "bytes": sum(len(v) for v in ref_files.values()),
+                              "overlaps": n_ref, "mismatches": bad[:8], "what": "the sampled block pair vs the reference daligner run on this host"}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "overlaps/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    if line.get("parity", {}).get("mismatches"):
+        sys.exit(3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,6 +356,9 @@ def main():
         dbdir, root, nblocks = make_db(args.workload)
         P = pow2_floor(cores)
         jobs = plan(nblocks)
+        if WORKLOADS[args.workload].get("sharded") and nblocks > 4:
+            # 231 block pairs of 200 Mbp blocks are hours of CPU: a step is ONE block pair, round-robin over a fixed sample
+            jobs = [(1, [1]), (2, [1]), (nblocks, [nblocks - 1]), (nblocks // 2, [nblocks // 2])]
         # A step is ONE job of the HPCdaligner plan, taken round-robin (step i runs job i mod J), so K steps cover the whole
         # plan K/J times and the run stays within a few minutes.  value = overlaps of the whole plan / sum of the mean wall
         # time of every job = the reference's throughput on the SAME workload the GPU arm runs per step.
@@ -215,6 +371,8 @@ def main():
         done = [j for j in range(len(jobs)) if cnt[j]]
         plan_s = sum(tsum[j] / cnt[j] for j in done)
         v = sum(nov[j] for j in done) / plan_s
+        if WORKLOADS[args.workload].get("sharded") and nblocks > 4:
+            config["reference_sample"] = "block pairs (1,1), (2,1), (n,n-1), (n/2,n/2) of the %d-pair plan, one per step" % (nblocks * (nblocks + 1) // 2)
         sample = (f"step i = job (i mod {len(jobs)}) of the {len(jobs)}-job plan (`daligner -j{P} {root}.a {root}.1 ... {root}.a`), "
                   f"{len(done)} of {len(jobs)} jobs sampled; whole plan = {nblocks * (nblocks + 1) // 2} block pairs, "
                   f"{sum(nov)} overlaps in {plan_s:.1f} s on {cores} host cores")
@@ -236,6 +394,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     api.init(local_rank)
+    if WORKLOADS[args.workload].get("sharded"):
+        return main_sharded(args, rank, world, local_rank, cores, config, torch, dist, api, dbio)
 
     dbdir, root, nblocks = make_db(args.workload, seed_shift=rank)
     blocks = {i: dbio.read_block(os.path.join(dbdir, f"{root}.{i}")) for i in range(1, nblocks + 1)}
@@ -250,6 +410,8 @@ def main():
         """All jobs of the plan.  resident=None -> blocks are uploaded inside (e2e)."""
         novl, d2h = 0, 0
         cache = dict(resident) if resident is not None else {}
+        for h in cache.values():
+            h.drop_indexes()                     # a step always sorts its k-mers: only the packed blocks stay resident
         files = api.daligner_plan([(blocks[a], [blocks[b] for b in bs]) for a, bs in jobs], s, dcache=cache, as_bytes=False)
         for v in files.values():
             novl += v.novl
@@ -359,34 +521,13 @@ def main():
     value = novl / dt
     e2e = novl_e / dt_e
 
-    peak, peak_src = peaks()
-    sc_ms, sc_el, sc_n = tm_alone["scatter_ms"], tm_alone["scatter_elems"], tm_alone["scatter_launches"]
-    alg_bytes = 32.0 * sc_el / max(sc_n, 1)                       # per launch: 16 B read + 16 B write per record
-    achieved = (32.0 * sc_el) / (sc_ms / 1000.0) / 1e9 if sc_ms > 0 else 0.0
-    in_step = (32.0 * tm["scatter_elems"]) / (tm["scatter_ms"] / 1000.0) / 1e9 if tm["scatter_ms"] > 0 else 0.0
-    roofline = {"kernel": "rs_scatter (radix sort pass: stable rank + scatter)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak,
-                "measured": "CUDA events around every rs_scatter launch of the k-mer sorts of all blocks x orientations of the workload, "
-                            "run one at a time after the timed steps (same data, same kernels)",
-                "in_step": {"achieved": in_step, "frac": in_step / peak, "launches": tm["scatter_launches"],
-                            "avg_launch_ms": tm["scatter_ms"] / max(tm["scatter_launches"], 1),
-                            "share_of_step": (tm["scatter_ms"] / 1000.0) / dt if world == 1 else None,
-                            "note": "event intervals inside the timed steps, several comparisons in flight: a launch also waits for "
-                                    "SMs held by other comparisons' wave kernels"},
-                # measured dram bytes per launch: 23.94 B/element (12 B SoA records in + out) in profiles/r01_rs_scatter_ncu.txt
-                "traffic": 23.94 * sc_el / max(sc_n, 1), "traffic_source": "ncu --set full dram__bytes_read+write per element x elements per launch",
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "launches": sc_n, "avg_launch_ms": sc_ms / max(sc_n, 1),
-                # device time the kernel needs for the elements it sorted inside the timed steps (k-mer AND seed-hit sorts),
-                # at the per-element rate measured alone, over the wall time of those steps: comparable with the kernel's
-                # share of the ncu launch list (profiles/), where every launch also runs alone
-                "share_of_step": ((sc_ms / max(sc_el, 1)) * tm["scatter_elems"] / 1000.0) / dt if world == 1 else None}
+    roofline, stage4 = roofline_lines(tm_alone, tm, dt, world, args.steps)
     line = {"metric": "daligner overlaps/s", "value": value, "unit": "overlaps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1000 * dt_e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stage4": stage4,
             "overlaps_per_step": novl // max(args.steps, 1) // max(world, 1),
             "device_event_ms_per_step_rank0": 1000 * dt_dev / args.steps,
             "align_kernel_ms_per_step": tm["align_kernel_ms"] / max(args.steps, 1)}

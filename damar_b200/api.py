@@ -36,6 +36,15 @@ class BlockDesc(C.Structure):
                 ("sizeof_db", C.c_int64), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
+class BlockView(C.Structure):
+    """damar_block_view: a resident block as device pointers (device-to-device transfer between ranks)."""
+    _fields_ = [("nreads", C.c_int32), ("maxlen", C.c_int32), ("ufirst", C.c_int32), ("part", C.c_int32),
+                ("totlen", C.c_int64), ("nbases", C.c_int64), ("sizeof_db", C.c_int64), ("freq", C.c_float * 4),
+                ("npacked_words", C.c_int64), ("packed", C.c_void_p), ("boff", C.c_void_p), ("rlen", C.c_void_p),
+                ("mask_len", C.c_int64), ("mask_anno", C.c_void_p), ("mask_data", C.c_void_p),
+                ("flags", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Options(C.Structure):
     _fields_ = [("verbose", C.c_int32), ("minover", C.c_int32), ("hgap_min", C.c_int32), ("symmetric", C.c_int32),
                 ("identity", C.c_int32), ("trace_spacing", C.c_int32), ("no_trace", C.c_int32),
@@ -58,7 +67,9 @@ class Timings(C.Structure):
                 ("wave_cells", C.c_int64), ("kernel_launches", C.c_int64),
                 ("scatter_ms", C.c_double), ("scatter_elems", C.c_int64), ("scatter_launches", C.c_int64),
                 ("align_kernel_ms", C.c_double), ("align_launches", C.c_int64), ("redo_pairs", C.c_int64),
-                ("redo_kernel_ms", C.c_double), ("scatter_bytes", C.c_int64)]
+                ("redo_kernel_ms", C.c_double), ("scatter_bytes", C.c_int64), ("wide_passes", C.c_int64),
+                ("sort_ms", C.c_double), ("sort_contract_bytes", C.c_int64), ("sort_elems", C.c_int64),
+                ("cells_total", C.c_int64), ("wide_total", C.c_int64), ("la_total", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -73,7 +84,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
            "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge",
-           "damar_las_compare", "damar_sort_selftest"]
+           "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view"]
 
 _lib = None
 
@@ -102,6 +113,9 @@ def load_library():
     L.damar_block_upload.restype = C.c_void_p
     L.damar_block_upload.argtypes = [C.POINTER(BlockDesc)]
     L.damar_block_free.argtypes = [C.c_void_p]
+    L.damar_block_view_get.argtypes = [C.c_void_p, C.POINTER(BlockView)]
+    L.damar_block_from_view.restype = C.c_void_p
+    L.damar_block_from_view.argtypes = [C.POINTER(BlockView)]
     L.damar_sort_kmers.restype = C.c_void_p
     L.damar_sort_kmers.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
     L.damar_index_free.argtypes = [C.c_void_p]
@@ -160,11 +174,20 @@ class Settings:
 
 
 class DeviceBlockHandle:
-    """A DB block resident in HBM (2-bit packed) plus its lazily built k-mer indexes."""
+    """A DB block resident in HBM (2-bit packed) plus the k-mer indexes built from it.
 
-    def __init__(self, blk: Block):
+    An index is built once per (orientation, k, -t) while the handle lives and shared by every comparison of a plan that
+    needs it (daligner.c rebuilds the B index in every job, 20 sorts for the 8 distinct block orientations of a 4-block plan);
+    drop_indexes() forgets them (bench.py does that at the start of every timed step, so a step always includes its sorts)."""
+
+    def __init__(self, blk: Optional[Block], handle: Optional[int] = None):
         L = load_library()
         self.blk = blk
+        self._idx: Dict[tuple, "Future"] = {}
+        self._idx_lock = threading.Lock()
+        if handle is not None:                               # adopted (damar_block_from_view)
+            self.handle, self._keep = handle, None
+            return
         self._keep = (np.ascontiguousarray(blk.bases, np.uint8), np.ascontiguousarray(blk.boff, np.int64),
                       np.ascontiguousarray(blk.rlen, np.int32),
                       None if blk.mask_anno is None else np.ascontiguousarray(blk.mask_anno, np.int64),
@@ -181,10 +204,57 @@ class DeviceBlockHandle:
             d.freq[i] = float(blk.freq[i])
         d.sizeof_db = blk.sizeof_db()
         self.handle = L.damar_block_upload(C.byref(d))
+        self._keep = None                                   # the library has its own (packed) copy now
         if not self.handle:
             raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
 
+    def view(self) -> "BlockView":
+        v = BlockView()
+        if load_library().damar_block_view_get(self.handle, C.byref(v)) != 0:
+            raise RuntimeError("damar_block_view_get failed")
+        return v
+
+    @classmethod
+    def from_view(cls, v: "BlockView", blk: Optional[Block] = None) -> "DeviceBlockHandle":
+        h = load_library().damar_block_from_view(C.byref(v))
+        if not h:
+            raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
+        return cls(blk, handle=h)
+
+    def index(self, comp: int, sig: tuple = ()) -> Optional["KmerIndex"]:
+        """The block's sorted k-mer list for orientation `comp` under the filter settings `sig`, built by the first caller
+        (on its worker context) and shared afterwards."""
+        from concurrent.futures import Future
+        key = (comp,) + tuple(sig)
+        with self._idx_lock:
+            fut = self._idx.get(key)
+            mine = fut is None
+            if mine:
+                fut = self._idx[key] = Future()
+        if mine:
+            try:
+                idx = sort_kmers(self, comp)
+                if idx is not None:
+                    idx.shared = True
+                fut.set_result(idx)
+            except BaseException as e:  # noqa: BLE001
+                with self._idx_lock:
+                    self._idx.pop(key, None)
+                fut.set_exception(e)
+                raise
+        return fut.result()
+
+    def drop_indexes(self):
+        with self._idx_lock:
+            futs, self._idx = list(self._idx.values()), {}
+        for f in futs:
+            idx = f.result() if f.done() and f.exception() is None else None
+            if idx is not None:
+                idx.shared = False
+                idx.free()
+
     def free(self):
+        self.drop_indexes()
         if self.handle:
             load_library().damar_block_free(self.handle)
             self.handle = None
@@ -193,6 +263,7 @@ class DeviceBlockHandle:
 class KmerIndex:
     def __init__(self, handle, length, dblock, comp):
         self.handle, self.len, self.dblock, self.comp = handle, length, dblock, comp
+        self.shared = False                                 # owned by the block handle's cache: free() is a no-op
 
     def download(self) -> np.ndarray:
         """Sorted list in the reference's KmerPos layout (for parity tests)."""
@@ -202,7 +273,7 @@ class KmerIndex:
         return out
 
     def free(self):
-        if self.handle:
+        if self.handle and not self.shared:
             load_library().damar_index_free(self.handle)
             self.handle = None
 
@@ -404,12 +475,15 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
         return dcache[b.name]
 
     J.da = da = resident(ablk)
-    J.aidx = aidx = sort_kmers(da, 0)
+    # -b fixes its base weights at the first Sort_Kmers of a job (filter.c:774): those lists are rebuilt per job like the reference does
+    sig = (s.kmer, s.suppress)
+    index_of = (lambda h, comp: sort_kmers(h, comp)) if s.biased else (lambda h, comp: h.index(comp, sig))
+    J.aidx = aidx = index_of(da, 0)
     inline = workers() == 1
 
     def compare(bblk, db, selfcmp, comp, sink, st):
         """one Match_Filter call (daligner.c:1041 / 1053) on the calling thread's worker context"""
-        bidx = aidx if (selfcmp and comp == 0) else sort_kmers(db, comp)
+        bidx = aidx if (selfcmp and comp == 0) else index_of(db, comp)
         ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
         sink.add(ov, comp)
         st[f"nhits{comp}"], st[f"nfilt{comp}"], st[f"novl{comp}"] = ov.nhits, ov.nfilt, ov.novl

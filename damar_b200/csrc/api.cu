@@ -294,6 +294,17 @@ damar_block *damar_block_upload(const damar_block_desc *desc) {
     return reinterpret_cast<damar_block *>(upload_block(desc));
 }
 void damar_block_free(damar_block *blk) { delete reinterpret_cast<DeviceBlock *>(blk); }
+int damar_block_view_get(damar_block *blk, damar_block_view *view) {
+    if (blk == nullptr || view == nullptr) return 1;
+    block_view(reinterpret_cast<DeviceBlock *>(blk), view);
+    return 0;
+}
+damar_block *damar_block_from_view(const damar_block_view *view) {
+    ensure_init();
+    if (view == nullptr || view->packed == nullptr || view->boff == nullptr || view->rlen == nullptr) { set_error("damar_block_from_view: incomplete view"); return nullptr; }
+    HostProf hp("block_from_view");
+    return reinterpret_cast<damar_block *>(block_from_view(view));
+}
 
 damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len) {
     ensure_init();
@@ -317,7 +328,7 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     g_hits_a = ab; g_hits_b = bb;
     memset(out, 0, sizeof(*out));
     c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
-    c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0;
+    c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0; c.tm.wide_passes = 0;
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
         ensure_revcomp(ab); ensure_revcomp(bb);               // the reverse wave pass runs on the reverse-complemented reads
         { HostProf hp("mf.seed_hits"); if (seed_hits(ai, bi, self, comp, g_hits) != 0) return 1; }
@@ -335,6 +346,7 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     out->ncheck = out->novl;
     out->limit = g_hits.limit;
     out->multi_la_pairs = (int32_t)g_out.multi;
+    c.tm.cells_total += g_out.cells; c.tm.wide_total += c.tm.wide_passes; c.tm.la_total += g_out.nfilt;
     c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
     c.tm.kernel_launches = c.launches;
     return 0;
@@ -417,18 +429,21 @@ void damar_dump_profile(void) { dump_profile(); }
 void damar_get_timings(damar_timings *t) {
     *t = ctx().tm;                                            // per-call fields of the calling worker ...
     t->kernel_launches = 0; t->scatter_ms = 0; t->scatter_elems = 0; t->scatter_launches = 0; t->scatter_bytes = 0;
+    t->sort_ms = 0; t->sort_contract_bytes = 0; t->sort_elems = 0; t->cells_total = 0; t->wide_total = 0; t->la_total = 0;
     t->align_kernel_ms = 0; t->align_launches = 0; t->redo_kernel_ms = 0;
     for (int i = 0; i < MAX_WORKERS; i++) {                   // ... accumulators summed over all workers
         const Context &c = g_ctx[i];
         t->kernel_launches += c.launches;
         t->scatter_ms += c.tm.scatter_ms; t->scatter_elems += c.tm.scatter_elems; t->scatter_launches += c.tm.scatter_launches; t->scatter_bytes += c.tm.scatter_bytes;
+        t->sort_ms += c.tm.sort_ms; t->sort_contract_bytes += c.tm.sort_contract_bytes; t->sort_elems += c.tm.sort_elems;
+        t->cells_total += c.tm.cells_total; t->wide_total += c.tm.wide_total; t->la_total += c.tm.la_total;
         t->align_kernel_ms += c.tm.align_kernel_ms; t->align_launches += c.tm.align_launches; t->redo_kernel_ms += c.tm.redo_kernel_ms;
     }
 }
 void damar_reset_kernel_timers(void) {
     for (int i = 0; i < MAX_WORKERS; i++) {
         damar_timings &t = g_ctx[i].tm;
-        t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.scatter_bytes = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
+        t.scatter_ms = 0; t.scatter_elems = 0; t.scatter_launches = 0; t.scatter_bytes = 0; t.sort_ms = 0; t.sort_contract_bytes = 0; t.sort_elems = 0; t.cells_total = 0; t.wide_total = 0; t.la_total = 0; t.align_kernel_ms = 0; t.align_launches = 0; t.redo_kernel_ms = 0;
     }
 }
 

@@ -195,6 +195,8 @@ void exclusive_scan_u32_inplace(uint32_t *data, int64_t n, uint32_t *total_dev, 
 
 // kmer_index.cu
 DeviceBlock *upload_block(const damar_block_desc *d);
+void block_view(DeviceBlock *b, damar_block_view *v);
+DeviceBlock *block_from_view(const damar_block_view *v);
 void ensure_revcomp(DeviceBlock *b);
 DeviceIndex *build_index(DeviceBlock *b, int comp);
 

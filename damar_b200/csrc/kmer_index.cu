@@ -371,6 +371,57 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
     return b;
 }
 
+// ---- device-to-device block transfer (damar_block_view, include/damar_b200.h) ----
+void block_view(DeviceBlock *b, damar_block_view *v) {
+    memset(v, 0, sizeof(*v));
+    v->nreads = b->nreads; v->maxlen = b->maxlen; v->ufirst = b->ufirst; v->part = b->part;
+    v->totlen = b->totlen; v->nbases = b->nbases; v->sizeof_db = b->sizeof_db;
+    memcpy(v->freq, b->freq, sizeof(v->freq));
+    v->npacked_words = b->npacked_words;
+    v->packed = b->packed[0] - PACK_FRONT_PAD; v->boff = b->boff; v->rlen = b->rlen;
+    v->mask_len = b->mask_len;
+    v->mask_anno = b->has_mask ? b->mask_anno[0] : nullptr;
+    v->mask_data = b->has_mask ? b->mask_data[0] : nullptr;
+    v->flags = b->as_is ? DAMAR_BLOCK_AS_IS : 0;
+}
+DeviceBlock *block_from_view(const damar_block_view *v) {
+    Context &c = ctx();
+    cudaStream_t st = c.stream;
+    DeviceBlock *b = new DeviceBlock();
+    b->nreads = v->nreads; b->maxlen = v->maxlen; b->ufirst = v->ufirst; b->part = v->part;
+    b->totlen = v->totlen; b->nbases = v->nbases; b->sizeof_db = v->sizeof_db;
+    memcpy(b->freq, v->freq, sizeof(b->freq));
+    b->as_is = (v->flags & DAMAR_BLOCK_AS_IS) != 0;
+    b->npacked_words = v->npacked_words;
+    uint32_t *pk = (uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (b->npacked_words + PACK_FRONT_PAD));
+    CUDA_CHECK(cudaMemcpyAsync(pk, v->packed, sizeof(uint32_t) * (b->npacked_words + PACK_FRONT_PAD), cudaMemcpyDeviceToDevice, st));
+    b->packed[0] = pk + PACK_FRONT_PAD;
+    b->boff = (uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (b->nreads + 1));
+    b->rlen = (int32_t *)dev_alloc_bytes(sizeof(int32_t) * (b->nreads + 1));
+    CUDA_CHECK(cudaMemcpyAsync(b->boff, v->boff, sizeof(uint32_t) * (b->nreads + 1), cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(b->rlen, v->rlen, sizeof(int32_t) * b->nreads, cudaMemcpyDeviceToDevice, st));
+    std::vector<uint32_t> hb((size_t)b->nreads + 1);
+    b->h_rlen.resize((size_t)b->nreads);
+    CUDA_CHECK(cudaMemcpyAsync(hb.data(), b->boff, sizeof(uint32_t) * (b->nreads + 1), cudaMemcpyDeviceToHost, st));
+    if (b->nreads) CUDA_CHECK(cudaMemcpyAsync(b->h_rlen.data(), b->rlen, sizeof(int32_t) * b->nreads, cudaMemcpyDeviceToHost, st));
+    {
+        const int64_t nt = (b->nbases >> RTAB_SHIFT) + 1;
+        b->rtab = (uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * nt);
+        build_rtab<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(b->boff, b->nreads, b->nbases, b->rtab, nt);
+        KERNEL_CHECK(); count_launch();
+    }
+    if (v->mask_anno != nullptr) {
+        b->has_mask = true; b->mask_len = v->mask_len;
+        b->mask_anno[0] = (int64_t *)dev_alloc_bytes(sizeof(int64_t) * (b->nreads + 1));
+        b->mask_data[0] = (int32_t *)dev_alloc_bytes(sizeof(int32_t) * (b->mask_len + 1));
+        CUDA_CHECK(cudaMemcpyAsync(b->mask_anno[0], v->mask_anno, sizeof(int64_t) * (b->nreads + 1), cudaMemcpyDeviceToDevice, st));
+        if (b->mask_len > 0) CUDA_CHECK(cudaMemcpyAsync(b->mask_data[0], v->mask_data, sizeof(int32_t) * b->mask_len, cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_CHECK(stream_wait(st));
+    b->h_boff.assign(hb.begin(), hb.end());
+    return b;
+}
+
 void ensure_revcomp(DeviceBlock *b) {
     static std::mutex mu;                        // several workers may want the same block's complement at once
     std::lock_guard<std::mutex> lock(mu);

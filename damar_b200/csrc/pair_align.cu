@@ -1489,7 +1489,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
         set_smem(wave_tasks<4, 14>, WaveCfg<14>::SMEM);
     });
 
-    unsigned int nredo = 0; unsigned long long nrec_fast = 0;
+    unsigned int nredo = 0; unsigned long long nrec_fast = 0; int64_t nwide_total = 0;
     DevBuf<uint8_t> dead; DevBuf<uint64_t> hr_keys; DevBuf<uint32_t> hr_vals, hr_pool; DevBuf<unsigned long long> hr_top;
     bool have_dead = false;
     unsigned long long rec_cap = 4 * nactive + 1024;
@@ -1544,7 +1544,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                     radix_sort_pairs(k0, v0, k1, v1, nt, 24, st);
                     Q.task_order = v0;
                 }
-                CUDA_CHECK(cudaMemsetAsync(wide_ready.p, 0, sizeof(uint32_t) * 2 * (size_t)ncand, st));
+                CUDA_CHECK(cudaMemsetAsync(wide_ready.p, 0, sizeof(uint32_t) * 2 * na, st));   // all of it: tickets run past this round's parks
                 if (wwarps == 8) wave_tasks<4, 8><<<wb, per, WaveCfg<8>::SMEM, st>>>(Q);
                 else if (wwarps == 10) wave_tasks<4, 10><<<wb, per, WaveCfg<10>::SMEM, st>>>(Q);
                 else if (wwarps == 12) wave_tasks<4, 12><<<wb, per, WaveCfg<12>::SMEM, st>>>(Q);
@@ -1553,6 +1553,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                 KERNEL_CHECK(); count_launch();
             }
             c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
+            { unsigned int nw = 0; CUDA_CHECK(cudaMemcpyAsync(&nw, ctr.p + CTR_NWIDE, sizeof(nw), cudaMemcpyDeviceToHost, st)); CUDA_CHECK(stream_wait(st)); nwide_total += nw; }
             const unsigned fb = (unsigned)std::min<uint64_t>((uint64_t)sblocks, ((uint64_t)ncand + 7) / 8);
             finish_las<<<fb, 256, 0, st>>>(Q);
             KERNEL_CHECK(); count_launch();
@@ -1665,6 +1666,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     const void *trace_out = h_trace.p;
     out.ovl = h_recs.p; out.toff = h_toff.p; out.seq = h_seq.p; out.trace = trace_out;
     out.novl = (int64_t)nkeep; out.ntrace = (int64_t)ntr_out; out.tbytes = tbytes; out.redo = (int64_t)nredo;
+    c.tm.wide_passes = nwide_total;
     out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)nwork;
     c.tm.download_ms = t_dl.stop();
     (void)rounds;

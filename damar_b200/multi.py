@@ -81,14 +81,106 @@ def exchange_blocks(dbdir: str, root: str, shards: Sequence[Sequence[Job]], rank
     return mine
 
 
+class _DevArray:
+    """A device buffer of the library seen as a CUDA array (zero copy), so torch.distributed can broadcast it."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def exchange_blocks_device(dbdir: str, root: str, shards: Sequence[Sequence[Job]], rank: int, world: int, dist, device: str,
+                           masks: Optional[List[str]] = None,
+                           loader: Callable[[str, Optional[List[str]]], dbio.Block] = dbio.read_block,
+                           host_blocks: Optional[Dict[int, dbio.Block]] = None, stats: Optional[dict] = None):
+    """GPU path of exchange_blocks: the owner reads a block (or takes it from `host_blocks`), ships it to its HBM where it is
+    packed to 2 bit/base, and broadcasts the PACKED words + read offsets / lengths (+ mask) device to device over NCCL, in a
+    group of exactly the ranks that need the block; receivers adopt the buffers (damar_block_from_view).  Nothing unpacked
+    crosses NVLink and nothing bounces through a host.  Returns ({block number: metadata Block}, {block name: handle})."""
+    import torch
+    from . import api
+    owners = block_owners(shards)
+    meta: Dict[int, dbio.Block] = {}
+    handles: Dict[str, api.DeviceBlockHandle] = {}
+    sent = 0
+    for b, (owner, ranks) in owners.items():
+        name = f"{root}.{b}"
+        blk, h = None, None
+        if rank == owner:
+            blk = host_blocks[b] if host_blocks is not None else loader(os.path.join(dbdir, name), masks)
+            h = api.DeviceBlockHandle(blk)
+        if len(ranks) > 1 and world > 1:
+            group = _group_for(dist, ranks, world)           # every rank must create every group
+            if rank in ranks:
+                if rank == owner:
+                    v = h.view()
+                    m = torch.tensor([v.nreads, v.maxlen, v.ufirst, v.part, v.totlen, v.nbases, v.sizeof_db, v.npacked_words,
+                                      v.mask_len, int(bool(v.mask_anno)), v.flags, blk.ureads], dtype=torch.int64, device=device)
+                    fq = torch.tensor([float(x) for x in v.freq], dtype=torch.float64, device=device)
+                else:
+                    m = torch.zeros(12, dtype=torch.int64, device=device)
+                    fq = torch.zeros(4, dtype=torch.float64, device=device)
+                dist.broadcast(m, src=owner, group=group)
+                dist.broadcast(fq, src=owner, group=group)
+                mm = [int(x) for x in m.cpu()]
+                nreads, npw, mask_len, has_mask = mm[0], mm[7], mm[8], mm[9]
+                spec = [("packed", torch.int32, "<i4", npw + 4), ("boff", torch.int32, "<i4", nreads + 1), ("rlen", torch.int32, "<i4", nreads)]
+                if has_mask:
+                    spec += [("mask_anno", torch.int64, "<i8", nreads + 1), ("mask_data", torch.int32, "<i4", max(mask_len, 1))]
+                bufs = {}
+                for nm, dt, ts, n in spec:
+                    if rank == owner:
+                        ptr = getattr(v, nm)
+                        t = torch.as_tensor(_DevArray(ptr, n, ts), device=device) if ptr else torch.zeros(n, dtype=dt, device=device)
+                    else:
+                        t = torch.empty(n, dtype=dt, device=device)
+                    dist.broadcast(t, src=owner, group=group)
+                    sent += t.numel() * t.element_size()
+                    bufs[nm] = t
+                torch.cuda.synchronize()
+                if rank != owner:
+                    nv = api.BlockView()
+                    nv.nreads, nv.maxlen, nv.ufirst, nv.part, nv.totlen, nv.nbases, nv.sizeof_db, nv.npacked_words = mm[:8]
+                    nv.mask_len, nv.flags = mask_len, mm[10]
+                    fqh = fq.cpu()
+                    for i in range(4):
+                        nv.freq[i] = float(fqh[i])
+                    nv.packed, nv.boff, nv.rlen = bufs["packed"].data_ptr(), bufs["boff"].data_ptr(), bufs["rlen"].data_ptr()
+                    if has_mask:
+                        nv.mask_anno, nv.mask_data = bufs["mask_anno"].data_ptr(), bufs["mask_data"].data_ptr()
+                    rl = bufs["rlen"].cpu().numpy().astype(np.int32)
+                    bo = bufs["boff"].cpu().numpy().astype(np.uint32).astype(np.int64)
+                    blk = dbio.Block(name=name, root=root, path=os.path.join(dbdir, "." + root), part=mm[3], ufirst=mm[2],
+                                     nreads=nreads, maxlen=mm[1], totlen=mm[4], ureads=mm[11],
+                                     freq=np.asarray([float(x) for x in fqh], np.float32), rlen=rl, boff=bo, bases=None,
+                                     track_names=list(masks or []))
+                    h = api.DeviceBlockHandle.from_view(nv, blk)
+                del bufs
+        if rank in ranks:
+            meta[b] = blk
+            handles[name] = h
+    if stats is not None:
+        stats["nvlink_bytes"] = stats.get("nvlink_bytes", 0) + sent
+    return meta, handles
+
+
 def run_sharded(dbdir: str, root: str, nblocks: int, settings, rank: int, world: int, dist=None, device: str = "cpu",
-                outdir: Optional[str] = None, masks: Optional[List[str]] = None):
-    """All-vs-all of a DB over `world` GPUs.  Returns (number of overlaps written by this rank, files)."""
+                outdir: Optional[str] = None, masks: Optional[List[str]] = None, resident=None, stats: Optional[dict] = None,
+                host_blocks: Optional[Dict[int, dbio.Block]] = None):
+    """All-vs-all of a DB over `world` GPUs.  Returns (number of overlaps written by this rank, files).
+    resident = (metadata blocks, handles) of an earlier exchange keeps the blocks in HBM across calls."""
     from . import api
     sizes = None
     shards = shard_pairs(nblocks, world, sizes)
-    blocks = exchange_blocks(dbdir, root, shards, rank, world, dist, device, masks)
-    cache: Dict[str, api.DeviceBlockHandle] = {}
+    own_cache = resident is None
+    if resident is not None:
+        blocks, cache = resident
+        for h in cache.values():
+            h.drop_indexes()
+    elif str(device).startswith("cuda"):
+        blocks, cache = exchange_blocks_device(dbdir, root, shards, rank, world, dist, device, masks, host_blocks=host_blocks, stats=stats)
+    else:
+        blocks = exchange_blocks(dbdir, root, shards, rank, world, dist, device, masks)
+        cache = {}
     novl, files = 0, {}
     def finish(pending):
         nonlocal novl
@@ -106,6 +198,7 @@ def run_sharded(dbdir: str, root: str, nblocks: int, settings, rank: int, world:
         pend = nxt
     if pend is not None:
         finish(pend)
-    for h in cache.values():
-        h.free()
+    if own_cache:
+        for h in cache.values():
+            h.free()
     return novl, files

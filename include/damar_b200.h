@@ -123,6 +123,26 @@ void damar_set_biased(int biased);
 damar_block *damar_block_upload(const damar_block_desc *desc);
 void         damar_block_free(damar_block *blk);
 
+/* A resident block as device pointers, for device-to-device transfer between the GPUs of one box (the multi-GPU driver
+ * broadcasts the PACKED block -- 2 bit/base -- over NCCL instead of shipping the unpacked bases through the host).
+ * damar_block_view_get fills the view of a resident block (pointers stay owned by the block); damar_block_from_view
+ * builds a new resident block from device buffers laid out the same way (device-to-device copies, no host bounce).     */
+typedef struct damar_block_view {
+    int32_t  nreads, maxlen, ufirst, part;
+    int64_t  totlen, nbases, sizeof_db;
+    float    freq[4];
+    int64_t  npacked_words;   /* 32-bit words of packed bases, the 4 zero words of front padding NOT counted           */
+    void    *packed;          /* device: uint32[4 + npacked_words], front padding included                             */
+    void    *boff;            /* device: uint32[nreads + 1]                                                            */
+    void    *rlen;            /* device: int32[nreads]                                                                 */
+    int64_t  mask_len;        /* number of int32 in mask_data; mask_anno == NULL: no mask                               */
+    void    *mask_anno;       /* device: int64[nreads + 1]                                                             */
+    void    *mask_data;       /* device: int32[mask_len]                                                               */
+    int32_t  flags, reserved;
+} damar_block_view;
+int          damar_block_view_get(damar_block *blk, damar_block_view *view);
+damar_block *damar_block_from_view(const damar_block_view *view);
+
 /* Sort_Kmers (filter.c:753-994).  comp != 0 builds the index of the reverse-complemented block
  * (what daligner.c:998-1003 obtains with complement_DB + Sort_Kmers) without touching host memory.
  * *len receives the k-mer count; NULL/0 when the block has no k-mers.                          */
@@ -166,6 +186,11 @@ typedef struct damar_timings {
     int64_t redo_pairs;          /* pairs whose wave front outgrew one warp (strided second pass) */
     double  redo_kernel_ms;      /* accumulated like align_kernel_ms */
     int64_t scatter_bytes;       /* bytes the sort passes moved (read + write), accumulated like scatter_ms */
+    int64_t wide_passes;         /* last call: wave passes whose front outgrew 32 diagonals (parked and resumed by a wide lane) */
+    /* accumulated since damar_reset_kernel_timers(): whole sorts (histogram + scan + passes) and the contract bytes of
+     * SURVEY section 8d for them (16-byte records, 8-bit digits: 16 n (1 + 2 ceil(bits / 8))); wave cells and passes */
+    double  sort_ms; int64_t sort_contract_bytes; int64_t sort_elems;
+    int64_t cells_total, wide_total, la_total;
 } damar_timings;
 /* The device radix sort on its own (stage 1 / stage 2 sorts, filter.c:230-435): n pseudo-random keys are sorted stably on
  * bits [lo_bit, hi_bit) (with a u32 payload when has_vals), `reps` times, and the result is checked ON THE DEVICE for order,

@@ -30,6 +30,11 @@ with open(os.path.join(GRAM, "cases.json")) as f:
     GRAM_CASES = json.load(f)
 
 
+LONG = os.path.join(GOLDEN, "long")        # reads of 34-86 kbp at 15 % error, -e.65 (tests/golden/make_long.py)
+with open(os.path.join(LONG, "cases.json")) as f:
+    LONG_CASES = json.load(f)
+
+
 def parse_flags(flags):
     """daligner flags -> dict(k,w,h,t,e,l,s,j,M,masks,I,O,A,T) (daligner.c:721-808)."""
     o = dict(k=14, w=6, h=35, t=0, e=0.70, l=1000, s=100, j=4, M=None, masks=[], I=False, O=False, A=False, T=False, b=False)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, GRAM, GRAM_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, GRAM, GRAM_CASES, LONG, LONG_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
 from damar_b200 import api, dbio
 
 pytestmark = pytest.mark.gpu
@@ -102,6 +102,59 @@ def test_las_matches_reference_on_repeats(case):
         assert stats[0]["t0"]["hits"] < 100000          # the shared element's k-mers were capped ...
     if case == "gram_M0":
         assert stats[0]["t0"]["hits"] > 3000000         # ... and are all there without the cap
+
+
+@pytest.mark.parametrize("case", sorted(LONG_CASES))
+def test_las_matches_reference_on_long_reads(case):
+    """Reads of 34-86 kbp at 15 % error with -e.65 (configs[3] in miniature, reference binary's files): every pair is cut
+    into several A-panels (filter.c:2251-2266), passes outgrow the 32-diagonal ring (parked and resumed by a wide lane) and
+    some the 64-diagonal one (the pair is redone by the strided warp kernel)."""
+    o = parse_flags(LONG_CASES[case]["flags"])
+    blk = load_block(LONG, "L.1", ())
+    assert int(blk.rlen.max()) > 50000 + 10000                  # more than one panel
+    stats = []
+    out = api.daligner(blk, [blk], settings(o), stats=stats)
+    gold = golden_files(case, LONG)
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+    wide = sum(st[f"t{c}"]["wide_passes"] for st in stats for c in (0, 1))
+    redo = sum(st[f"t{c}"]["redo_pairs"] for st in stats for c in (0, 1))
+    print(f"{case}: wide passes {wide}, pairs redone by the strided kernel {redo}")
+    assert wide > 0
+
+
+def test_midsize_block_pair_matches_reference():
+    """One non-self block pair of the bench workload (BASELINE configs[1]: two 70 Mbp blocks, ~276 k overlaps in four .las
+    files) against the reference daligner run on this host, byte for byte."""
+    import shutil
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    exe = os.path.join(ROOT, "oracle", "_ref", "daligner")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/daligner was not built (needs /root/reference at build time)")
+    dbdir, root, nblocks = bench.make_db("c2")
+    blks = [dbio.read_block(os.path.join(dbdir, f"{root}.{i}")) for i in (1, 2)]
+    s = api.Settings(mem_limit_gb=32)
+    out = api.daligner(blks[1], [blks[0]], s, as_bytes=False)
+    for d in os.listdir(dbdir):
+        if d.startswith("d001_"):
+            shutil.rmtree(os.path.join(dbdir, d))
+    subprocess.run([exe, f"-j{bench.pow2_floor(os.cpu_count() or 1)}", "-M32", f"{root}.2", f"{root}.1"], cwd=dbdir, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    n = 0
+    for fn, im in out.items():
+        part = int(fn.split(".")[1])
+        ref = open(os.path.join(dbdir, f"d001_{part:05d}", fn), "rb").read()
+        assert api.las_compare(ref, im) == -1, fn
+        n += im.novl
+    assert n > 200000
+    for d in os.listdir(dbdir):
+        if d.startswith("d001_"):
+            shutil.rmtree(os.path.join(dbdir, d))
 
 
 def test_unpacked_records_give_the_same_files():

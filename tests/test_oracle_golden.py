@@ -4,7 +4,7 @@ The golden files were written by the UNMODIFIED reference binary (tests/golden/m
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GRAM, GRAM_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GRAM, GRAM_CASES, LONG, LONG_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags
 from damar_b200 import dbio
 
 
@@ -66,6 +66,19 @@ def test_oracle_matches_reference_on_repeats(case):
     gold = golden_files(case, GRAM)
     assert sorted(out) == sorted(gold)
     for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why}"
+
+
+@pytest.mark.parametrize("case", sorted(LONG_CASES))
+def test_oracle_matches_reference_on_long_reads(case):
+    """Nanopore-like reads (34-86 kbp, 15 % error, -e.65): several A-panels per pair (filter.c:2251-2266) and wave fronts
+    of more than 64 diagonals (tests/golden/make_long.py)."""
+    from test_path_fuse import oracle_daligner_fused
+    o = parse_flags(LONG_CASES[case]["flags"])
+    blk = load_block(LONG, "L.1", ())
+    out, _ = oracle_daligner_fused(blk, [blk], oracle_kwargs(o), fuse=True)
+    for fn, ref in golden_files(case, LONG).items():
         ok, why = dbio.las_equal(ref, out[fn])
         assert ok, f"{case}/{fn}: {why}"
 
