@@ -108,6 +108,8 @@ struct AlignArgs {
     int afirst, bfirst;
     // parameters
     int K, W, H, minhit, TS, minover, comp, self, symmetric;
+    int reach;                         // Align_Spec.reach: 1 for daligner (daligner.c:951), 0 for datander (datander.c:246)
+    int tandem;                        // datander's report_thread (scrub/tandem.c:895): panels over apos, every read, A records only
     int ave_path, dscore; const int16_t *score_tab, *table_tab;
     // per-warp scratch
     int ring;                          // power of two
@@ -169,7 +171,7 @@ struct WarpLA {
     int4 *cells; int cells_cap; int ncell;
     int rmask;
     const int16_t *score_tab, *table_tab;
-    int TS, PATH_AVE;
+    int TS, PATH_AVE, reach;
     int overflow;
     unsigned long long ncells_done;
 };
@@ -407,7 +409,7 @@ __device__ void wave_pass(WarpLA &S, const uint32_t *__restrict__ aw, int64_t ab
         if (S.overflow) break;
     }
 
-    if (morem >= 0) { ex = morea - morey; ey = morey; ediff = mored; eha = moreha; ehb = morehb; }   // REACH = 1 (daligner.c:951)
+    if (morem >= 0 && S.reach) { ex = morea - morey; ey = morey; ediff = mored; eha = moreha; ehb = morehb; }   // REACH (align.c:1009)
     else { ex = trima - trimy; ey = trimy; ediff = trimd; eha = trimha; ehb = trimhb; }
 }
 
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
         S.NA = P.NA + (size_t)gw * r; S.NB = P.NB + (size_t)gw * r;
         S.cells = P.cells + (size_t)gw * P.cells_cap; S.cells_cap = P.cells_cap; S.ncell = 0;
         S.rmask = P.ring - 1; S.score_tab = P.score_tab; S.table_tab = P.table_tab;
-        S.TS = P.TS; S.PATH_AVE = P.ave_path; S.overflow = 0; S.ncells_done = 0;
+        S.TS = P.TS; S.PATH_AVE = P.ave_path; S.reach = P.reach; S.overflow = 0; S.ncells_done = 0;
     }
     uint16_t *tbuf = P.tbuf + (size_t)gw * 8 * P.maxtp;
     int32_t *score = P.bscore + (size_t)gw * 2 * P.nbuck - P.dmin + 2;   // +2 margin for d-1
@@ -710,7 +712,7 @@ struct PipeArgs {
     uint32_t *flag;                       // filter_pairs: per work pair
     uint32_t *cand0;                      // filter_pairs: the pair's first seed candidate, as an offset from the pair's first hit
     unsigned int *ctr;                    // device counters, see CTR_*
-    uint32_t *wide_list, *wide_ready; unsigned int wide_cap; int wide_warps;
+    uint32_t *wide_list, *wide_ready; unsigned int wide_cap; int wide_ctas;
     wc::Lane *wide_lane; uint32_t *wide_ring;   // state of the passes that outgrew the 32-diagonal ring: [task][32][FRONT_WORDS]
     const uint32_t *task_order;           // tasks of the round, longest expected pass first (or null: index order)
     wc::Cell *pool; unsigned int pool_cap;
@@ -941,10 +943,9 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) { return 
 // Task t of [0, 2 * ncand) = pass (t & 1) of alignment t >> 1.  A warp works in one of two SHAPES on the same 16 KB of
 // shared memory: NARROW -- 32 lanes, a 32-diagonal ring each, tasks drawn from the round's queue -- or WIDE -- 16 lanes, a
 // 64-diagonal ring each, resuming the passes that narrow lanes had to PARK because their front outgrew 32 diagonals
-// (state + ring copied to global memory, a ready flag raised).  `wide_warps` warps of every CTA are wide from the start,
-// so a parked pass continues within microseconds while the bulk of the round is still running; a narrow warp turns wide
-// when the queue is empty.  (Round 1 ran the parked passes in a second kernel after the first: 2 % of the passes, on 15
-// SMs, for a quarter of the stage's time.)  A wide lane leaves when every task has left the narrow queue's lanes
+// (state + ring copied to global memory, a ready flag raised).  A few CTAs of a launch are wide from the start, so a parked
+// pass continues within microseconds while the bulk of the round is still running, and the narrow CTAs leave as soon as
+// the queue is empty.  (Round 1 ran the parked passes in a second kernel after the first, with a host wait in between.)  A wide lane leaves when every task has left the narrow queue's lanes
 // (CTR_RETIRED == number of tasks: no pass can be parked any more) and no parked pass is unclaimed.
 template <int NWAY, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
@@ -967,7 +968,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     L.status = wc::ST_IDLE; L.k = 0; L.low = 0;
     unsigned task = 0;
     unsigned long long cells_done = 0;
-    bool wide = wib >= WARPS - Q.wide_warps;                  // warp-uniform; a narrow warp turns wide once, never back
+    // Warp-uniform shape.  The first wide_ctas CTAs are wide from the start (every warp); the others are narrow and LEAVE
+    // when the queue is empty, so their SMs go to the next kernel (another comparison's, usually) while the last parked
+    // passes finish on a few SMs.  A grid too small to set wide CTAs aside lets its narrow warps turn wide at the end.
+    const bool linger = Q.wide_ctas == 0;
+    bool wide = (int)blockIdx.x < Q.wide_ctas;
     wc::FrontRT F = wide ? wc::FrontRT{region + (lane & 15), 63, 4} : wc::FrontRT{region + lane, 31, 5};
     if (wide && lane >= 16) L.status = wc::ST_EXIT;
     unsigned await = 0;
@@ -1019,14 +1024,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
                     const bool selfie = P.self && !P.comp && ar == br;                       // align.c:1949
                     in.minp = (selfie && in.diag >= 0) ? 1 : -IMAX;                          // align.c:1951-1968
                     in.maxp = (selfie && in.diag <= 0) ? -1 : IMAX;
-                    in.TS = P.TS; in.path_ave = P.ave_path;
+                    in.TS = P.TS; in.path_ave = P.ave_path; in.reach = P.reach;
                     wc::setup(L, in, F, pool);
                 }
             }
-            if (__all_sync(FULL, L.status == wc::ST_EXIT)) {      // the queue is empty: help with the parked passes
+            if (__all_sync(FULL, L.status == wc::ST_EXIT)) {      // the queue is empty
                 __threadfence();                                  // this lane's parked passes are visible before its tasks count as retired
                 if (retired) atomicAdd(&Q.ctr[CTR_RETIRED], retired);
                 __syncwarp();
+                if (!linger) break;                               // the wide CTAs take care of the parked passes
                 wide = true;
                 F = wc::FrontRT{region + (lane & 15), 63, 4};
                 L.status = (lane < 16) ? wc::ST_IDLE : wc::ST_EXIT;
@@ -1473,10 +1479,9 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
-    // warps per CTA of the wave kernel (16 KB of shared memory each), `wide_warps` of them in the 64-diagonal shape from the start
-    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 13;
-    static const int wide_warps = getenv("DAMAR_WIDE_WARPS") ? std::max(0, std::min(4, atoi(getenv("DAMAR_WIDE_WARPS")))) : 1;
-    Q.wide_warps = wide_warps;
+    // warps per CTA of the wave kernel (16 KB of shared memory each)
+    static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 12;
+    static const int wide_ctas_max = getenv("DAMAR_WIDE_CTAS") ? std::max(0, std::min(64, atoi(getenv("DAMAR_WIDE_CTAS")))) : 12;
     // CTAs (= SMs, one CTA fills an SM's shared memory) of one comparison's wave kernel; fewer than 148 lets the kernels of
     // concurrent comparisons run side by side so that the tail of one overlaps the bulk of another
     static const int wave_ctas = getenv("DAMAR_WAVE_CTAS") ? std::max(1, std::min(NUM_SMS_B200, atoi(getenv("DAMAR_WAVE_CTAS")))) : NUM_SMS_B200;
@@ -1534,7 +1539,10 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
             Timer t_k(st);
             {
                 const unsigned per = (unsigned)wwarps * 32;
-                const unsigned wb = std::min<unsigned>((unsigned)wave_ctas, (2 * ncand + per - 1) / per);
+                unsigned wb = std::min<unsigned>((unsigned)wave_ctas, (2 * ncand + per - 1) / per);
+                // a full-size launch sets a few CTAs aside for the parked (wide) passes: ~2 % of the passes, but long ones
+                Q.wide_ctas = (wb >= 64) ? std::min<int>(wide_ctas_max, (int)wb / 8) : 0;
+                wb = std::min<unsigned>((unsigned)NUM_SMS_B200, wb + (unsigned)Q.wide_ctas);
                 Q.task_order = nullptr;
                 if (ncand >= 2048 && lpt) {                      // order the queue: longest passes first
                     const int64_t nt = 2 * (int64_t)ncand;

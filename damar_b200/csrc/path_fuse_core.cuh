@@ -353,7 +353,7 @@ PF_HD inline bool compute_bridge_path(const Path &path1, const Path &path2, Path
 // or -1 when the arena ran dry (the lists are then unusable).
 template <class SEQ, class ALLOC>
 PF_HD inline int handle_redundancies(Path *am, Path *bm, int novls, int comp, int ts, const SEQ &aseq, int alen, const SEQ &bseq, int blen,
-                                     ALLOC &al) {
+                                     ALLOC &al, bool do_bridge = true) {
     const bool hasB = (bm != nullptr);
     int awhen = 0, bwhen = 0, dist;
 
@@ -418,7 +418,8 @@ PF_HD inline int handle_redundancies(Path *am, Path *bm, int novls, int comp, in
     }
 
     // alignments with a narrow parallel overlap: bridge them with an exact realignment of the crossing
-    for (int j = 1; j < novls; j++) {
+    // (datander's Handle_Redundancies, scrub/tandem.c:767-850, is the loop above alone: do_bridge == false)
+    for (int j = 1; do_bridge && j < novls; j++) {
         Path &jp = am[j];
         if (jp.abpos < 0) continue;
         for (int k = j - 1; k >= 0; k--) {

@@ -193,6 +193,7 @@ struct TaskIn {
     int minp, maxp;                 // original coordinates (align.c:1951-1968)
     int rev;                        // 0 = forward pass, 1 = reverse pass
     int TS, path_ave;
+    int reach = 1;                  // Align_Spec.reach (align.c:1009): end at the boundary candidate when there is one (daligner: 1, datander: 0)
 };
 struct TaskOut {                    // original coordinates
     int32_t ex, ey, ediff;
@@ -205,7 +206,7 @@ struct Lane {
     // task constants
     const uint32_t *aw, *bw;
     uint32_t abase, bbase;
-    int alen, blen, minp, maxp, TS, path_ave, rev;
+    int alen, blen, minp, maxp, TS, path_ave, rev, reach;
     int goffA, goffB;               // trace grid offsets in pass coordinates
     uint64_t magic;                 // ceil(2^40 / TS)
     uint32_t magic32;               // ceil(2^32 / TS), or 0 when that is not exact for these reads
@@ -271,7 +272,7 @@ WC_HD int tp_index1(const Lane &L, int v, int goff) {
 template <class FRONT, class POOL>
 WC_HD void setup(Lane &L, const TaskIn &t, const FRONT &F, POOL &pool) {
     L.aw = t.aw; L.bw = t.bw; L.abase = t.abase; L.bbase = t.bbase;
-    L.alen = t.alen; L.blen = t.blen; L.TS = t.TS; L.path_ave = t.path_ave; L.rev = t.rev;
+    L.alen = t.alen; L.blen = t.blen; L.TS = t.TS; L.path_ave = t.path_ave; L.rev = t.rev; L.reach = t.reach;
     L.cell_left = 0; L.cell_next = 0;
     L.waves = 0; L.cells = 0;
     const int TS = t.TS;
@@ -555,10 +556,10 @@ WC_HD void cellsN(Lane &L, const FRONT &F, const TrimTabs &tabs, POOL &pool) {
     L.k = k0 - cnt;
 }
 
-// end point of the pass in original coordinates (REACH = 1, daligner.c:951; align.c:1001-1012)
+// end point of the pass in original coordinates (align.c:1001-1012; REACH = 1 for daligner, daligner.c:951, 0 for datander)
 WC_HD void finish(const Lane &L, TaskOut &o) {
     int ex, ey;
-    if (L.morem >= 0) { ex = L.morea - L.morey; ey = L.morey; o.ediff = L.mored; o.ha = o.hb = (int32_t)L.moreh; }
+    if (L.morem >= 0 && L.reach) { ex = L.morea - L.morey; ey = L.morey; o.ediff = L.mored; o.ha = o.hb = (int32_t)L.moreh; }
     else { ex = L.trima - L.trimy; ey = L.trimy; o.ediff = L.trimd; o.ha = o.hb = (int32_t)L.trimh; }
     if (L.rev) { ex = L.alen - ex; ey = L.blen - ey; }
     o.ex = ex; o.ey = ey;

@@ -934,6 +934,103 @@ void ora_report(const ora_block *ab, const ora_block *bb, const ora_hit *hits, i
     free(score0);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * datander: Match_Self (scrub/tandem.c:1182-1428).  The reference sorts all k-mers of the block by code (tandem.c:428),
+ * turns every entry into the distance to the previous occurrence of its k-mer IN THE SAME READ (0: none; count_thread,
+ * tandem.c:556-590), sorts back to (read, rpos) order (:1281) and lets report_thread walk every read's positions.  Per read
+ * that is: link[apos] = apos - (previous apos with the same k-mer in this read), which is computed here read by read.
+ * One deviation, undefined in the reference: count_thread never rewrites the FIRST entry of a thread's range (its zeroing
+ * store after the inner loop hits the next run's head, :588), so report_thread reads a raw k-mer code as a distance and
+ * indexes its bucket arrays out of range with it; that entry is a run head, i.e. "no link" (0), which is what it gets here.
+ * rpos = index of the k-mer's last base + 1 (tandem.c:412), so apos runs over [K, alen].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint64_t code; int32_t apos; } self_kmer;
+static int cmp_self_kmer(const void *x, const void *y)
+{
+    const self_kmer *a = (const self_kmer *)x, *b = (const self_kmer *)y;
+    if (a->code != b->code) return a->code < b->code ? -1 : 1;
+    return a->apos - b->apos;
+}
+
+void ora_match_self(const ora_block *blk, const ora_params *p, ora_result *res)
+{
+    const int K = p->kmer, W = p->binshift, H = p->hitmin, TS = p->tspace;
+    const int maxdiag = (blk->maxlen >> W), mindiag = ((-blk->maxlen) >> W);
+    const int span = maxdiag - mindiag + 1;
+    const uint64_t kmask = (K >= 32) ? ~0ull : ((1ull << (2 * K)) - 1);
+    int32_t *score0 = (int32_t *)xmalloc(sizeof(int32_t) * 3 * (span + 8));
+    int32_t *score = score0 + 4 - mindiag, *lastp = score + span + 8, *lasta = lastp + span + 8;
+    int32_t *link = (int32_t *)xmalloc(sizeof(int32_t) * ((size_t)blk->maxlen + 2));
+    self_kmer *km = (self_kmer *)xmalloc(sizeof(self_kmer) * ((size_t)blk->maxlen + 2));
+    la_ctx *c = new_la_ctx(p);
+    int ar;
+
+    c->reach = 0;                                 /* New_Align_Spec(..., reach = 0), scrub/datander.c:246 */
+    memset(score0, 0, sizeof(int32_t) * 3 * (span + 8));
+    for (ar = 0; ar < blk->nreads; ar++) {
+        const int alen = blk->rlen[ar];
+        const int8_t *aseq = blk->bases + blk->boff[ar];
+        int apos, n = 0, amarkb, amarke, novl0 = (int)res->novl;
+        uint64_t code = 0;
+        (void)novl0;
+        for (apos = 1; apos <= alen; apos++) {                       /* tuple_thread, tandem.c:406-418 */
+            code = ((code << 2) | (uint64_t)aseq[apos - 1]) & kmask;
+            link[apos] = 0;
+            if (apos >= K) { km[n].code = code; km[n].apos = apos; n++; }
+        }
+        qsort(km, (size_t)n, sizeof(self_kmer), cmp_self_kmer);
+        for (apos = 1; apos < n; apos++)                             /* count_thread, tandem.c:566-586 */
+            if (km[apos].code == km[apos - 1].code) link[km[apos].apos] = km[apos].apos - km[apos - 1].apos;
+
+        amarkb = K; amarke = PANEL_SIZE;                             /* report_thread, tandem.c:966-971 */
+        if (amarke >= alen) amarke = alen + 1;
+        for (;;) {
+            for (apos = amarkb; apos < amarke; apos++) {             /* :976-985 */
+                int d = link[apos];
+                if (d == 0) continue;
+                d >>= W;
+                score[d] += (apos - lastp[d] >= K) ? K : apos - lastp[d];
+                lastp[d] = apos;
+            }
+            for (apos = amarkb; apos < amarke; apos++) {             /* :989-1100 */
+                int diag = link[apos], d, bpos;
+                if (diag == 0) continue;
+                d = diag >> W;
+                if (apos > lasta[d] && (score[d] + score[d + 1] >= H || score[d] + score[d - 1] >= H)) {
+                    opath ap, bp; int lo, hi, dd, i;
+                    bpos = apos - diag;
+                    memset(&ap, 0, sizeof(ap)); memset(&bp, 0, sizeof(bp));
+                    res->nfilt++;
+                    local_alignment(c, aseq, alen, aseq, alen, 0, 1, diag, apos + bpos, &ap, &bp);
+                    dd = ap.abpos - ap.bbpos; lo = hi = dd;          /* Diagonal_Span, tandem.c:852-890 */
+                    dd = ap.aepos - ap.bepos; if (dd < lo) lo = dd; else if (dd > hi) hi = dd;
+                    dd = (ap.abpos / TS) * TS - ap.bbpos;
+                    for (i = 1; i < ap.tlen - 2; i += 2) { dd += TS - ap.trace[i]; if (dd < lo) lo = dd; else if (dd > hi) hi = dd; }
+                    lo = (lo >> W) - 1; hi = (hi >> W) + 1;
+                    if (d < lo) lo = d; else if (d > hi) hi = d;
+                    for (i = lo; i <= hi; i++) if (ap.aepos > lasta[i]) lasta[i] = ap.aepos;
+                    if ((ap.aepos - ap.abpos) + (ap.bepos - ap.bbpos) >= p->minover) {
+                        add_record(res, &ap, 0u, ar + blk->ufirst, ar + blk->ufirst);
+                        res->ncheck++;
+                    }
+                }
+            }
+            for (apos = amarkb; apos < amarke; apos++) {             /* :1103-1108 */
+                int d = link[apos];
+                if (d == 0) continue;
+                d >>= W; score[d] = lastp[d] = 0;
+            }
+            if (amarke > alen) break;
+            amarkb = amarke - PANEL_OVERLAP; amarke = amarkb + PANEL_SIZE;
+            if (amarke > alen) amarke = alen + 1;
+        }
+        memset(lasta + mindiag - 2, 0, sizeof(int32_t) * (span + 4));   /* :1119-1136 */
+    }
+    res->wave_cells += c->wave_cells; res->waves += c->waves;
+    free_la_ctx(c);
+    free(km); free(link); free(score0);
+}
+
 void ora_match_filter(const ora_block *ab, const ora_block *bb,
                       const ora_kmer *al, int64_t alen, const ora_kmer *bl, int64_t blen,
                       int self, int comp, const ora_params *p, ora_result *res)

@@ -89,6 +89,12 @@ void ora_match_filter(const ora_block *ab, const ora_block *bb,
                       const ora_kmer *al, int64_t alen, const ora_kmer *bl, int64_t blen,
                       int self, int comp, const ora_params *p, ora_result *res);
 
+/* datander: Match_Self (scrub/tandem.c:1182-1428) up to its Handle_Redundancies call (tandem.c:1148) -- k-mer links inside a
+ * read (Sort_Kmers :428, count_thread :556, the (read, rpos) re-sort :1281), report_thread's panel walk over the read's own
+ * positions (:895-1140), Local_Alignment of the read against itself.  Appends one record per alignment, aread == bread,
+ * per read in alignment order (unfused, like ora_report).  p->kmer/binshift/hitmin/minover/tspace/ave_corr as datander sets them. */
+void ora_match_self(const ora_block *blk, const ora_params *p, ora_result *res);
+
 /* complement_DB (daligner.c:529): returns a malloc'd mirror (bases+mask); free with ora_free_block */
 ora_block *ora_complement_block(const ora_block *blk);
 

@@ -35,6 +35,11 @@ with open(os.path.join(LONG, "cases.json")) as f:
     LONG_CASES = json.load(f)
 
 
+TAN = os.path.join(GOLDEN, "tan")          # datander: reads with tandem arrays (tests/golden/make_tandem.py)
+with open(os.path.join(TAN, "cases.json")) as f:
+    TAN_CASES = json.load(f)
+
+
 def parse_flags(flags):
     """daligner flags -> dict(k,w,h,t,e,l,s,j,M,masks,I,O,A,T) (daligner.c:721-808)."""
     o = dict(k=14, w=6, h=35, t=0, e=0.70, l=1000, s=100, j=4, M=None, masks=[], I=False, O=False, A=False, T=False, b=False)

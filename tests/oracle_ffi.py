@@ -76,6 +76,8 @@ def lib():
         L.ora_match_filter.argtypes = [C.POINTER(OraBlock), C.POINTER(OraBlock), C.c_void_p, C.c_int64,
                                        C.c_void_p, C.c_int64, C.c_int, C.c_int, C.POINTER(OraParams),
                                        C.POINTER(OraResult)]
+        L.ora_match_self.restype = None
+        L.ora_match_self.argtypes = [C.POINTER(OraBlock), C.POINTER(OraParams), C.POINTER(OraResult)]
         L.ora_complement_block.restype = C.POINTER(OraBlock)
         L.ora_complement_block.argtypes = [C.POINTER(OraBlock)]
         L.ora_free_block.argtypes = [C.POINTER(OraBlock)]
@@ -214,6 +216,35 @@ def daligner(ablk, bblks, p_kwargs, only_identity=0):
     if aptr:
         L.ora_free(aptr)
     return out
+
+
+def parse_tandem_flags(flags):
+    """datander's options (scrub/datander.c:142-176): -k12 -w4 -h35 -e.70 -l500 -s100 -j4."""
+    o = dict(k=12, w=4, h=35, e=0.70, l=500, s=100, j=4)
+    for f in flags:
+        c, v = f[1], f[2:]
+        if c in "kwhlsj":
+            o[c] = int(v)
+        elif c == "e":
+            o["e"] = float(v)
+        elif c != "v":
+            raise ValueError(f)
+    return o
+
+
+def datander(blk, o, fuse=None):
+    """Oracle equivalent of `datander [opts] <block>` (scrub/datander.c:236-256): {file name: bytes}.  `fuse` = the
+    pf_fuse_result_self entry of tests/path_fuse_host.cpp (Handle_Redundancies is the product's code run on the host)."""
+    L = lib()
+    hb = HostBlock(blk)
+    p = make_params(k=o["k"], w=o["w"], h=o["h"], nthreads=o["j"], minlen=o["l"], tspace=o["s"], ave_corr=o["e"],
+                    freq=tuple(float(x) for x in blk.freq))
+    res = L.ora_new_result()
+    L.ora_match_self(C.byref(hb.c), C.byref(p), res)
+    changed = fuse(res, 0, C.byref(hb.c), p.tspace) if fuse is not None else 0
+    b1, _ = serialise(res, p, 0, -1)
+    L.ora_free_result(res)
+    return {f"{blk.name}.{blk.name}.las": b1}, changed
 
 
 def trace_point_diffs(ablk, bblk, las: bytes, every: int = 1):

@@ -35,7 +35,7 @@ FusePath load(const ora_result *r, int64_t i) {
 }
 // runs the product's post-pass (path_fuse_core.cuh) on vector-backed lists
 void handle_redundancies(std::vector<FusePath> &am, std::vector<FusePath> *bm, int comp, int ts, const ora_block *ab, int ar,
-                         const ora_block *bb, int br) {
+                         const ora_block *bb, int br, bool do_bridge = true) {
     HostArena al;
     auto view = [](std::vector<FusePath> &v) {
         std::vector<pf::Path> o(v.size());
@@ -46,7 +46,7 @@ void handle_redundancies(std::vector<FusePath> &am, std::vector<FusePath> *bm, i
     std::vector<pf::Path> pa = view(am), pb;
     if (bm) pb = view(*bm);
     const ByteSeq sa{reinterpret_cast<const uint8_t *>(ab->bases + ab->boff[ar])}, sb{reinterpret_cast<const uint8_t *>(bb->bases + bb->boff[br])};
-    const int no = pf::handle_redundancies(pa.data(), bm ? pb.data() : nullptr, (int)am.size(), comp, ts, sa, ab->rlen[ar], sb, bb->rlen[br], al);
+    const int no = pf::handle_redundancies(pa.data(), bm ? pb.data() : nullptr, (int)am.size(), comp, ts, sa, ab->rlen[ar], sb, bb->rlen[br], al, do_bridge);
     auto back = [&](std::vector<pf::Path> &v, std::vector<FusePath> &dst) {
         std::vector<FusePath> o((size_t)no);
         for (int i = 0; i < no; i++) {
@@ -94,6 +94,39 @@ extern "C" int64_t pf_fuse_result(ora_result *r, int64_t from, const ora_block *
         if ((int64_t)am.size() != na || (int64_t)bm.size() != nb) changed++;
         for (size_t q = 0; q < am.size(); q++) emit(r->ovl[i], am[q]);
         for (size_t q = 0; q < bm.size(); q++) emit(r->ovl[i + na], bm[q]);
+        i = e;
+    }
+    if ((int64_t)out.size() > r->omax) { r->omax = (int64_t)out.size() + 16; r->ovl = (ora_ovl *)realloc(r->ovl, sizeof(ora_ovl) * r->omax); }
+    memcpy(r->ovl, out.data(), sizeof(ora_ovl) * out.size());
+    r->novl = (int64_t)out.size();
+    if ((int64_t)tr.size() > r->tmax) { r->tmax = (int64_t)tr.size() + 16; r->trace = (uint16_t *)realloc(r->trace, sizeof(uint16_t) * r->tmax); }
+    memcpy(r->trace, tr.data(), sizeof(uint16_t) * tr.size());
+    r->ttop = (int64_t)tr.size();
+    return changed;
+}
+
+// datander (scrub/tandem.c:1140-1165): records [from, r->novl) were buffered by ora_match_self, per read (aread == bread) in
+// alignment order; its Handle_Redundancies fuses and drops contained alignments but never bridges.
+extern "C" int64_t pf_fuse_result_self(ora_result *r, int64_t from, const ora_block *blk, int ts) {
+    std::vector<ora_ovl> out(r->ovl, r->ovl + from);
+    std::vector<uint16_t> tr(r->trace, r->trace + r->ttop);
+    int64_t changed = 0;
+    for (int64_t i = from; i < r->novl;) {
+        const int a = r->ovl[i].aread, ar = a - blk->ufirst;
+        int64_t e = i;
+        while (e < r->novl && r->ovl[e].aread == a) e++;
+        std::vector<FusePath> am;
+        for (int64_t q = i; q < e; q++) am.push_back(load(r, q));
+        if (am.size() > 1) handle_redundancies(am, nullptr, 0, ts, blk, ar, blk, ar, false);
+        if ((int64_t)am.size() != e - i) changed++;
+        for (size_t q = 0; q < am.size(); q++) {
+            ora_ovl o = r->ovl[i];
+            const FusePath &p = am[q];
+            o.abpos = p.abpos; o.bbpos = p.bbpos; o.aepos = p.aepos; o.bepos = p.bepos; o.diffs = p.diffs; o.tlen = (int32_t)p.trace.size();
+            o.toff = (int64_t)tr.size();
+            tr.insert(tr.end(), p.trace.begin(), p.trace.end());
+            out.push_back(o);
+        }
         i = e;
     }
     if ((int64_t)out.size() > r->omax) { r->omax = (int64_t)out.size() + 16; r->ovl = (ora_ovl *)realloc(r->ovl, sizeof(ora_ovl) * r->omax); }

@@ -131,6 +131,7 @@ def test_midsize_block_pair_matches_reference():
     import shutil
     import subprocess
     import sys
+    from cases import ROOT
     sys.path.insert(0, ROOT)
     import bench
     exe = os.path.join(ROOT, "oracle", "_ref", "daligner")

@@ -29,6 +29,8 @@ def _lib():
     L = C.CDLL(SO)
     L.pf_fuse_result.restype = C.c_int64
     L.pf_fuse_result.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pf_fuse_result_self.restype = C.c_int64
+    L.pf_fuse_result_self.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
     return L
 
 
@@ -103,3 +105,22 @@ def test_unfused_output_differs():
     got, _ = oracle_daligner_fused(blks[names[0]], [blks[n] for n in names[1:]], oracle_kwargs(o), fuse=False)
     d = os.path.join(REP, "ref", case)
     assert any(not dbio.las_equal(open(os.path.join(d, fn), "rb").read(), got[fn])[0] for fn in os.listdir(d))
+
+
+from cases import TAN, TAN_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("case", sorted(TAN_CASES))
+def test_oracle_datander_equals_reference(case):
+    """datander (scrub/tandem.c): the oracle's Match_Self restatement + the product's Handle_Redundancies pass without
+    bridging (tandem.c:767-850) == the reference datander's .las on reads with tandem arrays (tests/golden/make_tandem.py)."""
+    o = O.parse_tandem_flags(TAN_CASES[case]["flags"])
+    blk = load_block(TAN, TAN_CASES[case]["blocks"][0], ())
+    got, changed = O.datander(blk, o, fuse=_lib().pf_fuse_result_self)
+    d = os.path.join(TAN, "ref", case)
+    for fn in sorted(os.listdir(d)):
+        ref = open(os.path.join(d, fn), "rb").read()
+        ok, why = dbio.las_equal(ref, got[fn])
+        assert ok, f"{case}/{fn}: {why}"
+    if case == "tan_b2":
+        assert changed > 0                                   # block 2 has reads whose alignments fuse / contain each other
