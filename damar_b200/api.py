@@ -84,7 +84,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
            "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge",
-           "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view"]
+           "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view", "damar_match_self"]
 
 _lib = None
 
@@ -121,6 +121,7 @@ def load_library():
     L.damar_index_free.argtypes = [C.c_void_p]
     L.damar_match_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.POINTER(Overlaps)]
+    L.damar_match_self.argtypes = [C.c_void_p, C.POINTER(Overlaps)]
     L.damar_index_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.damar_last_hits_download.restype = C.c_int64
     L.damar_last_hits_download.argtypes = [C.c_void_p, C.c_int64]
@@ -326,6 +327,54 @@ def match_filter(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, atable: O
     if rc != 0:
         raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
     return out
+
+
+def match_self(block: DeviceBlockHandle) -> Overlaps:
+    """Match_Self (scrub/tandem.c:1182): every read of the block against itself; the result lives in the library until
+    the next call."""
+    out = Overlaps()
+    if load_library().damar_match_self(block.handle, C.byref(out)) != 0:
+        raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
+    return out
+
+
+@dataclass
+class TandemSettings:
+    """datander's command-line state (scrub/datander.c:142-176) -- defaults are the reference's."""
+    kmer: int = 12            # -k
+    binshift: int = 4         # -w
+    hitmin: int = 35          # -h
+    ave_corr: float = 0.70    # -e
+    minlen: int = 500         # -l  (MINOVER = 2*minlen)
+    trace_spacing: int = 100  # -s
+    nthreads: int = 4         # -j
+    verbose: bool = False     # -v
+
+
+def datander(blk: Block, s: Optional[TandemSettings] = None, dblock: Optional[DeviceBlockHandle] = None) -> Dict[str, bytes]:
+    """`datander [flags] <block>` (scrub/datander.c:236-256): {"<block>.<block>.las": bytes}, the file the reference
+    writes into its -o directory."""
+    s = s or TandemSettings()
+    init()
+    if set_filter_params(s.kmer, s.binshift, 0, s.hitmin, s.nthreads):
+        raise ValueError("Illegal combination of filter parameters")       # datander.c:218-222
+    if blk.nreads and int(blk.rlen.min()) < s.kmer:
+        raise ValueError(f"Block {blk.name} contains reads < {s.kmer}bp long !  Run DBsplit.")   # datander.c:84-88
+    ds = Settings(kmer=s.kmer, binshift=s.binshift, hitmin=s.hitmin, ave_corr=s.ave_corr, minlen=s.minlen,
+                  trace_spacing=s.trace_spacing, nthreads=s.nthreads, mem_limit_gb=0, verbose=s.verbose)
+    set_options(ds, blk.freq)
+    own = dblock is None
+    db = DeviceBlockHandle(blk) if own else dblock
+    try:
+        ov = match_self(db)
+        sink = LasSink()
+        sink.add(ov, 0)
+        b1, _ = sink.serialise(ds, -1)
+        sink.free()
+        return {f"{blk.name}.{blk.name}.las": b1.tobytes()}
+    finally:
+        if own:
+            db.free()
 
 
 def last_hits() -> np.ndarray:

@@ -352,6 +352,39 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     return 0;
 }
 
+/* datander's Match_Self (scrub/tandem.c:1182): every read of the block against itself. */
+int damar_match_self(damar_block *blk, damar_overlaps *out) {
+    ensure_init();
+    Context &c = ctx();
+    DeviceBlock *b = reinterpret_cast<DeviceBlock *>(blk);
+    g_out = HostOverlaps();
+    g_hits.release();
+    g_hits_a = b; g_hits_b = b;
+    memset(out, 0, sizeof(*out));
+    c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
+    c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0; c.tm.wide_passes = 0;
+    if (b == nullptr) { set_error("damar_match_self: no block"); return 1; }
+    if (b->has_mask) { set_error("damar_match_self: datander takes no mask tracks"); return 1; }
+    if (c.fp.suppress != 0 || c.fp.biased) { set_error("damar_match_self: datander has neither -t nor -b (scrub/tandem.c:137)"); return 1; }
+    DeviceIndex *idx = nullptr;
+    { HostProf hp("ms.sort_kmers"); idx = build_index(b, 0); }
+    int rc = 0;
+    if (idx->len > 0) {
+        ensure_revcomp(b);                                    // the reverse wave pass runs on the reverse-complemented reads
+        { HostProf hp("ms.self_hits"); rc = self_hits(idx, g_hits); }
+        if (rc == 0 && g_hits.n > 0) { HostProf hp("ms.report_and_align"); rc = report_and_align(b, b, 0, 1, g_hits, g_out, true); }
+    }
+    delete idx;
+    if (rc != 0) return rc;
+    out->novl = g_out.novl; out->ovl = g_out.ovl; out->trace_off = g_out.toff; out->seq = g_out.seq; out->trace = g_out.trace;
+    out->ntrace = g_out.ntrace; out->trace_bytes = g_out.tbytes; out->nhits = g_hits.n; out->nfilt = g_out.nfilt;
+    out->ncheck = out->novl; out->limit = g_hits.limit; out->multi_la_pairs = (int32_t)g_out.multi;
+    c.tm.cells_total += g_out.cells; c.tm.wide_total += c.tm.wide_passes; c.tm.la_total += g_out.nfilt;
+    c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
+    c.tm.kernel_launches = c.launches;
+    return 0;
+}
+
 int damar_trace_point_diffs(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
                             const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
                             int32_t *rec_diffs, uint16_t *seg_diffs) {

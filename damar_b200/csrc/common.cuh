@@ -213,6 +213,9 @@ struct SeedHits {
 };
 int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out);   // non-zero: error set
 
+// tandem.cu : datander's seed stage -- links between equal k-mers of one read as a hit list (scrub/tandem.c:556-590, 1281)
+int self_hits(const DeviceIndex *idx, SeedHits &out);
+
 // pair_align.cu
 struct HostOverlaps {                 // views of pinned staging buffers, valid until the next call
     const damar_overlap *ovl = nullptr;
@@ -245,6 +248,6 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
                            int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs);
 
 int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
-                     HostOverlaps &out);   // non-zero: error set (capacity limits are errors, not exits)
+                     HostOverlaps &out, bool tandem = false);   // non-zero: error set (capacity limits are errors, not exits)
 
 }  // namespace damar

@@ -493,6 +493,54 @@ __device__ void emit_record(const AlignArgs &P, const Path &p, int aread, int br
     }
 }
 
+// Opens the next panel of a pair's hits (warp-collective); false when the pair has none left.
+//   daligner (filter.c:2251-2266): a panel = the hits from nidx up to AND INCLUDING the first with apos > amark
+//     (amark = amark2 + 50000, amark2 <- amark - 10000, 0 at the pair's start); the next panel starts at the first hit with
+//     apos > amark2.
+//   datander (scrub/tandem.c:966-971, 1112-1116): panel n = the read's positions [amarkb, amarke) with amarkb = k (n = 0) or
+//     40000 n, amarke = 40000 n + 50000, replaced by alen + 1 once it reaches the read's end (>= for the first panel, > after
+//     it, as written); amark2 carries n here (-1: finished) and nidx the first hit of the previous panel.
+__device__ bool open_panel(const AlignArgs &P, int64_t pend, int alen, int64_t &nidx, int &amark2, int64_t &lidx, int64_t &pe) {
+    const int lane = threadIdx.x & 31;
+    if (!P.tandem) {
+        if (nidx >= pend) return false;
+        const int amark = amark2 + PANEL_SIZE; amark2 = amark - PANEL_OVERLAP;
+        lidx = nidx;
+        int64_t e = pend, h2 = pend;
+        bool gotpe = false, goth2 = false;
+        for (int64_t j0 = lidx; j0 < pend && !(gotpe && goth2); j0 += 32) {
+            const int64_t j = j0 + lane;
+            const int apos = (j < pend) ? hit_apos(P, j) : IMAX;
+            const unsigned over = __ballot_sync(FULL, (j < pend) && apos > amark);
+            const unsigned over2 = __ballot_sync(FULL, (j < pend) && apos > amark2);
+            if (!goth2 && over2) { h2 = j0 + __ffs(over2) - 1; goth2 = true; }
+            if (!gotpe && over) { e = j0 + __ffs(over) - 1 + 1; gotpe = true; }
+        }
+        if (h2 > e) h2 = e;
+        pe = e; nidx = h2;
+        return true;
+    }
+    const int n = amark2;
+    if (n < 0) return false;
+    const int amarkb = (n == 0) ? P.K : n * (PANEL_SIZE - PANEL_OVERLAP);
+    int amarke = n * (PANEL_SIZE - PANEL_OVERLAP) + PANEL_SIZE;
+    if (n == 0 ? (amarke >= alen) : (amarke > alen)) amarke = alen + 1;
+    int64_t b = pend, e = pend;
+    bool gotb = false, gote = false;
+    for (int64_t j0 = nidx; j0 < pend && !(gotb && gote); j0 += 32) {
+        const int64_t j = j0 + lane;
+        const int apos = (j < pend) ? hit_apos(P, j) : IMAX;
+        const unsigned inb = __ballot_sync(FULL, (j < pend) && apos >= amarkb);
+        const unsigned ine = __ballot_sync(FULL, (j < pend) && apos >= amarke);
+        if (!gotb && inb) { b = j0 + __ffs(inb) - 1; gotb = true; }
+        if (!gote && ine) { e = j0 + __ffs(ine) - 1; gote = true; }
+    }
+    if (b > e) b = e;
+    lidx = b; pe = e; nidx = b;
+    amark2 = (amarke > alen) ? -1 : n + 1;
+    return true;
+}
+
 __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArgs P) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * AL_WARPS + wib;
@@ -527,7 +575,7 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
         const int ar = (int)(pair & ((1ull << P.abits) - 1ull)), br = (int)(pair >> P.abits);
         const int alen = P.arlen[ar], blen = P.brlen[br];
         const bool selfie = P.self && !P.comp && ar == br;    // aseq == bseq pointer test, align.c:1949
-        const bool doB = P.symmetric && (ar != br || !P.self || !P.comp);   // filter.c:2301
+        const bool doB = !P.tandem && P.symmetric && (ar != br || !P.self || !P.comp);   // filter.c:2301; datander reports one record (tandem.c:1155)
         n_pairs++;
 
         // extent of the pair
@@ -543,24 +591,9 @@ __global__ void __launch_bounds__(AL_WARPS * 32, 3) align_pairs_strided(AlignArg
         int nla = 0, novl = 0;
         int amark2 = 0;
         int64_t nidx = sidx;
-        while (nidx < pend) {                                  // A-panels, filter.c:2251-2266
-            const int amark = amark2 + PANEL_SIZE; amark2 = amark - PANEL_OVERLAP;
-            const int64_t lidx = nidx;
-            // panel = hits up to and including the first with apos > amark; h2 = first with apos > amark2
-            int64_t pe = pend, h2 = pend;
-            {
-                bool gotpe = false, goth2 = false;
-                for (int64_t j0 = lidx; j0 < pend && !(gotpe && goth2); j0 += 32) {
-                    const int64_t j = j0 + lane;
-                    const int apos = (j < pend) ? hit_apos(P, j) : IMAX;
-                    const unsigned over = __ballot_sync(FULL, (j < pend) && apos > amark);
-                    const unsigned over2 = __ballot_sync(FULL, (j < pend) && apos > amark2);
-                    if (!goth2 && over2) { h2 = j0 + __ffs(over2) - 1; goth2 = true; }
-                    if (!gotpe && over) { pe = j0 + __ffs(over) - 1 + 1; gotpe = true; }
-                }
-                if (h2 > pe) h2 = pe;
-            }
-            nidx = h2;
+        for (;;) {                                             // panels (filter.c:2251-2266 / tandem.c:966-1116)
+            int64_t lidx, pe;
+            if (!open_panel(P, pend, alen, nidx, amark2, lidx, pe)) break;
             if (pe - lidx < P.minhit) continue;
 
             // pass 1: covered bases per bucket (filter.c:2268-2277)
@@ -719,7 +752,7 @@ struct PipeArgs {
 };
 enum { CTR_NCAND = 0, CTR_NEXT = 1, CTR_NWIDE = 2, CTR_POOL = 3, CTR_NEXT_WIDE = 4, CTR_RETRY = 5, CTR_RETIRED = 6, CTR_N = 8 };
 
-struct ScanState { int64_t pend, nidx, lidx, pe, j; int amark2; };
+struct ScanState { int64_t pend, nidx, lidx, pe, j; int amark2, alen; };
 
 // first index >= from whose pair differs (warp-collective)
 __device__ int64_t pair_extent(const AlignArgs &P, int64_t from, uint64_t pair) {
@@ -782,22 +815,9 @@ __device__ int64_t find_candidate(const AlignArgs &P, ScanState &S, int32_t *sco
     bool scored = false;
     for (;;) {
         if (S.j < 0) {                                         // open the next panel
-            if (S.nidx >= S.pend) return -1;
-            const int amark = S.amark2 + PANEL_SIZE; S.amark2 = amark - PANEL_OVERLAP;
-            const int64_t lidx = S.nidx;
-            // panel = hits up to and including the first with apos > amark; h2 = first with apos > amark2
-            int64_t pe = S.pend, h2 = S.pend;
-            bool gotpe = false, goth2 = false;
-            for (int64_t j0 = lidx; j0 < S.pend && !(gotpe && goth2); j0 += 32) {
-                const int64_t j = j0 + lane;
-                const int apos = (j < S.pend) ? hit_apos(P, j) : IMAX;
-                const unsigned over = __ballot_sync(FULL, (j < S.pend) && apos > amark);
-                const unsigned over2 = __ballot_sync(FULL, (j < S.pend) && apos > S.amark2);
-                if (!goth2 && over2) { h2 = j0 + __ffs(over2) - 1; goth2 = true; }
-                if (!gotpe && over) { pe = j0 + __ffs(over) - 1 + 1; gotpe = true; }
-            }
-            if (h2 > pe) h2 = pe;
-            S.nidx = h2; S.lidx = lidx; S.pe = pe;
+            int64_t lidx, pe;
+            if (!open_panel(P, S.pend, S.alen, S.nidx, S.amark2, lidx, pe)) return -1;
+            S.lidx = lidx; S.pe = pe;
             if (pe - lidx < P.minhit) continue;
             S.j = lidx;
         }
@@ -847,6 +867,7 @@ __global__ void __launch_bounds__(256) filter_pairs(PipeArgs Q) {
         const uint64_t pair = hit_pair(P, sidx);
         ScanState S;
         S.pend = pair_extent(P, sidx, pair); S.nidx = sidx; S.j = -1; S.amark2 = 0; S.lidx = S.pe = sidx;
+        S.alen = P.arlen[(int)(pair & ((1ull << P.abits) - 1ull))];
         const int64_t c = find_candidate(P, S, score, lastp, 0, nullptr, nullptr, nullptr);
         if (lane == 0) { Q.flag[w] = (c >= 0) ? 1u : 0u; Q.cand0[w] = (c >= 0) ? (uint32_t)(c - sidx) : 0u; }
     }
@@ -886,6 +907,7 @@ __global__ void __launch_bounds__(256) scan_round(PipeArgs Q) {
         S.pend = Q.pt.pend[p];
         if (S.pend < 0) S.pend = pair_extent(P, sidx, pair);
         S.nidx = Q.pt.nidx[p]; S.lidx = Q.pt.lidx[p]; S.pe = Q.pt.pe[p]; S.j = Q.pt.j[p]; S.amark2 = Q.pt.amark2[p];
+        S.alen = P.arlen[(int)(pair & ((1ull << P.abits) - 1ull))];
         const int nla = Q.pt.nla[p];
         const size_t lo = Q.pt.la_off[p];
         const int64_t c = find_candidate(P, S, score, lastp, nla, Q.pt.la_low + lo, Q.pt.la_hgh + lo, Q.pt.la_ae + lo);
@@ -1193,7 +1215,7 @@ __global__ void __launch_bounds__(256) finish_las(PipeArgs Q) {
             }
         } else if (lane == 0) atomicOr(&P.stats[3], 2ull);
         if ((ap.aepos - ap.abpos) + (ap.bepos - ap.bbpos) >= P.minover) {   // filter.c:2335
-            const bool doB = P.symmetric && (ar != br || !P.self || !P.comp);   // filter.c:2301
+            const bool doB = !P.tandem && P.symmetric && (ar != br || !P.self || !P.comp);   // filter.c:2301; datander: tandem.c:1155
             const uint64_t seq = ((uint64_t)wi << SEQ_PAIR_SHIFT) | (uint64_t)(novl & MAX_LA_PER_PAIR);
             emit_record(P, ap, ar + P.afirst, br + P.bfirst, seq);
             if (doB) emit_record(P, bp, br + P.bfirst, ar + P.afirst, seq | SEQ_B);
@@ -1246,7 +1268,7 @@ struct HrArgs {
     const uint32_t *order;                    // record indices sorted by emission rank
     void *trace; int tbytes; unsigned long long trace_cap; unsigned long long *trace_count;
     const uint32_t *aw, *bw; const uint32_t *aboff, *bboff; const int32_t *arlen, *brlen; int afirst, bfirst;
-    int comp, ts;
+    int comp, ts, bridge;                     // bridge == 0: datander's Handle_Redundancies (tandem.c:767), fusion and containment only
     uint32_t *pool; unsigned long long pool_cap; unsigned long long *pool_top;
     unsigned long long *stats;                // [3] |= 1 trace pool full, |= 8 value > 255 in an 8-bit trace, |= 16 scratch pool dry
     unsigned long long *nfused;
@@ -1320,11 +1342,11 @@ __global__ void __launch_bounds__(64) handle_redundancies_pairs(HrArgs H) {
     int sa_n = na, sb_n = nb;
     if (na > 1) {
         const bool both = nb > 1;
-        const int no = pf::handle_redundancies(am, both ? bm : nullptr, na, H.comp, H.ts, sa, alen, sb, blen, al);
+        const int no = pf::handle_redundancies(am, both ? bm : nullptr, na, H.comp, H.ts, sa, alen, sb, blen, al, H.bridge != 0);
         if (no < 0) { atomicOr(H.stats + 3, 16ull); return; }
         sa_n = no; if (both) sb_n = no;
     } else {
-        const int no = pf::handle_redundancies(bm, (pf::Path *)nullptr, nb, H.comp, H.ts, sa, alen, sb, blen, al);
+        const int no = pf::handle_redundancies(bm, (pf::Path *)nullptr, nb, H.comp, H.ts, sa, alen, sb, blen, al, H.bridge != 0);
         if (no < 0) { atomicOr(H.stats + 3, 16ull); return; }
         sb_n = no;
     }
@@ -1352,25 +1374,25 @@ __global__ void __launch_bounds__(64) handle_redundancies_pairs(HrArgs H) {
 
 }  // namespace
 
-int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out) {
+int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out, bool tandem) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const FilterParams &fp = c.fp;
     const int64_t n = hits.n;
-    const int minhit = (fp.hitmin - 1) / fp.kmer + 1;
+    // datander walks every read and has neither the minhit rule nor report slices (scrub/tandem.c:895-1000)
+    const int minhit = tandem ? 1 : (fp.hitmin - 1) / fp.kmer + 1;
     if (n >= (int64_t)0xffffffffll) { set_error("more than 2^32 seed hits in one comparison (%lld): lower -M or -t", (long long)n); return 1; }
 
     // ---- work list: first hit of every pair with at least minhit hits (filter.c:2210-2221) ----
     HostProf *hp1 = new HostProf("ra.worklist");
     Timer t_pairs(st);
-    const int nslices = fp.nthreads_pow2 > 1024 ? 1024 : fp.nthreads_pow2;
+    const int nslices = tandem ? 0 : (fp.nthreads_pow2 > 1024 ? 1024 : fp.nthreads_pow2);
     DevBuf<int64_t> ends; ends.reserve(fp.nthreads_pow2);
     DevBuf<uint32_t> flag; flag.reserve((size_t)n);
     DevBuf<uint64_t> off; off.reserve((size_t)n);
     DevBuf<uint64_t> total; total.reserve(1);
     const int kshift = hits.bpos ? 0 : hits.qbits;
-    slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits + kshift, ends.p);
-    KERNEL_CHECK();
+    if (nslices > 0) { slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits + kshift, ends.p); KERNEL_CHECK(); }
     const unsigned hb = (unsigned)((n + 255) / 256);
     flag_work_pairs<<<hb, 256, 0, st>>>(hits.keys, n, hits.pbits + kshift, minhit, ends.p, nslices, flag.p);
     KERNEL_CHECK();
@@ -1429,6 +1451,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     P.afirst = ab->ufirst; P.bfirst = bb->ufirst;
     P.K = fp.kmer; P.W = fp.binshift; P.H = fp.hitmin; P.minhit = minhit; P.TS = TS; P.minover = c.opt.minover;
     P.comp = comp ? 1 : 0; P.self = self; P.symmetric = c.opt.symmetric;
+    P.tandem = tandem ? 1 : 0; P.reach = tandem ? 0 : 1;
     P.ave_path = ave_path; P.dscore = dscore; P.score_tab = dscoret.p; P.table_tab = dtable.p;
     P.tbuf = tbuf.p; P.maxtp = maxtp;
     P.bscore = bscore.p; P.nbuck = nbuck; P.dmin = dmin;
@@ -1605,7 +1628,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
             H.pair_redo = nredo > 0 ? pair_redo.p : nullptr;
             H.trace = trace.p; H.tbytes = tbytes; H.trace_cap = trace_cap; H.trace_count = counters.p + 6;
             H.aw = ab->packed[0]; H.bw = bb->packed[bsel]; H.aboff = ab->boff; H.bboff = bb->boff; H.arlen = ab->rlen; H.brlen = bb->rlen;
-            H.afirst = ab->ufirst; H.bfirst = bb->ufirst; H.comp = comp ? 1 : 0; H.ts = TS;
+            H.afirst = ab->ufirst; H.bfirst = bb->ufirst; H.comp = comp ? 1 : 0; H.ts = TS; H.bridge = tandem ? 0 : 1;
             H.stats = counters.p; H.nfused = counters.p + 7;
             uint64_t *k0 = hr_keys.p, *k1 = hr_keys.p + nrec + 2; uint32_t *v0 = hr_vals.p, *v1 = hr_vals.p + nrec + 2;
             hr_sort_keys<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(H, k0, v0);

@@ -155,6 +155,12 @@ void         damar_index_free(damar_index *idx);
 int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
                        int self, int comp, damar_overlaps *out);
 
+/* datander (scrub/datander.c:52-66): Match_Self (scrub/tandem.c:1182-1428), every read of the block against itself for
+ * tandem repeats.  Parameters as datander sets them: damar_set_filter_params(kmer 12, binshift 4, suppress 0, hitmin 35,
+ * nthreads) = tandem.c:137, and damar_options {minover = 2 * -l (500), trace_spacing, ave_corr, freq}.  One record per
+ * alignment (aread == bread, flags 0); results are owned by the library like damar_match_filter's.  Returns 0 on success. */
+int damar_match_self(damar_block *blk, damar_overlaps *out);
+
 /* order[0..novl) = record indices sorted by emission rank (the order AddOverlapToBuffer would have
  * been called in by the reference's report threads)                                              */
 void damar_emission_order(const damar_overlaps *o, int64_t *order);

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
-from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, GRAM, GRAM_CASES, LONG, LONG_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
+from cases import BIAS, BIAS_CASES, CASES, EDGE, EDGE_CASES, GOLDEN, GRAM, GRAM_CASES, LONG, LONG_CASES, TAN, TAN_CASES, TINY, golden_files, load_block, oracle_kwargs, parse_flags, settings
 from damar_b200 import api, dbio
 
 pytestmark = pytest.mark.gpu
@@ -156,6 +156,43 @@ def test_midsize_block_pair_matches_reference():
     for d in os.listdir(dbdir):
         if d.startswith("d001_"):
             shutil.rmtree(os.path.join(dbdir, d))
+
+
+@pytest.mark.parametrize("case", sorted(TAN_CASES))
+def test_datander_matches_reference(case):
+    """datander (scrub/datander.c, scrub/tandem.c): every read against itself for tandem repeats -- reads with tandem arrays,
+    one longer than a 50 kbp panel, against the reference datander's files (tests/golden/make_tandem.py)."""
+    o = O.parse_tandem_flags(TAN_CASES[case]["flags"])
+    blk = load_block(TAN, TAN_CASES[case]["blocks"][0], ())
+    s = api.TandemSettings(kmer=o["k"], binshift=o["w"], hitmin=o["h"], ave_corr=o["e"], minlen=o["l"], trace_spacing=o["s"], nthreads=o["j"])
+    out = api.datander(blk, s)
+    d = os.path.join(TAN, "ref", case)
+    gold = {fn: open(os.path.join(d, fn), "rb").read() for fn in sorted(os.listdir(d))}
+    assert sorted(out) == sorted(gold)
+    for fn, ref in gold.items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
+
+
+@pytest.mark.parametrize("case", ["tan_default", "tan_k14"])
+def test_dropin_reference_datander_host(case, tmp_path):
+    """The UNMODIFIED scrub/datander.c linked against libdamar_b200.so through the tandem.h shim (oracle/_ref/datander_b200)."""
+    import shutil
+    import subprocess
+    from cases import ROOT
+    exe = os.path.join(ROOT, "oracle", "_ref", "datander_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/datander_b200 not built (needs /root/reference at build time)")
+    for fn in os.listdir(TAN):
+        p = os.path.join(TAN, fn)
+        if os.path.isfile(p):
+            shutil.copy(p, tmp_path / fn)
+    r = subprocess.run([exe] + TAN_CASES[case]["flags"] + ["-o", "tan"] + TAN_CASES[case]["blocks"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = os.path.join(TAN, "ref", case)
+    for fn in sorted(os.listdir(d)):
+        ok, why = dbio.las_equal(open(os.path.join(d, fn), "rb").read(), open(tmp_path / "tan" / fn, "rb").read())
+        assert ok, f"{case}/{fn}: {why}"
 
 
 def test_unpacked_records_give_the_same_files():
