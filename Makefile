@@ -3,7 +3,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC      := damar_b200/csrc
-OBJS      := $(CSRC)/api.o $(CSRC)/scan.o $(CSRC)/radix_sort.o $(CSRC)/kmer_index.o $(CSRC)/seed_merge.o $(CSRC)/tandem.o $(CSRC)/pair_align.o $(CSRC)/trace_pts.o $(CSRC)/las_sink.o
+OBJS      := $(CSRC)/api.o $(CSRC)/scan.o $(CSRC)/radix_sort.o $(CSRC)/kmer_index.o $(CSRC)/seed_merge.o $(CSRC)/tandem.o $(CSRC)/pair_align.o $(CSRC)/trace_pts.o $(CSRC)/las_sink.o $(CSRC)/las_device.o
 LIB       := damar_b200/libdamar_b200.so
 
 .PHONY: all lib host oracle clean

@@ -84,7 +84,8 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_sink_new", "damar_sink_free", "damar_sink_reset", "damar_sink_add", "damar_sink_count",
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
            "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge",
-           "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view", "damar_match_self"]
+           "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view", "damar_match_self",
+           "damar_dsink_new", "damar_dsink_free", "damar_dsink_reset", "damar_match_filter_sink", "damar_dsink_serialise"]
 
 _lib = None
 
@@ -122,6 +123,13 @@ def load_library():
     L.damar_match_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                      C.POINTER(Overlaps)]
     L.damar_match_self.argtypes = [C.c_void_p, C.POINTER(Overlaps)]
+    L.damar_dsink_new.restype = C.c_void_p
+    L.damar_dsink_free.argtypes = [C.c_void_p]
+    L.damar_dsink_reset.argtypes = [C.c_void_p]
+    L.damar_match_filter_sink.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                          C.POINTER(Overlaps)]
+    L.damar_dsink_serialise.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.damar_index_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.damar_last_hits_download.restype = C.c_int64
     L.damar_last_hits_download.argtypes = [C.c_void_p, C.c_int64]
@@ -461,6 +469,44 @@ class LasSink:
             self.h = None
 
 
+class DeviceSink:
+    """The records of one B block's Match_Filter calls kept in HBM; serialise() sorts them (SORT_OVL) and builds the .las
+    image(s) on the device and copies each finished image to the host once (align.c:6104-6367 on the device)."""
+
+    def __init__(self):
+        self.h = load_library().damar_dsink_new()
+
+    def match_filter(self, ablock, bblock, atable, btable, self_: bool, comp: int, ordinal: int) -> Overlaps:
+        out = Overlaps()
+        rc = load_library().damar_match_filter_sink(ablock.handle, bblock.handle, atable.handle if atable else None,
+                                                    btable.handle if btable else None, int(self_), comp, self.h, ordinal, C.byref(out))
+        if rc != 0:
+            raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
+        return out
+
+    def reset(self):
+        load_library().damar_dsink_reset(self.h)
+
+    def serialise(self, s: "Settings", split_read: int, maxlen: int, maxread: int):
+        L = load_library()
+        b1, b2 = C.c_void_p(), C.c_void_p()
+        l1, l2 = C.c_int64(0), C.c_int64(0)
+        if L.damar_dsink_serialise(self.h, s.trace_spacing, int(s.no_trace), int(s.only_identity), split_read, maxlen, maxread,
+                                   C.byref(b1), C.byref(l1), C.byref(b2), C.byref(l2)) != 0:
+            raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
+        return LasImage(b1.value, l1.value), (LasImage(b2.value, l2.value) if b2.value else None)
+
+    def free(self):
+        if self.h:
+            load_library().damar_dsink_free(self.h)
+            self.h = None
+
+
+def device_sinks() -> bool:
+    """DAMAR_DEVICE_SINK=0 keeps the round-1 output path (records shipped to the host, sorted and serialised there)."""
+    return os.environ.get("DAMAR_DEVICE_SINK", "1") != "0"
+
+
 # ---- worker pool: independent comparisons (B block x orientation) in flight at once ----------------
 # Every pool thread binds its own library context (stream, device-memory cache, result slots), so the serial
 # tail of one comparison (a few long wave passes, later lasta rounds) overlaps the bulk kernels of the next and
@@ -469,6 +515,7 @@ _pool = None
 _pool_lock = threading.Lock()
 _pool_next = [0]
 _free_sinks: List["LasSink"] = []
+_free_dsinks: List["DeviceSink"] = []
 
 
 def _bind_worker():
@@ -533,8 +580,11 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
     def compare(bblk, db, selfcmp, comp, sink, st):
         """one Match_Filter call (daligner.c:1041 / 1053) on the calling thread's worker context"""
         bidx = aidx if (selfcmp and comp == 0) else index_of(db, comp)
-        ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
-        sink.add(ov, comp)
+        if isinstance(sink, DeviceSink):
+            ov = sink.match_filter(da, db, aidx, bidx, selfcmp, comp, comp)
+        else:
+            ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
+            sink.add(ov, comp)
         st[f"nhits{comp}"], st[f"nfilt{comp}"], st[f"novl{comp}"] = ov.nhits, ov.nfilt, ov.novl
         st[f"multi{comp}"] = ov.multi_la_pairs
         st[f"t{comp}"] = timings()
@@ -545,7 +595,10 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
     for bblk in bblks:
         selfcmp = bblk.name == ablk.name
         db = da if selfcmp else resident(bblk)
-        sink = _free_sinks.pop() if _free_sinks else LasSink()   # kept for the process: host buffers stay warm
+        if device_sinks():
+            sink = _free_dsinks.pop() if _free_dsinks else DeviceSink()
+        else:
+            sink = _free_sinks.pop() if _free_sinks else LasSink()   # kept for the process: host buffers stay warm
         sink.reset()
         st = {}
         if inline:
@@ -570,18 +623,20 @@ def collect(J: _Job, stats: Optional[list] = None, as_bytes: bool = True) -> Dic
         if stats is not None:
             stats.append(st)
         an, bn = ablk.name, bblk.name
+        dev = isinstance(sink, DeviceSink)
+        dims = (max(ablk.maxlen, bblk.maxlen), max(ablk.ufirst + ablk.nreads, bblk.ufirst + bblk.nreads)) if dev else ()
         if selfcmp or not J.symmetric:                                      # align.c:6235
-            b1, _ = sink.serialise(s, -1)
+            b1, _ = sink.serialise(s, -1, *dims)
             out[f"{an}.{bn}.las"] = conv(b1)
         else:
             last = (bblk.ufirst + bblk.nreads - 1) if bblk.part < ablk.part else (ablk.ufirst + ablk.nreads - 1)
-            b1, b2 = sink.serialise(s, last)
+            b1, b2 = sink.serialise(s, last, *dims)
             n1, n2 = f"{an}.{bn}.las", f"{bn}.{an}.las"
             if bblk.part < ablk.part:                                       # align.c:6308-6313
                 n1, n2 = n2, n1
             out[n1], out[n2] = conv(b1), conv(b2)
         sink.reset()
-        _free_sinks.append(sink)
+        (_free_dsinks if dev else _free_sinks).append(sink)
     if J.aidx is not None:
         J.aidx.free()
     if J.own:

@@ -317,13 +317,14 @@ damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len) {
 }
 void damar_index_free(damar_index *idx) { delete reinterpret_cast<DeviceIndex *>(idx); }
 
-int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
-                       int self, int comp, damar_overlaps *out) {
+static int match_filter_impl(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
+                             int self, int comp, damar_overlaps *out, DeviceResult *keep) {
     ensure_init();
     Context &c = ctx();
     DeviceBlock *ab = reinterpret_cast<DeviceBlock *>(ablk), *bb = reinterpret_cast<DeviceBlock *>(bblk);
     DeviceIndex *ai = reinterpret_cast<DeviceIndex *>(aidx), *bi = reinterpret_cast<DeviceIndex *>(bidx);
     g_out = HostOverlaps();
+    g_out.keep = keep;
     g_hits.release();
     g_hits_a = ab; g_hits_b = bb;
     memset(out, 0, sizeof(*out));
@@ -349,6 +350,24 @@ int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, 
     c.tm.cells_total += g_out.cells; c.tm.wide_total += c.tm.wide_passes; c.tm.la_total += g_out.nfilt;
     c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
     c.tm.kernel_launches = c.launches;
+    return 0;
+}
+
+int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
+                       int self, int comp, damar_overlaps *out) {
+    return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, nullptr);
+}
+/* Match_Filter whose records stay in HBM: they are appended to `sink` as call number `ordinal` of the job (the order in
+ * which the reference would have buffered the calls breaks full SORT_OVL ties); `out` receives the counters only. */
+int damar_match_filter_sink(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx, int self, int comp,
+                            damar_device_sink *sink, int ordinal, damar_overlaps *out) {
+    if (sink == nullptr) { set_error("damar_match_filter_sink: no sink"); return 1; }
+    DeviceResult *r = new DeviceResult();
+    r->ordinal = ordinal;
+    const int rc = match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, r);
+    g_out.keep = nullptr;
+    if (rc != 0) { delete r; return rc; }
+    dsink_add(reinterpret_cast<DeviceSink *>(sink), r);
     return 0;
 }
 

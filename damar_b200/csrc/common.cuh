@@ -59,6 +59,7 @@ struct DevBuf {
         n = cap;
     }
     T *steal() { T *q = p; p = nullptr; n = 0; return q; }
+    void take(DevBuf &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
 };
 
 // ---- grow-only pinned host buffer (D2H / H2D staging at full PCIe rate) ----
@@ -217,6 +218,7 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
 int self_hits(const DeviceIndex *idx, SeedHits &out);
 
 // pair_align.cu
+struct DeviceResult;
 struct HostOverlaps {                 // views of pinned staging buffers, valid until the next call
     const damar_overlap *ovl = nullptr;
     const uint64_t *toff = nullptr, *seq = nullptr;
@@ -224,7 +226,16 @@ struct HostOverlaps {                 // views of pinned staging buffers, valid 
     int64_t novl = 0, ntrace = 0;
     int tbytes = 2;
     int64_t nfilt = 0, multi = 0, cells = 0, pairs = 0, redo = 0;
+    DeviceResult *keep = nullptr;     // set by the caller: leave the records on the device instead of downloading them
 };
+// One Match_Filter call's records left in HBM for the device-side writer (las_device.cu)
+struct DeviceResult {
+    DevBuf<damar_overlap> recs; DevBuf<uint64_t> toff, seq; DevBuf<uint8_t> trace, dead;
+    uint64_t nrec = 0, ntrace = 0; int tbytes = 0; bool have_dead = false; int ordinal = 0;
+};
+struct DeviceSink;
+void dsink_add(DeviceSink *s, DeviceResult *r);
+
 // buffers that used to be function statics, one set per worker context
 struct WorkerScratch {
     DevBuf<uint32_t> tile_hist;                  // radix_sort.cu

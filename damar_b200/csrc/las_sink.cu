@@ -37,34 +37,46 @@ struct SortKey {                     // SORT_OVL (align.c:6104-6164) flattened i
 
 // .las images are tens to hundreds of MB; glibc serves such requests with fresh mmaps (page faults on
 // first touch dominate the build).  Freed images are kept on a small free list and reused.
-struct ImgHdr { size_t cap; size_t magic; };
+struct ImgHdr { size_t cap; size_t magic; };          // magic's low bit: the block is pinned (cudaHostAlloc)
 static std::vector<ImgHdr *> g_img_free;
 static std::mutex g_img_mu;
-static const size_t IMG_MAGIC = 0x64616d61726c6173ull;
+static size_t g_img_pinned = 0;                        // bytes of pinned images alive (in use or pooled)
+static const size_t IMG_MAGIC = 0x64616d61726c6170ull;
+static const size_t IMG_PIN_CAP = (size_t)6 << 30;     // beyond this images are ordinary memory (the copy is then staged by the driver)
+static void img_release(ImgHdr *h) {
+    if (h->magic & 1) { g_img_pinned -= h->cap; cudaFreeHost(h); } else free(h);
+}
 static uint8_t *img_alloc(size_t n) {
     std::lock_guard<std::mutex> lock(g_img_mu);
     size_t best = (size_t)-1;
     for (size_t i = 0; i < g_img_free.size(); i++)
         if (g_img_free[i]->cap >= n && (best == (size_t)-1 || g_img_free[i]->cap < g_img_free[best]->cap)) best = i;
-    ImgHdr *h;
-    if (best != (size_t)-1) { h = g_img_free[best]; g_img_free.erase(g_img_free.begin() + best); }
+    ImgHdr *h = nullptr;
+    if (best != (size_t)-1 && g_img_free[best]->cap <= 2 * n + (1u << 20)) { h = g_img_free[best]; g_img_free.erase(g_img_free.begin() + best); }
     else {
         size_t cap = n + n / 8 + 4096;
-        h = (ImgHdr *)malloc(sizeof(ImgHdr) + cap);
+        bool pinned = false;
+        if (n >= (1u << 20) && g_img_pinned + cap <= IMG_PIN_CAP) {      // device-to-host copies run at full PCIe rate into pinned memory
+            void *q = nullptr;
+            if (cudaHostAlloc(&q, sizeof(ImgHdr) + cap, cudaHostAllocDefault) == cudaSuccess) { h = (ImgHdr *)q; pinned = true; g_img_pinned += cap; }
+            else cudaGetLastError();
+        }
+        if (!h) h = (ImgHdr *)malloc(sizeof(ImgHdr) + cap);
         if (!h) fatal("out of host memory serialising %zu bytes of .las", n);
-        h->cap = cap; h->magic = IMG_MAGIC;
+        h->cap = cap; h->magic = IMG_MAGIC | (pinned ? 1 : 0);
     }
     return reinterpret_cast<uint8_t *>(h + 1);
 }
+uint8_t *img_alloc_host(size_t n) { return img_alloc(n ? n : 1); }
 static void img_free(void *p) {
     if (!p) return;
     ImgHdr *h = reinterpret_cast<ImgHdr *>(p) - 1;
-    if (h->magic != IMG_MAGIC) { free(p); return; }
+    if ((h->magic & ~(size_t)1) != IMG_MAGIC) { free(p); return; }
     std::lock_guard<std::mutex> lock(g_img_mu);
-    if (g_img_free.size() >= 8) {                         // keep the 8 largest
+    if (g_img_free.size() >= 24) {                        // keep the 24 largest
         size_t small = 0;
         for (size_t i = 1; i < g_img_free.size(); i++) if (g_img_free[i]->cap < g_img_free[small]->cap) small = i;
-        if (g_img_free[small]->cap < h->cap) { free(g_img_free[small]); g_img_free[small] = h; } else free(h);
+        if (g_img_free[small]->cap < h->cap) { img_release(g_img_free[small]); g_img_free[small] = h; } else img_release(h);
         return;
     }
     g_img_free.push_back(h);

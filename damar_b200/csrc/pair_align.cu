@@ -1669,6 +1669,26 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
 
     // ---- download into pinned staging; records stay in device emission order, `seq` carries the
     //      order the reference's thread buffers would have had ----
+    if (out.keep != nullptr) {                         // the device-side writer takes the buffers as they are (las_device.cu)
+        DeviceResult &K = *out.keep;
+        const uint64_t nrec = hc[5];
+        K.recs.take(recs); K.toff.take(rtoff); K.seq.take(rseq); K.trace.take(trace);
+        K.nrec = nrec; K.ntrace = hc[6]; K.tbytes = tbytes; K.have_dead = have_dead && nrec > 0;
+        uint64_t nkeep = nrec;
+        if (K.have_dead) {
+            K.dead.take(dead);
+            std::vector<uint8_t> h_dead(nrec);
+            CUDA_CHECK(cudaMemcpyAsync(h_dead.data(), K.dead.p, nrec, cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(stream_wait(st));
+            for (uint64_t i = 0; i < nrec; i++) nkeep -= h_dead[i] ? 1 : 0;
+        }
+        out.ovl = nullptr; out.toff = nullptr; out.seq = nullptr; out.trace = nullptr;
+        out.novl = (int64_t)nkeep; out.ntrace = (int64_t)hc[6]; out.tbytes = tbytes; out.redo = (int64_t)nredo;
+        c.tm.wide_passes = nwide_total;
+        out.nfilt = (int64_t)hc[0]; out.multi = (int64_t)hc[1]; out.cells = (int64_t)hc[2]; out.pairs = (int64_t)nwork;
+        c.tm.download_ms = 0;
+        return 0;
+    }
     HostProf hp4("ra.download");
     Timer t_dl(st);
     WorkerScratch &ws = scratch();

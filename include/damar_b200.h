@@ -223,6 +223,20 @@ int64_t         damar_sink_count(const damar_las_sink *s);
 int  damar_sink_serialise(damar_las_sink *s, int trace_spacing, int no_trace, int only_identity, int split_read,
                           uint8_t **buf1, int64_t *len1, uint8_t **buf2, int64_t *len2);
 void damar_free(void *p);
+/* ---- the same on the device (section 8f-2): records never leave HBM before they are a finished .las image ----
+ * damar_match_filter_sink = damar_match_filter whose records are appended to a device sink as call number `ordinal` of the
+ * job (0 = B block in normal orientation, 1 = complemented); `out` receives the counters only (no record pointers).
+ * damar_dsink_serialise = Write_Overlap_Buffer: SORT_OVL order by a device radix sort, image(s) built in HBM, ONE
+ * device-to-host copy per file.  maxlen / maxread = largest read length and DB-wide read id among the two blocks (they
+ * size the key fields).  Buffers as for damar_sink_serialise (free with damar_free).                                     */
+typedef struct damar_device_sink damar_device_sink;
+damar_device_sink *damar_dsink_new(void);
+void               damar_dsink_free(damar_device_sink *s);
+void               damar_dsink_reset(damar_device_sink *s);
+int  damar_match_filter_sink(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx, int self, int comp,
+                             damar_device_sink *sink, int ordinal, damar_overlaps *out);
+int  damar_dsink_serialise(damar_device_sink *s, int trace_spacing, int no_trace, int only_identity, int split_read,
+                           int maxlen, int maxread, uint8_t **buf1, int64_t *len1, uint8_t **buf2, int64_t *len2);
 /* LAmerge (utils/LAmerge.c; heap merge utils/LAmergeUtils.c:31-145): merges n sorted .las images (e.g. a block's pair files
  * R.i.R.1.las ... R.i.R.n.las) into one image ordered like SORT_OVL; records are copied verbatim.  Returns 0, 1 for a
  * malformed image, 2 for mixed trace spacings.  Free *out with damar_free.  Host only.                                   */

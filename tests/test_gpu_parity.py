@@ -195,14 +195,17 @@ def test_dropin_reference_datander_host(case, tmp_path):
         assert ok, f"{case}/{fn}: {why}"
 
 
-def test_unpacked_records_give_the_same_files():
+@pytest.mark.parametrize("env", [{"DAMAR_PACK": "0"}, {"DAMAR_DEVICE_SINK": "0"}], ids=["unpacked", "host_sink"])
+def test_alternative_paths_give_the_same_files(env):
     """DAMAR_PACK=0 keeps (code, gpos) and (key, bpos) as pairs instead of one 64-bit word per k-mer / seed hit -- the
-    layout blocks too large for the packed words fall back to.  Run in a fresh process (the switch is read once)."""
+    layout blocks too large for the packed words fall back to.  DAMAR_DEVICE_SINK=0 ships the records to the host and sorts
+    and serialises them there (the path the drop-in shim uses) instead of building the .las image on the device.  Run in a
+    fresh process (the switches are read once)."""
     import subprocess
     import sys
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from cases import *\nfrom damar_b200 import api, dbio\n"
-            "for table, dbdir, names in ((CASES, TINY, ['default', 'identity', 'rndmask', 'k16s200']), (GRAM_CASES, GRAM, ['gram_M0']), (BIAS_CASES, BIAS, ['bias_b'])):\n"
+            "for table, dbdir, names in ((CASES, TINY, ['default', 'identity', 'rndmask', 'k16s200', 'asym', 'notrace', 'b2']), (GRAM_CASES, GRAM, ['gram_M0', 'many_la']), (BIAS_CASES, BIAS, ['bias_b'])):\n"
             "    for case in names:\n"
             "        o = parse_flags(table[case]['flags'])\n"
             "        blks = {n: load_block(dbdir, n, tuple(o['masks'])) for n in set(table[case]['blocks'])}\n"
@@ -212,7 +215,7 @@ def test_unpacked_records_give_the_same_files():
             "            ok, why = dbio.las_equal(ref, out[fn])\n"
             "            assert ok, (case, fn, why)\n"
             "print('unpacked ok')\n") % (os.path.dirname(GOLDEN).rsplit('/tests', 1)[0], os.path.dirname(GOLDEN))
-    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "DAMAR_PACK": "0"}, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "unpacked ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
