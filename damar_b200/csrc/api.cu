@@ -104,7 +104,8 @@ static int do_init(int device) {
 // milliseconds per GB and synchronise the device.  All library work is ordered on one stream, so
 // a freed block can be handed to the next request immediately.  Requests are rounded up to a
 // coarse size class and served best-fit from the free list (at most 1.5x the rounded size).
-static std::map<void *, size_t> g_block_size;
+struct BlockInfo { size_t size; int owner; };          // owner = the worker context whose request allocated the block
+static std::map<void *, BlockInfo> g_block_size;
 static size_t round_class(size_t b) {
     size_t q = b >= (256u << 20) ? (64u << 20) : b >= (16u << 20) ? (8u << 20) : b >= (1u << 20) ? (1u << 20) : (64u << 10);
     return (b + q - 1) / q * q;
@@ -154,11 +155,13 @@ void *dev_alloc_bytes(size_t bytes) {
         }
     }
     std::lock_guard<std::mutex> lock(g_mu);
-    g_block_size[p] = r;
+    g_block_size[p] = BlockInfo{r, c.index};
     return p;
 }
-// A block freed by a worker goes to THAT worker's cache: the caller guarantees that no other stream still
-// uses it (blocks and indices shared between workers are freed only after the workers have been joined).
+// A freed block goes back to the cache of the worker that allocated it, whoever frees it: records and k-mer lists are
+// produced on worker contexts and released by the thread that collects a job, and would otherwise pile up in that
+// thread's cache while the workers keep allocating fresh memory.  The caller guarantees that no stream still uses the
+// block (cross-context frees happen after the producing call returned and the consuming stream was waited for).
 void dev_free(void *p) {
     Context &c = ctx();
     if (!p) return;
@@ -167,15 +170,16 @@ void dev_free(void *p) {
         cudaFree(p);
         return;
     }
-    size_t sz = 0;
+    size_t sz = 0; int owner = c.index;
     {
         std::lock_guard<std::mutex> lock(g_mu);
         auto it = g_block_size.find(p);
-        if (it != g_block_size.end()) sz = it->second;
+        if (it != g_block_size.end()) { sz = it->second.size; owner = it->second.owner; }
     }
     if (sz == 0) { cudaFree(p); return; }
-    std::lock_guard<std::mutex> lk(c.cache_mu);
-    c.free_blocks.emplace(sz, p);
+    Context &o = (owner >= 0 && owner < MAX_WORKERS && g_ctx[owner].ready) ? g_ctx[owner] : c;
+    std::lock_guard<std::mutex> lk(o.cache_mu);
+    o.free_blocks.emplace(sz, p);
 }
 
 void ensure_init() {

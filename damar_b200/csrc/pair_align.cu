@@ -745,7 +745,7 @@ struct PipeArgs {
     uint32_t *flag;                       // filter_pairs: per work pair
     uint32_t *cand0;                      // filter_pairs: the pair's first seed candidate, as an offset from the pair's first hit
     unsigned int *ctr;                    // device counters, see CTR_*
-    uint32_t *wide_list, *wide_ready; unsigned int wide_cap; int wide_ctas;
+    uint32_t *wide_list, *wide_ready; unsigned int wide_cap; int wide_ctas, linger;
     wc::Lane *wide_lane; uint32_t *wide_ring;   // state of the passes that outgrew the 32-diagonal ring: [task][32][FRONT_WORDS]
     const uint32_t *task_order;           // tasks of the round, longest expected pass first (or null: index order)
     wc::Cell *pool; unsigned int pool_cap;
@@ -990,10 +990,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     L.status = wc::ST_IDLE; L.k = 0; L.low = 0;
     unsigned task = 0;
     unsigned long long cells_done = 0;
-    // Warp-uniform shape.  The first wide_ctas CTAs are wide from the start (every warp); the others are narrow and LEAVE
-    // when the queue is empty, so their SMs go to the next kernel (another comparison's, usually) while the last parked
-    // passes finish on a few SMs.  A grid too small to set wide CTAs aside lets its narrow warps turn wide at the end.
-    const bool linger = Q.wide_ctas == 0;
+    // Warp-uniform shape.  A full-size round is TWO launches of this kernel, back to back with no host wait between them:
+    // every CTA narrow, leaving when the queue is empty (their SMs go to the next kernel, usually another comparison's),
+    // then a few CTAs that are wide from the start (wide_ctas == gridDim.x) for the parked passes -- about 2 % of the
+    // passes, but long ones, which would otherwise keep every SM of the first launch waiting.  A small round is one
+    // launch whose narrow warps turn wide at the end (linger).
+    const bool linger = Q.linger != 0;
     bool wide = (int)blockIdx.x < Q.wide_ctas;
     wc::FrontRT F = wide ? wc::FrontRT{region + (lane & 15), 63, 4} : wc::FrontRT{region + lane, 31, 5};
     if (wide && lane >= 16) L.status = wc::ST_EXIT;
@@ -1496,15 +1498,24 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     okeys.reserve(4 * na); ovals.reserve(4 * na);
     static const bool lpt = !(getenv("DAMAR_LPT") && atoi(getenv("DAMAR_LPT")) == 0);
 
-    // pebble pool: measured need is ~300 cells per alignment on 10 kbp reads; a dry pool only delays alignments a round
-    size_t pool_cells = (size_t)nactive * (size_t)(2 * (maxlen / TS + 2) + 512) + (1u << 16);
+    // Pebble pool, sized from the measured need instead of the worst case: a pass logs one cell per trace point it crosses
+    // on either axis (~ 2 x length / TS per pass, the alive paths of a front share prefixes) plus up to one partly used
+    // 32-cell chunk per thread and pass -- about 300 cells per alignment on 10 kbp reads.  A dry pool is not an error: the
+    // alignments that found no cell are retried in the next round (CTR_RETRY), when most pairs are finished.
+    const int64_t avglen = std::max<int64_t>(ab->totlen / std::max(1, ab->nreads), bb->totlen / std::max(1, bb->nreads));
+    size_t pool_cells = (size_t)nactive * (size_t)(6 * (avglen / TS + 2) + 128) + (1u << 16);
+    {
+        const size_t worst = (size_t)nactive * (size_t)(2 * (maxlen / TS + 2) + 512) + (1u << 16);
+        if (pool_cells > worst) pool_cells = worst;
+    }
     if (pool_cells > 0x7ffffff0ull) pool_cells = 0x7ffffff0ull;
     DevBuf<wc::Cell> pool; pool.reserve(pool_cells);
     Q.pool = pool.p; Q.pool_cap = (unsigned int)pool_cells;
 
     // warps per CTA of the wave kernel (16 KB of shared memory each)
     static const int wwarps = getenv("DAMAR_WAVE_WARPS") ? atoi(getenv("DAMAR_WAVE_WARPS")) : 12;
-    static const int wide_ctas_max = getenv("DAMAR_WIDE_CTAS") ? std::max(0, std::min(64, atoi(getenv("DAMAR_WIDE_CTAS")))) : 12;
+    // CTAs of the second launch of a round (parked wide passes); 0: one launch, its narrow warps turn wide at the end
+    static const int wide_ctas_max = getenv("DAMAR_WIDE_CTAS") ? std::max(0, std::min(64, atoi(getenv("DAMAR_WIDE_CTAS")))) : 8;
     // CTAs (= SMs, one CTA fills an SM's shared memory) of one comparison's wave kernel; fewer than 148 lets the kernels of
     // concurrent comparisons run side by side so that the tail of one overlaps the bulk of another
     static const int wave_ctas = getenv("DAMAR_WAVE_CTAS") ? std::max(1, std::min(NUM_SMS_B200, atoi(getenv("DAMAR_WAVE_CTAS")))) : NUM_SMS_B200;
@@ -1562,10 +1573,8 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
             Timer t_k(st);
             {
                 const unsigned per = (unsigned)wwarps * 32;
-                unsigned wb = std::min<unsigned>((unsigned)wave_ctas, (2 * ncand + per - 1) / per);
-                // a full-size launch sets a few CTAs aside for the parked (wide) passes: ~2 % of the passes, but long ones
-                Q.wide_ctas = (wb >= 64) ? std::min<int>(wide_ctas_max, (int)wb / 8) : 0;
-                wb = std::min<unsigned>((unsigned)NUM_SMS_B200, wb + (unsigned)Q.wide_ctas);
+                const unsigned wb = std::min<unsigned>((unsigned)wave_ctas, (2 * ncand + per - 1) / per);
+                const bool two_launches = wb >= 64 && wide_ctas_max > 0;
                 Q.task_order = nullptr;
                 if (ncand >= 2048 && lpt) {                      // order the queue: longest passes first
                     const int64_t nt = 2 * (int64_t)ncand;
@@ -1576,12 +1585,17 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                     Q.task_order = v0;
                 }
                 CUDA_CHECK(cudaMemsetAsync(wide_ready.p, 0, sizeof(uint32_t) * 2 * na, st));   // all of it: tickets run past this round's parks
-                if (wwarps == 8) wave_tasks<4, 8><<<wb, per, WaveCfg<8>::SMEM, st>>>(Q);
-                else if (wwarps == 10) wave_tasks<4, 10><<<wb, per, WaveCfg<10>::SMEM, st>>>(Q);
-                else if (wwarps == 12) wave_tasks<4, 12><<<wb, per, WaveCfg<12>::SMEM, st>>>(Q);
-                else if (wwarps == 14) wave_tasks<4, 14><<<wb, per, WaveCfg<14>::SMEM, st>>>(Q);
-                else wave_tasks<4, 13><<<wb, per, WaveCfg<13>::SMEM, st>>>(Q);
-                KERNEL_CHECK(); count_launch();
+                auto launch = [&](unsigned grid) {
+                    if (wwarps == 8) wave_tasks<4, 8><<<grid, per, WaveCfg<8>::SMEM, st>>>(Q);
+                    else if (wwarps == 10) wave_tasks<4, 10><<<grid, per, WaveCfg<10>::SMEM, st>>>(Q);
+                    else if (wwarps == 13) wave_tasks<4, 13><<<grid, per, WaveCfg<13>::SMEM, st>>>(Q);
+                    else if (wwarps == 14) wave_tasks<4, 14><<<grid, per, WaveCfg<14>::SMEM, st>>>(Q);
+                    else wave_tasks<4, 12><<<grid, per, WaveCfg<12>::SMEM, st>>>(Q);
+                    KERNEL_CHECK(); count_launch();
+                };
+                Q.wide_ctas = 0; Q.linger = two_launches ? 0 : 1;
+                launch(wb);
+                if (two_launches) { Q.wide_ctas = wide_ctas_max; launch((unsigned)wide_ctas_max); }
             }
             c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
             { unsigned int nw = 0; CUDA_CHECK(cudaMemcpyAsync(&nw, ctr.p + CTR_NWIDE, sizeof(nw), cudaMemcpyDeviceToHost, st)); CUDA_CHECK(stream_wait(st)); nwide_total += nw; }

@@ -38,6 +38,7 @@ CASES = {
     "k16s200":   dict(flags=["-j8", "-M0", "-k16", "-s200", "-t12"], blocks=["T.1", "T.1"]),
     "memlimit":  dict(flags=["-j4", "-M1"], blocks=["T.1", "T.2"]),
     "notrace":   dict(flags=["-j4", "-M0", "-T"], blocks=["T.1", "T.2"]),
+    "onlyid":    dict(flags=["-j4", "-M0", "-O"], blocks=["T.1", "T.1", "T.2"]),
 }
 
 

@@ -174,6 +174,24 @@ def test_datander_matches_reference(case):
         assert ok, f"{case}/{fn}: {why} (ref {len(ref)} bytes, got {len(out[fn])})"
 
 
+@pytest.mark.parametrize("device_sink", ["1", "0"])
+def test_only_identity_on_tandem_reads(device_sink):
+    """daligner -O (ONLY_IDENTITY, daligner.c:756, align.c:6185-6194): only alignments of a read with itself are written --
+    non-trivial on the reads with tandem arrays (reference daligner's file), through both output paths."""
+    import subprocess
+    import sys
+    from cases import ROOT
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from cases import *\nfrom damar_b200 import api, dbio\n"
+            "blk = load_block(TAN, 'N.1', ())\n"
+            "out = api.daligner(blk, [blk], api.Settings(only_identity=True, minlen=500, mem_limit_gb=0))\n"
+            "ref = open(os.path.join(TAN, 'ref_dal', 'tan_dal_O', 'N.1.N.1.las'), 'rb').read()\n"
+            "ok, why = dbio.las_equal(ref, out['N.1.N.1.las'])\n"
+            "assert ok, why\nassert len(ref) > 10000\nprint('only identity ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "DAMAR_DEVICE_SINK": device_sink}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "only identity ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("case", ["tan_default", "tan_k14"])
 def test_dropin_reference_datander_host(case, tmp_path):
     """The UNMODIFIED scrub/datander.c linked against libdamar_b200.so through the tandem.h shim (oracle/_ref/datander_b200)."""
