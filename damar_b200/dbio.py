@@ -143,8 +143,81 @@ def read_block(path: str, tracks: Optional[List[str]] = None) -> Block:
     return blk
 
 
+MARVEL_CHUNK = 8 * 1024 * 1024        # COMPRESS_MAX_CHUNK, lib/compression.c:13
+
+
+def _uncompress_chunks(buf: bytes) -> bytes:
+    """uncompress_chunks (lib/compression.c:79-110): a sequence of {uint64 clen, zlib stream of clen bytes}."""
+    import zlib
+    out, i = [], 0
+    while i != len(buf):
+        clen = struct.unpack_from("<Q", buf, i)[0]
+        out.append(zlib.decompress(buf[i + 8: i + 8 + clen]))
+        i += 8 + clen
+    return b"".join(out)
+
+
+def _compress_chunks(buf: bytes) -> bytes:
+    """compress_chunks (lib/compression.c:15-77)."""
+    import zlib
+    out = []
+    for i in range(0, len(buf), MARVEL_CHUNK):
+        c = zlib.compress(buf[i: i + MARVEL_CHUNK])
+        out.append(struct.pack("<Q", len(c)) + c)
+    return b"".join(out)
+
+
+def write_marvel_track(db_path: str, name: str, anno: np.ndarray, data: np.ndarray) -> None:
+    """A MARVEL track of the WHOLE DB (lib/tracks.h:43-60, track_write): `<path>.<name>.a2` = 64-byte header
+    {u16 version 2, u16 size 8, u32 pad, u64 len, u64 clen, u64 cdlen, 4 x u64 reserved} + the chunk-compressed byte
+    offsets (uint64[len + 1]), `<path>.<name>.d2` = the chunk-compressed int32 data.  Used by the tests to make fixtures the
+    reference's track_load reads."""
+    anno = np.ascontiguousarray(anno, dtype="<u8")
+    canno, cdata = _compress_chunks(anno.tobytes()), _compress_chunks(np.ascontiguousarray(data, dtype="<i4").tobytes())
+    with open(f"{db_path}.{name}.a2", "wb") as f:
+        f.write(struct.pack("<HHIQQQ4Q", 2, 8, 0, len(anno) - 1, len(canno), len(cdata), 0, 0, 0, 0))
+        f.write(canno)
+    with open(f"{db_path}.{name}.d2", "wb") as f:
+        f.write(cdata)
+
+
+def _load_marvel_track(blk: Block, name: str) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+    """track_load (lib/tracks.c:20-126): the `.a2/.d2` pair if it exists (else None: the caller falls back to the Dazzler
+    track like :26-30), cut to the block.  As in the reference the cut is made only `if (db->ufirst > 1)` (:98) -- a block
+    that starts at read 1 gets the whole-DB arrays unshifted there, and so here."""
+    a2 = f"{blk.path}.{name}.a2"
+    if not os.path.exists(a2):
+        return None
+    with open(a2, "rb") as f:
+        version, size, _pad, tlen, clen, cdlen = struct.unpack("<HHIQQQ", f.read(32))
+        f.read(32)
+        if size <= 0:
+            raise ValueError(f"invalid size field in track {name}")
+        if blk.part == 0 and tlen != blk.nreads:
+            raise ValueError(f"invalid track length in header of track {name}")
+        canno = f.read(clen)
+    if size != 8:
+        raise ValueError("mask tracks must have 8-byte offsets (daligner.c:480-482)")
+    anno = np.frombuffer(_uncompress_chunks(canno), dtype="<u8")[: tlen + 1].astype(np.int64)
+    with open(f"{blk.path}.{name}.d2", "rb") as f:
+        data = _uncompress_chunks(f.read(cdlen))[: int(anno[tlen])]
+    if blk.ufirst > 1:
+        anno = anno[blk.ufirst: blk.ufirst + blk.nreads + 1].copy()
+        start, end = int(anno[0]), int(anno[blk.nreads])
+        anno -= start
+        data = data[start:end]
+    else:
+        anno = anno[: blk.nreads + 1].copy()
+    d32 = np.frombuffer(data, dtype="<i4")[: int(anno[blk.nreads]) // 4].copy()
+    return anno // 4, d32
+
+
 def _load_interval_track(blk: Block, name: str) -> Tuple[np.ndarray, np.ndarray]:
-    """Dazzler interval track for the block (db/DB.c:1113-1294), offsets converted to int units."""
+    """track_load (lib/tracks.c:20): the MARVEL `.a2/.d2` track if present, else the Dazzler interval track for the block
+    (db/DB.c:1113-1294); offsets converted to int units (daligner.c:480-482)."""
+    mt = _load_marvel_track(blk, name)
+    if mt is not None:
+        return mt
     cand = []
     if blk.part:
         cand.append((f"{blk.path}.{blk.part}.{name}", True))

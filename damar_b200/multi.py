@@ -109,8 +109,11 @@ def exchange_blocks_device(dbdir: str, root: str, shards: Sequence[Sequence[Job]
             blk = host_blocks[b] if host_blocks is not None else loader(os.path.join(dbdir, name), masks)
             h = api.DeviceBlockHandle(blk)
         if len(ranks) > 1 and world > 1:
-            group = _group_for(dist, ranks, world)           # every rank must create every group
-            if rank in ranks:
+            # a block most ranks need goes over the world group (the others drop it): a communicator per subset of ranks
+            # costs more to set up than the 50 MB cost to send
+            part = ranks if len(ranks) <= world // 2 else list(range(world))
+            group = _group_for(dist, part, world)            # every rank must create every group
+            if rank in part:
                 if rank == owner:
                     v = h.view()
                     m = torch.tensor([v.nreads, v.maxlen, v.ufirst, v.part, v.totlen, v.nbases, v.sizeof_db, v.npacked_words,
@@ -137,7 +140,7 @@ def exchange_blocks_device(dbdir: str, root: str, shards: Sequence[Sequence[Job]
                     sent += t.numel() * t.element_size()
                     bufs[nm] = t
                 torch.cuda.synchronize()
-                if rank != owner:
+                if rank != owner and rank in ranks:
                     nv = api.BlockView()
                     nv.nreads, nv.maxlen, nv.ufirst, nv.part, nv.totlen, nv.nbases, nv.sizeof_db, nv.npacked_words = mm[:8]
                     nv.mask_len, nv.flags = mask_len, mm[10]

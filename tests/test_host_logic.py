@@ -209,3 +209,35 @@ def test_las_merge_matches_reference_lamerge():
         api.las_merge([a, b])
     with pytest.raises(ValueError, match="malformed"):
         api.las_merge([a[:-3]])
+
+
+def test_marvel_track_loader(tmp_path):
+    """track_load (lib/tracks.c:20-126): a MARVEL `.a2/.d2` track is preferred over the Dazzler `.anno/.data` pair and cut to
+    the block.  The fixture is the tiny DB's random-interval track rewritten in MARVEL's format (dbio.write_marvel_track; the
+    reference daligner reads such a file and reproduces the Dazzler-track case byte for byte -- checked when the writer was
+    made); the oracle run with it must equal the reference's `rndmask` files."""
+    import shutil
+    import struct
+    import oracle_ffi as O
+    from cases import CASES, TINY, golden_files, oracle_kwargs, parse_flags
+    for fn in os.listdir(TINY):
+        if os.path.isfile(os.path.join(TINY, fn)):
+            shutil.copy(os.path.join(TINY, fn), tmp_path / fn)
+    with open(tmp_path / ".T.rnd.anno", "rb") as f:
+        n, size = struct.unpack("<ii", f.read(8))
+        anno = np.frombuffer(f.read(), dtype="<i8")
+    data = np.fromfile(tmp_path / ".T.rnd.data", dtype="<i4")
+    dbio.write_marvel_track(str(tmp_path / ".T"), "mrnd", anno, data)
+    for name in ("T.1", "T.2"):
+        d = dbio.read_block(str(tmp_path / name), ["rnd"])
+        m = dbio.read_block(str(tmp_path / name), ["mrnd"])
+        assert np.array_equal(d.mask_anno, m.mask_anno) and np.array_equal(d.mask_data, m.mask_data)
+        assert m.mask_data.size > 100
+    o = parse_flags(CASES["rndmask"]["flags"])
+    blks = [dbio.read_block(str(tmp_path / nm), ["mrnd"]) for nm in ("T.1", "T.2")]
+    for b in blks:
+        b.track_names = ["rnd"]                       # sizeof_DB counts the track's name (irrelevant with -M0, kept equal anyway)
+    out = O.daligner(blks[0], [blks[0], blks[1]], oracle_kwargs(o))
+    for fn, ref in golden_files("rndmask").items():
+        ok, why = dbio.las_equal(ref, out[fn])
+        assert ok, f"{fn}: {why}"
