@@ -85,7 +85,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
            "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge",
            "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view", "damar_match_self",
-           "damar_dsink_new", "damar_dsink_free", "damar_dsink_reset", "damar_match_filter_sink", "damar_dsink_serialise"]
+           "damar_trace_point_scripts", "damar_host_free", "damar_dsink_new", "damar_dsink_free", "damar_dsink_reset", "damar_match_filter_sink", "damar_dsink_serialise"]
 
 _lib = None
 
@@ -107,6 +107,10 @@ def load_library():
     L.damar_trace_point_diffs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                           C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     L.damar_trace_point_diffs.restype = C.c_int
+    L.damar_trace_point_scripts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
+                                            C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.damar_trace_point_scripts.restype = C.c_int
+    L.damar_host_free.argtypes = [C.c_void_p]
     L.damar_las_merge.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.damar_las_merge.restype = C.c_int
     L.damar_set_biased.argtypes = [C.c_int]
@@ -703,6 +707,34 @@ def trace_point_diffs(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las:
         raise RuntimeError("damar_b200: " + load_library().damar_last_error().decode())
     rec = rec[:novl]
     return (rec, seg[: ntrace // 2], (toff[:novl] // 2).astype(np.int64)) if segments else rec
+
+
+def trace_point_scripts(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las: bytes):
+    """Compute_Trace_PTS (align.c:5577-5692, mode GREEDIEST) over a whole .las image: per record the exact diffs AND the edit
+    script the reference leaves in path->trace.  Returns (rec_diffs int32[novl], script_off int64[novl + 1], script int32[])."""
+    from . import dbio
+    novl, tspace, recs, traces = dbio.parse_las(las)
+    tbytes = 1 if tspace <= 125 else 2
+    toff = np.zeros(novl + 1, np.uint64)
+    toff[1:] = np.cumsum(recs["tlen"].astype(np.uint64))
+    trace = np.frombuffer(b"".join(traces), dtype=np.uint8).copy() if novl else np.zeros(1, np.uint8)
+    if trace.size == 0:
+        trace = np.zeros(1, np.uint8)
+    recs = np.ascontiguousarray(recs)
+    rec = np.zeros(max(novl, 1), np.int32)
+    soff = np.zeros(novl + 1, np.int64)
+    sp, sl = C.c_void_p(), C.c_int64(0)
+    L = load_library()
+    rc = L.damar_trace_point_scripts(ablock.handle, bblock.handle, recs.ctypes.data, toff.ctypes.data, trace.ctypes.data, tbytes, novl,
+                                     int(toff[novl]), tspace, rec.ctypes.data, soff.ctypes.data, C.byref(sp), C.byref(sl))
+    if rc not in (0, 1):
+        raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
+    try:
+        script = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_int32)), shape=(max(sl.value, 1),))[: sl.value].copy() if sp.value else np.zeros(0, np.int32)
+    finally:
+        if sp.value:
+            L.damar_host_free(sp)
+    return rec[:novl], soff, script
 
 
 def las_merge(images: Sequence[bytes]) -> bytes:

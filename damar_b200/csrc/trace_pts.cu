@@ -13,7 +13,10 @@
 //     F[e][k] = slide(max(F[e-1][k] + 1, F[e-1][k-1] + 1, F[e-1][k+1])),   k = x - y,  done when F[e][M-N] = M.
 // Doubles as the on-device validator of the wave kernel's output: every emitted (d_i, b_i) is realisable, and
 // optimal unless the record went through bridging (tests/test_gpu_parity.py).
+#include <vector>
+
 #include "common.cuh"
+#include "trace_script_core.cuh"
 #include "wave_core.cuh"
 
 namespace damar {
@@ -119,13 +122,106 @@ __global__ void __launch_bounds__(128) trace_point_diffs(TpArgs P, int16_t *__re
     }
 }
 
+// ---- the edit script (Compute_Trace_PTS proper, align.c:5577-5692; iter_np in GREEDIEST mode via trace_script_core.cuh) ----
+struct SegArgs {
+    TpArgs P;
+    const uint16_t *segcost;                  // exact distance of every segment (trace_point_diffs)
+    int32_t *seg_ab, *seg_bb, *seg_m, *seg_n, *seg_dmax, *seg_rec;
+    uint32_t *need, *cap;                     // scratch ints / output slots per segment
+};
+// one warp per record: the segment table (align.c:5650-5680) and what every segment needs
+__global__ void __launch_bounds__(128) script_segments(SegArgs S) {
+    const TpArgs &P = S.P;
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = gw; r < P.novl; r += nw) {
+        const damar_overlap o = P.ovl[r];
+        const int nseg = o.tlen / 2;
+        const uint64_t t0 = P.toff[r];
+        const bool bad = P.rec[r] < 0;
+        int dmax = 0;
+        for (int s = lane; s < nseg; s += 32) { const int d = trace_at(P, t0 + 2 * (uint64_t)s); if (d > dmax) dmax = d; }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, dmax, d); if (t > dmax) dmax = t; }
+        int bb0 = o.bbpos;
+        for (int s0 = 0; s0 < nseg; s0 += 32) {
+            const int s = s0 + lane;
+            const bool v = s < nseg;
+            const int bi = v ? trace_at(P, t0 + 2 * (uint64_t)s + 1) : 0;
+            int inc = bi;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+            if (v) {
+                const uint64_t g = t0 / 2 + (uint64_t)s;
+                const int bb = bb0 + inc - bi;
+                const int grid0 = (o.abpos / P.TS) * P.TS;
+                const int ab = (s == 0) ? o.abpos : grid0 + s * P.TS;
+                const int ae = (s == nseg - 1) ? o.aepos : grid0 + (s + 1) * P.TS;
+                const int be = (s == nseg - 1) ? o.bepos : bb + bi;
+                const int M = ae - ab, N = be - bb, del = M - N, c = S.segcost[g];
+                const int D = c - (del < 0 ? -del : del);
+                S.seg_ab[g] = ab; S.seg_bb[g] = bb; S.seg_m[g] = M; S.seg_n[g] = N; S.seg_dmax[g] = dmax; S.seg_rec[g] = (int32_t)r;
+                S.need[g] = bad || D < 0 ? 0u : (uint32_t)ts::scratch_ints(D, del);
+                S.cap[g] = bad ? 0u : (uint32_t)c;
+            }
+            bb0 += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+}
+// base of one read at an index relative to a segment start; the read's terminators are 4, anything further out never matches
+struct PackedRel {
+    const uint32_t *words; uint32_t base; int pos, len; int oob;
+    __device__ int operator()(int i) const {
+        const int q = pos + i;
+        if (q < 0 || q >= len) return (q == -1 || q == len) ? 4 : oob;
+        const uint32_t p = base + (uint32_t)q;
+        return (int)((words[p >> 4] >> (30 - 2 * (int)(p & 15u))) & 3u);
+    }
+};
+// one thread per segment [g0, g1): iter_np with its tie-breaks
+__global__ void __launch_bounds__(128) script_emit(SegArgs S, uint64_t g0, uint64_t g1, const uint64_t *__restrict__ need_off, uint64_t need_base,
+                                                  const uint64_t *__restrict__ cap_off, int *__restrict__ scratch, int32_t *__restrict__ raw,
+                                                  uint32_t *__restrict__ count) {
+    const TpArgs &P = S.P;
+    const uint64_t g = g0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g1) return;
+    count[g] = 0;
+    if (S.need[g] == 0) return;                            // a rejected record, or a slot no live record owns
+    const damar_overlap o = P.ovl[S.seg_rec[g]];
+    const int ar = o.aread - P.afirst, br = o.bread - P.bfirst;
+    const int ab = S.seg_ab[g], bb = S.seg_bb[g], M = S.seg_m[g], N = S.seg_n[g], del = M - N;
+    const int D = (int)S.segcost[g] - (del < 0 ? -del : del);
+    const PackedRel A{P.aw, P.aboff[ar], ab, P.arlen[ar], 5}, B{P.bw[o.flags & 1u], P.bboff[br], bb, P.brlen[br], 6};
+    int cost = 0;
+    const int n = ts::np_script(A, M, B, N, S.seg_dmax[g], D, ab, bb, scratch + (need_off[g] - need_base), raw + cap_off[g], (int)S.cap[g], &cost);
+    if (n < 0 || cost != (int)S.segcost[g]) { atomicExch(P.err, 2); return; }
+    count[g] = (uint32_t)n;
+}
+__global__ void script_compact(const int32_t *__restrict__ raw, const uint64_t *__restrict__ cap_off, const uint32_t *__restrict__ count,
+                               const uint64_t *__restrict__ out_off, uint64_t nseg, int32_t *__restrict__ out) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nseg) return;
+    const uint32_t n = count[g];
+    const int32_t *src = raw + cap_off[g];
+    int32_t *dst = out + out_off[g];
+    for (uint32_t i = 0; i < n; i++) dst[i] = src[i];
+}
+__global__ void script_record_offsets(const uint64_t *__restrict__ toff, int64_t novl, const uint64_t *__restrict__ out_off, uint64_t nseg, uint64_t total,
+                                      int64_t *__restrict__ rec_off) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > novl) return;
+    const uint64_t g = (r == novl) ? nseg : toff[r] / 2;
+    rec_off[r] = (int64_t)(g >= nseg ? total : out_off[g]);
+}
+
 }  // namespace
 
 // rec_diffs[novl]: what Compute_Trace_PTS leaves in path->diffs (-1: trace point out of bounds, align.c:5667);
 // seg_diffs (optional): one value per segment, segment i of record r at trace_off[r] / 2 + i.  Returns 0, or 1 if any
 // record was out of bounds.
 int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap *ovl, const uint64_t *toff, const void *trace,
-                           int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs) {
+                           int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs,
+                           int64_t *script_off, int32_t **script_out, int64_t *script_len) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     if (novl <= 0) return 0;
@@ -136,7 +232,7 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
     DevBuf<int16_t> d_scr;
     d_ovl.reserve((size_t)novl); d_toff.reserve((size_t)novl); d_trace.reserve((size_t)ntrace * tbytes + 16); d_rec.reserve((size_t)novl);
     d_err.reserve(1);
-    if (seg_diffs) d_seg.reserve((size_t)ntrace / 2 + 1);
+    if (seg_diffs || script_off) d_seg.reserve((size_t)ntrace / 2 + 1);
     CUDA_CHECK(cudaMemcpyAsync(d_ovl.p, ovl, sizeof(damar_overlap) * novl, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(d_toff.p, toff, sizeof(uint64_t) * novl, cudaMemcpyHostToDevice, st));
     if (ntrace > 0) CUDA_CHECK(cudaMemcpyAsync(d_trace.p, trace, (size_t)ntrace * tbytes, cudaMemcpyHostToDevice, st));
@@ -148,7 +244,7 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
     P.aboff = ab->boff; P.bboff = bb->boff; P.arlen = ab->rlen; P.brlen = bb->rlen;
     P.afirst = ab->ufirst; P.bfirst = bb->ufirst; P.anreads = ab->nreads; P.bnreads = bb->nreads;
     P.ovl = d_ovl.p; P.toff = d_toff.p; P.trace = d_trace.p; P.tbytes = tbytes; P.novl = novl; P.TS = TS;
-    P.rec = d_rec.p; P.seg = seg_diffs ? d_seg.p : nullptr; P.err = d_err.p;
+    P.rec = d_rec.p; P.seg = (seg_diffs || script_off) ? d_seg.p : nullptr; P.err = d_err.p;
     trace_point_diffs<<<blocks, threads, 0, st>>>(P, d_scr.p);
     KERNEL_CHECK(); count_launch();
     int err = 0;
@@ -156,6 +252,61 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
     if (seg_diffs && ntrace > 0) CUDA_CHECK(cudaMemcpyAsync(seg_diffs, d_seg.p, sizeof(uint16_t) * (size_t)(ntrace / 2), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(stream_wait(st));
+    if (script_off == nullptr) return err;
+
+    // ---- the edit scripts: segment table, per-segment scratch / output slots by prefix sums, one thread per segment ----
+    *script_out = nullptr; *script_len = 0;
+    const uint64_t nseg = (uint64_t)ntrace / 2;
+    if (nseg == 0) { for (int64_t r = 0; r <= novl; r++) script_off[r] = 0; return err; }
+    DevBuf<int32_t> tab; DevBuf<uint32_t> need, cap, count; DevBuf<uint64_t> need_off, cap_off, out_off, tot;
+    tab.reserve(6 * (size_t)nseg); need.reserve((size_t)nseg + 1); cap.reserve((size_t)nseg + 1); count.reserve((size_t)nseg + 1);
+    need_off.reserve((size_t)nseg + 1); cap_off.reserve((size_t)nseg + 1); out_off.reserve((size_t)nseg + 1); tot.reserve(4);
+    CUDA_CHECK(cudaMemsetAsync(need.p, 0, sizeof(uint32_t) * nseg, st));
+    CUDA_CHECK(cudaMemsetAsync(cap.p, 0, sizeof(uint32_t) * nseg, st));
+    SegArgs S{};
+    S.P = P; S.segcost = d_seg.p;
+    S.seg_ab = tab.p; S.seg_bb = tab.p + nseg; S.seg_m = tab.p + 2 * nseg; S.seg_n = tab.p + 3 * nseg; S.seg_dmax = tab.p + 4 * nseg; S.seg_rec = tab.p + 5 * nseg;
+    S.need = need.p; S.cap = cap.p;
+    script_segments<<<blocks, threads, 0, st>>>(S);
+    KERNEL_CHECK();
+    exclusive_scan_u32_to_u64(need.p, need_off.p, (int64_t)nseg, tot.p, st);
+    exclusive_scan_u32_to_u64(cap.p, cap_off.p, (int64_t)nseg, tot.p + 1, st);
+    uint64_t htot[2];
+    CUDA_CHECK(cudaMemcpyAsync(htot, tot.p, sizeof(htot), cudaMemcpyDeviceToHost, st));
+    std::vector<uint64_t> h_need_off((size_t)nseg);
+    CUDA_CHECK(cudaMemcpyAsync(h_need_off.data(), need_off.p, sizeof(uint64_t) * nseg, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(stream_wait(st));
+    DevBuf<int32_t> raw; raw.reserve((size_t)htot[1] + 4);
+    const uint64_t budget = (uint64_t)1 << 28;                     // ints of scratch per launch (1 GB)
+    DevBuf<int> scr; scr.reserve((size_t)std::min<uint64_t>(htot[0] + 4, budget + ((uint64_t)1 << 24)));
+    for (uint64_t g0 = 0; g0 < nseg;) {                            // batches of segments whose scratch fits the budget
+        uint64_t lo = g0 + 1, hi = nseg;                           // largest g1 with need_off[g1] - need_off[g0] <= budget
+        while (lo < hi) { const uint64_t m = (lo + hi + 1) >> 1; if (h_need_off[m - 1] - h_need_off[g0] <= budget || m == g0 + 1) lo = m; else hi = m - 1; }
+        const uint64_t g1 = lo;
+        const uint64_t span = ((g1 < nseg) ? h_need_off[g1] : htot[0]) - h_need_off[g0];
+        if (span + 4 > scr.n) scr.reserve((size_t)span + 4);
+        script_emit<<<(unsigned)((g1 - g0 + 127) / 128), 128, 0, st>>>(S, g0, g1, need_off.p, h_need_off[g0], cap_off.p, scr.p, raw.p, count.p);
+        KERNEL_CHECK(); count_launch();
+        g0 = g1;
+    }
+    exclusive_scan_u32_to_u64(count.p, out_off.p, (int64_t)nseg, tot.p + 2, st);
+    uint64_t total = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&total, tot.p + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(stream_wait(st));
+    if (err == 2) { set_error("damar_trace_point_scripts: a segment's script disagrees with its distance"); return 2; }
+    DevBuf<int32_t> outb; outb.reserve((size_t)total + 4);
+    DevBuf<int64_t> roff; roff.reserve((size_t)novl + 2);
+    script_compact<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(raw.p, cap_off.p, count.p, out_off.p, nseg, outb.p);
+    KERNEL_CHECK();
+    script_record_offsets<<<(unsigned)((novl + 1 + 255) / 256), 256, 0, st>>>(d_toff.p, novl, out_off.p, nseg, total, roff.p);
+    KERNEL_CHECK(); count_launch(3);
+    int32_t *hs = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total + 1));
+    if (hs == nullptr) { set_error("out of host memory for %llu script values", (unsigned long long)total); return 2; }
+    if (total) CUDA_CHECK(cudaMemcpyAsync(hs, outb.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(script_off, roff.p, sizeof(int64_t) * (novl + 1), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(stream_wait(st));
+    *script_out = hs; *script_len = (int64_t)total;
     return err;
 }
 

@@ -176,6 +176,17 @@ int damar_trace_point_diffs(damar_block *ablk, damar_block *bblk, const damar_ov
                             const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
                             int32_t *rec_diffs, uint16_t *seg_diffs);
 
+/* Compute_Trace_PTS proper: the cost form above PLUS the edit script the reference leaves in path->trace (align.c:5686-5688),
+ * mode GREEDIEST (the mode LAshow and filter.c's bridging use): per record the concatenation over its segments of iter_np's
+ * output (align.c:5238-5254) -- one value per inserted / deleted base, positive = B coordinate + 1 where an A base stands
+ * alone, negative = -(A coordinate + 1) where a B base stands alone; substitutions write nothing.  script_off[novl + 1]
+ * receives the records' offsets into *script (malloc'd, free with damar_host_free); rec_diffs as for damar_trace_point_diffs.
+ * Returns 0, 1 when a record was rejected (its script is empty), 2 on failure.                                          */
+int damar_trace_point_scripts(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
+                              const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
+                              int32_t *rec_diffs, int64_t *script_off, int32_t **script, int64_t *script_len);
+void damar_host_free(void *p);
+
 /* ---- stage-level read-backs (used by the parity tests; not needed by a host) ---- */
 /* sorted k-mer list in the reference's KmerPos layout {u64 code; i32 rpos; i32 read}           */
 int damar_index_download(const damar_index *idx, void *kmerpos_out, int64_t capacity);

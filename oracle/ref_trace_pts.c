@@ -6,7 +6,9 @@
  * Built by oracle/Makefile into oracle/_ref/trace_pts_ref; used by tests/golden/make_trace_pts.py to pin
  * ora_trace_point_diffs() and the CUDA kernel.  Nothing of the product links or runs this.
  *
- *      trace_pts_ref <db> <las>
+ *      trace_pts_ref <db> <las>            one line per record: aread bread comp diffs-before diffs-after
+ *      trace_pts_ref <db> <las> script     the same plus the length of the edit script Compute_Trace_PTS wrote (path->tlen
+ *                                          ints) and the script itself (GREEDIEST mode, the one LAshow uses)
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,7 +28,7 @@ int main(int argc, char *argv[])
     uint16 *trace = NULL;
 
     Prog_Name = "trace_pts_ref";
-    if (argc != 3) { fprintf(stderr, "usage: trace_pts_ref <db> <las>\n"); return 1; }
+    if (argc != 3 && argc != 4) { fprintf(stderr, "usage: trace_pts_ref <db> <las> [script]\n"); return 1; }
     if (Open_DB(argv[1], &db)) return 1;
     if ((f = fopen(argv[2], "r")) == NULL) return 1;
     if (fread(&novl, sizeof(int64), 1, f) != 1 || fread(&tspace, sizeof(int), 1, f) != 1) return 1;
@@ -49,7 +51,13 @@ int main(int argc, char *argv[])
         {
             int before = ovl.path.diffs;
             if (Compute_Trace_PTS(&aln, work, tspace, GREEDIEST)) return 1;
-            printf("%d %d %d %d %d\n", ovl.aread, ovl.bread, COMP(ovl.flags) ? 1 : 0, before, ovl.path.diffs);
+            printf("%d %d %d %d %d", ovl.aread, ovl.bread, COMP(ovl.flags) ? 1 : 0, before, ovl.path.diffs);
+            if (argc == 4) {
+                int t, *scr = (int *)ovl.path.trace;
+                printf(" %d", ovl.path.tlen);
+                for (t = 0; t < ovl.path.tlen; t++) printf(" %d", scr[t]);
+            }
+            printf("\n");
         }
     }
     return 0;

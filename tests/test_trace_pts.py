@@ -94,3 +94,34 @@ def test_cuda_trace_point_diffs_rejects_out_of_bounds():
     rec = api.trace_point_diffs(da, da, bytes(buf))
     assert rec[0] == -1 and np.array_equal(rec[1:], np.array(GOLD[key]["diffs"])[1:])
     da.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["tiny/default/T.1.T.2.las", "rep/rep_default/R.1.R.1.las", "long/long_default/L.1.L.1.las", "tan/tan_default/N.1.N.1.las"])
+def test_gpu_edit_scripts_equal_reference(key):
+    """damar_trace_point_scripts (trace_pts.cu + trace_script_core.cuh) against the UNMODIFIED Compute_Trace_PTS's output
+    (tests/golden/trace_script.json): script length and hash of every record, every 400th script in full, and the diffs."""
+    import json
+    from cases import GOLDEN, load_block
+    from damar_b200 import api, dbio
+    from test_trace_script import fnv
+    with open(os.path.join(GOLDEN, "trace_script.json")) as f:
+        g = json.load(f)[key]
+    db, case, fn = key.split("/")
+    root = {"tiny": "T", "rep": "R", "long": "L", "tan": "N"}[db]
+    an, bn = ".".join(fn.split(".")[0:2]), ".".join(fn.split(".")[2:4])
+    api.init()
+    da = api.DeviceBlockHandle(load_block(os.path.join(GOLDEN, db), an, ()))
+    dbh = da if bn == an else api.DeviceBlockHandle(load_block(os.path.join(GOLDEN, db), bn, ()))
+    las = open(os.path.join(GOLDEN, db, "ref", case, fn), "rb").read()
+    rec, soff, script = api.trace_point_scripts(da, dbh, las)
+    assert len(rec) == g["n"] and soff[-1] == len(script)
+    for i, (tl, h, gd) in enumerate(g["records"]):
+        scr = script[soff[i]: soff[i + 1]]
+        assert len(scr) == tl and rec[i] == gd, (i, len(scr), tl, rec[i], gd)
+        assert "%016x" % fnv(scr) == h, i
+        if str(i) in g["full"]:
+            assert list(map(int, scr)) == g["full"][str(i)]
+    da.free()
+    if dbh is not da:
+        dbh.free()
