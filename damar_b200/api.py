@@ -581,8 +581,29 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
     J.aidx = aidx = index_of(da, 0)
     inline = workers() == 1
 
-    def compare(bblk, db, selfcmp, comp, sink, st):
-        """one Match_Filter call (daligner.c:1041 / 1053) on the calling thread's worker context"""
+    def write_buffer(bblk, selfcmp, sink):
+        """Write_Overlap_Buffer for one B block (align.c:6166-6367): {file name: LasImage}"""
+        an, bn = ablk.name, bblk.name
+        dev = isinstance(sink, DeviceSink)
+        dims = (max(ablk.maxlen, bblk.maxlen), max(ablk.ufirst + ablk.nreads, bblk.ufirst + bblk.nreads)) if dev else ()
+        files = {}
+        if selfcmp or not s.symmetric:                                      # align.c:6235
+            b1, _ = sink.serialise(s, -1, *dims)
+            files[f"{an}.{bn}.las"] = b1
+        else:
+            last = (bblk.ufirst + bblk.nreads - 1) if bblk.part < ablk.part else (ablk.ufirst + ablk.nreads - 1)
+            b1, b2 = sink.serialise(s, last, *dims)
+            n1, n2 = f"{an}.{bn}.las", f"{bn}.{an}.las"
+            if bblk.part < ablk.part:                                       # align.c:6308-6313
+                n1, n2 = n2, n1
+            files[n1], files[n2] = b1, b2
+        return files
+
+    def compare(bblk, db, selfcmp, comp, sink, st, box):
+        """one Match_Filter call (daligner.c:1041 / 1053) on the calling thread's worker context; the call that finishes a B
+        block's pair of comparisons also writes the block's .las images, on its own worker context -- the sort and the image
+        build are a chain of small kernels that would otherwise queue, one after the other, behind the long alignment kernels
+        of the comparisons in flight while the collecting thread waits"""
         bidx = aidx if (selfcmp and comp == 0) else index_of(db, comp)
         if isinstance(sink, DeviceSink):
             ov = sink.match_filter(da, db, aidx, bidx, selfcmp, comp, comp)
@@ -594,6 +615,11 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
         st[f"t{comp}"] = timings()
         if bidx is not None and bidx is not aidx:
             bidx.free()
+        with box["lock"]:
+            box["done"] += 1
+            last = box["done"] == 2
+        if last:
+            box["files"] = write_buffer(bblk, selfcmp, sink)
 
     J.cmps = []
     for bblk in bblks:
@@ -605,42 +631,31 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
             sink = _free_sinks.pop() if _free_sinks else LasSink()   # kept for the process: host buffers stay warm
         sink.reset()
         st = {}
+        box = {"lock": threading.Lock(), "done": 0, "files": None}
         if inline:
             futs = None
             for comp in (0, 1):
-                compare(bblk, db, selfcmp, comp, sink, st)
+                compare(bblk, db, selfcmp, comp, sink, st, box)
         else:
-            futs = [_get_pool().submit(compare, bblk, db, selfcmp, comp, sink, st) for comp in (0, 1)]
-        J.cmps.append((bblk, selfcmp, sink, st, futs))
+            futs = [_get_pool().submit(compare, bblk, db, selfcmp, comp, sink, st, box) for comp in (0, 1)]
+        J.cmps.append((bblk, selfcmp, sink, st, futs, box))
     return J
 
 
 def collect(J: _Job, stats: Optional[list] = None, as_bytes: bool = True) -> Dict[str, bytes]:
-    """Second half of a job: Write_Overlap_Buffer for every B block (align.c:6166-6367)."""
+    """Second half of a job: waits for the comparisons and hands out the .las images they wrote."""
     out: Dict[str, bytes] = {}
     conv = (lambda im: im.tobytes()) if as_bytes else (lambda im: im)
-    ablk, s = J.ablk, J.s
-    for bblk, selfcmp, sink, st, futs in J.cmps:
+    for bblk, selfcmp, sink, st, futs, box in J.cmps:
         if futs is not None:
             for f in futs:
                 f.result()
         if stats is not None:
             stats.append(st)
-        an, bn = ablk.name, bblk.name
-        dev = isinstance(sink, DeviceSink)
-        dims = (max(ablk.maxlen, bblk.maxlen), max(ablk.ufirst + ablk.nreads, bblk.ufirst + bblk.nreads)) if dev else ()
-        if selfcmp or not J.symmetric:                                      # align.c:6235
-            b1, _ = sink.serialise(s, -1, *dims)
-            out[f"{an}.{bn}.las"] = conv(b1)
-        else:
-            last = (bblk.ufirst + bblk.nreads - 1) if bblk.part < ablk.part else (ablk.ufirst + ablk.nreads - 1)
-            b1, b2 = sink.serialise(s, last, *dims)
-            n1, n2 = f"{an}.{bn}.las", f"{bn}.{an}.las"
-            if bblk.part < ablk.part:                                       # align.c:6308-6313
-                n1, n2 = n2, n1
-            out[n1], out[n2] = conv(b1), conv(b2)
+        for name, im in box["files"].items():
+            out[name] = conv(im)
         sink.reset()
-        (_free_dsinks if dev else _free_sinks).append(sink)
+        (_free_dsinks if isinstance(sink, DeviceSink) else _free_sinks).append(sink)
     if J.aidx is not None:
         J.aidx.free()
     if J.own:
