@@ -82,30 +82,34 @@ __device__ int64_t run_end(const KList &L, int64_t p) {
     }
     return L.len;
 }
-// the same inside a staged segment s[0, n)
+// the same inside a staged segment: the codes of its entries, already separated from the positions (CT = uint32_t when a
+// code has at most 32 bits -- k <= 16 -- which halves the shared-memory traffic of the bisections)
+template <typename CT>
 struct Staged {
-    const uint64_t *s; int n; int gbits; bool pairs;
-    __device__ __forceinline__ uint64_t code(int i) const { return pairs ? s[i] : (s[i] >> gbits); }
+    const CT *c; int n;
+    __device__ __forceinline__ CT code(int i) const { return c[i]; }
 };
-template <bool GT>
-__device__ __forceinline__ int sbound(const Staged &S, int lo, int hi, uint64_t c) {
-    while (lo < hi) { const int m = (lo + hi) >> 1; const uint64_t x = S.code(m); if (GT ? (x <= c) : (x < c)) lo = m + 1; else hi = m; }
+template <bool GT, typename CT>
+__device__ __forceinline__ int sbound(const Staged<CT> &S, int lo, int hi, CT c) {
+    while (lo < hi) { const int m = (lo + hi) >> 1; const CT x = S.c[m]; if (GT ? (x <= c) : (x < c)) lo = m + 1; else hi = m; }
     return lo;
 }
-__device__ __forceinline__ int srun_start(const Staged &S, int p, uint64_t c) {
+template <typename CT>
+__device__ __forceinline__ int srun_start(const Staged<CT> &S, int p, CT c) {
     int lo = p, w = 1;
     while (lo > 0) {
         int q = lo - w; if (q < 0) q = 0;
-        if (S.code(q) == c) { lo = q; w <<= 1; }
+        if (S.c[q] == c) { lo = q; w <<= 1; }
         else return sbound<false>(S, q + 1, lo, c);
     }
     return 0;
 }
-__device__ __forceinline__ int srun_end(const Staged &S, int p, uint64_t c) {
+template <typename CT>
+__device__ __forceinline__ int srun_end(const Staged<CT> &S, int p, CT c) {
     int hi = p + 1, w = 1;
     while (hi < S.n) {
         int q = hi + w - 1; if (q >= S.n) q = S.n - 1;
-        if (S.code(q) == c) { hi = q + 1; w <<= 1; }
+        if (S.c[q] == c) { hi = q + 1; w <<= 1; }
         else return sbound<true>(S, hi, q, c);
     }
     return S.n;
@@ -156,27 +160,30 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
     return t;
 }
 
+constexpr int MT_SGRAM = 512;                       // histogram bins kept in shared memory; rarer, larger counts go to global atomics
+template <typename CT, bool EMIT>
 struct MtSmem {
-    uint64_t sA[MT_CAPA];
-    uint64_t sB[MT_CAPB];
+    CT ac[MT_CAPA];                               // codes of the staged A entries
+    CT bc[MT_CAPB];                               // ... of the B window
+    uint32_t ap[MT_CAPA], bp[MT_CAPB];            // their positions (gpos)
     uint32_t cnt[MT_CAPA + 4];                    // partners per entry, then their exclusive scan
     uint32_t gct[MT_CAPA];                        // match count of the run that starts at this entry
     uint16_t jbw[MT_CAPA];                        // start of the entry's B run inside the window | HAS_RUN
     uint16_t rsw[MT_CAPA];                        // start of the entry's A run inside the segment
-    union { uint32_t gram[MAXGRAM]; uint64_t klow[MT_CAPA]; } u;   // COUNT: histogram; EMIT: aread << pbits | apos per entry
+    union { uint32_t gram[EMIT ? 1 : MT_SGRAM]; uint64_t klow[EMIT ? MT_CAPA : 1]; } u;   // COUNT: histogram; EMIT: aread << pbits | apos
     unsigned long long red[MT_THREADS / 32];
     uint32_t wsum[MT_THREADS / 32];
     int64_t seg[4];                               // q, we, giant, -
 };
 
-template <bool EMIT>
+template <bool EMIT, typename CT>
 __global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MtSmem &S = *reinterpret_cast<MtSmem *>(smem_raw);
+    MtSmem<CT, EMIT> &S = *reinterpret_cast<MtSmem<CT, EMIT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool histo = !EMIT && a.gram != nullptr;
     const bool packed_out = a.bpos == nullptr;
-    if (histo) { for (int i = tid; i < MAXGRAM; i += MT_THREADS) S.u.gram[i] = 0; }
+    if (histo) { for (int i = tid; i < MT_SGRAM; i += MT_THREADS) S.u.gram[i] = 0; }
     __syncthreads();
 
     for (uint32_t tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -218,24 +225,32 @@ __global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
                 // ================= fast path: the segment and its window in shared memory =================
                 const int na = (int)(q - p), nb = a.same_list ? na : (int)(we - wb);
                 __syncthreads();
-                for (int i = tid; i < na; i += MT_THREADS) { S.sA[i] = a.A.ent[p + i]; S.gct[i] = 0; }
-                if (!a.same_list) for (int i = tid; i < nb; i += MT_THREADS) S.sB[i] = a.B.ent[wb + i];
-                __syncthreads();
-                const Staged SA{S.sA, na, a.A.gbits, a.A.gpos != nullptr};
-                const Staged SB{a.same_list ? S.sA : S.sB, nb, a.B.gbits, a.B.gpos != nullptr};
                 for (int i = tid; i < na; i += MT_THREADS) {
-                    const uint64_t c = SA.code(i);
+                    const uint64_t e = a.A.ent[p + i];
+                    S.ac[i] = (CT)a.A.ecode(e); S.ap[i] = a.A.epos(e, p + i); S.gct[i] = 0;
+                }
+                if (!a.same_list)
+                    for (int i = tid; i < nb; i += MT_THREADS) {
+                        const uint64_t e = a.B.ent[wb + i];
+                        S.bc[i] = (CT)a.B.ecode(e); S.bp[i] = a.B.epos(e, wb + i);
+                    }
+                __syncthreads();
+                const Staged<CT> SA{S.ac, na};
+                const Staged<CT> SB{a.same_list ? S.ac : S.bc, nb};
+                const uint32_t *bpos = a.same_list ? S.ap : S.bp;
+                for (int i = tid; i < na; i += MT_THREADS) {
+                    const CT c = S.ac[i];
                     const int rs = srun_start(SA, i, c);
                     int jb, ib;
                     if (a.same_list) { jb = rs; ib = srun_end(SA, i, c); }
-                    else { jb = sbound<false>(SB, 0, nb, c); ib = (jb < nb && SB.code(jb) == c) ? srun_end(SB, jb, c) : jb; }
+                    else { jb = sbound<false>(SB, 0, nb, c); ib = (jb < nb && S.bc[jb] == c) ? srun_end(SB, jb, c) : jb; }
                     const int nbr = ib - jb;
                     uint32_t cn = 0;
                     if (nbr > 0 && !(a.same_list && a.self && nbr == 1)) {     // a run of one k-mer of the list itself has no partner
                         if (a.self) {
-                            const uint32_t thr = self_threshold(a, a.A.epos(S.sA[i], p + i));
+                            const uint32_t thr = self_threshold(a, S.ap[i]);
                             int lo = jb, hi = ib;                               // partners = B run entries with gpos < thr
-                            while (lo < hi) { const int m = (lo + hi) >> 1; if (a.B.epos(SB.s[m], (a.same_list ? p : wb) + m) < thr) lo = m + 1; else hi = m; }
+                            while (lo < hi) { const int m = (lo + hi) >> 1; if (bpos[m] < thr) lo = m + 1; else hi = m; }
                             cn = (uint32_t)(lo - jb);
                         } else cn = (uint32_t)nbr;
                     }
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
                     const uint32_t ct = S.gct[rs];
                     const bool has = (S.jbw[i] & HAS_RUN) != 0;
                     if (!(has && ct < a.limit)) S.cnt[i] = 0;
-                    if (histo && i == rs && has && ct < MAXGRAM) atomicAdd(&S.u.gram[ct], 1u);
+                    if (histo && i == rs && has && ct < MAXGRAM) { if (ct < MT_SGRAM) atomicAdd(&S.u.gram[ct], 1u); else atomicAdd(&a.gram[ct], 1ull); }
                 }
                 __syncthreads();
                 // exclusive scan of cnt[0, na) in place; cnt[na] = total
@@ -282,18 +297,17 @@ __global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
                     __syncthreads();
                     for (int i = tid; i < na; i += MT_THREADS)
                         if (S.cnt[i + 1] > S.cnt[i]) {
-                            const uint32_t ga = a.A.epos(S.sA[i], p + i);
+                            const uint32_t ga = S.ap[i];
                             const int ar = read_of(a.amap, ga);
                             S.u.klow[i] = ((uint64_t)ar << a.pbits) | (uint64_t)(ga - a.amap.boff[ar]);
                         }
                     __syncthreads();
-                    const int64_t bgl = a.same_list ? p : wb;               // global index of window entry 0
                     for (uint32_t h = tid; h < total; h += MT_THREADS) {
                         int lo = 0, hi = na;                                 // last entry whose scan value is <= h
                         while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (S.cnt[m] <= h) lo = m; else hi = m; }
                         const int i = lo;
                         const int j = (int)(S.jbw[i] & (HAS_RUN - 1u)) + (int)(h - S.cnt[i]);
-                        const uint32_t gb = a.B.epos(SB.s[j], bgl + j);
+                        const uint32_t gb = bpos[j];
                         const int br = read_of(a.bmap, gb);
                         const uint32_t bp = gb - a.bmap.boff[br];
                         const unsigned long long o = tile_hits + h;
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
                     }
                     const unsigned long long hits_of_run = a.self ? ct : (lonely ? 0ull : ct);
                     const uint32_t ct32 = ct > 0xffffffffull ? 0xffffffffu : (uint32_t)ct;
-                    if (histo && tid == 0 && ct32 < MAXGRAM) atomicAdd(&S.u.gram[ct32], 1u);
+                    if (histo && tid == 0 && ct32 < MAXGRAM) atomicAdd(&a.gram[ct32], 1ull);
                     if (ct32 < a.limit) {
                         if (EMIT) {
                             for (int64_t base = p; base < q; base += MT_THREADS) {      // entries of the run, a block at a time
@@ -372,7 +386,7 @@ __global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
     }
     if (histo) {
         __syncthreads();
-        for (int i = tid; i < MAXGRAM; i += MT_THREADS)
+        for (int i = tid; i < MT_SGRAM; i += MT_THREADS)
             if (S.u.gram[i]) atomicAdd(&a.gram[i], (unsigned long long)S.u.gram[i]);
     }
 }
@@ -441,14 +455,21 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
 
     static std::once_flag attr;
     std::call_once(attr, [] {
-        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem)));
-        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem)));
+        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<false, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem<uint32_t, false>)));
+        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<true, uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem<uint32_t, true>)));
+        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<false, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem<uint64_t, false>)));
+        CUDA_CHECK(cudaFuncSetAttribute(merge_tiles<true, uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MtSmem<uint64_t, true>)));
     });
-    const unsigned grid = ntiles < 2u * NUM_SMS_B200 ? ntiles : 2u * NUM_SMS_B200;
+    const bool code32 = c.fp.kmer <= 16;                    // a k-mer code has 2k bits
+    auto count_sweep = [&](const MergeArgs &mm, unsigned g) {
+        if (code32) merge_tiles<false, uint32_t><<<g, MT_THREADS, sizeof(MtSmem<uint32_t, false>), st>>>(mm);
+        else merge_tiles<false, uint64_t><<<g, MT_THREADS, sizeof(MtSmem<uint64_t, false>), st>>>(mm);
+        KERNEL_CHECK();
+    };
+    const unsigned grid = ntiles < 3u * NUM_SMS_B200 ? ntiles : 3u * NUM_SMS_B200;
     merge_bounds<<<(ntiles + 1 + 127) / 128, 128, 0, st>>>(m);
     KERNEL_CHECK();
-    merge_tiles<false><<<grid, MT_THREADS, sizeof(MtSmem), st>>>(m);
-    KERNEL_CHECK();
+    count_sweep(m, grid);
     scan_counts<<<1, 1024, 0, st>>>(tcount.p, ntiles, tcount.p + ntiles);
     KERNEL_CHECK();
     count_launch(3);
@@ -473,8 +494,7 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
         if (c.opt.verbose) printf("   Capping mutual k-mer matches over %d (effectively -t%d)\n", (int)limit, (int)__builtin_sqrt(1. * limit));
         if (limit != MAXGRAM) {                         // a tighter cap than assumed: count again with it
             m.limit = (uint32_t)limit; m.gram = nullptr;
-            merge_tiles<false><<<grid, MT_THREADS, sizeof(MtSmem), st>>>(m);
-            KERNEL_CHECK();
+            count_sweep(m, grid);
             scan_counts<<<1, 1024, 0, st>>>(tcount.p, ntiles, tcount.p + ntiles);
             KERNEL_CHECK();
             count_launch(2);
@@ -509,7 +529,8 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
     }
     m.keys = k0; m.bpos = v0; m.pbits = out.pbits; m.abits = out.abits; m.qbits = out.qbits;
     m.limit = (uint32_t)limit; m.gram = nullptr;
-    merge_tiles<true><<<grid, MT_THREADS, sizeof(MtSmem), st>>>(m);
+    if (code32) merge_tiles<true, uint32_t><<<grid, MT_THREADS, sizeof(MtSmem<uint32_t, true>), st>>>(m);
+    else merge_tiles<true, uint64_t><<<grid, MT_THREADS, sizeof(MtSmem<uint64_t, true>), st>>>(m);
     KERNEL_CHECK(); count_launch();
     c.tm.merge_ms = t_merge.stop();
     delete hp2;
