@@ -278,8 +278,9 @@ def main_sharded(args, rank, world, local_rank, cores, config, torch, dist, api,
     barrier()
     t1 = time.perf_counter()
     novl_e, d2h = 0, 0
+    st_e = {}
     for _ in range(args.steps):
-        n, files = multi.run_sharded(dbdir, root, nblocks, s, rank, world, dist=dist, device=device, host_blocks=host_blocks)
+        n, files = multi.run_sharded(dbdir, root, nblocks, s, rank, world, dist=dist, device=device, host_blocks=host_blocks, stats=st_e)
         novl_e += n
         d2h = sum(files.values())
     barrier()
@@ -303,7 +304,8 @@ def main_sharded(args, rank, world, local_rank, cores, config, torch, dist, api,
             "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
             "e2e": {"value": novl_e / dt_e, "unit": "overlaps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1000 * dt_e / args.steps, "nvlink_bytes_per_step": nvl},
+                    "ms_per_step": 1000 * dt_e / args.steps, "nvlink_bytes_per_step": nvl,
+                    "exchange_ms_per_step_rank0": 1000 * st_e.get("exchange_s", 0.0) / max(args.steps, 1)},
             "all_vs_all": {"wall_ms": 1000 * dt_e / args.steps, "overlaps": novl_e // max(args.steps, 1), "n_gpus": world,
                            "what": "whole all-vs-all from host buffers on the owner ranks to sorted .las images in host memory"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stage4": stage4,

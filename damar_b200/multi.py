@@ -180,7 +180,11 @@ def run_sharded(dbdir: str, root: str, nblocks: int, settings, rank: int, world:
         for h in cache.values():
             h.drop_indexes()
     elif str(device).startswith("cuda"):
+        import time
+        t0 = time.perf_counter()
         blocks, cache = exchange_blocks_device(dbdir, root, shards, rank, world, dist, device, masks, host_blocks=host_blocks, stats=stats)
+        if stats is not None:
+            stats["exchange_s"] = stats.get("exchange_s", 0.0) + time.perf_counter() - t0
     else:
         blocks = exchange_blocks(dbdir, root, shards, rank, world, dist, device, masks)
         cache = {}
