@@ -177,7 +177,7 @@ struct MtSmem {
 };
 
 template <bool EMIT, typename CT>
-__global__ void __launch_bounds__(MT_THREADS, 2) merge_tiles(MergeArgs a) {
+__global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MtSmem<CT, EMIT> &S = *reinterpret_cast<MtSmem<CT, EMIT> *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
