@@ -160,6 +160,8 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v, un
     return t;
 }
 
+constexpr int MT_NBUCK = 1024;                      // buckets over the code range of a window (lookup instead of an 11-step bisection)
+constexpr int MT_DIRECT = 8;                        // entries with at most this many partners write their hits themselves
 constexpr int MT_SGRAM = 512;                       // histogram bins kept in shared memory; rarer, larger counts go to global atomics
 template <typename CT, bool EMIT>
 struct MtSmem {
@@ -174,6 +176,8 @@ struct MtSmem {
     unsigned long long red[MT_THREADS / 32];
     uint32_t wsum[MT_THREADS / 32];
     int64_t seg[4];                               // q, we, giant, -
+    uint16_t bstart[MT_NBUCK + 2];                // first window entry whose code bucket is >= b: a bucket holds a handful of entries
+    uint32_t big;                                 // some entry of the segment has more than MT_DIRECT partners
 };
 
 template <bool EMIT, typename CT>
@@ -238,12 +242,46 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                 const Staged<CT> SA{S.ac, na};
                 const Staged<CT> SB{a.same_list ? S.ac : S.bc, nb};
                 const uint32_t *bpos = a.same_list ? S.ap : S.bp;
+                // Bucket table over the window's code range: bstart[b] = first window entry whose bucket is >= b, so the run
+                // of a code is found by a lookup and a bisection of the few entries of its bucket instead of the whole window.
+                CT c0 = 0; int bshift = 0;
+                if (!a.same_list && nb > 0) {
+                    c0 = S.bc[0];
+                    const CT range = S.bc[nb - 1] - c0;
+                    while ((range >> bshift) >= (CT)MT_NBUCK) bshift++;
+                    for (int b = tid; b <= MT_NBUCK; b += MT_THREADS) S.bstart[b] = (uint16_t)nb;
+                    __syncthreads();
+                    for (int j = tid; j < nb; j += MT_THREADS) {
+                        const int b = (int)((S.bc[j] - c0) >> bshift);
+                        if (j == 0 || (int)((S.bc[j - 1] - c0) >> bshift) != b) S.bstart[b] = (uint16_t)j;   // the bucket's first entry
+                    }
+                    __syncthreads();
+                    if (tid < 32) {                               // empty buckets take the start of the next non-empty one (suffix minimum)
+                        constexpr int PERL = (MT_NBUCK + 32) / 32;
+                        int run = nb;
+                        uint16_t loc[PERL];
+                        for (int x = PERL - 1; x >= 0; x--) { const int b = tid * PERL + x; int v = (b <= MT_NBUCK) ? S.bstart[b] : nb; if (v < run) run = v; loc[x] = (uint16_t)run; }
+                        int suf = run;                            // minimum over this lane's buckets; now over all later lanes too
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_down_sync(0xffffffffu, suf, o); if (tid + o < 32 && t < suf) suf = t; }
+                        const int later = __shfl_down_sync(0xffffffffu, suf, 1);
+                        const int cap = (tid < 31) ? later : nb;
+                        for (int x = 0; x < PERL; x++) { const int b = tid * PERL + x; if (b <= MT_NBUCK) S.bstart[b] = (uint16_t)(loc[x] < cap ? loc[x] : cap); }
+                    }
+                    __syncthreads();
+                }
+                if (tid == 0) S.big = 0;
                 for (int i = tid; i < na; i += MT_THREADS) {
                     const CT c = S.ac[i];
                     const int rs = srun_start(SA, i, c);
                     int jb, ib;
                     if (a.same_list) { jb = rs; ib = srun_end(SA, i, c); }
-                    else { jb = sbound<false>(SB, 0, nb, c); ib = (jb < nb && S.bc[jb] == c) ? srun_end(SB, jb, c) : jb; }
+                    else if (nb == 0 || c < c0 || c > S.bc[nb - 1]) { jb = ib = 0; }
+                    else {
+                        const int b = (int)((c - c0) >> bshift);
+                        jb = sbound<false>(SB, (int)S.bstart[b], (int)S.bstart[b + 1], c);
+                        ib = (jb < nb && S.bc[jb] == c) ? srun_end(SB, jb, c) : jb;
+                    }
                     const int nbr = ib - jb;
                     uint32_t cn = 0;
                     if (nbr > 0 && !(a.same_list && a.self && nbr == 1)) {     // a run of one k-mer of the list itself has no partner
@@ -269,6 +307,7 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                     const uint32_t ct = S.gct[rs];
                     const bool has = (S.jbw[i] & HAS_RUN) != 0;
                     if (!(has && ct < a.limit)) S.cnt[i] = 0;
+                    else if (EMIT && S.cnt[i] > (uint32_t)MT_DIRECT) S.big = 1;
                     if (histo && i == rs && has && ct < MAXGRAM) { if (ct < MT_SGRAM) atomicAdd(&S.u.gram[ct], 1u); else atomicAdd(&a.gram[ct], 1ull); }
                 }
                 __syncthreads();
@@ -302,6 +341,24 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                             S.u.klow[i] = ((uint64_t)ar << a.pbits) | (uint64_t)(ga - a.amap.boff[ar]);
                         }
                     __syncthreads();
+                    if (!S.big) {
+                        // every entry has a handful of partners (the usual case): the entry's thread writes them; neighbouring
+                        // threads write neighbouring slots
+                        for (int i = tid; i < na; i += MT_THREADS) {
+                            const uint32_t o0 = S.cnt[i], cn = S.cnt[i + 1] - o0;
+                            if (cn == 0) continue;
+                            const int jb = (int)(S.jbw[i] & (HAS_RUN - 1u));
+                            const uint64_t klow = S.u.klow[i];
+                            for (uint32_t x = 0; x < cn; x++) {
+                                const uint32_t gb = bpos[jb + (int)x];
+                                const int br = read_of(a.bmap, gb);
+                                const uint32_t bp = gb - a.bmap.boff[br];
+                                const unsigned long long o = tile_hits + o0 + x;
+                                if (packed_out) a.keys[o] = ((((uint64_t)br << (a.pbits + a.abits)) | klow) << a.qbits) | bp;
+                                else { a.keys[o] = ((uint64_t)br << (a.pbits + a.abits)) | klow; a.bpos[o] = bp; }
+                            }
+                        }
+                    } else
                     for (uint32_t h = tid; h < total; h += MT_THREADS) {
                         int lo = 0, hi = na;                                 // last entry whose scan value is <= h
                         while (hi - lo > 1) { const int m = (lo + hi) >> 1; if (S.cnt[m] <= h) lo = m; else hi = m; }
