@@ -57,8 +57,11 @@ def shard_pairs(nblocks: int, world: int, sizes: Dict[int, int] | None = None) -
     sizes = sizes or {i: 1 for i in range(1, nblocks + 1)}
     units = block_pairs(nblocks)
     total = sum(pair_cost(a, b, sizes) for a, b in units)
-    target = total / world
-    # split rows (A blocks) into chunks no bigger than the per-rank target
+    # Pieces of a quarter of a rank's share: small enough for the longest-first deal to balance the ranks to a few percent
+    # (21 blocks on 8 ranks: 0.90 -> 0.99 of ideal), large enough to keep a rank on one A block for a while.  A rank keeps
+    # the k-mer indexes of all its blocks for the whole plan (api.DeviceBlockHandle.index), so a piece costs no extra sort.
+    target = total / world / 4
+    # split rows (A blocks) into chunks no bigger than that
     chunks: List[Tuple[float, int, List[int]]] = []
     for a in range(1, nblocks + 1):
         cur: List[int] = []
