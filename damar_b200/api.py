@@ -578,7 +578,11 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
     # -b fixes its base weights at the first Sort_Kmers of a job (filter.c:774): those lists are rebuilt per job like the reference does
     sig = (s.kmer, s.suppress)
     index_of = (lambda h, comp: sort_kmers(h, comp)) if s.biased else (lambda h, comp: h.index(comp, sig))
-    J.aidx = aidx = index_of(da, 0)
+    # The A index: with -b it belongs to the job and is built here; otherwise it is the handle's shared index, built by the
+    # first comparison that asks for it on ITS worker context, so that submit() returns at once and the caller can queue
+    # the next job while the pool is still busy with this one
+    J.aidx = aidx = index_of(da, 0) if s.biased else None
+    a_index = (lambda: aidx) if s.biased else (lambda: da.index(0, sig))
     inline = workers() == 1
 
     def write_buffer(bblk, selfcmp, sink):
@@ -604,16 +608,17 @@ def submit(ablk: Block, bblks: List[Block], s: Settings, dcache: Optional[Dict[s
         block's pair of comparisons also writes the block's .las images, on its own worker context -- the sort and the image
         build are a chain of small kernels that would otherwise queue, one after the other, behind the long alignment kernels
         of the comparisons in flight while the collecting thread waits"""
-        bidx = aidx if (selfcmp and comp == 0) else index_of(db, comp)
+        ai = a_index()
+        bidx = ai if (selfcmp and comp == 0) else index_of(db, comp)
         if isinstance(sink, DeviceSink):
-            ov = sink.match_filter(da, db, aidx, bidx, selfcmp, comp, comp)
+            ov = sink.match_filter(da, db, ai, bidx, selfcmp, comp, comp)
         else:
-            ov = match_filter(da, db, aidx, bidx, selfcmp, comp)
+            ov = match_filter(da, db, ai, bidx, selfcmp, comp)
             sink.add(ov, comp)
         st[f"nhits{comp}"], st[f"nfilt{comp}"], st[f"novl{comp}"] = ov.nhits, ov.nfilt, ov.novl
         st[f"multi{comp}"] = ov.multi_la_pairs
         st[f"t{comp}"] = timings()
-        if bidx is not None and bidx is not aidx:
+        if bidx is not None and bidx is not ai:
             bidx.free()
         with box["lock"]:
             box["done"] += 1
@@ -671,27 +676,41 @@ def daligner(ablk: Block, bblks: List[Block], s: Settings, stats: Optional[list]
     return collect(submit(ablk, bblks, s, dcache), stats, as_bytes)
 
 
-def daligner_plan(jobs: List[tuple], s: Settings, stats: Optional[list] = None,
-                  dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
-    """The jobs of an HPCdaligner plan (dalign/HPCdaligner.c:709-788), [(A block, [B blocks]), ...], one after the other
-    like the script would run them -- except that job i+1 is submitted (its A block shipped and indexed, its comparisons
-    queued) BEFORE job i is collected, so the GPU does not idle while the host sorts and serialises job i's records.
-    Jobs whose process-wide options differ (base frequencies of another DB, -b) are not overlapped."""
-    own = dcache is None
+def plan_iter(jobs, s: Settings, stats: Optional[list] = None, dcache: Optional[Dict[str, DeviceBlockHandle]] = None,
+              as_bytes: bool = True):
+    """Generator over the .las files of a list of jobs [(A block, [B blocks]), ...] run one after the other like the
+    HPCdaligner script would (dalign/HPCdaligner.c:709-788): yields (file name, image) as jobs complete, in job order.
+    Later jobs are submitted (blocks shipped, comparisons queued) BEFORE the earlier ones are collected, so the pool always
+    has comparisons waiting (a plan starts with its smallest jobs, `A.1 A.1` is one block pair): up to `DAMAR_LOOKAHEAD`
+    (default 4 x workers) comparisons queued or running beyond the job being collected.  Jobs whose process-wide options
+    differ (base frequencies of another DB, -b) are not overlapped."""
     dcache = {} if dcache is None else dcache
-    out: Dict[str, bytes] = {}
-    pend, pend_key = None, None
+    ahead = int(os.environ.get("DAMAR_LOOKAHEAD", str(4 * workers())))
+    pend: List[_Job] = []
+    pend_key = None
+
+    def unfinished() -> int:
+        return sum(1 for J in pend for c in J.cmps if c[4] is not None for f in c[4] if not f.done())
+
     for ablk, bblks in jobs:
         key = _job_options(ablk, bblks, s)
-        if pend is not None and (key != pend_key or s.biased):
-            out.update(collect(pend, stats, as_bytes))
-            pend = None
-        nxt = submit(ablk, bblks, s, dcache)
-        if pend is not None:
-            out.update(collect(pend, stats, as_bytes))
-        pend, pend_key = nxt, key
-    if pend is not None:
-        out.update(collect(pend, stats, as_bytes))
+        if pend and (key != pend_key or s.biased):
+            while pend:
+                yield from collect(pend.pop(0), stats, as_bytes).items()
+        while len(pend) > 1 and unfinished() >= ahead:
+            yield from collect(pend.pop(0), stats, as_bytes).items()
+        pend.append(submit(ablk, bblks, s, dcache))
+        pend_key = key
+    while pend:
+        yield from collect(pend.pop(0), stats, as_bytes).items()
+
+
+def daligner_plan(jobs: List[tuple], s: Settings, stats: Optional[list] = None,
+                  dcache: Optional[Dict[str, DeviceBlockHandle]] = None, as_bytes: bool = True) -> Dict[str, bytes]:
+    """The jobs of an HPCdaligner plan through plan_iter(): {las file name: image} of the whole plan."""
+    own = dcache is None
+    dcache = {} if dcache is None else dcache
+    out: Dict[str, bytes] = dict(plan_iter(jobs, s, stats, dcache, as_bytes))
     if own:
         for h in dcache.values():
             h.free()

@@ -45,13 +45,38 @@ Context &ctx() { return *tl_ctx; }
 static std::map<std::string, std::pair<double, long>> g_prof;
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 HostProf::HostProf(const char *n) : name(n), t0(now_s()) {}
-HostProf::~HostProf() { std::lock_guard<std::mutex> lock(g_mu); auto &e = g_prof[name]; e.first += now_s() - t0; e.second++; }
+// DAMAR_TRACE=<file>: every profiled scope also leaves a line "thread name start_ms end_ms" (written at exit): the
+// poor man's timeline of which worker was where
+struct TraceRec { int tid; const char *name; double t0, t1; };
+static std::vector<TraceRec> g_trace;
+static const char *g_trace_path = nullptr;
+static thread_local int tl_tid = -1;
+static int g_next_tid = 0;
+HostProf::~HostProf() {
+    const double t1 = now_s();
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto &e = g_prof[name]; e.first += t1 - t0; e.second++;
+    static const bool tracing = [] {
+        g_trace_path = getenv("DAMAR_TRACE");
+        if (!g_trace_path || !*g_trace_path) return false;
+        atexit([] {
+            if (FILE *f = fopen(g_trace_path, "w")) {
+                for (auto &r : g_trace) fprintf(f, "%d %s %.3f %.3f\n", r.tid, r.name, r.t0 * 1e3, r.t1 * 1e3);
+                fclose(f);
+            }
+        });
+        return true;
+    }();
+    if (tracing) { if (tl_tid < 0) tl_tid = g_next_tid++; g_trace.push_back(TraceRec{tl_tid, name, t0, t1}); }
+}
 void dump_profile() {
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto &kv : g_prof) fprintf(stderr, "[damar profile] %-28s %9.1f ms  (%ld calls)\n", kv.first.c_str(), kv.second.first * 1e3, kv.second.second);
     g_prof.clear();
 }
 
+static bool pool_alloc();
+static cudaError_t make_pool(Context &c);
 static int pick_device() {
     const char *e = getenv("DAMAR_DEVICE");
     if (e && *e) return atoi(e);
@@ -90,6 +115,7 @@ static int do_init(int device) {
     }
     CUDA_CHECK(cudaSetDevice(g_device));
     CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (pool_alloc()) CUDA_CHECK(make_pool(c));
     c.index = (int)(&c - g_ctx);
     c.device = g_device;
     if (!c.ws) c.ws = new WorkerScratch();
@@ -99,48 +125,83 @@ static int do_init(int device) {
     return 0;
 }
 
-// ---- caching device allocator ----------------------------------------------------------------
-// A block pair allocates and frees tens of GB of tuple / hit lists; cudaMalloc/cudaFree cost
-// milliseconds per GB and synchronise the device.  All library work is ordered on one stream, so
-// a freed block can be handed to the next request immediately.  Requests are rounded up to a
-// coarse size class and served best-fit from the free list (at most 1.5x the rounded size).
+// ---- caching device allocator --------------------------------------------------------------------
+// A block pair allocates and frees tens of GB of tuple / hit lists of data-dependent sizes.  cudaMalloc costs ~70 ms per
+// GB and cudaFree waits for every running kernel (0.3 s behind a wave kernel, measured: tools/exp/malloc_stall.cu).  All
+// work of a worker context is ordered on its stream, so a freed block can be handed to the context's next request
+// immediately: requests are rounded up to a coarse size class and served best-fit from the context's free list (at most
+// 1.5x the rounded size); after the first pass of a plan a step asks the driver for memory a handful of times.  A block
+// freed by another thread (the collector releasing a job's records) returns to the cache of the context that allocated
+// it; that caller guarantees that no stream still uses it.
+// DAMAR_ALLOC=pool selects per-worker stream-ordered pools (cudaMemPool) instead: measured slower -- while the pools grow
+// every request waits for the driver to map memory (a first pass of 9 s instead of 0.9 s) and the steady state is the same.
 struct BlockInfo { size_t size; int owner; };          // owner = the worker context whose request allocated the block
-static std::map<void *, BlockInfo> g_block_size;
+static std::map<void *, BlockInfo> g_block_size;       // legacy allocator only
+static bool pool_alloc() {
+    static const bool on = [] { const char *e = getenv("DAMAR_ALLOC"); return e && strcmp(e, "pool") == 0; }();
+    return on;
+}
 static size_t round_class(size_t b) {
     size_t q = b >= (256u << 20) ? (64u << 20) : b >= (16u << 20) ? (8u << 20) : b >= (1u << 20) ? (1u << 20) : (64u << 10);
     return (b + q - 1) / q * q;
 }
+static cudaError_t make_pool(Context &c) {
+    cudaMemPoolProps pr{};
+    pr.allocType = cudaMemAllocationTypePinned; pr.handleTypes = cudaMemHandleTypeNone;
+    pr.location.type = cudaMemLocationTypeDevice; pr.location.id = g_device;
+    cudaError_t e = cudaMemPoolCreate(&c.pool, &pr);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = ~0ull;
+    int off = 0;
+    cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // never make this stream wait for another worker's stream in order to reuse a block freed there
+    cudaMemPoolSetAttribute(c.pool, cudaMemPoolReuseAllowInternalDependencies, &off);
+    return cudaSuccess;
+}
 static void release_cached_blocks(Context &c) {
+    if (c.pool) { cudaMemPoolTrimTo(c.pool, 0); return; }
     std::lock_guard<std::mutex> lk(c.cache_mu);
     std::lock_guard<std::mutex> lock(g_mu);
     for (auto &kv : c.free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
     c.free_blocks.clear();
 }
-// Memory pressure between workers: a worker whose cudaMalloc fails frees the cached blocks of EVERY worker (cudaFree waits
-// for the device, so blocks whose last kernels are still queued on another stream are safe to give back) and then retries
-// for a while -- the other comparisons in flight finish and hand their lists back.
+// Memory pressure between workers: a worker whose request fails hands the unused memory of EVERY worker's pool back to the
+// driver and then retries for a while -- the other comparisons in flight finish and release their lists.
 static void release_all_caches() {
-    for (int i = 0; i < MAX_WORKERS; i++) {
-        Context &o = g_ctx[i];
-        std::lock_guard<std::mutex> lk(o.cache_mu);
-        std::lock_guard<std::mutex> lock(g_mu);
-        for (auto &kv : o.free_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
-        o.free_blocks.clear();
-    }
+    for (int i = 0; i < MAX_WORKERS; i++) release_cached_blocks(g_ctx[i]);
 }
 void *dev_alloc_bytes(size_t bytes) {
     Context &c = ctx();
+    void *p = nullptr;
+    if (pool_alloc() && c.pool) {
+        const size_t r = (std::max<size_t>(bytes, 1) + 511) & ~(size_t)511;
+        cudaError_t e = cudaMallocFromPoolAsync(&p, r, c.pool, c.stream);
+        if (e != cudaSuccess) {
+            HostProf hp("alloc.retry");
+            cudaGetLastError();
+            CUDA_CHECK(stream_wait(c.stream));
+            for (int attempt = 0;; attempt++) {
+                release_all_caches();
+                e = cudaMallocFromPoolAsync(&p, r, c.pool, c.stream);
+                if (e == cudaSuccess) break;
+                cudaGetLastError();
+                if (attempt >= 600) fatal("out of device memory: %zu bytes requested (%s)", r, cudaGetErrorString(e));
+                std::this_thread::sleep_for(std::chrono::milliseconds(50));
+            }
+        }
+        return p;
+    }
     const size_t r = round_class(bytes ? bytes : 1);
     {
         std::lock_guard<std::mutex> lk(c.cache_mu);
         auto it = c.free_blocks.lower_bound(r);
         if (it != c.free_blocks.end() && it->first <= r + r / 2) {
-            void *p = it->second;
+            p = it->second;
             c.free_blocks.erase(it);
             return p;
         }
     }
-    void *p = nullptr;
+    HostProf hp("cudaMalloc");
     cudaError_t e = cudaMalloc(&p, r);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -158,18 +219,15 @@ void *dev_alloc_bytes(size_t bytes) {
     g_block_size[p] = BlockInfo{r, c.index};
     return p;
 }
-// A freed block goes back to the cache of the worker that allocated it, whoever frees it: records and k-mer lists are
-// produced on worker contexts and released by the thread that collects a job, and would otherwise pile up in that
-// thread's cache while the workers keep allocating fresh memory.  The caller guarantees that no stream still uses the
-// block (cross-context frees happen after the producing call returned and the consuming stream was waited for).
 void dev_free(void *p) {
     Context &c = ctx();
     if (!p) return;
-    if (!c.ready) {                                // after damar_shutdown: no cache to return it to
+    if (!c.ready) {                                // after damar_shutdown: no stream / cache to return it to
         { std::lock_guard<std::mutex> lock(g_mu); g_block_size.erase(p); }
         cudaFree(p);
         return;
     }
+    if (pool_alloc()) { cudaFreeAsync(p, c.stream); return; }      // goes back to the pool it was carved from
     size_t sz = 0; int owner = c.index;
     {
         std::lock_guard<std::mutex> lock(g_mu);
@@ -197,6 +255,7 @@ bool blocking_sync() {
     return on;
 }
 cudaError_t stream_wait(cudaStream_t st) {
+    HostProf hp("wait");
     if (!blocking_sync()) return cudaStreamSynchronize(st);
     Context &c = ctx();
     if (!c.wait_ev) { cudaError_t e = cudaEventCreateWithFlags(&c.wait_ev, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
@@ -248,6 +307,7 @@ void damar_shutdown(void) {
         cudaStreamSynchronize(c.stream);
         delete c.ws; c.ws = nullptr;                 // scratch buffers go back to the cache, pinned staging and events are released
         release_cached_blocks(c);
+        if (c.pool) { cudaMemPoolDestroy(c.pool); c.pool = nullptr; }     // blocks still held by the host stay valid until freed
         if (c.wait_ev) { cudaEventDestroy(c.wait_ev); c.wait_ev = nullptr; }
         cudaStreamDestroy(c.stream);
         c.stream = nullptr;

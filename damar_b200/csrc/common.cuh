@@ -102,6 +102,7 @@ struct Timer {
         CUDA_CHECK(cudaEventCreateWithFlags(&a, timing_event_flags())); CUDA_CHECK(cudaEventCreateWithFlags(&b, timing_event_flags()));
         CUDA_CHECK(cudaEventRecord(a, s));
     }
+    float lap() { return stop(); }      // elapsed so far; the timer keeps its start
     float stop() {
         float ms = 0;
         CUDA_CHECK(cudaEventRecord(b, s)); CUDA_CHECK(cudaEventSynchronize(b));
@@ -137,6 +138,7 @@ struct Context {
     int64_t launches = 0;
     bool ready = false;
     cudaEvent_t wait_ev = nullptr;               // blocking-sync event of stream_wait()
+    cudaMemPool_t pool = nullptr;                // this worker's stream-ordered device memory pool (api.cu)
     std::mutex cache_mu;                         // guards free_blocks: another worker may trim it under memory pressure
     std::multimap<size_t, void *> free_blocks;   // caching allocator (api.cu)
     WorkerScratch *ws = nullptr;                 // buffers that outlive a call (api.cu)

@@ -749,6 +749,7 @@ struct PipeArgs {
     wc::Lane *wide_lane; uint32_t *wide_ring;   // state of the passes that outgrew the 32-diagonal ring: [task][32][FRONT_WORDS]
     const uint32_t *task_order;           // tasks of the round, longest expected pass first (or null: index order)
     wc::Cell *pool; unsigned int pool_cap;
+    unsigned long long *wlog; unsigned int *wlog_n; unsigned int wlog_cap;   // DAMAR_WAVE_LOG: per-warp residency log (debug)
 };
 enum { CTR_NCAND = 0, CTR_NEXT = 1, CTR_NWIDE = 2, CTR_POOL = 3, CTR_NEXT_WIDE = 4, CTR_RETRY = 5, CTR_RETIRED = 6, CTR_N = 8 };
 
@@ -944,6 +945,16 @@ __global__ void task_length_keys(PipeArgs Q, unsigned ntasks, uint64_t *__restri
     vals[t] = t;
 }
 
+// The sorted queue hands the 32 longest passes to the first warp that asks, and that warp -- 32 long passes in 32 different
+// phases of the wave step -- is the last to finish.  Deal the head of the queue out like cards instead: chunk c (one warp's
+// first batch) gets sorted[c], sorted[chunks + c], sorted[2 chunks + c], ...: one pass of every length band.
+__global__ void spread_order(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, unsigned n, unsigned chunks) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned c = i >> 5, l = i & 31u;
+    out[i] = (c < chunks) ? in[l * chunks + c] : in[i];
+}
+
 // ---- stage 4: one thread per wave pass ----
 struct DevPool {
     wc::Cell *cells; unsigned int *top; unsigned int cap;
@@ -960,6 +971,34 @@ struct WaveCfg {
     static constexpr int SMEM = WARPS * wc::FRONT_WORDS * wc::FrontRT::ARR * 4;
 };
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// DAMAR_WAVE_LOG=<file>: every warp of every wave_tasks launch of the process logs {start, first idle lane, end, SM | shape |
+// grid} (ns of %globaltimer); written as raw u64 quadruples at exit.  A debugging aid for the step's SM occupancy.
+struct WaveLog {
+    unsigned long long *buf = nullptr; unsigned int *n = nullptr; unsigned int cap = 0; std::string path;
+    static WaveLog &get() {
+        static WaveLog w;
+        static std::once_flag once;
+        std::call_once(once, [] {
+            const char *e = getenv("DAMAR_WAVE_LOG");
+            if (!e || !*e) return;
+            w.path = e; w.cap = 4u << 20;
+            CUDA_CHECK(cudaMalloc(&w.buf, (size_t)w.cap * 32)); CUDA_CHECK(cudaMalloc(&w.n, 4)); CUDA_CHECK(cudaMemset(w.n, 0, 4));
+            atexit([] {
+                WaveLog &g = WaveLog::get();
+                unsigned int cnt = 0;
+                if (cudaMemcpy(&cnt, g.n, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+                if (cnt > g.cap) cnt = g.cap;
+                std::vector<unsigned long long> h((size_t)cnt * 4);
+                if (cnt && cudaMemcpy(h.data(), g.buf, (size_t)cnt * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+                if (FILE *f = fopen(g.path.c_str(), "wb")) { fwrite(h.data(), 32, cnt, f); fclose(f); }
+            });
+        });
+        return w;
+    }
+};
+
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) { return *reinterpret_cast<const volatile unsigned *>(p); }
 
 // Task t of [0, 2 * ncand) = pass (t & 1) of alignment t >> 1.  A warp works in one of two SHAPES on the same 16 KB of
@@ -969,8 +1008,8 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) { return 
 // pass continues within microseconds while the bulk of the round is still running, and the narrow CTAs leave as soon as
 // the queue is empty.  (Round 1 ran the parked passes in a second kernel after the first, with a host wait in between.)  A wide lane leaves when every task has left the narrow queue's lanes
 // (CTR_RETIRED == number of tasks: no pass can be parked any more) and no parked pass is unclaimed.
-template <int NWAY, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
+template <int NWAY, int WARPS, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB) wave_tasks(PipeArgs Q) {
     extern __shared__ uint32_t front_smem[];
     __shared__ int16_t s_t7[128], s_t8[256];                  // the trim test tables (wave_core.cuh)
     const AlignArgs &P = Q.A;
@@ -990,6 +1029,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     L.status = wc::ST_IDLE; L.k = 0; L.low = 0;
     unsigned task = 0;
     unsigned long long cells_done = 0;
+    unsigned long long t_begin = 0, t_dry = 0;                // debug log: start, first lane without a task
+    if (Q.wlog) t_begin = globaltimer_ns();
     // Warp-uniform shape.  A full-size round is TWO launches of this kernel, back to back with no host wait between them:
     // every CTA narrow, leaving when the queue is empty (their SMs go to the next kernel, usually another comparison's),
     // then a few CTAs that are wide from the start (wide_ctas == gridDim.x) for the parked passes -- about 2 % of the
@@ -998,7 +1039,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
     const bool linger = Q.linger != 0;
     bool wide = (int)blockIdx.x < Q.wide_ctas;
     wc::FrontRT F = wide ? wc::FrontRT{region + (lane & 15), 63, 4} : wc::FrontRT{region + lane, 31, 5};
-    if (wide && lane >= 16) L.status = wc::ST_EXIT;
+    // a launch of wide CTAs only starts when the narrow launch is over: the number of parked passes is final, and a warp
+    // takes no more of them than its share (a warp with few lanes steps through fewer phases per iteration)
+    int wide_lanes = 16;
+    if (wide) {
+        const unsigned nw = ld_volatile_u32(&Q.ctr[CTR_NWIDE]), warps = gridDim.x * WARPS;
+        wide_lanes = (int)min(16u, max(1u, (nw + warps - 1) / warps));
+    }
+    if (wide && lane >= wide_lanes) L.status = wc::ST_EXIT;
     unsigned await = 0;
     bool waiting = false;
     for (unsigned iter = 0;; iter++) {
@@ -1033,7 +1081,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
                 if (lane == leader) base = atomicAdd(&Q.ctr[CTR_NEXT], (unsigned)__popc(idle));
                 base = __shfl_sync(idle, base, leader);
                 const unsigned t = base + __popc(idle & ((1u << lane) - 1u));
-                if (t >= ntasks) L.status = wc::ST_EXIT;
+                if (t >= ntasks) { L.status = wc::ST_EXIT; if (Q.wlog && !t_dry) t_dry = globaltimer_ns(); }
                 else {
                     task = Q.task_order ? Q.task_order[t] : t;
                     const unsigned slot = task >> 1;
@@ -1064,7 +1112,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
             }
         } else {
             // ---------------- WIDE: 16 lanes x 64 diagonals, parked passes ----------------
-            const bool mine = lane < 16;
+            const bool mine = lane < wide_lanes;
             if (mine && !waiting && L.status != wc::ST_RUN && L.status != wc::ST_EXIT) {
                 if (L.status != wc::ST_IDLE) {                    // retire; a front beyond 64 diagonals stays ST_WIDE: the pair goes to the strided kernel
                     wc::TaskOut o;
@@ -1105,6 +1153,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) wave_tasks(PipeArgs Q) {
         } else if (!any_run) __nanosleep(256);
     }
     if (cells_done) atomicAdd(&P.stats[2], cells_done);
+    if (Q.wlog) {
+        if (!t_dry) t_dry = ~0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(FULL, t_dry, o); if (v < t_dry) t_dry = v; }
+        if (lane == 0) {
+            const unsigned i = atomicAdd(Q.wlog_n, 1u);
+            if (i < Q.wlog_cap) {
+                unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                Q.wlog[4 * (size_t)i] = t_begin; Q.wlog[4 * (size_t)i + 1] = t_dry; Q.wlog[4 * (size_t)i + 2] = globaltimer_ns();
+                Q.wlog[4 * (size_t)i + 3] = (unsigned long long)smid | ((unsigned long long)(Q.wide_ctas ? 1 : 0) << 16) | ((unsigned long long)gridDim.x << 32);
+            }
+        }
+    }
 }
 
 // ---- stage 4 epilogue: one warp per alignment of the round ----
@@ -1494,9 +1555,13 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     DevBuf<wc::Lane> wide_lane; DevBuf<uint32_t> wide_ring, wide_ready;
     wide_lane.reserve(2 * na); wide_ring.reserve(2 * na * 32 * wc::FRONT_WORDS); wide_ready.reserve(2 * na);
     Q.wide_lane = wide_lane.p; Q.wide_ring = wide_ring.p; Q.wide_ready = wide_ready.p; Q.wide_cap = (unsigned int)(2 * na);
+    { WaveLog &wl = WaveLog::get(); Q.wlog = wl.buf; Q.wlog_n = wl.n; Q.wlog_cap = wl.cap; }
     DevBuf<uint64_t> okeys; DevBuf<uint32_t> ovals;
     okeys.reserve(4 * na); ovals.reserve(4 * na);
     static const bool lpt = !(getenv("DAMAR_LPT") && atoi(getenv("DAMAR_LPT")) == 0);
+    static const bool spread = getenv("DAMAR_SPREAD") && atoi(getenv("DAMAR_SPREAD")) != 0;
+    static const bool wide_spread = getenv("DAMAR_WIDE_SPREAD") && atoi(getenv("DAMAR_WIDE_SPREAD")) != 0;
+    static const bool timeline = getenv("DAMAR_TIMELINE") && atoi(getenv("DAMAR_TIMELINE")) != 0;   // per-round kernel times on stderr
 
     // Pebble pool, sized from the measured need instead of the worst case: a pass logs one cell per trace point it crosses
     // on either axis (~ 2 x length / TS per pass, the alive paths of a front share prefixes) plus up to one partly used
@@ -1526,7 +1591,14 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
         set_smem(wave_tasks<4, 12>, WaveCfg<12>::SMEM);
         set_smem(wave_tasks<4, 13>, WaveCfg<13>::SMEM);
         set_smem(wave_tasks<4, 14>, WaveCfg<14>::SMEM);
+        set_smem(wave_tasks<4, 1, 12>, 2 * WaveCfg<1>::SMEM);
+        set_smem(wave_tasks<4, 1, 8>, 2 * WaveCfg<1>::SMEM);
+        set_smem(wave_tasks<4, 2, 6>, 2 * WaveCfg<2>::SMEM);
+        set_smem(wave_tasks<4, 4, 3>, 2 * WaveCfg<4>::SMEM);
     });
+    // warps per CTA: a CTA of all the SM's warps holds the SM until its LAST pass ends (the longest pass of a round runs
+    // ~25 ms on one lane); small CTAs hand their share of the SM to the next kernel as they finish
+    static const int cta_warps = getenv("DAMAR_WAVE_CTA_WARPS") ? atoi(getenv("DAMAR_WAVE_CTA_WARPS")) : 0;
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0; int64_t nwide_total = 0;
     DevBuf<uint8_t> dead; DevBuf<uint64_t> hr_keys; DevBuf<uint32_t> hr_vals, hr_pool; DevBuf<unsigned long long> hr_top;
@@ -1571,10 +1643,15 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
             }
             if (ncand == 0) break;
             Timer t_k(st);
+            float t_narrow = 0;
             {
-                const unsigned per = (unsigned)wwarps * 32;
-                const unsigned wb = std::min<unsigned>((unsigned)wave_ctas, (2 * ncand + per - 1) / per);
-                const bool two_launches = wb >= 64 && wide_ctas_max > 0;
+                const bool small_ctas = cta_warps == 1 || cta_warps == 2 || cta_warps == 4;
+                const unsigned per = (unsigned)(small_ctas ? cta_warps : wwarps) * 32;
+                const unsigned per_sm = small_ctas ? (unsigned)(wwarps / cta_warps) : 1u;          // CTAs of one SM
+                const unsigned wb = std::min<unsigned>((unsigned)wave_ctas * per_sm, (2 * ncand + per - 1) / per);
+                const bool two_launches = wb >= 64 * per_sm && wide_ctas_max > 0;
+                // small CTAs: shared memory padded so that exactly per_sm of them share an SM
+                const int pad_smem = small_ctas ? std::max((int)per / 32 * WaveCfg<1>::SMEM, (int)((216 * 1024) / per_sm) - 2048) : 0;
                 Q.task_order = nullptr;
                 if (ncand >= 2048 && lpt) {                      // order the queue: longest passes first
                     const int64_t nt = 2 * (int64_t)ncand;
@@ -1583,10 +1660,20 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                     KERNEL_CHECK(); count_launch();
                     radix_sort_pairs(k0, v0, k1, v1, nt, 24, st);
                     Q.task_order = v0;
+                    if (spread) {
+                        const unsigned chunks = (unsigned)std::min<int64_t>(nt / 32, (int64_t)wb * (per / 32));
+                        spread_order<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(v0, v1, (unsigned)nt, chunks);
+                        KERNEL_CHECK(); count_launch();
+                        Q.task_order = v1;
+                    }
                 }
                 CUDA_CHECK(cudaMemsetAsync(wide_ready.p, 0, sizeof(uint32_t) * 2 * na, st));   // all of it: tickets run past this round's parks
                 auto launch = [&](unsigned grid) {
-                    if (wwarps == 8) wave_tasks<4, 8><<<grid, per, WaveCfg<8>::SMEM, st>>>(Q);
+                    if (small_ctas && cta_warps == 1 && wwarps <= 8) wave_tasks<4, 1, 8><<<grid, per, pad_smem, st>>>(Q);
+                    else if (small_ctas && cta_warps == 1) wave_tasks<4, 1, 12><<<grid, per, pad_smem, st>>>(Q);
+                    else if (small_ctas && cta_warps == 2) wave_tasks<4, 2, 6><<<grid, per, pad_smem, st>>>(Q);
+                    else if (small_ctas && cta_warps == 4) wave_tasks<4, 4, 3><<<grid, per, pad_smem, st>>>(Q);
+                    else if (wwarps == 8) wave_tasks<4, 8><<<grid, per, WaveCfg<8>::SMEM, st>>>(Q);
                     else if (wwarps == 10) wave_tasks<4, 10><<<grid, per, WaveCfg<10>::SMEM, st>>>(Q);
                     else if (wwarps == 13) wave_tasks<4, 13><<<grid, per, WaveCfg<13>::SMEM, st>>>(Q);
                     else if (wwarps == 14) wave_tasks<4, 14><<<grid, per, WaveCfg<14>::SMEM, st>>>(Q);
@@ -1595,10 +1682,18 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                 };
                 Q.wide_ctas = 0; Q.linger = two_launches ? 0 : 1;
                 launch(wb);
-                if (two_launches) { Q.wide_ctas = wide_ctas_max; launch((unsigned)wide_ctas_max); }
+                if (timeline) t_narrow = t_k.lap();
+                if (two_launches && wide_spread) {            // one-warp CTAs all over the device, as few parked passes per warp as possible
+                    const unsigned grid = (unsigned)wave_ctas * 12u;
+                    Q.wide_ctas = (int)grid;
+                    wave_tasks<4, 1, 12><<<grid, 32, WaveCfg<1>::SMEM, st>>>(Q);
+                    KERNEL_CHECK(); count_launch();
+                } else if (two_launches) { Q.wide_ctas = wide_ctas_max * (int)per_sm; launch((unsigned)wide_ctas_max * per_sm); }
             }
-            c.tm.align_kernel_ms += t_k.stop(); c.tm.align_launches += 1;
-            { unsigned int nw = 0; CUDA_CHECK(cudaMemcpyAsync(&nw, ctr.p + CTR_NWIDE, sizeof(nw), cudaMemcpyDeviceToHost, st)); CUDA_CHECK(stream_wait(st)); nwide_total += nw; }
+            const float t_round = t_k.stop();
+            c.tm.align_kernel_ms += t_round; c.tm.align_launches += 1;
+            { unsigned int nw = 0; CUDA_CHECK(cudaMemcpyAsync(&nw, ctr.p + CTR_NWIDE, sizeof(nw), cudaMemcpyDeviceToHost, st)); CUDA_CHECK(stream_wait(st)); nwide_total += nw;
+              if (timeline) fprintf(stderr, "[timeline] round %d: %u candidates, narrow %.3f ms, wide %.3f ms (%u parked)\n", rounds, ncand, t_narrow, t_round - t_narrow, nw); }
             const unsigned fb = (unsigned)std::min<uint64_t>((uint64_t)sblocks, ((uint64_t)ncand + 7) / 8);
             finish_las<<<fb, 256, 0, st>>>(Q);
             KERNEL_CHECK(); count_launch();
@@ -1625,7 +1720,9 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
             Timer t_r(st);
             align_pairs_strided<<<lblocks, AL_WARPS * 32, 0, st>>>(R);
             KERNEL_CHECK(); count_launch();
-            c.tm.redo_kernel_ms += t_r.stop();
+            const float t_redo = t_r.stop();
+            c.tm.redo_kernel_ms += t_redo;
+            if (timeline) fprintf(stderr, "[timeline] strided kernel: %u pairs, %.3f ms\n", nredo, t_redo);
         }
         CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(stream_wait(st));
@@ -1673,6 +1770,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
         break;
     }
     c.tm.align_ms = t_align.stop();
+    if (timeline) fprintf(stderr, "[timeline] stage 4 total %.3f ms, %d rounds\n", c.tm.align_ms, rounds);
     delete hp3;
     // capacity errors are reported to the caller (damar_match_filter returns non-zero), never a silent truncation
     if (hc[3] & 4ull) { set_error("alignment scratch overflow: wave wider than %d diagonals or pebble arena exhausted", ring); return 1; }

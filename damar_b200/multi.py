@@ -189,22 +189,13 @@ def run_sharded(dbdir: str, root: str, nblocks: int, settings, rank: int, world:
         blocks = exchange_blocks(dbdir, root, shards, rank, world, dist, device, masks)
         cache = {}
     novl, files = 0, {}
-    def finish(pending):
-        nonlocal novl
-        for name, im in api.collect(pending, as_bytes=False).items():
-            novl += im.novl
-            if outdir is not None:
-                api.write_outputs(outdir, {name: im}, settings.run_id)
-            files[name] = len(im)
-
-    pend = None                                   # job i+1 is queued on the GPU before job i's records are sorted and written
-    for job in shards[rank]:
-        nxt = api.submit(blocks[job.a], [blocks[b] for b in job.bs], settings, dcache=cache)
-        if pend is not None:
-            finish(pend)
-        pend = nxt
-    if pend is not None:
-        finish(pend)
+    # the rank's jobs through the library's pipelined plan runner (later jobs are queued while earlier ones finish)
+    for name, im in api.plan_iter(((blocks[job.a], [blocks[b] for b in job.bs]) for job in shards[rank]), settings,
+                                  dcache=cache, as_bytes=False):
+        novl += im.novl
+        if outdir is not None:
+            api.write_outputs(outdir, {name: im}, settings.run_id)
+        files[name] = len(im)
     if own_cache:
         for h in cache.values():
             h.free()

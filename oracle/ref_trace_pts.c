@@ -9,9 +9,12 @@
  *      trace_pts_ref <db> <las>            one line per record: aread bread comp diffs-before diffs-after
  *      trace_pts_ref <db> <las> script     the same plus the length of the edit script Compute_Trace_PTS wrote (path->tlen
  *                                          ints) and the script itself (GREEDIEST mode, the one LAshow uses)
+ *      trace_pts_ref <db> <las> mid        the same through Compute_Trace_MID (dalign/align.c:5694-5830, GREEDIEST as
+ *                                          corrector/LAcorrect.c:545 calls it)
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include "DB.h"
 #include "align.h"
 
@@ -28,7 +31,7 @@ int main(int argc, char *argv[])
     uint16 *trace = NULL;
 
     Prog_Name = "trace_pts_ref";
-    if (argc != 3 && argc != 4) { fprintf(stderr, "usage: trace_pts_ref <db> <las> [script]\n"); return 1; }
+    if (argc != 3 && argc != 4) { fprintf(stderr, "usage: trace_pts_ref <db> <las> [script|mid]\n"); return 1; }
     if (Open_DB(argv[1], &db)) return 1;
     if ((f = fopen(argv[2], "r")) == NULL) return 1;
     if (fread(&novl, sizeof(int64), 1, f) != 1 || fread(&tspace, sizeof(int), 1, f) != 1) return 1;
@@ -50,7 +53,8 @@ int main(int argc, char *argv[])
         if (COMP(ovl.flags)) Complement_Seq(bbuf, aln.blen);
         {
             int before = ovl.path.diffs;
-            if (Compute_Trace_PTS(&aln, work, tspace, GREEDIEST)) return 1;
+            if (argc == 4 && strcmp(argv[3], "mid") == 0) { if (Compute_Trace_MID(&aln, work, tspace, GREEDIEST)) return 1; }
+            else if (Compute_Trace_PTS(&aln, work, tspace, GREEDIEST)) return 1;
             printf("%d %d %d %d %d", ovl.aread, ovl.bread, COMP(ovl.flags) ? 1 : 0, before, ovl.path.diffs);
             if (argc == 4) {
                 int t, *scr = (int *)ovl.path.trace;

@@ -3,7 +3,9 @@
 utils/LAshow.c:261 calls it): for every record of committed reference .las files the length of the script the UNMODIFIED
 reference function writes and a 64-bit FNV-1a hash of its values; every 400th record's script in full.
 
-    python tests/golden/make_trace_script.py      ->  tests/golden/trace_script.json"""
+The same for Compute_Trace_MID (align.c:5694-5830, GREEDIEST as corrector/LAcorrect.c:545 calls it).
+
+    python tests/golden/make_trace_script.py      ->  tests/golden/trace_script.json, tests/golden/trace_mid.json"""
 import json
 import os
 import subprocess
@@ -24,10 +26,15 @@ def fnv(vals):
 
 
 def main():
+    make("script", "trace_script.json")
+    make("mid", "trace_mid.json")           # Compute_Trace_MID (align.c:5694-5830), same layout
+
+
+def make(mode, target):
     out = {}
     for db, root, case, fn in FILES:
         las = os.path.join(HERE, db, "ref", case, fn)
-        txt = subprocess.run([EXE, os.path.join(HERE, db, root), las, "script"], check=True, capture_output=True, text=True).stdout
+        txt = subprocess.run([EXE, os.path.join(HERE, db, root), las, mode], check=True, capture_output=True, text=True).stdout
         recs, full = [], {}
         for i, ln in enumerate(txt.splitlines()):
             f = list(map(int, ln.split()))
@@ -38,7 +45,7 @@ def main():
                 full[str(i)] = scr
         out[f"{db}/{case}/{fn}"] = {"n": len(recs), "records": recs, "full": full}
         print(db, case, fn, len(recs), sum(r[0] for r in recs))
-    with open(os.path.join(HERE, "trace_script.json"), "w") as fh:
+    with open(os.path.join(HERE, target), "w") as fh:
         json.dump(out, fh, separators=(",", ":"))
 
 

@@ -19,6 +19,8 @@ SO = os.path.join(HERE, "_build", "libtracescript_host.so")
 SRC = [os.path.join(HERE, "trace_script_host.cpp"), os.path.join(ROOT, "damar_b200", "csrc", "trace_script_core.cuh")]
 with open(os.path.join(GOLDEN, "trace_script.json")) as _f:
     GOLD = json.load(_f)
+with open(os.path.join(GOLDEN, "trace_mid.json")) as _f:        # Compute_Trace_MID (align.c:5694-5830) on the same files
+    GOLD_MID = json.load(_f)
 
 
 def _lib():
@@ -26,9 +28,10 @@ def _lib():
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.run(["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", SO, SRC[0]], check=True)
     L = C.CDLL(SO)
-    L.ts_record_script.restype = C.c_int
-    L.ts_record_script.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                   C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    for f in (L.ts_record_script, L.ts_record_mid):
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                      C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     return L
 
 
@@ -44,8 +47,9 @@ def complement_read(seq):
     return (3 - seq[::-1]).astype(np.int8)
 
 
-def record_scripts(L, blk_of, las):
+def record_scripts(L, blk_of, las, fn="ts_record_script"):
     """yields (script, diffs) per record of a .las image; blk_of(read id) -> (block, local index)"""
+    call = getattr(L, fn)
     novl, tspace, recs, traces = dbio.parse_las(las)
     tb = np.uint8 if tspace <= 125 else np.uint16
     out = np.zeros(1 << 20, np.int32)
@@ -61,14 +65,15 @@ def record_scripts(L, blk_of, las):
         sa, sb = seq(ab_, ai, False), seq(bb_, bi, bool(r["flags"] & 1))
         tr = np.frombuffer(t, dtype=tb).astype(np.uint16)
         d = C.c_int(0)
-        n = L.ts_record_script(sa.ctypes.data + 1, len(sa) - 2, sb.ctypes.data + 1, len(sb) - 2, int(r["abpos"]), int(r["bbpos"]),
-                               int(r["aepos"]), int(r["bepos"]), tr.ctypes.data, len(tr), tspace, out.ctypes.data, len(out), C.byref(d))
+        n = call(sa.ctypes.data + 1, len(sa) - 2, sb.ctypes.data + 1, len(sb) - 2, int(r["abpos"]), int(r["bbpos"]),
+                 int(r["aepos"]), int(r["bepos"]), tr.ctypes.data, len(tr), tspace, out.ctypes.data, len(out), C.byref(d))
         assert n >= 0, n
         yield out[:n].copy(), d.value
 
 
+@pytest.mark.parametrize("flavour", ["pts", "mid"])
 @pytest.mark.parametrize("key", sorted(GOLD))
-def test_edit_scripts_equal_reference(key):
+def test_edit_scripts_equal_reference(key, flavour):
     db, case, fn = key.split("/")
     root = {"tiny": "T", "rep": "R", "long": "L", "tan": "N"}[db]
     d = os.path.join(GOLDEN, db)
@@ -81,10 +86,10 @@ def test_edit_scripts_equal_reference(key):
                 return b, rid - b.ufirst
         raise KeyError(rid)
     las = open(os.path.join(d, "ref", case, fn), "rb").read()
-    g = GOLD[key]
+    g = (GOLD if flavour == "pts" else GOLD_MID)[key]
     L = _lib()
     n = 0
-    for i, (scr, diffs) in enumerate(record_scripts(L, blk_of, las)):
+    for i, (scr, diffs) in enumerate(record_scripts(L, blk_of, las, "ts_record_script" if flavour == "pts" else "ts_record_mid")):
         tl, h, gd = g["records"][i]
         assert len(scr) == tl and "%016x" % fnv(scr) == h and diffs == gd, f"{key} record {i}: {len(scr)} vs {tl}"
         if str(i) in g["full"]:
