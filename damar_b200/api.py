@@ -85,7 +85,7 @@ EXPORTS = ["damar_abi_version", "damar_init", "damar_shutdown", "damar_last_erro
            "damar_sink_serialise", "damar_free", "damar_reset_kernel_timers", "damar_emission_order",
            "damar_dump_profile", "damar_worker_bind", "damar_worker_count", "damar_sink_add_at", "damar_set_biased", "damar_trace_point_diffs", "damar_las_merge",
            "damar_las_compare", "damar_sort_selftest", "damar_block_view_get", "damar_block_from_view", "damar_match_self",
-           "damar_trace_point_scripts", "damar_host_free", "damar_dsink_new", "damar_dsink_free", "damar_dsink_reset", "damar_match_filter_sink", "damar_dsink_serialise"]
+           "damar_trace_point_scripts", "damar_trace_mid_scripts", "damar_host_free", "damar_dsink_new", "damar_dsink_free", "damar_dsink_reset", "damar_match_filter_sink", "damar_dsink_serialise"]
 
 _lib = None
 
@@ -110,6 +110,8 @@ def load_library():
     L.damar_trace_point_scripts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                             C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.damar_trace_point_scripts.restype = C.c_int
+    L.damar_trace_mid_scripts.argtypes = L.damar_trace_point_scripts.argtypes
+    L.damar_trace_mid_scripts.restype = C.c_int
     L.damar_host_free.argtypes = [C.c_void_p]
     L.damar_las_merge.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.damar_las_merge.restype = C.c_int
@@ -682,10 +684,11 @@ def plan_iter(jobs, s: Settings, stats: Optional[list] = None, dcache: Optional[
     HPCdaligner script would (dalign/HPCdaligner.c:709-788): yields (file name, image) as jobs complete, in job order.
     Later jobs are submitted (blocks shipped, comparisons queued) BEFORE the earlier ones are collected, so the pool always
     has comparisons waiting (a plan starts with its smallest jobs, `A.1 A.1` is one block pair): up to `DAMAR_LOOKAHEAD`
-    (default 4 x workers) comparisons queued or running beyond the job being collected.  Jobs whose process-wide options
+    (default workers + 2) comparisons queued or running beyond the job being collected -- measured on the C2 plan: 1 -> 585-685
+    ms per step, 8 -> 585-594, 24 -> 591-601 (results wait in HBM until their job is collected, so deeper is not better).  Jobs whose process-wide options
     differ (base frequencies of another DB, -b) are not overlapped."""
     dcache = {} if dcache is None else dcache
-    ahead = int(os.environ.get("DAMAR_LOOKAHEAD", str(4 * workers())))
+    ahead = int(os.environ.get("DAMAR_LOOKAHEAD", str(workers() + 2)))
     pend: List[_Job] = []
     pend_key = None
 
@@ -743,9 +746,11 @@ def trace_point_diffs(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las:
     return (rec, seg[: ntrace // 2], (toff[:novl] // 2).astype(np.int64)) if segments else rec
 
 
-def trace_point_scripts(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las: bytes):
+def trace_point_scripts(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, las: bytes, middles: bool = False):
     """Compute_Trace_PTS (align.c:5577-5692, mode GREEDIEST) over a whole .las image: per record the exact diffs AND the edit
-    script the reference leaves in path->trace.  Returns (rec_diffs int32[novl], script_off int64[novl + 1], script int32[])."""
+    script the reference leaves in path->trace.  middles=True: Compute_Trace_MID (align.c:5694-5830), the flavour that aligns
+    between the middles of successive trace-point segments (corrector/LAcorrect.c:545).
+    Returns (rec_diffs int32[novl], script_off int64[novl + 1], script int32[])."""
     from . import dbio
     novl, tspace, recs, traces = dbio.parse_las(las)
     tbytes = 1 if tspace <= 125 else 2
@@ -759,8 +764,9 @@ def trace_point_scripts(ablock: DeviceBlockHandle, bblock: DeviceBlockHandle, la
     soff = np.zeros(novl + 1, np.int64)
     sp, sl = C.c_void_p(), C.c_int64(0)
     L = load_library()
-    rc = L.damar_trace_point_scripts(ablock.handle, bblock.handle, recs.ctypes.data, toff.ctypes.data, trace.ctypes.data, tbytes, novl,
-                                     int(toff[novl]), tspace, rec.ctypes.data, soff.ctypes.data, C.byref(sp), C.byref(sl))
+    fn = L.damar_trace_mid_scripts if middles else L.damar_trace_point_scripts
+    rc = fn(ablock.handle, bblock.handle, recs.ctypes.data, toff.ctypes.data, trace.ctypes.data, tbytes, novl,
+            int(toff[novl]), tspace, rec.ctypes.data, soff.ctypes.data, C.byref(sp), C.byref(sl))
     if rc not in (0, 1):
         raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
     try:

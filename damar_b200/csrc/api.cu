@@ -488,6 +488,17 @@ int damar_trace_point_scripts(damar_block *ablk, damar_block *bblk, const damar_
                                   trace_bytes, novl, ntrace, trace_spacing, rec_diffs, nullptr, script_off, script, script_len);
 }
 
+int damar_trace_mid_scripts(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
+                            const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
+                            int32_t *rec_diffs, int64_t *script_off, int32_t **script, int64_t *script_len) {
+    ensure_init();
+    if (trace_spacing <= 0 || (trace_bytes != 1 && trace_bytes != 2) || !rec_diffs || !script_off || !script || !script_len) {
+        set_error("damar_trace_mid_scripts: bad arguments"); return 2;
+    }
+    return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
+                                  trace_bytes, novl, ntrace, trace_spacing, rec_diffs, nullptr, script_off, script, script_len, 1);
+}
+
 void damar_host_free(void *p) { free(p); }
 
 void damar_emission_order(const damar_overlaps *o, int64_t *order) {

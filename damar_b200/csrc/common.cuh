@@ -259,7 +259,8 @@ inline WorkerScratch &scratch() { return *ctx().ws; }
 // trace_pts.cu
 int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap *ovl, const uint64_t *toff, const void *trace,
                            int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs,
-                           int64_t *script_off = nullptr, int32_t **script_out = nullptr, int64_t *script_len = nullptr);
+                           int64_t *script_off = nullptr, int32_t **script_out = nullptr, int64_t *script_len = nullptr,
+                           int flavour = 0);   // 0: Compute_Trace_PTS, 1: Compute_Trace_MID
 
 int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
                      HostOverlaps &out, bool tandem = false);   // non-zero: error set (capacity limits are errors, not exits)

@@ -128,6 +128,8 @@ struct SegArgs {
     const uint16_t *segcost;                  // exact distance of every segment (trace_point_diffs)
     int32_t *seg_ab, *seg_bb, *seg_m, *seg_n, *seg_dmax, *seg_rec;
     uint32_t *need, *cap;                     // scratch ints / output slots per segment
+    const int32_t *dcap;                      // Compute_Trace_MID pieces: waves the scratch was sized for (their distance is not known beforehand)
+    int32_t *cost_out;                        // ... and where their distance goes
 };
 // one warp per record: the segment table (align.c:5650-5680) and what every segment needs
 __global__ void __launch_bounds__(128) script_segments(SegArgs S) {
@@ -190,12 +192,79 @@ __global__ void __launch_bounds__(128) script_emit(SegArgs S, uint64_t g0, uint6
     const damar_overlap o = P.ovl[S.seg_rec[g]];
     const int ar = o.aread - P.afirst, br = o.bread - P.bfirst;
     const int ab = S.seg_ab[g], bb = S.seg_bb[g], M = S.seg_m[g], N = S.seg_n[g], del = M - N;
-    const int D = (int)S.segcost[g] - (del < 0 ? -del : del);
+    const int D = S.dcap ? S.dcap[g] : (int)S.segcost[g] - (del < 0 ? -del : del);
     const PackedRel A{P.aw, P.aboff[ar], ab, P.arlen[ar], 5}, B{P.bw[o.flags & 1u], P.bboff[br], bb, P.brlen[br], 6};
     int cost = 0;
     const int n = ts::np_script(A, M, B, N, S.seg_dmax[g], D, ab, bb, scratch + (need_off[g] - need_base), raw + cap_off[g], (int)S.cap[g], &cost);
-    if (n < 0 || cost != (int)S.segcost[g]) { atomicExch(P.err, 2); return; }
+    if (n < 0 || (!S.dcap && cost != (int)S.segcost[g])) { atomicExch(P.err, 2); return; }
+    if (S.cost_out) S.cost_out[g] = cost;
     count[g] = (uint32_t)n;
+}
+
+// ---- Compute_Trace_MID (align.c:5694-5830): iter_np between the MIDDLES of successive trace-point segments ----
+// one thread per trace-point segment [g0, g1): middle_np, the middle as absolute read coordinates
+__global__ void __launch_bounds__(128) mid_points(SegArgs S, uint64_t g0, uint64_t g1, const uint64_t *__restrict__ need_off, uint64_t need_base,
+                                                 int *__restrict__ scratch, int32_t *__restrict__ mid_a, int32_t *__restrict__ mid_b) {
+    const TpArgs &P = S.P;
+    const uint64_t g = g0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g1 || S.need[g] == 0) return;
+    const damar_overlap o = P.ovl[S.seg_rec[g]];
+    const int ar = o.aread - P.afirst, br = o.bread - P.bfirst;
+    const int ab = S.seg_ab[g], bb = S.seg_bb[g], M = S.seg_m[g], N = S.seg_n[g], del = M - N;
+    const int D = (int)S.segcost[g] - (del < 0 ? -del : del);
+    const PackedRel A{P.aw, P.aboff[ar], ab, P.arlen[ar], 5}, B{P.bw[o.flags & 1u], P.bboff[br], bb, P.brlen[br], 6};
+    int ma = 0, mb = 0;
+    if (ts::np_middle(A, M, B, N, S.seg_dmax[g], D, scratch + (need_off[g] - need_base), &ma, &mb)) { atomicExch(P.err, 2); return; }
+    mid_a[g] = ab + ma; mid_b[g] = bb + mb;
+}
+// pieces per record (segments + 1; 0 for a rejected record), to be scanned into the records' first piece slots
+__global__ void mid_piece_counts(TpArgs P, uint32_t *__restrict__ cnt) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.novl) return;
+    cnt[r] = (P.rec[r] < 0 || P.ovl[r].tlen < 2) ? 0u : (uint32_t)(P.ovl[r].tlen / 2 + 1);
+}
+// one thread per piece slot: piece q of record r runs from the middle of segment q - 1 (or the start of the alignment) to
+// the middle of segment q (or its end).  Its distance is at most that of the two half segments it is made of, which sizes
+// the scratch; more than dmax waves is the reference's "Bad alignment between trace points".
+__global__ void mid_pieces(SegArgs S, SegArgs Q, const uint64_t *__restrict__ pbase, uint64_t npieces, const int32_t *__restrict__ mid_a,
+                           const int32_t *__restrict__ mid_b, int32_t *__restrict__ dcap) {
+    const TpArgs &P = S.P;
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npieces) return;
+    int64_t lo = 0, hi = P.novl - 1;                           // the record that owns slot q: last r with pbase[r] <= q
+    while (lo < hi) { const int64_t m = (lo + hi + 1) >> 1; if (pbase[m] <= q) lo = m; else hi = m - 1; }
+    const int64_t r = lo;
+    const damar_overlap o = P.ovl[r];
+    const int nseg = o.tlen / 2, i = (int)(q - pbase[r]);
+    const uint64_t gb = P.toff[r] / 2;
+    const int a0 = i == 0 ? o.abpos : mid_a[gb + i - 1], b0 = i == 0 ? o.bbpos : mid_b[gb + i - 1];
+    const int a1 = i == nseg ? o.aepos : mid_a[gb + i], b1 = i == nseg ? o.bepos : mid_b[gb + i];
+    const int M = a1 - a0, N = b1 - b0, del = M - N, ad = del < 0 ? -del : del;
+    const int c = (i > 0 ? (int)S.segcost[gb + i - 1] : 0) + (i < nseg ? (int)S.segcost[gb + i] : 0);
+    const int dmax = S.seg_dmax[gb];
+    int D = c - ad; if (D < 0) D = 0; if (D > dmax) D = dmax;
+    Q.seg_ab[q] = a0; Q.seg_bb[q] = b0; Q.seg_m[q] = M; Q.seg_n[q] = N; Q.seg_dmax[q] = dmax; Q.seg_rec[q] = (int32_t)r;
+    dcap[q] = D;
+    Q.need[q] = (uint32_t)ts::scratch_ints(D, del);
+    Q.cap[q] = (uint32_t)c;
+}
+// path->diffs as Compute_Trace_MID leaves it: the distances of the pieces, the one that ends at the last middle twice
+// (`d += iter_np(...); diffs += d;`, align.c:5814-5817)
+__global__ void mid_record_diffs(TpArgs P, const uint64_t *__restrict__ pbase, const int32_t *__restrict__ cost, int32_t *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.novl) return;
+    if (P.rec[r] < 0 || P.ovl[r].tlen < 2) { out[r] = -1; return; }
+    const int nseg = P.ovl[r].tlen / 2;
+    int t = 0;
+    for (int i = 0; i <= nseg; i++) t += cost[pbase[r] + i];
+    out[r] = t + cost[pbase[r] + nseg - 1];
+}
+__global__ void mid_record_offsets(const uint64_t *__restrict__ pbase, int64_t novl, const uint64_t *__restrict__ out_off, uint64_t npieces, uint64_t total,
+                                   int64_t *__restrict__ rec_off) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > novl) return;
+    const uint64_t q = (r == novl) ? npieces : pbase[r];
+    rec_off[r] = (int64_t)(q >= npieces ? total : out_off[q]);
 }
 __global__ void script_compact(const int32_t *__restrict__ raw, const uint64_t *__restrict__ cap_off, const uint32_t *__restrict__ count,
                                const uint64_t *__restrict__ out_off, uint64_t nseg, int32_t *__restrict__ out) {
@@ -221,7 +290,7 @@ __global__ void script_record_offsets(const uint64_t *__restrict__ toff, int64_t
 // record was out of bounds.
 int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap *ovl, const uint64_t *toff, const void *trace,
                            int tbytes, int64_t novl, int64_t ntrace, int TS, int32_t *rec_diffs, uint16_t *seg_diffs,
-                           int64_t *script_off, int32_t **script_out, int64_t *script_len) {
+                           int64_t *script_off, int32_t **script_out, int64_t *script_len, int flavour) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     if (novl <= 0) return 0;
@@ -260,7 +329,7 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
     if (nseg == 0) { for (int64_t r = 0; r <= novl; r++) script_off[r] = 0; return err; }
     DevBuf<int32_t> tab; DevBuf<uint32_t> need, cap, count; DevBuf<uint64_t> need_off, cap_off, out_off, tot;
     tab.reserve(6 * (size_t)nseg); need.reserve((size_t)nseg + 1); cap.reserve((size_t)nseg + 1); count.reserve((size_t)nseg + 1);
-    need_off.reserve((size_t)nseg + 1); cap_off.reserve((size_t)nseg + 1); out_off.reserve((size_t)nseg + 1); tot.reserve(4);
+    need_off.reserve((size_t)nseg + 1); cap_off.reserve((size_t)nseg + 1); out_off.reserve((size_t)nseg + 1); tot.reserve(8);
     CUDA_CHECK(cudaMemsetAsync(need.p, 0, sizeof(uint32_t) * nseg, st));
     CUDA_CHECK(cudaMemsetAsync(cap.p, 0, sizeof(uint32_t) * nseg, st));
     SegArgs S{};
@@ -276,31 +345,90 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
     std::vector<uint64_t> h_need_off((size_t)nseg);
     CUDA_CHECK(cudaMemcpyAsync(h_need_off.data(), need_off.p, sizeof(uint64_t) * nseg, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(stream_wait(st));
-    DevBuf<int32_t> raw; raw.reserve((size_t)htot[1] + 4);
     const uint64_t budget = (uint64_t)1 << 28;                     // ints of scratch per launch (1 GB)
-    DevBuf<int> scr; scr.reserve((size_t)std::min<uint64_t>(htot[0] + 4, budget + ((uint64_t)1 << 24)));
-    for (uint64_t g0 = 0; g0 < nseg;) {                            // batches of segments whose scratch fits the budget
-        uint64_t lo = g0 + 1, hi = nseg;                           // largest g1 with need_off[g1] - need_off[g0] <= budget
-        while (lo < hi) { const uint64_t m = (lo + hi + 1) >> 1; if (h_need_off[m - 1] - h_need_off[g0] <= budget || m == g0 + 1) lo = m; else hi = m - 1; }
-        const uint64_t g1 = lo;
-        const uint64_t span = ((g1 < nseg) ? h_need_off[g1] : htot[0]) - h_need_off[g0];
-        if (span + 4 > scr.n) scr.reserve((size_t)span + 4);
-        script_emit<<<(unsigned)((g1 - g0 + 127) / 128), 128, 0, st>>>(S, g0, g1, need_off.p, h_need_off[g0], cap_off.p, scr.p, raw.p, count.p);
-        KERNEL_CHECK(); count_launch();
-        g0 = g1;
+    DevBuf<int> scr;
+    // runs fn(g0, g1, scratch base) over batches of slots whose scratch fits the budget
+    auto batches = [&](uint64_t n, const std::vector<uint64_t> &off, uint64_t tot_need, auto fn) {
+        scr.reserve((size_t)std::min<uint64_t>(tot_need + 4, budget + ((uint64_t)1 << 24)));
+        for (uint64_t g0 = 0; g0 < n;) {
+            uint64_t lo = g0 + 1, hi = n;                          // largest g1 with off[g1] - off[g0] <= budget
+            while (lo < hi) { const uint64_t m = (lo + hi + 1) >> 1; if (off[m - 1] - off[g0] <= budget || m == g0 + 1) lo = m; else hi = m - 1; }
+            const uint64_t g1 = lo;
+            const uint64_t span = ((g1 < n) ? off[g1] : tot_need) - off[g0];
+            if (span + 4 > scr.n) scr.reserve((size_t)span + 4);
+            fn(g0, g1, off[g0]);
+            g0 = g1;
+        }
+    };
+    // what the scripts are cut into: the trace-point segments themselves (PTS), or the pieces between their middles (MID)
+    SegArgs E = S;
+    uint64_t nslot = nseg, cap_total = htot[1];
+    DevBuf<int32_t> mid, ptab, dcap, pcost; DevBuf<uint32_t> pneed, pcap, pcnt; DevBuf<uint64_t> pbase, pneed_off;
+    std::vector<uint64_t> h_pneed_off;
+    const uint64_t *slot_need_off = need_off.p;
+    const std::vector<uint64_t> *h_slot_need_off = &h_need_off;
+    uint64_t slot_need_total = htot[0];
+    if (flavour == 1) {
+        mid.reserve(2 * (size_t)nseg);
+        batches(nseg, h_need_off, htot[0], [&](uint64_t g0, uint64_t g1, uint64_t base) {
+            mid_points<<<(unsigned)((g1 - g0 + 127) / 128), 128, 0, st>>>(S, g0, g1, need_off.p, base, scr.p, mid.p, mid.p + nseg);
+            KERNEL_CHECK(); count_launch();
+        });
+        pcnt.reserve((size_t)novl + 1); pbase.reserve((size_t)novl + 1);
+        mid_piece_counts<<<(unsigned)((novl + 255) / 256), 256, 0, st>>>(P, pcnt.p);
+        KERNEL_CHECK();
+        exclusive_scan_u32_to_u64(pcnt.p, pbase.p, novl, tot.p + 3, st);
+        uint64_t npieces = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&npieces, tot.p + 3, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(stream_wait(st));
+        if (err == 2) { set_error("Bad alignment between trace points (Compute_Trace_MID)"); return 2; }
+        nslot = npieces;
+        if (nslot == 0) { for (int64_t r = 0; r <= novl; r++) script_off[r] = 0; for (int64_t r = 0; r < novl; r++) rec_diffs[r] = -1; return err; }
+        ptab.reserve(6 * (size_t)nslot); dcap.reserve((size_t)nslot); pcost.reserve((size_t)nslot);
+        pneed.reserve((size_t)nslot + 1); pcap.reserve((size_t)nslot + 1); pneed_off.reserve((size_t)nslot + 1);
+        E.seg_ab = ptab.p; E.seg_bb = ptab.p + nslot; E.seg_m = ptab.p + 2 * nslot; E.seg_n = ptab.p + 3 * nslot; E.seg_dmax = ptab.p + 4 * nslot;
+        E.seg_rec = ptab.p + 5 * nslot; E.need = pneed.p; E.cap = pcap.p; E.dcap = dcap.p; E.cost_out = pcost.p;
+        mid_pieces<<<(unsigned)((nslot + 127) / 128), 128, 0, st>>>(S, E, pbase.p, nslot, mid.p, mid.p + nseg, dcap.p);
+        KERNEL_CHECK(); count_launch(3);
+        count.reserve((size_t)nslot + 1); cap_off.reserve((size_t)nslot + 1); out_off.reserve((size_t)nslot + 1);
+        exclusive_scan_u32_to_u64(pneed.p, pneed_off.p, (int64_t)nslot, tot.p, st);
+        exclusive_scan_u32_to_u64(pcap.p, cap_off.p, (int64_t)nslot, tot.p + 1, st);
+        CUDA_CHECK(cudaMemcpyAsync(htot, tot.p, sizeof(htot), cudaMemcpyDeviceToHost, st));
+        h_pneed_off.resize((size_t)nslot);
+        CUDA_CHECK(cudaMemcpyAsync(h_pneed_off.data(), pneed_off.p, sizeof(uint64_t) * nslot, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(stream_wait(st));
+        slot_need_off = pneed_off.p; h_slot_need_off = &h_pneed_off; slot_need_total = htot[0]; cap_total = htot[1];
     }
-    exclusive_scan_u32_to_u64(count.p, out_off.p, (int64_t)nseg, tot.p + 2, st);
+    DevBuf<int32_t> raw; raw.reserve((size_t)cap_total + 4);
+    batches(nslot, *h_slot_need_off, slot_need_total, [&](uint64_t g0, uint64_t g1, uint64_t base) {
+        script_emit<<<(unsigned)((g1 - g0 + 127) / 128), 128, 0, st>>>(E, g0, g1, slot_need_off, base, cap_off.p, scr.p, raw.p, count.p);
+        KERNEL_CHECK(); count_launch();
+    });
+    exclusive_scan_u32_to_u64(count.p, out_off.p, (int64_t)nslot, tot.p + 2, st);
     uint64_t total = 0;
     CUDA_CHECK(cudaMemcpyAsync(&total, tot.p + 2, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(&err, d_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(stream_wait(st));
-    if (err == 2) { set_error("damar_trace_point_scripts: a segment's script disagrees with its distance"); return 2; }
+    if (err == 2) {
+        set_error(flavour == 1 ? "Bad alignment between trace points (Compute_Trace_MID)" : "damar_trace_point_scripts: a segment's script disagrees with its distance");
+        return 2;
+    }
     DevBuf<int32_t> outb; outb.reserve((size_t)total + 4);
     DevBuf<int64_t> roff; roff.reserve((size_t)novl + 2);
-    script_compact<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(raw.p, cap_off.p, count.p, out_off.p, nseg, outb.p);
+    script_compact<<<(unsigned)((nslot + 255) / 256), 256, 0, st>>>(raw.p, cap_off.p, count.p, out_off.p, nslot, outb.p);
     KERNEL_CHECK();
-    script_record_offsets<<<(unsigned)((novl + 1 + 255) / 256), 256, 0, st>>>(d_toff.p, novl, out_off.p, nseg, total, roff.p);
-    KERNEL_CHECK(); count_launch(3);
+    if (flavour == 1) {
+        mid_record_offsets<<<(unsigned)((novl + 1 + 255) / 256), 256, 0, st>>>(pbase.p, novl, out_off.p, nslot, total, roff.p);
+        KERNEL_CHECK();
+        mid_record_diffs<<<(unsigned)((novl + 255) / 256), 256, 0, st>>>(P, pbase.p, pcost.p, d_rec.p);
+        KERNEL_CHECK(); count_launch();
+        CUDA_CHECK(cudaMemcpyAsync(rec_diffs, d_rec.p, sizeof(int32_t) * novl, cudaMemcpyDeviceToHost, st));
+    } else {
+        script_record_offsets<<<(unsigned)((novl + 1 + 255) / 256), 256, 0, st>>>(d_toff.p, novl, out_off.p, nseg, total, roff.p);
+        KERNEL_CHECK();
+    }
+    count_launch(3);
     int32_t *hs = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total + 1));
     if (hs == nullptr) { set_error("out of host memory for %llu script values", (unsigned long long)total); return 2; }
     if (total) CUDA_CHECK(cudaMemcpyAsync(hs, outb.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, st));

@@ -185,6 +185,14 @@ int damar_trace_point_diffs(damar_block *ablk, damar_block *bblk, const damar_ov
 int damar_trace_point_scripts(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
                               const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
                               int32_t *rec_diffs, int64_t *script_off, int32_t **script, int64_t *script_len);
+/* Compute_Trace_MID (align.c:5694-5830, mode GREEDIEST as corrector/LAcorrect.c:545 calls it): the same outputs, but iter_np
+ * runs between the MIDDLES (middle_np, align.c:5263-5566) of successive trace-point segments instead of between the trace
+ * points -- the nearer-optimal trace align.h:271-277 describes.  rec_diffs receives what the reference leaves in path->diffs,
+ * including its double count of the piece that ends at the last middle (align.c:5814-5817).  A piece that needs more waves
+ * than the largest d_i of its record is the reference's fatal "Bad alignment between trace points": returns 2.            */
+int damar_trace_mid_scripts(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
+                            const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
+                            int32_t *rec_diffs, int64_t *script_off, int32_t **script, int64_t *script_len);
 void damar_host_free(void *p);
 
 /* ---- stage-level read-backs (used by the parity tests; not needed by a host) ---- */

@@ -97,15 +97,17 @@ def test_cuda_trace_point_diffs_rejects_out_of_bounds():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("middles", [False, True])
 @pytest.mark.parametrize("key", ["tiny/default/T.1.T.2.las", "rep/rep_default/R.1.R.1.las", "long/long_default/L.1.L.1.las", "tan/tan_default/N.1.N.1.las"])
-def test_gpu_edit_scripts_equal_reference(key):
-    """damar_trace_point_scripts (trace_pts.cu + trace_script_core.cuh) against the UNMODIFIED Compute_Trace_PTS's output
-    (tests/golden/trace_script.json): script length and hash of every record, every 400th script in full, and the diffs."""
+def test_gpu_edit_scripts_equal_reference(key, middles):
+    """damar_trace_point_scripts / damar_trace_mid_scripts (trace_pts.cu + trace_script_core.cuh) against the output of the
+    UNMODIFIED Compute_Trace_PTS / Compute_Trace_MID (tests/golden/trace_script.json, trace_mid.json): script length and hash
+    of every record, every 400th script in full, and the diffs."""
     import json
     from cases import GOLDEN, load_block
     from damar_b200 import api, dbio
     from test_trace_script import fnv
-    with open(os.path.join(GOLDEN, "trace_script.json")) as f:
+    with open(os.path.join(GOLDEN, "trace_mid.json" if middles else "trace_script.json")) as f:
         g = json.load(f)[key]
     db, case, fn = key.split("/")
     root = {"tiny": "T", "rep": "R", "long": "L", "tan": "N"}[db]
@@ -114,7 +116,7 @@ def test_gpu_edit_scripts_equal_reference(key):
     da = api.DeviceBlockHandle(load_block(os.path.join(GOLDEN, db), an, ()))
     dbh = da if bn == an else api.DeviceBlockHandle(load_block(os.path.join(GOLDEN, db), bn, ()))
     las = open(os.path.join(GOLDEN, db, "ref", case, fn), "rb").read()
-    rec, soff, script = api.trace_point_scripts(da, dbh, las)
+    rec, soff, script = api.trace_point_scripts(da, dbh, las, middles=middles)
     assert len(rec) == g["n"] and soff[-1] == len(script)
     for i, (tl, h, gd) in enumerate(g["records"]):
         scr = script[soff[i]: soff[i + 1]]
