@@ -381,23 +381,102 @@ damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len) {
 }
 void damar_index_free(damar_index *idx) { delete reinterpret_cast<DeviceIndex *>(idx); }
 
+// One sort takes fewer than 2^30 elements and the alignment stage indexes hits with 32 bits; the reference's hit array has no
+// such bound (int64 counts, filter.c:2529).  A comparison with more hits is cut into chunks of B reads: hits are ordered by
+// B read first, so the chunks are consecutive ranges of the reference's hit array and every read pair lies in one chunk.
+// DAMAR_MAX_HITS lowers the bound (the tests force dozens of chunks on small fixtures).
+static int64_t max_hits_per_sort() {
+    static const int64_t v = [] { const char *e = getenv("DAMAR_MAX_HITS"); const int64_t x = (e && *e) ? atoll(e) : 0; return x > 0 ? x : ((int64_t)1 << 30) - 4096; }();
+    return v;
+}
+
 static int match_filter_impl(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
-                             int self, int comp, damar_overlaps *out, DeviceResult *keep) {
+                             int self, int comp, damar_overlaps *out, DeviceSink *sink, int ordinal) {
     ensure_init();
     Context &c = ctx();
     DeviceBlock *ab = reinterpret_cast<DeviceBlock *>(ablk), *bb = reinterpret_cast<DeviceBlock *>(bblk);
     DeviceIndex *ai = reinterpret_cast<DeviceIndex *>(aidx), *bi = reinterpret_cast<DeviceIndex *>(bidx);
     g_out = HostOverlaps();
-    g_out.keep = keep;
     g_hits.release();
     g_hits_a = ab; g_hits_b = bb;
     memset(out, 0, sizeof(*out));
     c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
     c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0; c.tm.wide_passes = 0;
+    int64_t nhits = 0;
+    // stages 3 + 4 on the hits in g_hits; with a sink every call leaves its own result there
+    auto align = [&](const HitSpan *span) -> int {
+        DeviceResult *r = nullptr;
+        if (sink) { r = new DeviceResult(); r->ordinal = ordinal; }
+        g_out.keep = r;
+        int rc = 0;
+        if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); rc = report_and_align(ab, bb, comp, self, g_hits, g_out, false, span); }
+        g_out.keep = nullptr;
+        if (r) { if (rc == 0) dsink_add(sink, r); else delete r; }
+        return rc;
+    };
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
         ensure_revcomp(ab); ensure_revcomp(bb);               // the reverse wave pass runs on the reverse-complemented reads
-        { HostProf hp("mf.seed_hits"); if (seed_hits(ai, bi, self, comp, g_hits) != 0) return 1; }
-        if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); if (report_and_align(ab, bb, comp, self, g_hits, g_out) != 0) return 1; }
+        int rc;
+        { HostProf hp("mf.seed_hits"); rc = seed_hits(ai, bi, self, comp, g_hits, nullptr, max_hits_per_sort()); }
+        if (rc == 1) return 1;
+        nhits = g_hits.total;
+        if (rc == 0) { if (align(nullptr) != 0) return 1; }
+        else {
+            // ---- too many hits for one sort: chunks of B reads, in order ----
+            HostProf hp("mf.chunked");
+            const int64_t total = g_hits.total;
+            const int32_t limit = g_hits.limit;
+            const int nreads = bb->nreads;
+            const std::vector<int64_t> &boff = bb->h_boff;
+            std::vector<std::pair<int, int>> todo;            // ranges of B reads still to do, last = next
+            {
+                int64_t want = (total + max_hits_per_sort() / 2 - 1) / std::max<int64_t>(1, max_hits_per_sort() / 2);
+                const int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(nreads, want));
+                std::vector<int> cut(1, 0);
+                for (int k = 1; k < nchunk; k++) {            // equal shares of the bases, at read boundaries
+                    const int64_t g = boff[nreads] / nchunk * k;
+                    int r = (int)(std::upper_bound(boff.begin(), boff.begin() + nreads + 1, g) - boff.begin()) - 1;
+                    if (r > cut.back()) cut.push_back(r);
+                }
+                cut.push_back(nreads);
+                for (size_t k = cut.size() - 1; k >= 1; k--) todo.emplace_back(cut[k - 1], cut[k]);
+            }
+            WorkerScratch &ws = scratch();
+            ws.acc_recs.clear(); ws.acc_toff.clear(); ws.acc_seq.clear(); ws.acc_trace.clear();
+            HostOverlaps sum;
+            HitSpan span; span.total = total;
+            while (!todo.empty()) {
+                const std::pair<int, int> rg = todo.back(); todo.pop_back();
+                HitChunk ch{(uint32_t)boff[rg.first], (uint32_t)boff[rg.second], limit};
+                { HostProf hp2("mf.seed_hits"); rc = seed_hits(ai, bi, self, comp, g_hits, &ch, max_hits_per_sort()); }
+                if (rc == 1) return 1;
+                if (rc == 2) {                                // still too many: halve the range of reads
+                    if (rg.second - rg.first < 2) { set_error("one B read alone has %lld seed hits, more than one sort takes: lower -M or -t", (long long)g_hits.total); return 1; }
+                    const int mid = rg.first + (rg.second - rg.first) / 2;
+                    todo.emplace_back(mid, rg.second); todo.emplace_back(rg.first, mid);
+                    continue;
+                }
+                g_out = HostOverlaps();
+                if (align(&span) != 0) return 1;
+                span.base += g_hits.n; span.pair_base += (uint64_t)g_out.pairs;
+                sum.nfilt += g_out.nfilt; sum.multi += g_out.multi; sum.cells += g_out.cells; sum.pairs += g_out.pairs; sum.redo += g_out.redo;
+                sum.novl += g_out.novl; sum.tbytes = g_out.tbytes;
+                if (!sink && g_out.novl > 0) {                // the host path returns ONE set of arrays: append this chunk's
+                    const uint64_t tbase = (uint64_t)sum.ntrace;
+                    ws.acc_recs.insert(ws.acc_recs.end(), g_out.ovl, g_out.ovl + g_out.novl);
+                    for (int64_t k = 0; k < g_out.novl; k++) ws.acc_toff.push_back(g_out.toff[k] + tbase);
+                    ws.acc_seq.insert(ws.acc_seq.end(), g_out.seq, g_out.seq + g_out.novl);
+                    const uint8_t *tp = (const uint8_t *)g_out.trace;
+                    ws.acc_trace.insert(ws.acc_trace.end(), tp, tp + (size_t)g_out.ntrace * g_out.tbytes);
+                }
+                sum.ntrace += g_out.ntrace;
+                g_hits.release();
+            }
+            if (span.base != total) { set_error("chunked comparison: %lld hits emitted, %lld counted", (long long)span.base, (long long)total); return 1; }
+            if (!sink) { sum.ovl = ws.acc_recs.data(); sum.toff = ws.acc_toff.data(); sum.seq = ws.acc_seq.data(); sum.trace = ws.acc_trace.data(); }
+            g_out = sum;
+            g_hits.limit = limit;
+        }
     }
     out->novl = g_out.novl;
     out->ovl = g_out.ovl;
@@ -406,33 +485,27 @@ static int match_filter_impl(damar_block *ablk, damar_block *bblk, damar_index *
     out->trace = g_out.trace;
     out->ntrace = g_out.ntrace;
     out->trace_bytes = g_out.tbytes;
-    out->nhits = g_hits.n;
+    out->nhits = nhits;
     out->nfilt = g_out.nfilt;
     out->ncheck = out->novl;
     out->limit = g_hits.limit;
     out->multi_la_pairs = (int32_t)g_out.multi;
     c.tm.cells_total += g_out.cells; c.tm.wide_total += c.tm.wide_passes; c.tm.la_total += g_out.nfilt;
-    c.tm.hits = g_hits.n; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
+    c.tm.hits = nhits; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
     c.tm.kernel_launches = c.launches;
     return 0;
 }
 
 int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
                        int self, int comp, damar_overlaps *out) {
-    return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, nullptr);
+    return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, nullptr, 0);
 }
 /* Match_Filter whose records stay in HBM: they are appended to `sink` as call number `ordinal` of the job (the order in
  * which the reference would have buffered the calls breaks full SORT_OVL ties); `out` receives the counters only. */
 int damar_match_filter_sink(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx, int self, int comp,
                             damar_device_sink *sink, int ordinal, damar_overlaps *out) {
     if (sink == nullptr) { set_error("damar_match_filter_sink: no sink"); return 1; }
-    DeviceResult *r = new DeviceResult();
-    r->ordinal = ordinal;
-    const int rc = match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, r);
-    g_out.keep = nullptr;
-    if (rc != 0) { delete r; return rc; }
-    dsink_add(reinterpret_cast<DeviceSink *>(sink), r);
-    return 0;
+    return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, reinterpret_cast<DeviceSink *>(sink), ordinal);
 }
 
 /* datander's Match_Self (scrub/tandem.c:1182): every read of the block against itself. */

@@ -212,9 +212,13 @@ struct SeedHits {
     int64_t n = 0;
     int pbits = 0, abits = 0, bbits = 0, qbits = 0;
     int32_t limit = 0;
+    int64_t total = 0;           // hits counted (== n unless the call stopped at the count: too many for one sort)
     void release();
 };
-int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out);   // non-zero: error set
+struct HitChunk { uint32_t g_lo, g_hi; int32_t limit; };      // B positions [g_lo, g_hi) of a comparison cut into chunks of B reads
+// 0: ok; 1: error set; 2: more than max_hits hits (nothing emitted, out.total / out.limit say what was counted)
+int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out, const HitChunk *chunk = nullptr,
+              int64_t max_hits = INT64_MAX);
 
 // tandem.cu : datander's seed stage -- links between equal k-mers of one read as a hit list (scrub/tandem.c:556-590, 1281)
 int self_hits(const DeviceIndex *idx, SeedHits &out);
@@ -251,6 +255,7 @@ struct WorkerScratch {
     PinnedBuf<uint8_t> h_up[2]; cudaEvent_t up_ev[2] = {nullptr, nullptr};   // upload_block: pinned double buffer
     PinnedBuf<damar_overlap> h_recs; PinnedBuf<uint64_t> h_toff, h_seq; PinnedBuf<uint8_t> h_trace;   // pair_align.cu
     HostOverlaps out;                            // results of the last match_filter call
+    std::vector<damar_overlap> acc_recs; std::vector<uint64_t> acc_toff, acc_seq; std::vector<uint8_t> acc_trace;   // ... of one cut into chunks (api.cu)
     SeedHits hits;
     const DeviceBlock *hits_a = nullptr, *hits_b = nullptr;
 };
@@ -262,7 +267,9 @@ int trace_point_diffs_host(DeviceBlock *ab, DeviceBlock *bb, const damar_overlap
                            int64_t *script_off = nullptr, int32_t **script_out = nullptr, int64_t *script_len = nullptr,
                            int flavour = 0);   // 0: Compute_Trace_PTS, 1: Compute_Trace_MID
 
+// span: the hits are chunk [base, base + hits.n) of a comparison with `total` hits whose earlier chunks held pair_base work pairs
+struct HitSpan { int64_t base = 0, total = 0; uint64_t pair_base = 0; };
 int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits,
-                     HostOverlaps &out, bool tandem = false);   // non-zero: error set (capacity limits are errors, not exits)
+                     HostOverlaps &out, bool tandem = false, const HitSpan *span = nullptr);   // non-zero: error set (capacity limits are errors, not exits)
 
 }  // namespace damar

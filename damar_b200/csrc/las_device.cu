@@ -33,9 +33,8 @@ struct CallView {                        // one call's arrays inside the concate
     const damar_overlap *recs; const uint64_t *toff, *seq; const uint8_t *trace, *dead;
     uint32_t first, n; uint32_t ordinal; int tbytes;
 };
-constexpr int MAX_CALLS = 8;
 struct SinkArgs {
-    CallView call[MAX_CALLS]; int ncalls; uint32_t n;
+    const CallView *call; int ncalls; uint32_t n;    // device table: a job's two Match_Filter calls, more when one was cut into chunks
     int only_identity, no_trace, pb, rb;             // pb: bits of a read coordinate, rb: bits of a DB-wide read id
     uint64_t *key; uint32_t *idx;
     unsigned int *counts;                            // [0] excluded records, [1] records of the first file
@@ -43,9 +42,9 @@ struct SinkArgs {
 };
 
 __device__ __forceinline__ int call_of(const SinkArgs &a, uint32_t i) {
-    int c = 0;
-    while (c + 1 < a.ncalls && i >= a.call[c + 1].first) c++;
-    return c;
+    int lo = 0, hi = a.ncalls - 1;                   // last call whose first record is <= i
+    while (lo < hi) { const int m = (lo + hi + 1) >> 1; if (a.call[m].first <= i) lo = m; else hi = m - 1; }
+    return lo;
 }
 // Key word `w` of record i (most significant first): 3 = aread | bread, 2 = comp | abpos | aepos, 1 = bbpos | bepos,
 // 0 = call ordinal | emission rank.  Excluded records (dropped by Handle_Redundancies, or not aread == bread under -O,
@@ -122,11 +121,12 @@ int dsink_serialise(DeviceSink *s, int trace_spacing, int no_trace, int only_ide
     { std::lock_guard<std::mutex> lock(s->mu); calls = s->calls; }
     std::sort(calls.begin(), calls.end(), [](const DeviceResult *x, const DeviceResult *y) { return x->ordinal < y->ordinal; });
     uint64_t n = 0;
+    std::vector<CallView> table;
     for (DeviceResult *r : calls) {
         if (r->nrec == 0) continue;
-        if (a.ncalls >= MAX_CALLS) { set_error("damar_dsink_serialise: more than %d calls in one sink", MAX_CALLS); return 1; }
         if (!no_trace && r->tbytes != tbytes) { set_error("trace width of the buffered overlaps (%d) does not match -s%d", r->tbytes, trace_spacing); return 1; }
-        CallView &v = a.call[a.ncalls++];
+        table.emplace_back();
+        CallView &v = table.back();
         v.recs = r->recs.p; v.toff = r->toff.p; v.seq = r->seq.p; v.trace = r->trace.p; v.dead = r->have_dead ? r->dead.p : nullptr;
         v.first = (uint32_t)n; v.n = (uint32_t)r->nrec; v.ordinal = (uint32_t)r->ordinal; v.tbytes = r->tbytes;
         n += r->nrec;
@@ -140,6 +140,9 @@ int dsink_serialise(DeviceSink *s, int trace_spacing, int no_trace, int only_ide
     if (buf2) { *buf2 = nullptr; *len2 = 0; }
     if (n == 0) { header_only(buf1, len1); if (split_read >= 0 && buf2) header_only(buf2, len2); return 0; }
     if (n >= 0xfffffff0ull) { set_error("damar_dsink_serialise: %llu records in one file", (unsigned long long)n); return 1; }
+    DevBuf<CallView> dtable; dtable.reserve(table.size());
+    CUDA_CHECK(cudaMemcpyAsync(dtable.p, table.data(), sizeof(CallView) * table.size(), cudaMemcpyHostToDevice, st));
+    a.call = dtable.p; a.ncalls = (int)table.size();
     a.n = (uint32_t)n; a.only_identity = only_identity; a.no_trace = no_trace; a.split_read = split_read;
     a.pb = bits_for_u((uint64_t)maxlen + 1); a.rb = bits_for_u((uint64_t)maxread + 1);
 

@@ -53,12 +53,15 @@ constexpr unsigned FULL = 0xffffffffu;
 // ---------------------------------------------------------------------------------------------
 
 // slice ends of the reference's NTHREADS report threads (filter.c:2804-2816); ends[T-1] = n
+// A comparison cut into chunks of B reads (api.cu) presents hits [base, base + n) of `total`: a slice end outside the chunk
+// is -1 (no pair ends there); one at the chunk's first hit stays there, the previous chunk ended a B read.
 __global__ void slice_ends(const uint64_t *__restrict__ keys, int64_t n, int nthreads, int nshift, int rshift,
-                           int64_t *__restrict__ ends) {
+                           int64_t *__restrict__ ends, int64_t base, int64_t total) {
     int t = threadIdx.x + 1;
     if (t > nthreads) return;
-    if (t == nthreads) { ends[t - 1] = n; return; }
-    int64_t p = (n * t) >> nshift;
+    if (t == nthreads) { ends[t - 1] = total - base; return; }
+    int64_t p = ((total * t) >> nshift) - base;
+    if (p < 0 || p > n) { ends[t - 1] = -1; return; }
     if (p > 0) {
         uint64_t d = keys[p - 1] >> rshift;          // bread of the previous hit
         int64_t l = p, r = n;                        // first index with bread > d
@@ -1437,11 +1440,19 @@ __global__ void __launch_bounds__(64) handle_redundancies_pairs(HrArgs H) {
 
 }  // namespace
 
-int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out, bool tandem) {
+__global__ void add_seq_base(uint64_t *__restrict__ seq, unsigned long long n, uint64_t add) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) seq[i] += add;
+}
+
+int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int self, const SeedHits &hits, HostOverlaps &out, bool tandem,
+                     const HitSpan *span) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const FilterParams &fp = c.fp;
     const int64_t n = hits.n;
+    const int64_t hit_base = span ? span->base : 0, hit_total = span ? span->total : n;
+    const uint64_t pair_base = span ? span->pair_base : 0;
     // datander walks every read and has neither the minhit rule nor report slices (scrub/tandem.c:895-1000)
     const int minhit = tandem ? 1 : (fp.hitmin - 1) / fp.kmer + 1;
     if (n >= (int64_t)0xffffffffll) { set_error("more than 2^32 seed hits in one comparison (%lld): lower -M or -t", (long long)n); return 1; }
@@ -1455,7 +1466,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     DevBuf<uint64_t> off; off.reserve((size_t)n);
     DevBuf<uint64_t> total; total.reserve(1);
     const int kshift = hits.bpos ? 0 : hits.qbits;
-    if (nslices > 0) { slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits + kshift, ends.p); KERNEL_CHECK(); }
+    if (nslices > 0) { slice_ends<<<1, 1024, 0, st>>>(hits.keys, n, nslices, fp.nshift, hits.pbits + hits.abits + kshift, ends.p, hit_base, hit_total); KERNEL_CHECK(); }
     const unsigned hb = (unsigned)((n + 255) / 256);
     flag_work_pairs<<<hb, 256, 0, st>>>(hits.keys, n, hits.pbits + kshift, minhit, ends.p, nslices, flag.p);
     KERNEL_CHECK();
@@ -1559,6 +1570,10 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     DevBuf<uint64_t> okeys; DevBuf<uint32_t> ovals;
     okeys.reserve(4 * na); ovals.reserve(4 * na);
     static const bool lpt = !(getenv("DAMAR_LPT") && atoi(getenv("DAMAR_LPT")) == 0);
+    // Two latency options for a host that runs ONE comparison at a time (the drop-in daligner process): deal the longest
+    // passes out over all warps (narrow launch 28 -> 25 ms on a C2 block pair) and run the parked passes one per warp all
+    // over the device (wide launch 16 -> 10 ms).  With several comparisons in flight both cost throughput (every CTA then
+    // holds its SM to the end: C2 step 590 -> 700-750 ms), so they are off unless asked for.
     static const bool spread = getenv("DAMAR_SPREAD") && atoi(getenv("DAMAR_SPREAD")) != 0;
     static const bool wide_spread = getenv("DAMAR_WIDE_SPREAD") && atoi(getenv("DAMAR_WIDE_SPREAD")) != 0;
     static const bool timeline = getenv("DAMAR_TIMELINE") && atoi(getenv("DAMAR_TIMELINE")) != 0;   // per-round kernel times on stderr
@@ -1592,12 +1607,10 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
         set_smem(wave_tasks<4, 13>, WaveCfg<13>::SMEM);
         set_smem(wave_tasks<4, 14>, WaveCfg<14>::SMEM);
         set_smem(wave_tasks<4, 1, 12>, 2 * WaveCfg<1>::SMEM);
-        set_smem(wave_tasks<4, 1, 8>, 2 * WaveCfg<1>::SMEM);
-        set_smem(wave_tasks<4, 2, 6>, 2 * WaveCfg<2>::SMEM);
-        set_smem(wave_tasks<4, 4, 3>, 2 * WaveCfg<4>::SMEM);
     });
-    // warps per CTA: a CTA of all the SM's warps holds the SM until its LAST pass ends (the longest pass of a round runs
-    // ~25 ms on one lane); small CTAs hand their share of the SM to the next kernel as they finish
+    // DAMAR_WAVE_CTA_WARPS=1 (experiment): one-warp CTAs, twelve to an SM.  A CTA of all the SM's warps holds the SM until its
+    // LAST pass ends (the longest pass of a round runs ~10 ms on one lane after the queue is empty); one-warp CTAs hand
+    // their share of the SM to the next kernel as they finish.  Measured on the C2 step: no gain (620-646 ms against 585-620).
     static const int cta_warps = getenv("DAMAR_WAVE_CTA_WARPS") ? atoi(getenv("DAMAR_WAVE_CTA_WARPS")) : 0;
 
     unsigned int nredo = 0; unsigned long long nrec_fast = 0; int64_t nwide_total = 0;
@@ -1645,7 +1658,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
             Timer t_k(st);
             float t_narrow = 0;
             {
-                const bool small_ctas = cta_warps == 1 || cta_warps == 2 || cta_warps == 4;
+                const bool small_ctas = cta_warps == 1;
                 const unsigned per = (unsigned)(small_ctas ? cta_warps : wwarps) * 32;
                 const unsigned per_sm = small_ctas ? (unsigned)(wwarps / cta_warps) : 1u;          // CTAs of one SM
                 const unsigned wb = std::min<unsigned>((unsigned)wave_ctas * per_sm, (2 * ncand + per - 1) / per);
@@ -1669,10 +1682,7 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
                 }
                 CUDA_CHECK(cudaMemsetAsync(wide_ready.p, 0, sizeof(uint32_t) * 2 * na, st));   // all of it: tickets run past this round's parks
                 auto launch = [&](unsigned grid) {
-                    if (small_ctas && cta_warps == 1 && wwarps <= 8) wave_tasks<4, 1, 8><<<grid, per, pad_smem, st>>>(Q);
-                    else if (small_ctas && cta_warps == 1) wave_tasks<4, 1, 12><<<grid, per, pad_smem, st>>>(Q);
-                    else if (small_ctas && cta_warps == 2) wave_tasks<4, 2, 6><<<grid, per, pad_smem, st>>>(Q);
-                    else if (small_ctas && cta_warps == 4) wave_tasks<4, 4, 3><<<grid, per, pad_smem, st>>>(Q);
+                    if (small_ctas) wave_tasks<4, 1, 12><<<grid, per, pad_smem, st>>>(Q);
                     else if (wwarps == 8) wave_tasks<4, 8><<<grid, per, WaveCfg<8>::SMEM, st>>>(Q);
                     else if (wwarps == 10) wave_tasks<4, 10><<<grid, per, WaveCfg<10>::SMEM, st>>>(Q);
                     else if (wwarps == 13) wave_tasks<4, 13><<<grid, per, WaveCfg<13>::SMEM, st>>>(Q);
@@ -1779,6 +1789,11 @@ int report_and_align(const DeviceBlock *ab, const DeviceBlock *bb, int comp, int
     if (hc[3] & 16ull) { set_error("Handle_Redundancies scratch pool exhausted; raise DAMAR_HR_POOL_MB"); return 1; }
     if (hc[3] & 8ull) { set_error("Compression of trace to bytes fails, value too big"); return 1; }   // align.c:3385-3388
 
+    if (pair_base && hc[5] > 0) {                     // a later chunk of a comparison: its pairs rank after those of the chunks before
+        add_seq_base<<<(unsigned)((hc[5] + 255) / 256), 256, 0, st>>>(rseq.p, hc[5], pair_base << SEQ_PAIR_SHIFT);
+        KERNEL_CHECK(); count_launch();
+        CUDA_CHECK(stream_wait(st));                   // the records may be picked up by another worker's stream
+    }
     // ---- download into pinned staging; records stay in device emission order, `seq` carries the
     //      order the reference's thread buffers would have had ----
     if (out.keep != nullptr) {                         // the device-side writer takes the buffers as they are (las_device.cu)

@@ -126,6 +126,10 @@ struct MergeArgs {
     unsigned long long *gram;                     // MAXGRAM bins or nullptr
     uint64_t *keys; uint32_t *bpos;               // EMIT: bpos == nullptr -> one packed word per hit
     int pbits, abits, qbits;
+    // A comparison with more hits than one sort takes is cut into chunks of B reads (api.cu): only partners whose position
+    // lies in [g_lo, g_hi) count and are emitted.  The match count of a run that the -M limit looks at stays that of the
+    // whole run.
+    int ranged; uint32_t g_lo, g_hi;
 };
 
 __global__ void merge_bounds(MergeArgs a) {
@@ -283,19 +287,29 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                         ib = (jb < nb && S.bc[jb] == c) ? srun_end(SB, jb, c) : jb;
                     }
                     const int nbr = ib - jb;
-                    uint32_t cn = 0;
+                    uint32_t cn = 0, cn_run = 0;                                // partners emitted / partners in the whole run
+                    int jr = jb;                                                // first partner
                     if (nbr > 0 && !(a.same_list && a.self && nbr == 1)) {     // a run of one k-mer of the list itself has no partner
+                        int pe = ib;                                            // partners = [jb, pe)
                         if (a.self) {
                             const uint32_t thr = self_threshold(a, S.ap[i]);
-                            int lo = jb, hi = ib;                               // partners = B run entries with gpos < thr
+                            int lo = jb, hi = ib;                               // B run entries with gpos < thr
                             while (lo < hi) { const int m = (lo + hi) >> 1; if (bpos[m] < thr) lo = m + 1; else hi = m; }
-                            cn = (uint32_t)(lo - jb);
-                        } else cn = (uint32_t)nbr;
+                            pe = lo;
+                        }
+                        cn = cn_run = (uint32_t)(pe - jb);
+                        if (a.ranged) {                                         // ... of which those in [g_lo, g_hi): a run is in gpos order
+                            int lo = jb, hi = pe;
+                            while (lo < hi) { const int m = (lo + hi) >> 1; if (bpos[m] < a.g_lo) lo = m + 1; else hi = m; }
+                            jr = lo; hi = pe;
+                            while (lo < hi) { const int m = (lo + hi) >> 1; if (bpos[m] < a.g_hi) lo = m + 1; else hi = m; }
+                            cn = (uint32_t)(lo - jr);
+                        }
                     }
                     S.cnt[i] = cn;
-                    S.jbw[i] = (uint16_t)((uint32_t)jb | (nbr > 0 ? HAS_RUN : 0u));
+                    S.jbw[i] = (uint16_t)((uint32_t)jr | (nbr > 0 ? HAS_RUN : 0u));
                     S.rsw[i] = (uint16_t)rs;
-                    if (a.self) { if (cn) atomicAdd(&S.gct[rs], cn); }
+                    if (a.self) { if (cn_run) atomicAdd(&S.gct[rs], cn_run); }
                     else if (i == rs) {                                          // ct = |A run| x |B run| (filter.c:1148-1149)
                         const unsigned long long ct = (unsigned long long)(srun_end(SA, i, c) - rs) * (unsigned long long)nbr;
                         S.gct[rs] = ct > 0xffffffffull ? 0xffffffffu : (uint32_t)ct;
@@ -387,13 +401,24 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                 const int64_t jb = S.seg[0], ib = S.seg[1], nbr = ib - jb, nA = q - p;
                 if (nbr > 0) {
                     const bool lonely = a.same_list && a.self && nbr == 1;
-                    auto partners = [&](int64_t i) -> unsigned long long {
+                    auto below = [&](int64_t lo, int64_t hi, uint32_t thr) -> int64_t {      // first run entry in [lo, hi) with gpos >= thr
+                        while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (a.B.epos(a.B.ent[m], m) < thr) lo = m + 1; else hi = m; }
+                        return lo;
+                    };
+                    auto partners = [&](int64_t i) -> unsigned long long {     // in the whole run
                         if (lonely) return 0ull;
                         if (!a.self) return (unsigned long long)nbr;
-                        const uint32_t thr = self_threshold(a, a.A.epos(a.A.ent[i], i));
-                        int64_t lo = jb, hi = ib;
-                        while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (a.B.epos(a.B.ent[m], m) < thr) lo = m + 1; else hi = m; }
-                        return (unsigned long long)(lo - jb);
+                        return (unsigned long long)(below(jb, ib, self_threshold(a, a.A.epos(a.A.ent[i], i))) - jb);
+                    };
+                    // the partners that count for this chunk: [*first, *first + result)
+                    auto chunk_partners = [&](int64_t i, int64_t *first) -> unsigned long long {
+                        *first = jb;
+                        if (lonely) return 0ull;
+                        const int64_t pe = a.self ? below(jb, ib, self_threshold(a, a.A.epos(a.A.ent[i], i))) : ib;
+                        if (!a.ranged) return (unsigned long long)(pe - jb);
+                        const int64_t jr = below(jb, pe, a.g_lo);
+                        *first = jr;
+                        return (unsigned long long)(below(jr, pe, a.g_hi) - jr);
                     };
                     unsigned long long ct;
                     if (!a.self) ct = (unsigned long long)nA * (unsigned long long)nbr;
@@ -402,14 +427,20 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                         for (int64_t i = p + tid; i < q; i += MT_THREADS) mine += partners(i);
                         ct = block_sum(mine, S.red);
                     }
-                    const unsigned long long hits_of_run = a.self ? ct : (lonely ? 0ull : ct);
+                    unsigned long long hits_of_run = a.self ? ct : (lonely ? 0ull : ct);
+                    if (a.ranged && !EMIT) {
+                        unsigned long long mine = 0; int64_t f;
+                        for (int64_t i = p + tid; i < q; i += MT_THREADS) mine += chunk_partners(i, &f);
+                        hits_of_run = block_sum(mine, S.red);
+                    }
                     const uint32_t ct32 = ct > 0xffffffffull ? 0xffffffffu : (uint32_t)ct;
                     if (histo && tid == 0 && ct32 < MAXGRAM) atomicAdd(&a.gram[ct32], 1ull);
                     if (ct32 < a.limit) {
                         if (EMIT) {
                             for (int64_t base = p; base < q; base += MT_THREADS) {      // entries of the run, a block at a time
                                 const int64_t i = base + tid;
-                                const unsigned long long cn = (i < q) ? partners(i) : 0ull;
+                                int64_t jr = jb;
+                                const unsigned long long cn = (i < q) ? chunk_partners(i, &jr) : 0ull;
                                 unsigned long long inc = cn;
 #pragma unroll
                                 for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -424,7 +455,7 @@ __global__ void __launch_bounds__(MT_THREADS, EMIT ? 2 : 3) merge_tiles(MergeArg
                                     const uint64_t klow = ((uint64_t)ar << a.pbits) | (uint64_t)(ga - a.amap.boff[ar]);
                                     unsigned long long o = tile_hits + off + inc - cn;
                                     for (unsigned long long x = 0; x < cn; x++, o++) {
-                                        const uint32_t gb = a.B.epos(a.B.ent[jb + (int64_t)x], jb + (int64_t)x);
+                                        const uint32_t gb = a.B.epos(a.B.ent[jr + (int64_t)x], jr + (int64_t)x);
                                         const int br = read_of(a.bmap, gb);
                                         const uint32_t bp = gb - a.bmap.boff[br];
                                         if (packed_out) a.keys[o] = ((((uint64_t)br << (a.pbits + a.abits)) | klow) << a.qbits) | bp;
@@ -482,14 +513,17 @@ int bits_for(int64_t maxval_exclusive) {   // smallest b with 2^b >= maxval_excl
 
 }  // namespace
 
-int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out) {
+// chunk == nullptr: the whole comparison; returns 2 without emitting anything (out.total and out.limit set) when it has more
+// than max_hits hits.  chunk != nullptr: the hits whose B position lies in [g_lo, g_hi), under the limit the whole
+// comparison's count found; returns 2 when even the chunk has more than max_hits.
+int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, SeedHits &out, const HitChunk *chunk, int64_t max_hits) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
     const DeviceBlock *ab = ai->blk, *bb = bi->blk;
     const int64_t alen = ai->len, blen = bi->len;
     const int same_list = (ai == bi) ? 1 : 0;
     out.release();
-    out.limit = INT32_MAX;
+    out.limit = INT32_MAX; out.total = 0;
 
     HostProf *hp1 = new HostProf("sh.count");
     Timer t_count(st);
@@ -497,7 +531,7 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
     DevBuf<int64_t> tbounds; tbounds.reserve(2 * ((size_t)ntiles + 1));
     DevBuf<unsigned long long> tcount; tcount.reserve((size_t)ntiles + 2);
     DevBuf<unsigned long long> gram;
-    const bool use_limit = (c.opt.mem_limit > 0);
+    const bool use_limit = (c.opt.mem_limit > 0) && chunk == nullptr;
     if (use_limit) { gram.reserve(MAXGRAM); CUDA_CHECK(cudaMemsetAsync(gram.p, 0, sizeof(unsigned long long) * MAXGRAM, st)); }
 
     MergeArgs m{};
@@ -509,6 +543,7 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
     m.gram = use_limit ? gram.p : nullptr;
     // the -M rule yields MAXGRAM whenever the hits fit the allowance (filter.c:2650-2656): count with that limit first
     m.limit = use_limit ? (uint32_t)MAXGRAM : (uint32_t)INT32_MAX;
+    if (chunk) { m.ranged = 1; m.g_lo = chunk->g_lo; m.g_hi = chunk->g_hi; m.limit = (uint32_t)chunk->limit; }
 
     static std::once_flag attr;
     std::call_once(attr, [] {
@@ -533,7 +568,7 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
 
     // the limit (filter.c:2634-2699), evaluated on the host from the histogram like the reference's main thread
     unsigned long long nhits = 0;
-    int64_t limit = INT32_MAX;
+    int64_t limit = chunk ? chunk->limit : INT32_MAX;
     std::vector<unsigned long long> histo;
     if (use_limit) { histo.resize(MAXGRAM); CUDA_CHECK(cudaMemcpyAsync(histo.data(), gram.p, sizeof(unsigned long long) * MAXGRAM, cudaMemcpyDeviceToHost, st)); }
     CUDA_CHECK(cudaMemcpyAsync(&nhits, tcount.p + ntiles, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -559,13 +594,14 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
             CUDA_CHECK(stream_wait(st));
         }
     }
-    out.limit = (int32_t)limit;
+    out.limit = (int32_t)limit; out.total = (int64_t)nhits;
     c.tm.count_ms = t_count.stop();
     delete hp1;
+    if (c.opt.verbose && chunk == nullptr) { printf("   Hit count = %lld\n", (long long)nhits); fflush(stdout); }
+    if ((int64_t)nhits > max_hits) return 2;
 
     HostProf *hp2 = new HostProf("sh.merge");
     Timer t_merge(st);
-    if (c.opt.verbose) { printf("   Hit count = %lld\n", (long long)nhits); fflush(stdout); }
     if (nhits == 0) { c.tm.merge_ms = t_merge.stop(); delete hp2; return 0; }
 
     out.pbits = bits_for(ab->maxlen);

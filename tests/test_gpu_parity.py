@@ -213,17 +213,26 @@ def test_dropin_reference_datander_host(case, tmp_path):
         assert ok, f"{case}/{fn}: {why}"
 
 
-@pytest.mark.parametrize("env", [{"DAMAR_PACK": "0"}, {"DAMAR_DEVICE_SINK": "0"}], ids=["unpacked", "host_sink"])
+@pytest.mark.parametrize("env", [{"DAMAR_PACK": "0"}, {"DAMAR_DEVICE_SINK": "0"}, {"DAMAR_MAX_HITS": "30000", "DAMAR_PROFILE": "1"},
+                                 {"DAMAR_MAX_HITS": "30000", "DAMAR_DEVICE_SINK": "0", "DAMAR_PROFILE": "1"},
+                                 {"DAMAR_MAX_HITS": "30000", "DAMAR_PACK": "0", "DAMAR_PROFILE": "1"}],
+                         ids=["unpacked", "host_sink", "chunked", "chunked_host_sink", "chunked_unpacked"])
 def test_alternative_paths_give_the_same_files(env):
     """DAMAR_PACK=0 keeps (code, gpos) and (key, bpos) as pairs instead of one 64-bit word per k-mer / seed hit -- the
     layout blocks too large for the packed words fall back to.  DAMAR_DEVICE_SINK=0 ships the records to the host and sorts
-    and serialises them there (the path the drop-in shim uses) instead of building the .las image on the device.  Run in a
-    fresh process (the switches are read once)."""
+    and serialises them there (the path the drop-in shim uses) instead of building the .las image on the device.
+    DAMAR_MAX_HITS lowers the number of seed hits one sort takes (2^30 by default), so that these small comparisons are cut
+    into chunks of B reads the way a comparison with billions of hits is (the reference's hit array is int64-indexed,
+    filter.c:2529): slice rule, emission ranks and the -M limit must come out as for the whole.  Run in a fresh process
+    (the switches are read once)."""
     import subprocess
     import sys
     code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
             "from cases import *\nfrom damar_b200 import api, dbio\n"
-            "for table, dbdir, names in ((CASES, TINY, ['default', 'identity', 'rndmask', 'k16s200', 'asym', 'notrace', 'b2']), (GRAM_CASES, GRAM, ['gram_M0', 'many_la']), (BIAS_CASES, BIAS, ['bias_b'])):\n"
+            "import json, os\n"
+            "REP = os.path.join(GOLDEN, 'rep'); REP_CASES = json.load(open(os.path.join(REP, 'cases.json')))\n"
+            "chunked = 'DAMAR_MAX_HITS' in os.environ\n"   # one read of gram_M0 alone has 8.9 M hits (a poly-A run): no chunk of reads is that small
+            "for table, dbdir, names in ((CASES, TINY, ['default', 'identity', 'rndmask', 'k16s200', 'asym', 'notrace', 'b2']), (GRAM_CASES, GRAM, ['many_la'] if chunked else ['gram_M0', 'many_la']), (BIAS_CASES, BIAS, ['bias_b']), (REP_CASES, REP, sorted(REP_CASES) if chunked else []), (LONG_CASES, LONG, sorted(LONG_CASES) if chunked else [])):\n"
             "    for case in names:\n"
             "        o = parse_flags(table[case]['flags'])\n"
             "        blks = {n: load_block(dbdir, n, tuple(o['masks'])) for n in set(table[case]['blocks'])}\n"
@@ -235,6 +244,8 @@ def test_alternative_paths_give_the_same_files(env):
             "print('unpacked ok')\n") % (os.path.dirname(GOLDEN).rsplit('/tests', 1)[0], os.path.dirname(GOLDEN))
     r = subprocess.run([sys.executable, "-c", code], env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "unpacked ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    if "DAMAR_MAX_HITS" in env:
+        assert "mf.chunked" in r.stderr, "no comparison was cut into chunks"
 
 
 def test_reads_shorter_than_k_are_refused():
