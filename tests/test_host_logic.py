@@ -241,3 +241,50 @@ def test_marvel_track_loader(tmp_path):
     for fn, ref in golden_files("rndmask").items():
         ok, why = dbio.las_equal(ref, out[fn])
         assert ok, f"{fn}: {why}"
+
+
+def test_plan_iter_keeps_the_pool_fed_and_the_order(monkeypatch):
+    """api.plan_iter (the plan runner behind daligner_plan and multi.run_sharded): jobs are collected in plan order, later jobs
+    are submitted while at most DAMAR_LOOKAHEAD comparisons of the pending jobs are unfinished, and jobs whose process-wide
+    options differ are never in flight together."""
+    from concurrent.futures import Future
+    from types import SimpleNamespace
+    log, live = [], []
+
+    class Blk(SimpleNamespace):
+        pass
+
+    def fake_submit(ablk, bblks, s, dcache=None):
+        J = SimpleNamespace(name=ablk.name)
+        J.cmps = [(b, False, None, {}, [Future(), Future()], {"files": {f"{ablk.name}.{b.name}.las": b"x"}}) for b in bblks]
+        log.append(("submit", ablk.name, sum(1 for P in live for c in P.cmps for f in c[4] if not f.done())))
+        live.append(J)
+        return J
+
+    def fake_collect(J, stats=None, as_bytes=True):
+        for c in J.cmps:                       # the pool "finishes" a job's comparisons when the caller waits for them
+            for f in c[4]:
+                f.set_result(None)
+        live.remove(J)
+        log.append(("collect", J.name))
+        return {k: v for c in J.cmps for k, v in c[5]["files"].items()}
+
+    monkeypatch.setattr(api, "submit", fake_submit)
+    monkeypatch.setattr(api, "collect", fake_collect)
+    monkeypatch.setattr(api, "workers", lambda: 2)
+    monkeypatch.setenv("DAMAR_LOOKAHEAD", "4")
+    blk = lambda i, root="R": Blk(name=f"{root}.{i}", root=root, freq=(.25, .25, .25, .25))
+    jobs = [(blk(a), [blk(b) for b in range(1, a + 1)]) for a in range(1, 6)]          # HPCdaligner's plan of 5 blocks
+    files = list(api.plan_iter(jobs, api.Settings()))
+    assert [k for k, _ in files] == [f"R.{a}.R.{b}.las" for a in range(1, 6) for b in range(1, a + 1)]
+    assert [e[1] for e in log if e[0] == "collect"] == [f"R.{a}" for a in range(1, 6)]
+    # a job is submitted only while fewer than 4 comparisons of MORE THAN ONE pending job are unfinished
+    pend_at_submit = [e[2] for e in log if e[0] == "submit"]
+    assert pend_at_submit[0] == 0 and pend_at_submit[1] == 2            # R.2 goes in while R.1 (one pair, two orientations) runs
+    assert max(pend_at_submit) <= 2 * 4                                  # never more than the job being collected plus the lookahead
+    # a second DB (other base frequencies): nothing of the first plan is in flight when its first job is submitted
+    log.clear()
+    other = Blk(name="S.1", root="S", freq=(.3, .2, .2, .3))
+    list(api.plan_iter(jobs[:3] + [(other, [other])], api.Settings()))
+    i = log.index(("submit", "S.1", 0))
+    assert [e[1] for e in log[:i] if e[0] == "collect"] == ["R.1", "R.2", "R.3"]
