@@ -326,8 +326,11 @@ def set_options(s: Settings, freq: Sequence[float]) -> None:
 def sort_kmers(dblock: DeviceBlockHandle, comp: int = 0) -> Optional[KmerIndex]:
     """Sort_Kmers (filter.c:753).  comp=1 indexes the reverse-complemented block on the device."""
     n = C.c_int64(0)
-    h = load_library().damar_sort_kmers(dblock.handle, comp, C.byref(n))
+    L = load_library()
+    h = L.damar_sort_kmers(dblock.handle, comp, C.byref(n))
     if not h:
+        if n.value < 0:
+            raise RuntimeError("damar_b200: " + L.damar_last_error().decode())
         return None
     return KmerIndex(h, n.value, dblock, comp)
 

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 
 #include "common.cuh"
 
@@ -185,7 +187,7 @@ void *dev_alloc_bytes(size_t bytes) {
                 e = cudaMallocFromPoolAsync(&p, r, c.pool, c.stream);
                 if (e == cudaSuccess) break;
                 cudaGetLastError();
-                if (attempt >= 600) fatal("out of device memory: %zu bytes requested (%s)", r, cudaGetErrorString(e));
+                if (attempt >= 40) throw OutOfDeviceMemory{r};
                 std::this_thread::sleep_for(std::chrono::milliseconds(50));
             }
         }
@@ -201,9 +203,15 @@ void *dev_alloc_bytes(size_t bytes) {
             return p;
         }
     }
+    // DAMAR_FAKE_OOM=n (tests): the n-th request of the process that reaches the driver fails once
+    static const long fake_at = getenv("DAMAR_FAKE_OOM") ? atol(getenv("DAMAR_FAKE_OOM")) : 0;
+    static std::atomic<long> misses{0};
+    if (fake_at > 0 && ++misses == fake_at) throw OutOfDeviceMemory{r};
     HostProf hp("cudaMalloc");
     cudaError_t e = cudaMalloc(&p, r);
     if (e != cudaSuccess) {
+        // the other workers' cached blocks first, then a short wait for comparisons in flight to hand their lists back; after
+        // that the caller is unwound (its own buffers return to the cache) and runs again alone: run_with_memory_retry()
         cudaGetLastError();
         CUDA_CHECK(stream_wait(c.stream));
         for (int attempt = 0;; attempt++) {
@@ -211,7 +219,7 @@ void *dev_alloc_bytes(size_t bytes) {
             e = cudaMalloc(&p, r);
             if (e == cudaSuccess) break;
             cudaGetLastError();
-            if (attempt >= 600) fatal("out of device memory: %zu bytes requested (%s)", r, cudaGetErrorString(e));
+            if (attempt >= 40) throw OutOfDeviceMemory{r};
             std::this_thread::sleep_for(std::chrono::milliseconds(50));
         }
     }
@@ -238,6 +246,29 @@ void dev_free(void *p) {
     Context &o = (owner >= 0 && owner < MAX_WORKERS && g_ctx[owner].ready) ? g_ctx[owner] : c;
     std::lock_guard<std::mutex> lk(o.cache_mu);
     o.free_blocks.emplace(sz, p);
+}
+
+// Admission under memory pressure.  Calls that allocate hold g_solo shared; one that ran out of memory has been unwound
+// (everything it held is back in its worker's cache), takes g_solo exclusively -- i.e. waits for the calls in flight --
+// gives every cache back to the driver and runs again with the device to itself.  Workers that wait here hold no device
+// memory, so the retry cannot deadlock; only a call that does not fit the device ALONE is an error.
+static std::shared_mutex g_solo;
+int run_with_memory_retry(const char *what, int oom_rc, const std::function<int()> &fn) {
+    try {
+        std::shared_lock<std::shared_mutex> lk(g_solo);
+        return fn();
+    } catch (const OutOfDeviceMemory &) {
+    }
+    std::unique_lock<std::shared_mutex> lk(g_solo);
+    HostProf hp("memory.solo_rerun");
+    cudaDeviceSynchronize();
+    release_all_caches();
+    try {
+        return fn();
+    } catch (const OutOfDeviceMemory &e) {
+        set_error("%s: out of device memory (%zu bytes requested with the device to itself)", what, e.bytes);
+        return oom_rc;
+    }
 }
 
 void ensure_init() {
@@ -355,7 +386,9 @@ void damar_set_options(const damar_options *opt) { std::lock_guard<std::mutex> l
 damar_block *damar_block_upload(const damar_block_desc *desc) {
     ensure_init();
     HostProf hp("block_upload");
-    return reinterpret_cast<damar_block *>(upload_block(desc));
+    DeviceBlock *b = nullptr;
+    if (run_with_memory_retry("damar_block_upload", 1, [&] { b = upload_block(desc); return 0; }) != 0) return nullptr;
+    return reinterpret_cast<damar_block *>(b);
 }
 void damar_block_free(damar_block *blk) { delete reinterpret_cast<DeviceBlock *>(blk); }
 int damar_block_view_get(damar_block *blk, damar_block_view *view) {
@@ -367,13 +400,19 @@ damar_block *damar_block_from_view(const damar_block_view *view) {
     ensure_init();
     if (view == nullptr || view->packed == nullptr || view->boff == nullptr || view->rlen == nullptr) { set_error("damar_block_from_view: incomplete view"); return nullptr; }
     HostProf hp("block_from_view");
-    return reinterpret_cast<damar_block *>(block_from_view(view));
+    DeviceBlock *b = nullptr;
+    if (run_with_memory_retry("damar_block_from_view", 1, [&] { b = block_from_view(view); return 0; }) != 0) return nullptr;
+    return reinterpret_cast<damar_block *>(b);
 }
 
 damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len) {
     ensure_init();
     HostProf hp("sort_kmers");
-    DeviceIndex *idx = build_index(reinterpret_cast<DeviceBlock *>(blk), comp);
+    DeviceIndex *idx = nullptr;
+    if (run_with_memory_retry("damar_sort_kmers", 1, [&] { idx = build_index(reinterpret_cast<DeviceBlock *>(blk), comp); return 0; }) != 0) {
+        if (len) *len = -1;                                   // NULL with *len == 0 means "no k-mers" (filter.c:990-993); -1: failed, error set
+        return nullptr;
+    }
     if (len) *len = idx->len;
     ctx().tm.kernel_launches = ctx().launches;
     if (idx->len == 0) { delete idx; return nullptr; }        // filter.c:990-993
@@ -403,15 +442,16 @@ static int match_filter_impl(damar_block *ablk, damar_block *bblk, damar_index *
     c.tm.count_ms = c.tm.merge_ms = c.tm.hsort_ms = c.tm.pairs_ms = c.tm.align_ms = c.tm.download_ms = 0;
     c.tm.hits = c.tm.pairs = c.tm.la_calls = c.tm.wave_cells = 0; c.tm.wide_passes = 0;
     int64_t nhits = 0;
-    // stages 3 + 4 on the hits in g_hits; with a sink every call leaves its own result there
+    // stages 3 + 4 on the hits in g_hits; with a sink every call (chunk) leaves its own result, handed over when the whole
+    // comparison has succeeded (a comparison that ran out of memory is run again from the start)
+    struct Pending { std::vector<DeviceResult *> v; ~Pending() { for (auto *r : v) delete r; } } pending;
     auto align = [&](const HitSpan *span) -> int {
         DeviceResult *r = nullptr;
-        if (sink) { r = new DeviceResult(); r->ordinal = ordinal; }
+        if (sink) { r = new DeviceResult(); r->ordinal = ordinal; pending.v.push_back(r); }
         g_out.keep = r;
         int rc = 0;
         if (g_hits.n > 0) { HostProf hp("mf.report_and_align"); rc = report_and_align(ab, bb, comp, self, g_hits, g_out, false, span); }
         g_out.keep = nullptr;
-        if (r) { if (rc == 0) dsink_add(sink, r); else delete r; }
         return rc;
     };
     if (ai != nullptr && bi != nullptr && ai->len > 0 && bi->len > 0) {   // filter.c:2592-2593
@@ -493,23 +533,27 @@ static int match_filter_impl(damar_block *ablk, damar_block *bblk, damar_index *
     c.tm.cells_total += g_out.cells; c.tm.wide_total += c.tm.wide_passes; c.tm.la_total += g_out.nfilt;
     c.tm.hits = nhits; c.tm.la_calls = g_out.nfilt; c.tm.wave_cells = g_out.cells; c.tm.pairs = g_out.pairs; c.tm.redo_pairs = g_out.redo;
     c.tm.kernel_launches = c.launches;
+    for (auto *r : pending.v) dsink_add(sink, r);
+    pending.v.clear();
     return 0;
 }
 
 int damar_match_filter(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx,
                        int self, int comp, damar_overlaps *out) {
-    return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, nullptr, 0);
+    return run_with_memory_retry("damar_match_filter", 1, [&] { return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, nullptr, 0); });
 }
 /* Match_Filter whose records stay in HBM: they are appended to `sink` as call number `ordinal` of the job (the order in
  * which the reference would have buffered the calls breaks full SORT_OVL ties); `out` receives the counters only. */
 int damar_match_filter_sink(damar_block *ablk, damar_block *bblk, damar_index *aidx, damar_index *bidx, int self, int comp,
                             damar_device_sink *sink, int ordinal, damar_overlaps *out) {
     if (sink == nullptr) { set_error("damar_match_filter_sink: no sink"); return 1; }
-    return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, reinterpret_cast<DeviceSink *>(sink), ordinal);
+    return run_with_memory_retry("damar_match_filter_sink", 1, [&] {
+        return match_filter_impl(ablk, bblk, aidx, bidx, self, comp, out, reinterpret_cast<DeviceSink *>(sink), ordinal);
+    });
 }
 
 /* datander's Match_Self (scrub/tandem.c:1182): every read of the block against itself. */
-int damar_match_self(damar_block *blk, damar_overlaps *out) {
+static int match_self_impl(damar_block *blk, damar_overlaps *out) {
     ensure_init();
     Context &c = ctx();
     DeviceBlock *b = reinterpret_cast<DeviceBlock *>(blk);
@@ -522,15 +566,15 @@ int damar_match_self(damar_block *blk, damar_overlaps *out) {
     if (b == nullptr) { set_error("damar_match_self: no block"); return 1; }
     if (b->has_mask) { set_error("damar_match_self: datander takes no mask tracks"); return 1; }
     if (c.fp.suppress != 0 || c.fp.biased) { set_error("damar_match_self: datander has neither -t nor -b (scrub/tandem.c:137)"); return 1; }
-    DeviceIndex *idx = nullptr;
-    { HostProf hp("ms.sort_kmers"); idx = build_index(b, 0); }
+    std::unique_ptr<DeviceIndex> idx;
+    { HostProf hp("ms.sort_kmers"); idx.reset(build_index(b, 0)); }
     int rc = 0;
     if (idx->len > 0) {
         ensure_revcomp(b);                                    // the reverse wave pass runs on the reverse-complemented reads
-        { HostProf hp("ms.self_hits"); rc = self_hits(idx, g_hits); }
+        { HostProf hp("ms.self_hits"); rc = self_hits(idx.get(), g_hits); }
         if (rc == 0 && g_hits.n > 0) { HostProf hp("ms.report_and_align"); rc = report_and_align(b, b, 0, 1, g_hits, g_out, true); }
     }
-    delete idx;
+    idx.reset();
     if (rc != 0) return rc;
     out->novl = g_out.novl; out->ovl = g_out.ovl; out->trace_off = g_out.toff; out->seq = g_out.seq; out->trace = g_out.trace;
     out->ntrace = g_out.ntrace; out->trace_bytes = g_out.tbytes; out->nhits = g_hits.n; out->nfilt = g_out.nfilt;
@@ -541,13 +585,19 @@ int damar_match_self(damar_block *blk, damar_overlaps *out) {
     return 0;
 }
 
+int damar_match_self(damar_block *blk, damar_overlaps *out) {
+    return run_with_memory_retry("damar_match_self", 1, [&] { return match_self_impl(blk, out); });
+}
+
 int damar_trace_point_diffs(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
                             const void *trace, int trace_bytes, int64_t novl, int64_t ntrace, int trace_spacing,
                             int32_t *rec_diffs, uint16_t *seg_diffs) {
     ensure_init();
     if (trace_spacing <= 0 || (trace_bytes != 1 && trace_bytes != 2)) { set_error("damar_trace_point_diffs: bad trace spacing / width"); return 1; }
-    return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
-                                  trace_bytes, novl, ntrace, trace_spacing, rec_diffs, seg_diffs);
+    return run_with_memory_retry("damar_trace_point_diffs", 1, [&] {
+        return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
+                                      trace_bytes, novl, ntrace, trace_spacing, rec_diffs, seg_diffs);
+    });
 }
 
 int damar_trace_point_scripts(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
@@ -557,8 +607,10 @@ int damar_trace_point_scripts(damar_block *ablk, damar_block *bblk, const damar_
     if (trace_spacing <= 0 || (trace_bytes != 1 && trace_bytes != 2) || !rec_diffs || !script_off || !script || !script_len) {
         set_error("damar_trace_point_scripts: bad arguments"); return 2;
     }
-    return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
-                                  trace_bytes, novl, ntrace, trace_spacing, rec_diffs, nullptr, script_off, script, script_len);
+    return run_with_memory_retry("damar_trace_point_scripts", 2, [&] {
+        return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
+                                      trace_bytes, novl, ntrace, trace_spacing, rec_diffs, nullptr, script_off, script, script_len);
+    });
 }
 
 int damar_trace_mid_scripts(damar_block *ablk, damar_block *bblk, const damar_overlap *ovl, const uint64_t *trace_off,
@@ -568,8 +620,10 @@ int damar_trace_mid_scripts(damar_block *ablk, damar_block *bblk, const damar_ov
     if (trace_spacing <= 0 || (trace_bytes != 1 && trace_bytes != 2) || !rec_diffs || !script_off || !script || !script_len) {
         set_error("damar_trace_mid_scripts: bad arguments"); return 2;
     }
-    return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
-                                  trace_bytes, novl, ntrace, trace_spacing, rec_diffs, nullptr, script_off, script, script_len, 1);
+    return run_with_memory_retry("damar_trace_mid_scripts", 2, [&] {
+        return trace_point_diffs_host(reinterpret_cast<DeviceBlock *>(ablk), reinterpret_cast<DeviceBlock *>(bblk), ovl, trace_off, trace,
+                                      trace_bytes, novl, ntrace, trace_spacing, rec_diffs, nullptr, script_off, script, script_len, 1);
+    });
 }
 
 void damar_host_free(void *p) { free(p); }

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -33,8 +34,21 @@ constexpr int PACK_FRONT_PAD = 4;     // words of zero padding in front of every
 constexpr int RTAB_SHIFT = 9;         // one read-lookup entry per 512 base slots (reads are mostly longer than that)
 
 // ---- device memory: caching allocator (api.cu); all work is ordered on the context stream ----
+// Device memory that the driver will not give even after every worker's cache was handed back and a wait: thrown by
+// dev_alloc_bytes, caught at the C-ABI (api.cu: the call is run again alone on the device, then reported as an error).
+struct OutOfDeviceMemory { size_t bytes; };
 void *dev_alloc_bytes(size_t bytes);
 void dev_free(void *p);
+// raw device blocks a function holds outside a DevBuf: released if the function is left by an exception
+struct FreeOnUnwind {
+    void *slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; int n = 0; bool armed = true;
+    template <typename T> T *add(T *p) { slot[n++] = p; return p; }
+    void dismiss() { armed = false; }
+    ~FreeOnUnwind() { if (armed) for (int i = 0; i < n; i++) if (slot[i]) dev_free(slot[i]); }
+};
+// runs fn() -> int under the library's admission rule: normally alongside the other workers' calls; if it runs out of device
+// memory, once more ALONE (after the calls in flight have finished and every cache was released); then `oom_rc` with the error set
+int run_with_memory_retry(const char *what, int oom_rc, const std::function<int()> &fn);
 template <typename T> inline T *dev_alloc(size_t n) { return reinterpret_cast<T *>(dev_alloc_bytes(n * sizeof(T))); }
 
 // ---- simple owning device buffer ----

@@ -61,6 +61,7 @@ void *Sort_Kmers(DAMAR_HITS_DB *block, int *len)
     free(boff); free(rlen);
     if (t->blk == NULL) { fprintf(stderr, "%s\n", damar_last_error()); exit(1); }
     t->idx = damar_sort_kmers(t->blk, 0, &n);
+    if (n < 0) { fprintf(stderr, "%s\n", damar_last_error()); exit(1); }      /* failed (NULL with n == 0 is an empty list) */
     *len = (int)n;
     if (t->idx == NULL) { damar_block_free(t->blk); free(t); return NULL; }   /* filter.c:990-993 */
     return t;

@@ -14,6 +14,8 @@
 #include <thread>
 #include <type_traits>
 
+#include <memory>
+
 #include "common.cuh"
 
 namespace damar {
@@ -293,7 +295,8 @@ static uint32_t *alloc_packed(int64_t nwords, cudaStream_t st) {
 DeviceBlock *upload_block(const damar_block_desc *d) {
     Context &c = ctx();
     Timer tm(c.stream);
-    DeviceBlock *b = new DeviceBlock();
+    std::unique_ptr<DeviceBlock> holder(new DeviceBlock());        // freed with its device arrays if an allocation below throws
+    DeviceBlock *b = holder.get();
     b->nreads = d->nreads; b->maxlen = d->maxlen; b->totlen = d->totlen; b->ufirst = d->ufirst; b->part = d->part;
     b->sizeof_db = d->sizeof_db;
     b->as_is = (d->flags & DAMAR_BLOCK_AS_IS) != 0;
@@ -368,7 +371,7 @@ DeviceBlock *upload_block(const damar_block_desc *d) {
     CUDA_CHECK(stream_wait(c.stream));
     dev_free(dbytes);
     c.tm.upload_ms = tm.stop();
-    return b;
+    return holder.release();
 }
 
 // ---- device-to-device block transfer (damar_block_view, include/damar_b200.h) ----
@@ -387,7 +390,8 @@ void block_view(DeviceBlock *b, damar_block_view *v) {
 DeviceBlock *block_from_view(const damar_block_view *v) {
     Context &c = ctx();
     cudaStream_t st = c.stream;
-    DeviceBlock *b = new DeviceBlock();
+    std::unique_ptr<DeviceBlock> holder(new DeviceBlock());
+    DeviceBlock *b = holder.get();
     b->nreads = v->nreads; b->maxlen = v->maxlen; b->ufirst = v->ufirst; b->part = v->part;
     b->totlen = v->totlen; b->nbases = v->nbases; b->sizeof_db = v->sizeof_db;
     memcpy(b->freq, v->freq, sizeof(b->freq));
@@ -419,7 +423,7 @@ DeviceBlock *block_from_view(const damar_block_view *v) {
     }
     CUDA_CHECK(stream_wait(st));
     b->h_boff.assign(hb.begin(), hb.end());
-    return b;
+    return holder.release();
 }
 
 void ensure_revcomp(DeviceBlock *b) {
@@ -486,9 +490,10 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
         CUDA_CHECK(stream_wait(st));
     }
     int64_t kmers = total32;
-    DeviceIndex *idx = new DeviceIndex();
+    std::unique_ptr<DeviceIndex> iholder(new DeviceIndex());
+    DeviceIndex *idx = iholder.get();
     idx->blk = b; idx->comp = comp; idx->len = 0;
-    if (kmers <= 0) { c.tm.extract_ms = t_ex.stop(); c.tm.ksort_ms = 0; c.tm.kmers = 0; return idx; }
+    if (kmers <= 0) { c.tm.extract_ms = t_ex.stop(); c.tm.ksort_ms = 0; c.tm.kmers = 0; return iholder.release(); }
 
     // one 64-bit word per k-mer (code << gbits | gpos) whenever that fits: 8-byte records through the sort and the merge
     int gbits = 1;
@@ -496,11 +501,12 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
     static const bool pack_ok = !(getenv("DAMAR_PACK") && atoi(getenv("DAMAR_PACK")) == 0);
     const bool packed = pack_ok && 2 * K + gbits <= 64;
     uint64_t *k0, *k1; uint32_t *g0 = nullptr, *g1 = nullptr;
-    k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
-    k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2));
+    FreeOnUnwind raw;
+    k0 = raw.add((uint64_t *)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2)));
+    k1 = raw.add((uint64_t *)dev_alloc_bytes(sizeof(uint64_t) * (kmers + 2)));
     if (!packed) {
-        g0 = (std::remove_reference<decltype(g0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 4));
-        g1 = (std::remove_reference<decltype(g1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 4));
+        g0 = raw.add((uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 4)));
+        g1 = raw.add((uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (kmers + 4)));
     }
     if (fp.biased)
         biased_tuples<true><<<(b->nreads + 63) / 64, 64, 0, st>>>(b->packed[comp], b->boff, b->rlen, b->nreads, K, fp.kmask, anno, data,
@@ -530,10 +536,11 @@ DeviceIndex *build_index(DeviceBlock *b, int comp) {
         std::swap(k0, k1); std::swap(g0, g1);
     }
     c.tm.ksort_ms = t_sort.stop();
+    raw.dismiss();
     dev_free(k1); if (g1) dev_free(g1);
     idx->codes = k0; idx->gpos = g0; idx->gbits = packed ? gbits : 0; idx->len = kmers;
     c.tm.kmers = kmers;
-    return idx;
+    return iholder.release();
 }
 
 }  // namespace damar

@@ -225,8 +225,10 @@ int damar_dsink_serialise(damar_device_sink *s, int trace_spacing, int no_trace,
                           uint8_t **buf1, int64_t *len1, uint8_t **buf2, int64_t *len2) {
     ensure_init();
     HostProf hp("dsink_serialise");
-    return dsink_serialise(reinterpret_cast<DeviceSink *>(s), trace_spacing, no_trace, only_identity, split_read, maxlen, maxread,
-                           buf1, len1, buf2, len2);
+    return run_with_memory_retry("damar_dsink_serialise", 1, [&] {
+        return dsink_serialise(reinterpret_cast<DeviceSink *>(s), trace_spacing, no_trace, only_identity, split_read, maxlen, maxread,
+                               buf1, len1, buf2, len2);
+    });
 }
 
 }  // extern "C"

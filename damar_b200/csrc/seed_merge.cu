@@ -594,11 +594,12 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
     const bool packed = pack_ok && kbits + out.qbits <= 64;
 
     uint64_t *k0, *k1; uint32_t *v0 = nullptr, *v1 = nullptr;
-    k0 = (std::remove_reference<decltype(k0)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2));
-    k1 = (std::remove_reference<decltype(k1)>::type)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2));
+    FreeOnUnwind raw;
+    k0 = raw.add((uint64_t *)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2)));
+    k1 = raw.add((uint64_t *)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2)));
     if (!packed) {
-        v0 = (std::remove_reference<decltype(v0)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4));
-        v1 = (std::remove_reference<decltype(v1)>::type)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4));
+        v0 = raw.add((uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4)));
+        v1 = raw.add((uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4)));
     }
     m.keys = k0; m.bpos = v0; m.pbits = out.pbits; m.abits = out.abits; m.qbits = out.qbits;
     m.limit = (uint32_t)limit; m.gram = nullptr;
@@ -613,6 +614,7 @@ int seed_hits(const DeviceIndex *ai, const DeviceIndex *bi, int self, int comp, 
     const int rc = packed ? radix_sort(k0, v0, k1, v1, (int64_t)nhits, out.qbits, out.qbits + kbits, st)
                           : radix_sort(k0, v0, k1, v1, (int64_t)nhits, 0, kbits, st);
     c.tm.hsort_ms = t_sort.stop();
+    raw.dismiss();
     dev_free(k1); if (v1) dev_free(v1);
     if (rc != 0) { dev_free(k0); if (v0) dev_free(v0); return 1; }
     out.keys = k0; out.bpos = v0; out.n = (int64_t)nhits;

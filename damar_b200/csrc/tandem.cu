@@ -98,8 +98,10 @@ int self_hits(const DeviceIndex *idx, SeedHits &out) {
     if (kbits > 64) { set_error("seed-hit key needs %d bits (> 64): block too large for this build", kbits); return 1; }
     static const bool pack_ok = !(getenv("DAMAR_PACK") && atoi(getenv("DAMAR_PACK")) == 0);
     const bool packed = pack_ok && kbits + out.qbits <= 64;
-    uint64_t *k0 = (uint64_t *)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2));
-    uint32_t *v0 = packed ? nullptr : (uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4));
+    FreeOnUnwind raw;
+    uint64_t *k0 = raw.add((uint64_t *)dev_alloc_bytes(sizeof(uint64_t) * (nhits + 2)));
+    uint32_t *v0 = packed ? nullptr : raw.add((uint32_t *)dev_alloc_bytes(sizeof(uint32_t) * (nhits + 4)));
+    raw.dismiss();                                          // nothing below allocates
     link_hits<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(link.p, off.p, nb, b->boff, b->rtab, out.pbits, out.abits, out.qbits, k0, v0);
     KERNEL_CHECK(); count_launch();
     c.tm.merge_ms = t_merge.stop();

@@ -145,7 +145,11 @@ damar_block *damar_block_from_view(const damar_block_view *view);
 
 /* Sort_Kmers (filter.c:753-994).  comp != 0 builds the index of the reverse-complemented block
  * (what daligner.c:998-1003 obtains with complement_DB + Sort_Kmers) without touching host memory.
- * *len receives the k-mer count; NULL/0 when the block has no k-mers.                          */
+ * *len receives the k-mer count; NULL/0 when the block has no k-mers, NULL/-1 on failure (error set).
+ *
+ * Device memory: every call below that allocates runs alongside the calls of the other worker threads; one that runs out of
+ * device memory is unwound, waits for the calls in flight, hands all cached memory back to the driver and is run again with
+ * the device to itself.  Only a call that does not fit the device alone fails ("out of device memory").            */
 damar_index *damar_sort_kmers(damar_block *blk, int comp, int64_t *len);
 void         damar_index_free(damar_index *idx);
 

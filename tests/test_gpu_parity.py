@@ -468,3 +468,27 @@ def test_radix_sort_is_stable_and_sorted(n, lo, hi, vals, skew):
     checked on the device against order, stability (payload = input index / low key bits = input index) and a
     permutation checksum."""
     api.sort_selftest(n, lo, hi, vals, reps=2, seed=n, skew=skew)
+
+
+@pytest.mark.parametrize("nth", [2, 15, 40, 80, 130])
+def test_out_of_device_memory_is_retried_alone(nth):
+    """DAMAR_FAKE_OOM=n makes the n-th device-memory request that reaches the driver fail once.  Whatever call it hits (block
+    upload, Sort_Kmers, the seed stage, the alignment stage, the .las writer) is unwound, run again with the device to itself
+    (`memory.solo_rerun` in the host profile) and the job's files are those of an undisturbed run -- the library neither exits
+    nor returns a partial result."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from cases import *\nfrom damar_b200 import api, dbio\n"
+            "o = parse_flags(CASES['default']['flags'])\n"
+            "blks = {n: load_block(TINY, n, tuple(o['masks'])) for n in set(CASES['default']['blocks'])}\n"
+            "nm = CASES['default']['blocks']\n"
+            "out = api.daligner(blks[nm[0]], [blks[n] for n in nm[1:]], settings(o))\n"
+            "for fn, ref in golden_files('default', TINY).items():\n"
+            "    ok, why = dbio.las_equal(ref, out[fn])\n"
+            "    assert ok, (fn, why)\n"
+            "print('files ok')\n") % (os.path.dirname(GOLDEN).rsplit('/tests', 1)[0], os.path.dirname(GOLDEN))
+    r = subprocess.run([sys.executable, "-c", code], env={**os.environ, "DAMAR_FAKE_OOM": str(nth), "DAMAR_PROFILE": "1"},
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "files ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "memory.solo_rerun" in r.stderr, "the injected failure did not happen: fewer requests than expected"
