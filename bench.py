@@ -186,8 +186,12 @@ def roofline_lines(tm_alone, tm, dt, world, steps):
               "kernel_ms_per_step_summed_over_comparisons": 1000 * ak / max(steps, 1),
               "cells_per_s_per_launch": tm["cells_total"] / ak if ak > 0 else None,
               "cells_per_s_of_step": tm["cells_total"] / dt if dt > 0 else None,
+              # the kernel running alone on one C2 block pair: committed ncu capture of this build (not measured in this run)
+              "alone": {"cells": 803728653, "launch_ms": 28.02, "sms_full_ms": 16.0, "cells_per_s_while_full": 5.0e10,
+                        "issue_active": 0.596, "lanes_active_of_32": 19.46, "registers": 154, "warps_per_sm": 12,
+                        "source": "profiles/r02_ncu_wave_tasks.txt (ncu --set full), profiles/r02_wave_residency.txt (per-warp residency log)"},
               "note": "kernel_ms sums the event intervals of up to 6 concurrent comparisons, so cells_per_s_per_launch understates a launch "
-                      "running alone; issue-slot / lane figures of the kernel alone are in profiles/ (ncu --set full)"}
+                      "running alone; `alone` cites the committed capture of the same kernel"}
     return roofline, stage4
 
 
