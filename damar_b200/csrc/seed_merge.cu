@@ -21,6 +21,9 @@
 //                  then one thread per HIT: which entry it belongs to (bisection of the scan), which B partner,
 //                  (bread, bpos) of that partner -- all lanes busy and the stores coalesced, whatever the run lengths
 // A run (or a window) too large for shared memory is handled by its CTA straight from global memory.
+// The B run of a code is found through a bucket table over the window's code range (a lookup and a bisection of the few
+// entries of one bucket).  A comparison with more hits than one sort takes is cut into chunks of B reads (api.cu): the
+// sweeps then run `ranged`, counting and emitting only the partners whose position lies in the chunk.
 // A hit is ONE 64-bit word  bread | aread | apos | bpos  whenever those fit (they do for every configuration of
 // BASELINE.json), sorted keys-only on its upper fields; the stable sort keeps ties in merge order (= bpos ascending),
 // which report_thread depends on.  Otherwise key + bpos pairs as in round 1.
