@@ -132,13 +132,21 @@ static int do_init(int device) {
 // GB and cudaFree waits for every running kernel (0.3 s behind a wave kernel, measured: tools/exp/malloc_stall.cu).  All
 // work of a worker context is ordered on its stream, so a freed block can be handed to the context's next request
 // immediately: requests are rounded up to a coarse size class and served best-fit from the context's free list (at most
-// 1.5x the rounded size); after the first pass of a plan a step asks the driver for memory a handful of times.  A block
-// freed by another thread (the collector releasing a job's records) returns to the cache of the context that allocated
-// it; that caller guarantees that no stream still uses it.
+// 1.5x the rounded size).  A block freed by ANOTHER context than the one that allocated it (the collector releasing a
+// job's records, a plan dropping its k-mer indexes) comes with the caller's guarantee that no stream still uses it: it
+// goes to one shared pool that every context draws from before it asks the driver -- the lists of a plan circulate
+// between the workers (an index is built by whichever worker needs it first) instead of piling up where they were last
+// freed.  DAMAR_SHARED_POOL=0 returns such a block to the cache of the context that allocated it instead.
 // DAMAR_ALLOC=pool selects per-worker stream-ordered pools (cudaMemPool) instead: measured slower -- while the pools grow
 // every request waits for the driver to map memory (a first pass of 9 s instead of 0.9 s) and the steady state is the same.
 struct BlockInfo { size_t size; int owner; };          // owner = the worker context whose request allocated the block
-static std::map<void *, BlockInfo> g_block_size;       // legacy allocator only
+static std::map<void *, BlockInfo> g_block_size;
+static std::mutex g_shared_mu;
+static std::multimap<size_t, void *> g_shared_blocks;  // quiescent blocks any context may take
+static bool shared_pool() {
+    static const bool on = !(getenv("DAMAR_SHARED_POOL") && atoi(getenv("DAMAR_SHARED_POOL")) == 0);
+    return on;
+}
 static bool pool_alloc() {
     static const bool on = [] { const char *e = getenv("DAMAR_ALLOC"); return e && strcmp(e, "pool") == 0; }();
     return on;
@@ -169,8 +177,15 @@ static void release_cached_blocks(Context &c) {
 }
 // Memory pressure between workers: a worker whose request fails hands the unused memory of EVERY worker's pool back to the
 // driver and then retries for a while -- the other comparisons in flight finish and release their lists.
+static void release_shared_blocks() {
+    std::lock_guard<std::mutex> lk(g_shared_mu);
+    std::lock_guard<std::mutex> lock(g_mu);
+    for (auto &kv : g_shared_blocks) { g_block_size.erase(kv.second); cudaFree(kv.second); }
+    g_shared_blocks.clear();
+}
 static void release_all_caches() {
     for (int i = 0; i < MAX_WORKERS; i++) release_cached_blocks(g_ctx[i]);
+    release_shared_blocks();
 }
 void *dev_alloc_bytes(size_t bytes) {
     Context &c = ctx();
@@ -200,6 +215,17 @@ void *dev_alloc_bytes(size_t bytes) {
         if (it != c.free_blocks.end() && it->first <= r + r / 2) {
             p = it->second;
             c.free_blocks.erase(it);
+            return p;
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(g_shared_mu);
+        auto it = g_shared_blocks.lower_bound(r);
+        if (it != g_shared_blocks.end() && it->first <= r + r / 2) {
+            p = it->second;
+            g_shared_blocks.erase(it);
+            std::lock_guard<std::mutex> lock(g_mu);
+            g_block_size[p].owner = c.index;
             return p;
         }
     }
@@ -243,6 +269,11 @@ void dev_free(void *p) {
         if (it != g_block_size.end()) { sz = it->second.size; owner = it->second.owner; }
     }
     if (sz == 0) { cudaFree(p); return; }
+    if (owner != c.index && shared_pool()) {       // freed by another context: quiescent by the caller's guarantee
+        std::lock_guard<std::mutex> lk(g_shared_mu);
+        g_shared_blocks.emplace(sz, p);
+        return;
+    }
     Context &o = (owner >= 0 && owner < MAX_WORKERS && g_ctx[owner].ready) ? g_ctx[owner] : c;
     std::lock_guard<std::mutex> lk(o.cache_mu);
     o.free_blocks.emplace(sz, p);
@@ -345,6 +376,7 @@ void damar_shutdown(void) {
         c.ready = false;
     }
     tl_ctx = saved;
+    release_shared_blocks();
     g_device = -1;
 }
 
