@@ -470,7 +470,7 @@ def test_radix_sort_is_stable_and_sorted(n, lo, hi, vals, skew):
     api.sort_selftest(n, lo, hi, vals, reps=2, seed=n, skew=skew)
 
 
-@pytest.mark.parametrize("nth", [2, 15, 40, 80, 130])
+@pytest.mark.parametrize("nth", [2, 15, 40, 80, 110])
 def test_out_of_device_memory_is_retried_alone(nth):
     """DAMAR_FAKE_OOM=n makes the n-th device-memory request that reaches the driver fail once.  Whatever call it hits (block
     upload, Sort_Kmers, the seed stage, the alignment stage, the .las writer) is unwound, run again with the device to itself
