@@ -1,7 +1,7 @@
 # Builds the B200-native daligner library (sm_100a only) and the oracle.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-unknown-pragmas -Xptxas -v
 CSRC      := damar_b200/csrc
 OBJS      := $(CSRC)/api.o $(CSRC)/scan.o $(CSRC)/radix_sort.o $(CSRC)/kmer_index.o $(CSRC)/seed_merge.o $(CSRC)/tandem.o $(CSRC)/pair_align.o $(CSRC)/trace_pts.o $(CSRC)/las_sink.o $(CSRC)/las_device.o
 LIB       := damar_b200/libdamar_b200.so
